@@ -1,0 +1,1646 @@
+// ba_engine.cu -- B200 (sm_100a) full bundle-adjustment engine behind the C-ABI of include/ba_b200.h.
+//
+// Device pipeline of one LM iteration (reference: core/full_bundle_adjustment_solver.cpp:709-1008):
+//   K1 k_linearize_by_point : per-observation projection/residual/Huber weight/Jacobians, observations
+//                             sorted by (point,pose,insertion); warp-shuffle segmented sums -> C, b per
+//                             point, B per (pose,point) pair (last-writer flag), then damping + 3x3
+//                             LDLT inverse in registers (K3 fused) (:716-831 point side, :846-856)
+//   K2 k_linearize_by_pose  : same per-observation math in pose order -> per-chunk partial A (21) / a (6)
+//      k_finish_poses       : ordered sum of the partials, fill-lower, damping, S diagonal + rhs init
+//                             (:795-810, :833-844, diagonal of :878-888)
+//   K4 k_schur              : per point E = B C^-1, rhs -= E b, S -= E B^T for pose pairs j<=k (:858-888)
+//   K5 cholesky_solve       : dense FP64 Cholesky of S with rhs carried as an extra row (:890-908)
+//   K6 k_backsub_pairs/points: y = C^-1 b - C^-1 sum_j B^T x_j, model change, trial points (:910-917,:435-455)
+//   K7 k_update_poses, k_cost, k_decide : se3Exp update, trial cost, rho / accept / lambda / convergence
+//                             on the device (:922-1007)
+// There is no CPU fallback: every entry point that computes requires a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ba_b200.h"
+#include "ba_cholesky.cuh"
+#include "ba_device.cuh"
+
+namespace ba {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kPtBlk = 18;  // per-point SoA rows: b(3) Cd(6) Cinv(6) Cinv_b(3)
+constexpr int PB_b = 0, PB_Cd = 3, PB_Cinv = 9, PB_Cinvb = 15;
+
+struct ChunkA {  // by-pose chunk: one free pose per chunk
+  int obs_start;
+  int obs_count;
+  int j_opt;
+  int _pad;
+};
+
+// parameter double buffer
+struct Params {
+  const double *poses[2];  // [N_total*12]
+  const double *points[2]; // [M_total*3]
+};
+struct ParamsW {
+  double *poses[2];
+  double *points[2];
+};
+
+// ---------------------------------------------------------------------------
+// K1: linearise in point order.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void finish_point(const double *Craw, const double *braw, double lambda,
+                                             double *__restrict__ ptblk, size_t Mp, int pt) {
+  // fill-lower is implicit (symmetric 6-pack); damping (:850-852); Cinv = ldlt().solve(I) (:854)
+  const double lp1 = 1.0 + lambda;
+  double cd[6] = {Craw[0] * lp1, Craw[1], Craw[2], Craw[3] * lp1, Craw[4], Craw[5] * lp1};
+  double inv[9];
+  ldlt3_inverse(cd, inv);
+  const double cb0 = inv[0] * braw[0] + inv[1] * braw[1] + inv[2] * braw[2];
+  const double cb1 = inv[3] * braw[0] + inv[4] * braw[1] + inv[5] * braw[2];
+  const double cb2 = inv[6] * braw[0] + inv[7] * braw[1] + inv[8] * braw[2];
+  ptblk[(PB_b + 0) * Mp + pt] = braw[0];
+  ptblk[(PB_b + 1) * Mp + pt] = braw[1];
+  ptblk[(PB_b + 2) * Mp + pt] = braw[2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ptblk[(PB_Cd + k) * Mp + pt] = cd[k];
+  // the LDLT inverse is symmetric up to rounding; keep the upper triangle (r<=c) of the row-major result
+  ptblk[(PB_Cinv + 0) * Mp + pt] = inv[0];
+  ptblk[(PB_Cinv + 1) * Mp + pt] = inv[1];
+  ptblk[(PB_Cinv + 2) * Mp + pt] = inv[2];
+  ptblk[(PB_Cinv + 3) * Mp + pt] = inv[4];
+  ptblk[(PB_Cinv + 4) * Mp + pt] = inv[5];
+  ptblk[(PB_Cinv + 5) * Mp + pt] = inv[8];
+  ptblk[(PB_Cinvb + 0) * Mp + pt] = cb0;
+  ptblk[(PB_Cinvb + 1) * Mp + pt] = cb1;
+  ptblk[(PB_Cinvb + 2) * Mp + pt] = cb2;
+}
+
+template <bool ACCUM_B>
+__global__ void __launch_bounds__(kThreads)
+k_linearize_by_point(const Chunk *__restrict__ chunks, const double2 *__restrict__ obs_uv,
+                     const int *__restrict__ obs_pose, const int *__restrict__ obs_point,
+                     const int *__restrict__ obs_camflags, const int *__restrict__ obs_pair,
+                     Params prm, const double *__restrict__ cams, double thres_huber,
+                     double *__restrict__ ptblk, size_t Mp, double *__restrict__ Bsoa, size_t Pp,
+                     const LmState *__restrict__ st) {
+  if (st->done) return;
+  __shared__ SegSmem<9, kWarps> sm9;
+  __shared__ SegSmem<18, kWarps> sm18;
+  const Chunk ch = chunks[blockIdx.x];
+  const int t = threadIdx.x;
+  const bool active = t < ch.obs_count;
+  const int k = ch.obs_start + t;
+  const double *poses = prm.poses[st->cur];
+  const double *points = prm.points[st->cur];
+  double v[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) v[i] = 0.0;
+  double Bv[18];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
+  int pt = -1 - t, cf = 0, pair = -1, ps = -1;
+  if (active) {
+    pt = obs_point[k];
+    ps = obs_pose[k];
+    cf = obs_camflags[k];
+    pair = obs_pair[k];
+    if (cf & kFlagPointFree) {
+      const double2 uv = obs_uv[k];
+      double T[12], X[3];
+      const double *Tp = poses + (size_t)ps * 12;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) T[i] = __ldg(Tp + i);
+      X[0] = __ldg(points + (size_t)pt * 3);
+      X[1] = __ldg(points + (size_t)pt * 3 + 1);
+      X[2] = __ldg(points + (size_t)pt * 3 + 2);
+      const double *cam = cams + (cf & kCamMask) * kCamStride;
+      Proj p;
+      project(T, X, cam, uv.x, uv.y, p);
+      const double w = huber_weight(p.r0, p.r1, thres_huber);
+      const double wr0 = w * p.r0, wr1 = w * p.r1;
+      double G[6], Rm[6];
+      jac_G(p, cam, G);
+      jac_R(G, T, Rm);
+      // C_i(upper) += w Rm^T Rm (:503-517,821) ; b_i -= Rm^T (w r) (:823)
+      v[0] = w * (Rm[0] * Rm[0] + Rm[3] * Rm[3]);
+      v[1] = w * (Rm[0] * Rm[1] + Rm[3] * Rm[4]);
+      v[2] = w * (Rm[0] * Rm[2] + Rm[3] * Rm[5]);
+      v[3] = w * (Rm[1] * Rm[1] + Rm[4] * Rm[4]);
+      v[4] = w * (Rm[1] * Rm[2] + Rm[4] * Rm[5]);
+      v[5] = w * (Rm[2] * Rm[2] + Rm[5] * Rm[5]);
+      v[6] = -(Rm[0] * wr0 + Rm[3] * wr1);
+      v[7] = -(Rm[1] * wr0 + Rm[4] * wr1);
+      v[8] = -(Rm[2] * wr0 + Rm[5] * wr1);
+      if (pair >= 0 && (ACCUM_B || (cf & kFlagLastOfPair))) {
+        double Q[12];
+        jac_Q(G, p.Xb, Q);
+        // B_ji = w Q^T Rm (:826), 6x3 row-major
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Bv[r * 3 + c] = w * (Q[r] * Rm[c] + Q[6 + r] * Rm[3 + c]);
+      }
+    }
+  }
+  // segment heads / tails by point
+  const bool head = !active || t == 0 || obs_point[k - 1] != pt;
+  const bool tail = active && (t == ch.obs_count - 1 || obs_point[k + 1] != pt);
+  block_segmented_sum<9, kWarps>(v, head, tail, sm9);
+  if (tail && (cf & kFlagPointFree)) {
+    if (ch.flags & kChunkSplit) {
+      // rare: a point with more observations than one chunk holds; raw sums are completed by
+      // k_finish_split_points
+#pragma unroll
+      for (int i = 0; i < 6; ++i) atomicAdd(&ptblk[(PB_Cd + i) * Mp + pt], v[i]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) atomicAdd(&ptblk[(PB_b + i) * Mp + pt], v[6 + i]);
+    } else {
+      finish_point(v, v + 6, st->lambda, ptblk, Mp, pt);
+    }
+  }
+  if (!ACCUM_B) {
+    if (active && pair >= 0 && (cf & kFlagLastOfPair)) {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) Bsoa[(size_t)i * Pp + pair] = Bv[i];
+    }
+  } else {
+    // corrected mode: B_ji += over the observations of the pair (adjacent in this order)
+    const bool phead = !active || t == 0 || obs_pair[k - 1] != pair || pair < 0;
+    const bool ptail = active && pair >= 0 && (t == ch.obs_count - 1 || obs_pair[k + 1] != pair);
+    block_segmented_sum<18, kWarps>(Bv, phead, ptail, sm18);
+    if (ptail) {
+      if (ch.flags & kChunkSplit) {
+#pragma unroll
+        for (int i = 0; i < 18; ++i) atomicAdd(&Bsoa[(size_t)i * Pp + pair], Bv[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 18; ++i) Bsoa[(size_t)i * Pp + pair] = Bv[i];
+      }
+    }
+  }
+}
+
+__global__ void k_zero_split(const int *__restrict__ split_points, int n_split, double *__restrict__ ptblk,
+                             size_t Mp, const int *__restrict__ split_pairs, int n_split_pairs,
+                             double *__restrict__ Bsoa, size_t Pp, int accum_b, const LmState *st) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_split) {
+    const int pt = split_points[i];
+    for (int k = 0; k < 9; ++k) ptblk[(size_t)k * Mp + pt] = 0.0;
+  }
+  if (accum_b && i < n_split_pairs) {
+    const int p = split_pairs[i];
+    for (int k = 0; k < 18; ++k) Bsoa[(size_t)k * Pp + p] = 0.0;
+  }
+}
+
+__global__ void k_finish_split_points(const int *__restrict__ split_points, int n_split,
+                                      double *__restrict__ ptblk, size_t Mp, const LmState *st) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_split) return;
+  const int pt = split_points[i];
+  double c[6], b[3];
+  for (int k = 0; k < 6; ++k) c[k] = ptblk[(PB_Cd + k) * Mp + pt];
+  for (int k = 0; k < 3; ++k) b[k] = ptblk[(PB_b + k) * Mp + pt];
+  finish_point(c, b, st->lambda, ptblk, Mp, pt);
+}
+
+// ---------------------------------------------------------------------------
+// K2: linearise in pose order -> per-chunk partial A (upper 21) and a (6).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_linearize_by_pose(const ChunkA *__restrict__ chunks, const double2 *__restrict__ uvA,
+                    const int *__restrict__ pointA, const int *__restrict__ camA, const int *__restrict__ poseidA,
+                    Params prm, const double *__restrict__ cams, double thres_huber,
+                    double *__restrict__ partials /*[n_chunks][27]*/, const LmState *__restrict__ st) {
+  if (st->done) return;
+  __shared__ double sm[kWarps][27];
+  const ChunkA ch = chunks[blockIdx.x];
+  const double *poses = prm.poses[st->cur];
+  const double *points = prm.points[st->cur];
+  double T[12];
+  {
+    const double *Tp = poses + (size_t)poseidA[ch.obs_start] * 12;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = __ldg(Tp + i);
+  }
+  double acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+  for (int t = threadIdx.x; t < ch.obs_count; t += kThreads) {
+    const int k = ch.obs_start + t;
+    const double2 uv = uvA[k];
+    const int pt = pointA[k];
+    const double *cam = cams + (camA[k] & kCamMask) * kCamStride;
+    double X[3] = {__ldg(points + (size_t)pt * 3), __ldg(points + (size_t)pt * 3 + 1),
+                   __ldg(points + (size_t)pt * 3 + 2)};
+    Proj p;
+    project(T, X, cam, uv.x, uv.y, p);
+    const double w = huber_weight(p.r0, p.r1, thres_huber);
+    const double wr0 = w * p.r0, wr1 = w * p.r1;
+    double G[6], Q[12];
+    jac_G(p, cam, G);
+    jac_Q(G, p.Xb, Q);
+    // A_j(upper) += (w Q)^T Q (:519-556,807) ; a_j -= Q^T (w r) (:809)
+    int e = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const double wa0 = w * Q[r], wa1 = w * Q[6 + r];
+#pragma unroll
+      for (int c = r; c < 6; ++c) acc[e++] += wa0 * Q[c] + wa1 * Q[6 + c];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) acc[21 + r] -= Q[r] * wr0 + Q[6 + r] * wr1;
+  }
+  block_sum<27, kWarps>(acc, sm);
+  if (threadIdx.x == 0) {
+    double *o = partials + (size_t)blockIdx.x * 27;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) o[i] = acc[i];
+  }
+}
+
+// one warp per free pose: ordered sum of its chunk partials, fill-lower, damping, A/a store,
+// S diagonal block and rhs initialisation.
+__global__ void k_finish_poses(const int *__restrict__ pose_chunk_ptr, const double *__restrict__ partials,
+                               int N, double *__restrict__ A /*[N][36]*/, double *__restrict__ a /*[N][6]*/,
+                               double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= N) return;
+  double s = 0.0;
+  if (lane < 27)
+    for (int c = pose_chunk_ptr[j]; c < pose_chunk_ptr[j + 1]; ++c) s += partials[(size_t)c * 27 + lane];
+  const double lp1 = 1.0 + st->lambda;
+  // lane e<21 holds packed upper element e ; lanes 21..26 hold a.  Scatter to the full 6x6 in two
+  // warp-wide rounds (36 entries > 32 lanes); every lane takes part in both shuffles.
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    const int e = lane + 32 * round;
+    const int ee = e < 36 ? e : 35;
+    const int r = ee / 6, c = ee % 6;
+    const int rr = r < c ? r : c, cc = r < c ? c : r;
+    const int idx = rr * 6 - rr * (rr - 1) / 2 + (cc - rr);  // packed upper index
+    double val = __shfl_sync(0xffffffffu, s, idx);
+    if (r == c) val *= lp1;
+    if (e < 36) {
+      A[(size_t)j * 36 + e] = val;
+      Saug[(size_t)(6 * j + r) * ld + 6 * j + c] = val;  // row-major (6j+r, 6j+c)
+    }
+  }
+  if (lane >= 21 && lane < 27) {
+    a[(size_t)j * 6 + (lane - 21)] = s;
+    Saug[(size_t)(6 * j + (lane - 21)) * ld + (ld - 1)] = s;  // rhs column
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4 (v1): Schur complement, one thread per pair p1; S -= E_p1 B_p2^T for p2 >= p1 of the same point.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_schur_pairs(int P, const int *__restrict__ pair_pose, const int *__restrict__ pair_point,
+              const int *__restrict__ pair_end /*index one past the last pair of this pair's point*/,
+              const double *__restrict__ Bsoa, size_t Pp, const double *__restrict__ ptblk, size_t Mp,
+              double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int p1 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p1 >= P) return;
+  const int pt = pair_point[p1];
+  const int j1 = pair_pose[p1];
+  double B1[18];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) B1[i] = Bsoa[(size_t)i * Pp + p1];
+  double ci[6], cb[3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ci[i] = ptblk[(PB_Cinv + i) * Mp + pt];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) cb[i] = ptblk[(PB_Cinvb + i) * Mp + pt];
+  // E = B Cinv (:862) ; Cinv symmetric-packed {00,01,02,11,12,22}
+  double E[18];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const double b0 = B1[r * 3], b1 = B1[r * 3 + 1], b2 = B1[r * 3 + 2];
+    E[r * 3 + 0] = b0 * ci[0] + b1 * ci[1] + b2 * ci[2];
+    E[r * 3 + 1] = b0 * ci[1] + b1 * ci[3] + b2 * ci[4];
+    E[r * 3 + 2] = b0 * ci[2] + b1 * ci[4] + b2 * ci[5];
+  }
+  // rhs_j -= BCinv b = B (Cinv b) (:864,888)
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const double g = B1[r * 3] * cb[0] + B1[r * 3 + 1] * cb[1] + B1[r * 3 + 2] * cb[2];
+    atomicAdd(&Saug[(size_t)(6 * j1 + r) * ld + (ld - 1)], -g);
+  }
+  const int pend = pair_end[p1];
+  for (int p2 = p1; p2 < pend; ++p2) {
+    const int j2 = pair_pose[p2];
+    double B2[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) B2[i] = Bsoa[(size_t)i * Pp + p2];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        if (p2 == p1 && c < r) continue;
+        const double val = E[r * 3] * B2[c * 3] + E[r * 3 + 1] * B2[c * 3 + 1] + E[r * 3 + 2] * B2[c * 3 + 2];
+        atomicAdd(&Saug[(size_t)(6 * j1 + r) * ld + 6 * j2 + c], -val);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K6: back-substitution.
+// ---------------------------------------------------------------------------
+// per pair: w = B^T x_j ; segmented sum by point -> Btx[pt]
+__global__ void __launch_bounds__(kThreads)
+k_backsub_pairs(const Chunk *__restrict__ chunks, const int *__restrict__ chunk_pair_count,
+                const int *__restrict__ pair_pose, const int *__restrict__ pair_point,
+                const double *__restrict__ Bsoa, size_t Pp, const double *__restrict__ x,
+                double *__restrict__ Btx /*[3][Mp]*/, size_t Mp, const LmState *__restrict__ st) {
+  if (st->done) return;
+  __shared__ SegSmem<3, kWarps> sm3;
+  const Chunk ch = chunks[blockIdx.x];
+  const int cnt = chunk_pair_count[blockIdx.x];
+  const int t = threadIdx.x;
+  const bool active = t < cnt;
+  const int p = ch.pair_start + t;
+  double v[3] = {0.0, 0.0, 0.0};
+  int pt = -1 - t;
+  if (active) {
+    pt = pair_point[p];
+    const double *xj = x + (size_t)pair_pose[p] * 6;
+    double xv[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) xv[r] = __ldg(xj + r);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) s += Bsoa[(size_t)(r * 3 + c) * Pp + p] * xv[r];
+      v[c] = s;
+    }
+  }
+  const bool head = !active || t == 0 || pair_point[p - 1] != pt;
+  const bool tail = active && (t == cnt - 1 || pair_point[p + 1] != pt);
+  block_segmented_sum<3, kWarps>(v, head, tail, sm3);
+  if (tail) {
+    if (ch.flags & kChunkSplit) {
+      for (int c = 0; c < 3; ++c) atomicAdd(&Btx[(size_t)c * Mp + pt], v[c]);
+    } else {
+      for (int c = 0; c < 3; ++c) Btx[(size_t)c * Mp + pt] = v[c];
+    }
+  }
+}
+
+// per point: y = Cinv_b - Cinv Btx (:916) ; model terms b.y + y^T C y + 2 y.Btx (:443-452) ;
+// |y| ; trial point X + y (:498).  Partials per block: {model, step}.
+__global__ void __launch_bounds__(kThreads)
+k_backsub_points(int M_total, const int *__restrict__ point_has_pairs, const uint8_t *__restrict__ point_free,
+                 const double *__restrict__ ptblk, size_t Mp, const double *__restrict__ Btx,
+                 double *__restrict__ y /*[M_total][3]*/, Params prm, ParamsW prw,
+                 double *__restrict__ partials /*[grid][2]*/, const LmState *__restrict__ st) {
+  if (st->done) return;
+  __shared__ double sm[kWarps][2];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[2] = {0.0, 0.0};
+  if (i < M_total) {
+    const double *Xc = prm.points[st->cur] + (size_t)i * 3;
+    double *Xt = prw.points[st->cur ^ 1] + (size_t)i * 3;
+    double yv[3] = {0.0, 0.0, 0.0};
+    if (point_free[i]) {
+      double b[3], cd[6], ci[6], cb[3], bx[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) b[k] = ptblk[(PB_b + k) * Mp + i];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cd[k] = ptblk[(PB_Cd + k) * Mp + i];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ci[k] = ptblk[(PB_Cinv + k) * Mp + i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cb[k] = ptblk[(PB_Cinvb + k) * Mp + i];
+      if (point_has_pairs[i]) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bx[k] = Btx[(size_t)k * Mp + i];
+      }
+      yv[0] = cb[0] - (ci[0] * bx[0] + ci[1] * bx[1] + ci[2] * bx[2]);
+      yv[1] = cb[1] - (ci[1] * bx[0] + ci[3] * bx[1] + ci[4] * bx[2]);
+      yv[2] = cb[2] - (ci[2] * bx[0] + ci[4] * bx[1] + ci[5] * bx[2]);
+      const double by = b[0] * yv[0] + b[1] * yv[1] + b[2] * yv[2];
+      const double c0 = cd[0] * yv[0] + cd[1] * yv[1] + cd[2] * yv[2];
+      const double c1 = cd[1] * yv[0] + cd[3] * yv[1] + cd[4] * yv[2];
+      const double c2 = cd[2] * yv[0] + cd[4] * yv[1] + cd[5] * yv[2];
+      const double ycy = yv[0] * c0 + yv[1] * c1 + yv[2] * c2;
+      const double ybx = yv[0] * bx[0] + yv[1] * bx[1] + yv[2] * bx[2];
+      acc[0] = by + ycy + 2.0 * ybx;
+      acc[1] = sqrt(yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
+    }
+    y[(size_t)i * 3] = yv[0];
+    y[(size_t)i * 3 + 1] = yv[1];
+    y[(size_t)i * 3 + 2] = yv[2];
+    Xt[0] = Xc[0] + yv[0];
+    Xt[1] = Xc[1] + yv[1];
+    Xt[2] = Xc[2] + yv[2];
+  }
+  block_sum<2, kWarps>(acc, sm);
+  if (threadIdx.x == 0) {
+    partials[(size_t)blockIdx.x * 2] = acc[0];
+    partials[(size_t)blockIdx.x * 2 + 1] = acc[1];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K7: pose update + pose part of the model change; trial cost; decision.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_update_poses(int N_total, const int *__restrict__ pose_opt, const double *__restrict__ x,
+               const double *__restrict__ A, const double *__restrict__ a, Params prm, ParamsW prw,
+               double *__restrict__ partials /*[grid][2]*/, const LmState *__restrict__ st) {
+  if (st->done) return;
+  __shared__ double sm[kWarps][2];
+  const int jt = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[2] = {0.0, 0.0};
+  if (jt < N_total) {
+    const double *Tc = prm.poses[st->cur] + (size_t)jt * 12;
+    double *Tt = prw.poses[st->cur ^ 1] + (size_t)jt * 12;
+    const int j = pose_opt[jt];
+    if (j < 0) {
+      for (int k = 0; k < 12; ++k) Tt[k] = Tc[k];
+    } else {
+      double xi[6], d[12], T[12];
+      for (int k = 0; k < 6; ++k) xi[k] = x[(size_t)j * 6 + k];
+      for (int k = 0; k < 12; ++k) T[k] = Tc[k];
+      se3_exp(xi, d);
+      // T_jw = delta * T_jw (:493): R = Rd R, t = Rd t + td
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          Tt[r * 3 + c] = d[r * 3] * T[c] + d[r * 3 + 1] * T[3 + c] + d[r * 3 + 2] * T[6 + c];
+        Tt[9 + r] = d[r * 3] * T[9] + d[r * 3 + 1] * T[10] + d[r * 3 + 2] * T[11] + d[9 + r];
+      }
+      // a.x + x^T A x (:438-440), damped A
+      double m = 0.0, q = 0.0, nrm = 0.0;
+      for (int r = 0; r < 6; ++r) {
+        m += a[(size_t)j * 6 + r] * xi[r];
+        double s = 0.0;
+        for (int c = 0; c < 6; ++c) s += A[(size_t)j * 36 + r * 6 + c] * xi[c];
+        q += xi[r] * s;
+        nrm += xi[r] * xi[r];
+      }
+      acc[0] = m + q;
+      acc[1] = sqrt(nrm);
+    }
+  }
+  block_sum<2, kWarps>(acc, sm);
+  if (threadIdx.x == 0) {
+    partials[(size_t)blockIdx.x * 2] = acc[0];
+    partials[(size_t)blockIdx.x * 2 + 1] = acc[1];
+  }
+}
+
+// EvaluateCurrentCost (:381-433): sum over observations of ||r||_2 ; which = 0 current, 1 trial.
+__global__ void __launch_bounds__(kThreads)
+k_cost(long long n_obs, const double2 *__restrict__ obs_uv, const int *__restrict__ obs_pose,
+       const int *__restrict__ obs_point, const int *__restrict__ obs_camflags, Params prm, int which,
+       const double *__restrict__ cams, double *__restrict__ partials, int ignore_done,
+       const LmState *__restrict__ st) {
+  if (!ignore_done && st->done) return;
+  __shared__ double sm[kWarps][1];
+  const int buf = st->cur ^ which;
+  const double *poses = prm.poses[buf];
+  const double *points = prm.points[buf];
+  double acc[1] = {0.0};
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_obs;
+       k += (long long)gridDim.x * blockDim.x) {
+    const double2 uv = obs_uv[k];
+    const int ps = obs_pose[k], pt = obs_point[k];
+    const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
+    double T[12], X[3];
+    const double *Tp = poses + (size_t)ps * 12;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = __ldg(Tp + i);
+    X[0] = __ldg(points + (size_t)pt * 3);
+    X[1] = __ldg(points + (size_t)pt * 3 + 1);
+    X[2] = __ldg(points + (size_t)pt * 3 + 2);
+    Proj p;
+    project(T, X, cam, uv.x, uv.y, p);
+    acc[0] += sqrt(p.r0 * p.r0 + p.r1 * p.r1);
+  }
+  block_sum<1, kWarps>(acc, sm);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
+}
+
+struct DecideArgs {
+  const double *cost_partials; int n_cost;
+  const double *point_partials; int n_point;   // {model, step} per block
+  const double *pose_partials; int n_pose;     // {model, step} per block
+  double *scal;   // [8] reduced scalars {cost, model_point, step_point, model_pose, step_pose}
+  double thr_step, thr_cost, dec_ratio, inc_ratio, inverse_scaler;
+  double n_obs_global, n_params_global;  // num_observations ; N_opt + M_opt
+  int max_iteration;
+  int n_ranks;
+};
+
+// ordered (deterministic) sums of the per-block partials into scal[]
+__global__ void __launch_bounds__(kThreads) k_reduce_scalars(DecideArgs g, int init_only,
+                                                            const LmState *__restrict__ st) {
+  if (!init_only && st->done) return;
+  __shared__ double sm[kWarps][5];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < g.n_cost; i += kThreads) acc[0] += g.cost_partials[i];
+  if (!init_only) {
+    for (int i = threadIdx.x; i < g.n_point; i += kThreads) {
+      acc[1] += g.point_partials[2 * i];
+      acc[2] += g.point_partials[2 * i + 1];
+    }
+    for (int i = threadIdx.x; i < g.n_pose; i += kThreads) {
+      acc[3] += g.pose_partials[2 * i];
+      acc[4] += g.pose_partials[2 * i + 1];
+    }
+  }
+  block_sum<5, kWarps>(acc, sm);
+  if (threadIdx.x == 0) {
+    g.scal[0] = acc[0];
+    g.scal[1] = acc[1];
+    g.scal[2] = acc[2];
+    // the pose part is computed redundantly on every rank from the replicated x and the rank's
+    // PARTIAL A/a: the model term is additive over ranks, the step norm is not (divide it)
+    g.scal[3] = acc[3];
+    g.scal[4] = acc[4] / (double)g.n_ranks;
+  }
+}
+
+__global__ void k_init_state(LmState *st, const double *scal, double lambda0) {
+  st->lambda = lambda0;
+  st->prev_cost = scal[0];
+  st->cur = st->cur;  // keep
+  st->done = 0;
+  st->iteration = 0;
+  st->converged = 0;
+}
+
+// trust-region decision (:930-1007), one thread.
+__global__ void k_decide(DecideArgs g, LmState *st, ba_iter_info *infos, int cap) {
+  if (st->done) return;
+  const double current_cost = g.scal[0];
+  const double model = -(g.scal[3] + g.scal[1]);  // EvaluateCostChangeByQuadraticModel (:435-455)
+  const double previous_cost = st->prev_cost;
+  const double rho = (current_cost - previous_cost) * g.inverse_scaler / model;
+  double lambda = st->lambda;
+  st->last_cost_new = current_cost;
+  st->last_model = model;
+  st->last_rho = rho;
+  st->last_lambda = lambda;
+  int status;
+  if (rho > 0.25) {
+    status = 0;       // UPDATE: trial buffer becomes current
+    st->cur ^= 1;
+  } else {
+    status = 2;       // SKIPPED: keep current (RevertToReservedParameters)
+  }
+  if (rho > 0.5) {
+    lambda = fmax(1e-10, lambda * g.dec_ratio);
+    status = 1;       // UPDATE_TRUST_MORE
+  } else if (rho <= 0.25) {
+    lambda = fmin(100.0, lambda * g.inc_ratio);
+  }
+  const double average_error = current_cost / g.n_obs_global;
+  const double cost_change = fabs(current_cost - previous_cost);
+  const double total_step = g.scal[2] + g.scal[4];
+  const double avg_step = total_step / g.n_params_global;
+  bool converged = (avg_step < g.thr_step) || (cost_change < g.thr_cost);
+  const int iteration = st->iteration;
+  if (iteration >= g.max_iteration - 1) converged = false;
+  if (infos != nullptr && iteration < cap) {
+    ba_iter_info I;
+    I.cost = current_cost;
+    I.cost_change = cost_change;
+    I.average_reprojection_error = average_error;
+    I.abs_gradient = 0.0;
+    I.abs_step = avg_step;
+    I.damping_term = lambda;
+    I.iter_time = 0.0;
+    I.iteration_status = status;
+    I._pad = 0;
+    if (status == 2) {
+      I.cost = previous_cost;
+      I.cost_change = 0.0;
+      I.average_reprojection_error = sqrt(previous_cost / g.n_obs_global);
+    }
+    infos[iteration] = I;
+  }
+  st->lambda = lambda;
+  st->prev_cost = current_cost;  // unconditionally (:1005)
+  st->iteration = iteration + 1;
+  st->converged = converged ? 1 : 0;
+  if (converged || iteration + 1 >= g.max_iteration) st->done = 1;
+}
+
+}  // namespace ba
+
+// =============================================================================
+// Host side
+// =============================================================================
+using namespace ba;
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      s->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+      return BA_ERR_CUDA;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+namespace {
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    // prefer a libnccl already loaded into the process (torch's), then the system one
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void **)&p, count * sizeof(T));
+  }
+  cudaError_t upload(const std::vector<T> &h, cudaStream_t st) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace
+
+struct ba_solver {
+  int device = 0;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool profile = false, debug_keep = false;
+
+  // host problem
+  std::unordered_map<int, int> cam_slot;
+  std::vector<double> h_cams;
+  int n_cam = 0;
+  std::vector<double> h_poses, h_points;
+  std::vector<uint8_t> h_pose_fixed, h_point_fixed;
+  std::vector<int> h_obs_cam, h_obs_pose, h_obs_point;
+  std::vector<double> h_obs_uv;
+  long long n_obs = 0;
+  int N_total = 0, M_total = 0, N = 0, M = 0;
+  long long P = 0;
+  bool finalized = false;
+  std::vector<int> h_pose_opt, h_point_opt, h_opt_pose, h_opt_point;
+  std::vector<int> h_pair_pose, h_pair_point;  // j_opt, original point id
+  int n_chunks = 0, n_chunksA = 0, n_split = 0, n_split_pairs = 0;
+
+  // device problem
+  DevBuf<double> d_cams, d_poses[2], d_points[2];
+  DevBuf<double2> d_obs_uv, d_uvA;
+  DevBuf<int> d_obs_pose, d_obs_point, d_obs_camflags, d_obs_pair;
+  DevBuf<int> d_pointA, d_camA, d_poseidA;
+  DevBuf<Chunk> d_chunks;
+  DevBuf<int> d_chunk_pair_count;
+  DevBuf<ChunkA> d_chunksA;
+  DevBuf<int> d_pose_chunk_ptr, d_pose_opt, d_pair_pose, d_pair_point, d_pair_end, d_point_has_pairs;
+  DevBuf<uint8_t> d_point_free;
+  DevBuf<int> d_split_points, d_split_pairs;
+  // blocks
+  size_t Mp = 0, Pp = 0;
+  DevBuf<double> d_ptblk, d_Bsoa, d_A, d_a, d_partialsA, d_Saug, d_Scopy, d_x, d_z, d_Btx, d_y;
+  DevBuf<double> d_cost_partials, d_point_partials, d_pose_partials, d_scal;
+  DevBuf<LmState> d_state;
+  DevBuf<ba_iter_info> d_infos;
+  int cost_grid = 0, point_grid = 0, pose_grid = 0;
+  LmState *h_state = nullptr;  // pinned
+  double *h_scal = nullptr;    // pinned
+
+  // graph
+  cudaGraphExec_t graph_exec = nullptr;
+  ba_options graph_opt{};       // kernel arguments are baked into the graph: rebuilt when options change
+  long long graph_nodes = 0;    // kernel nodes per replay
+
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  long long global_M = -1, global_n_obs = -1;
+
+  long long launches = 0;
+  std::vector<cudaEvent_t> ev;
+};
+
+static int ensure_stream(ba_solver *s) {
+  if (!s->stream) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+  }
+  return BA_OK;
+}
+
+static void destroy_graph(ba_solver *s) {
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  s->graph_exec = nullptr;
+}
+
+extern "C" {
+
+const char *ba_version(void) { return "ba_b200 0.1 (sm_100a)"; }
+
+int ba_create(ba_solver **out, int device) {
+  if (!out) return BA_ERR_INVALID;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    // fail loudly: there is no CPU fallback
+    fprintf(stderr, "ba_b200: no CUDA device available (%s); the engine has no CPU fallback\n",
+            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    *out = nullptr;
+    return BA_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) return BA_ERR_INVALID;
+  ba_solver *s = new ba_solver();
+  s->device = device;
+  *out = s;
+  return BA_OK;
+}
+
+static void free_device(ba_solver *s) {
+  destroy_graph(s);
+  s->d_cams.release();
+  for (int i = 0; i < 2; ++i) { s->d_poses[i].release(); s->d_points[i].release(); }
+  s->d_obs_uv.release(); s->d_uvA.release(); s->d_obs_pose.release(); s->d_obs_point.release();
+  s->d_obs_camflags.release(); s->d_obs_pair.release(); s->d_pointA.release(); s->d_camA.release();
+  s->d_poseidA.release(); s->d_chunks.release(); s->d_chunk_pair_count.release(); s->d_chunksA.release();
+  s->d_pose_chunk_ptr.release(); s->d_pose_opt.release(); s->d_pair_pose.release(); s->d_pair_point.release();
+  s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
+  s->d_split_points.release(); s->d_split_pairs.release(); s->d_ptblk.release(); s->d_Bsoa.release();
+  s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
+  s->d_x.release(); s->d_z.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
+  s->d_point_partials.release(); s->d_pose_partials.release(); s->d_scal.release(); s->d_state.release();
+  s->d_infos.release();
+}
+
+void ba_destroy(ba_solver *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  free_device(s);
+  for (auto e : s->ev) cudaEventDestroy(e);
+  if (s->h_state) cudaFreeHost(s->h_state);
+  if (s->h_scal) cudaFreeHost(s->h_scal);
+  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int ba_reset(ba_solver *s) {
+  if (!s) return BA_ERR_INVALID;
+  s->cam_slot.clear(); s->h_cams.clear(); s->n_cam = 0;
+  s->h_poses.clear(); s->h_points.clear(); s->h_pose_fixed.clear(); s->h_point_fixed.clear();
+  s->h_obs_cam.clear(); s->h_obs_pose.clear(); s->h_obs_point.clear(); s->h_obs_uv.clear();
+  s->n_obs = 0; s->N_total = s->M_total = s->N = s->M = 0; s->P = 0;
+  s->finalized = false;
+  destroy_graph(s);
+  return BA_OK;
+}
+
+const char *ba_last_error(const ba_solver *s) { return s ? s->err.c_str() : "null handle"; }
+
+int ba_set_stream(ba_solver *s, void *cuda_stream) {
+  if (!s) return BA_ERR_INVALID;
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  s->stream = (cudaStream_t)cuda_stream;
+  s->own_stream = false;
+  destroy_graph(s);
+  return BA_OK;
+}
+int ba_set_profile(ba_solver *s, int enable) { if (!s) return BA_ERR_INVALID; s->profile = enable != 0; return BA_OK; }
+int ba_set_debug(ba_solver *s, int keep) { if (!s) return BA_ERR_INVALID; s->debug_keep = keep != 0; destroy_graph(s); return BA_OK; }
+
+int ba_set_cameras(ba_solver *s, int n_cam, const int *ids, const double *intr, const double *T) {
+  if (!s || n_cam <= 0 || n_cam > 256 || !ids || !intr || !T) return BA_ERR_INVALID;
+  s->cam_slot.clear();
+  s->h_cams.clear();
+  s->n_cam = 0;
+  for (int k = 0; k < n_cam; ++k) {
+    if (s->cam_slot.count(ids[k])) continue;  // duplicate ids ignored (unordered_map::insert, :80)
+    s->cam_slot[ids[k]] = s->n_cam++;
+    for (int i = 0; i < 4; ++i) s->h_cams.push_back(intr[4 * k + i]);
+    for (int i = 0; i < 12; ++i) s->h_cams.push_back(T[12 * k + i]);
+  }
+  s->finalized = false;
+  return BA_OK;
+}
+
+int ba_set_poses(ba_solver *s, int n, const double *T_jw, const uint8_t *fixed) {
+  if (!s || n < 0 || (n > 0 && !T_jw)) return BA_ERR_INVALID;
+  s->h_poses.assign(T_jw, T_jw + (size_t)n * 12);
+  s->h_pose_fixed.assign(n, 0);
+  if (fixed) s->h_pose_fixed.assign(fixed, fixed + n);
+  s->N_total = n;
+  s->finalized = false;
+  return BA_OK;
+}
+
+int ba_set_points(ba_solver *s, int m, const double *X, const uint8_t *fixed) {
+  if (!s || m < 0 || (m > 0 && !X)) return BA_ERR_INVALID;
+  s->h_points.assign(X, X + (size_t)m * 3);
+  s->h_point_fixed.assign(m, 0);
+  if (fixed) s->h_point_fixed.assign(fixed, fixed + m);
+  s->M_total = m;
+  s->finalized = false;
+  return BA_OK;
+}
+
+int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const int *pose, const int *point,
+                        const double *uv, long long *n_kept) {
+  if (!s || n_obs < 0 || (n_obs > 0 && (!cam_id || !pose || !point || !uv))) return BA_ERR_INVALID;
+  if (n_obs > 2000000000LL) { s->err = "too many observations for 32-bit indexing"; return BA_ERR_INVALID; }
+  s->h_obs_cam.clear(); s->h_obs_pose.clear(); s->h_obs_point.clear(); s->h_obs_uv.clear();
+  s->h_obs_cam.reserve(n_obs); s->h_obs_pose.reserve(n_obs); s->h_obs_point.reserve(n_obs);
+  s->h_obs_uv.reserve(2 * n_obs);
+  for (long long k = 0; k < n_obs; ++k) {
+    auto it = s->cam_slot.find(cam_id[k]);
+    if (it == s->cam_slot.end()) continue;                       // "Invalid camera index." (:160-163)
+    if (pose[k] < 0 || pose[k] >= s->N_total) continue;          // "Nonexisting pose." (:164-167)
+    if (point[k] < 0 || point[k] >= s->M_total) continue;        // "Nonexisting point." (:168-171)
+    s->h_obs_cam.push_back(it->second);
+    s->h_obs_pose.push_back(pose[k]);
+    s->h_obs_point.push_back(point[k]);
+    s->h_obs_uv.push_back(uv[2 * k]);
+    s->h_obs_uv.push_back(uv[2 * k + 1]);
+  }
+  s->n_obs = (long long)s->h_obs_cam.size();
+  if (n_kept) *n_kept = s->n_obs;
+  s->finalized = false;
+  return BA_OK;
+}
+
+int ba_finalize(ba_solver *s) {
+  if (!s) return BA_ERR_INVALID;
+  if (s->finalized) return BA_OK;
+  if (s->n_cam == 0) { s->err = "no cameras"; return BA_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (int rc = ensure_stream(s)) return rc;
+  destroy_graph(s);
+  const int Nt = s->N_total, Mt = s->M_total;
+  const long long n = s->n_obs;
+  // --- free indices in id order (FinalizeParameters :182-206; insertion order replaces hash order)
+  s->h_pose_opt.assign(Nt, -1); s->h_point_opt.assign(Mt, -1);
+  s->h_opt_pose.clear(); s->h_opt_point.clear();
+  for (int j = 0; j < Nt; ++j) if (!s->h_pose_fixed[j]) { s->h_pose_opt[j] = (int)s->h_opt_pose.size(); s->h_opt_pose.push_back(j); }
+  for (int i = 0; i < Mt; ++i) if (!s->h_point_fixed[i]) { s->h_point_opt[i] = (int)s->h_opt_point.size(); s->h_opt_point.push_back(i); }
+  s->N = (int)s->h_opt_pose.size();
+  s->M = (int)s->h_opt_point.size();
+  // --- stable counting sort by pose, then by point  => order (point, pose, insertion)
+  std::vector<int> by_pose(n), by_point(n);
+  {
+    std::vector<long long> cnt(Nt + 1, 0);
+    for (long long k = 0; k < n; ++k) cnt[s->h_obs_pose[k] + 1]++;
+    for (int j = 0; j < Nt; ++j) cnt[j + 1] += cnt[j];
+    for (long long k = 0; k < n; ++k) by_pose[cnt[s->h_obs_pose[k]]++] = (int)k;
+    std::vector<long long> cnt2(Mt + 1, 0);
+    for (long long k = 0; k < n; ++k) cnt2[s->h_obs_point[k] + 1]++;
+    for (int i = 0; i < Mt; ++i) cnt2[i + 1] += cnt2[i];
+    for (long long q = 0; q < n; ++q) { const int k = by_pose[q]; by_point[cnt2[s->h_obs_point[k]]++] = k; }
+  }
+  // --- point-ordered observation arrays, pairs, last-writer flags
+  std::vector<double2> uv(n);
+  std::vector<int> o_pose(n), o_point(n), o_cf(n), o_pair(n);
+  s->h_pair_pose.clear(); s->h_pair_point.clear();
+  std::vector<int> point_has_pairs(Mt, 0);
+  {
+    int prev_pt = -1, prev_ps = -1;
+    for (long long q = 0; q < n; ++q) {
+      const int k = by_point[q];
+      const int ps = s->h_obs_pose[k], pt = s->h_obs_point[k];
+      const bool pf = s->h_pose_opt[ps] >= 0, qf = s->h_point_opt[pt] >= 0;
+      uv[q] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
+      o_pose[q] = ps; o_point[q] = pt;
+      int cf = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
+      int pair = -1;
+      if (pf && qf) {
+        if (pt != prev_pt || ps != prev_ps) {
+          s->h_pair_pose.push_back(s->h_pose_opt[ps]);
+          s->h_pair_point.push_back(pt);
+          point_has_pairs[pt] = 1;
+        }
+        pair = (int)s->h_pair_pose.size() - 1;
+      }
+      o_pair[q] = pair;
+      o_cf[q] = cf;
+      prev_pt = pt; prev_ps = ps;
+    }
+    // last observation of each (point,pose) run = last inserted of the pair (stable sort)
+    for (long long q = 0; q < n; ++q) {
+      if (o_pair[q] < 0) continue;
+      if (q + 1 == n || o_pair[q + 1] != o_pair[q]) o_cf[q] |= kFlagLastOfPair;
+    }
+  }
+  s->P = (long long)s->h_pair_pose.size();
+  const long long P = s->P;
+  std::vector<int> pair_end(P);
+  for (long long p = P - 1; p >= 0; --p)
+    pair_end[p] = (p + 1 < P && s->h_pair_point[p + 1] == s->h_pair_point[p]) ? pair_end[p + 1] : (int)(p + 1);
+  // --- chunks of whole points (<= kThreads observations); longer points are split
+  std::vector<Chunk> chunks;
+  std::vector<int> chunk_pair_count;
+  std::vector<int> split_points, split_pairs;
+  {
+    long long q = 0;
+    Chunk cur{0, 0, 0, 0};
+    int cur_pairs_first = -1, cur_pairs_last = -1;
+    auto flush = [&]() {
+      if (cur.obs_count == 0) return;
+      cur.pair_start = cur_pairs_first < 0 ? 0 : cur_pairs_first;
+      chunks.push_back(cur);
+      chunk_pair_count.push_back(cur_pairs_first < 0 ? 0 : cur_pairs_last - cur_pairs_first + 1);
+      cur = Chunk{0, 0, 0, 0};
+      cur_pairs_first = cur_pairs_last = -1;
+    };
+    auto add_range = [&](long long a, long long b) {  // obs [a,b) appended to the current chunk
+      if (cur.obs_count == 0) cur.obs_start = (int)a;
+      cur.obs_count += (int)(b - a);
+      for (long long r = a; r < b; ++r)
+        if (o_pair[r] >= 0 && (o_cf[r] & kFlagLastOfPair)) { if (cur_pairs_first < 0) cur_pairs_first = o_pair[r]; cur_pairs_last = o_pair[r]; }
+    };
+    while (q < n) {
+      long long e = q;
+      while (e < n && o_point[e] == o_point[q]) ++e;
+      const long long len = e - q;
+      if (len > kThreads) {
+        flush();
+        if (s->h_point_opt[o_point[q]] >= 0) split_points.push_back(o_point[q]);
+        for (long long a = q; a < e; a += kThreads) {
+          const long long b = std::min(e, a + kThreads);
+          add_range(a, b);
+          cur.flags = kChunkSplit;
+          flush();
+        }
+        for (long long r = q; r < e; ++r)
+          if (o_pair[r] >= 0 && (split_pairs.empty() || split_pairs.back() != o_pair[r])) split_pairs.push_back(o_pair[r]);
+      } else {
+        if (cur.obs_count + len > kThreads) flush();
+        add_range(q, e);
+      }
+      q = e;
+    }
+    flush();
+  }
+  s->n_chunks = (int)chunks.size();
+  s->n_split = (int)split_points.size();
+  s->n_split_pairs = (int)split_pairs.size();
+  // --- pose-ordered arrays (free poses only) and their chunks
+  std::vector<double2> uvA; std::vector<int> pointA, camA, poseidA;
+  std::vector<ChunkA> chunksA; std::vector<int> pose_chunk_ptr(s->N + 1, 0);
+  {
+    long long nA = 0;
+    for (long long q = 0; q < n; ++q) if (s->h_pose_opt[s->h_obs_pose[by_pose[q]]] >= 0) ++nA;
+    uvA.reserve(nA); pointA.reserve(nA); camA.reserve(nA); poseidA.reserve(nA);
+    // chunk size adapts to observations per pose so that a pose yields only a few partials
+    const long long per_pose = s->N > 0 ? (nA + s->N - 1) / s->N : 0;
+    int per_thread = (int)std::min<long long>(8, std::max<long long>(1, per_pose / (kThreads * 2)));
+    const long long chunk_cap = (long long)kThreads * per_thread;
+    long long q = 0;
+    while (q < n) {
+      const int ps = s->h_obs_pose[by_pose[q]];
+      long long e = q;
+      while (e < n && s->h_obs_pose[by_pose[e]] == ps) ++e;
+      const int j = s->h_pose_opt[ps];
+      if (j >= 0) {
+        pose_chunk_ptr[j] = (int)chunksA.size();
+        for (long long a = q; a < e; a += chunk_cap) {
+          const long long b = std::min(e, a + chunk_cap);
+          chunksA.push_back(ChunkA{(int)uvA.size(), (int)(b - a), j, 0});
+          for (long long r = a; r < b; ++r) {
+            const int k = by_pose[r];
+            uvA.push_back(make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]));
+            pointA.push_back(s->h_obs_point[k]);
+            camA.push_back(s->h_obs_cam[k]);
+            poseidA.push_back(ps);
+          }
+        }
+      }
+      q = e;
+    }
+    // poses without observations keep an empty chunk range: fix up the CSR (chunks are in pose order)
+    std::vector<int> cnt(s->N, 0);
+    for (auto &c : chunksA) cnt[c.j_opt]++;
+    pose_chunk_ptr[0] = 0;
+    for (int j = 0; j < s->N; ++j) pose_chunk_ptr[j + 1] = pose_chunk_ptr[j] + cnt[j];
+  }
+  s->n_chunksA = (int)chunksA.size();
+  // --- upload
+  cudaStream_t st = s->stream;
+  std::vector<uint8_t> point_free(Mt);
+  for (int i = 0; i < Mt; ++i) point_free[i] = s->h_point_fixed[i] ? 0 : 1;
+  CUDA_TRY(s->d_cams.upload(s->h_cams, st));
+  CUDA_TRY(s->d_poses[0].upload(s->h_poses, st));
+  CUDA_TRY(s->d_poses[1].upload(s->h_poses, st));
+  CUDA_TRY(s->d_points[0].upload(s->h_points, st));
+  CUDA_TRY(s->d_points[1].upload(s->h_points, st));
+  CUDA_TRY(s->d_obs_uv.upload(uv, st));
+  CUDA_TRY(s->d_obs_pose.upload(o_pose, st));
+  // +1 sentinel so that obs_point[k+1] / pair_point[p+1] reads stay in bounds
+  o_point.push_back(-1);
+  CUDA_TRY(s->d_obs_point.upload(o_point, st));
+  CUDA_TRY(s->d_obs_camflags.upload(o_cf, st));
+  o_pair.push_back(-2);
+  CUDA_TRY(s->d_obs_pair.upload(o_pair, st));
+  CUDA_TRY(s->d_uvA.upload(uvA, st));
+  CUDA_TRY(s->d_pointA.upload(pointA, st));
+  CUDA_TRY(s->d_camA.upload(camA, st));
+  CUDA_TRY(s->d_poseidA.upload(poseidA, st));
+  CUDA_TRY(s->d_chunks.upload(chunks, st));
+  CUDA_TRY(s->d_chunk_pair_count.upload(chunk_pair_count, st));
+  CUDA_TRY(s->d_chunksA.upload(chunksA, st));
+  CUDA_TRY(s->d_pose_chunk_ptr.upload(pose_chunk_ptr, st));
+  CUDA_TRY(s->d_pose_opt.upload(s->h_pose_opt, st));
+  CUDA_TRY(s->d_pair_pose.upload(s->h_pair_pose, st));
+  {
+    std::vector<int> pp = s->h_pair_point;
+    pp.push_back(-1);
+    CUDA_TRY(s->d_pair_point.upload(pp, st));
+  }
+  CUDA_TRY(s->d_pair_end.upload(pair_end, st));
+  CUDA_TRY(s->d_point_has_pairs.upload(point_has_pairs, st));
+  CUDA_TRY(s->d_point_free.upload(point_free, st));
+  CUDA_TRY(s->d_split_points.upload(split_points, st));
+  CUDA_TRY(s->d_split_pairs.upload(split_pairs, st));
+  // --- block storage
+  s->Mp = ((size_t)Mt + 31) / 32 * 32;
+  s->Pp = ((size_t)P + 31) / 32 * 32;
+  const size_t nS = (size_t)6 * s->N + 1;
+  CUDA_TRY(s->d_ptblk.alloc(std::max<size_t>(1, kPtBlk * s->Mp)));
+  CUDA_TRY(s->d_Bsoa.alloc(std::max<size_t>(1, 18 * s->Pp)));
+  CUDA_TRY(s->d_A.alloc(std::max<size_t>(1, (size_t)s->N * 36)));
+  CUDA_TRY(s->d_a.alloc(std::max<size_t>(1, (size_t)s->N * 6)));
+  CUDA_TRY(s->d_partialsA.alloc(std::max<size_t>(1, (size_t)s->n_chunksA * 27)));
+  CUDA_TRY(s->d_Saug.alloc(nS * nS));
+  CUDA_TRY(s->d_x.alloc(std::max<size_t>(1, (size_t)6 * s->N)));
+  CUDA_TRY(s->d_z.alloc(std::max<size_t>(1, (size_t)6 * s->N)));
+  CUDA_TRY(s->d_Btx.alloc(std::max<size_t>(1, 3 * s->Mp)));
+  CUDA_TRY(s->d_y.alloc(std::max<size_t>(1, (size_t)Mt * 3)));
+  CUDA_TRY(cudaMemsetAsync(s->d_ptblk.p, 0, s->d_ptblk.n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_Bsoa.p, 0, s->d_Bsoa.n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_x.p, 0, s->d_x.n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_y.p, 0, s->d_y.n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_Btx.p, 0, s->d_Btx.n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_A.p, 0, s->d_A.n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_a.p, 0, s->d_a.n * sizeof(double), st));
+  s->cost_grid = (int)std::min<long long>(148 * 8, std::max<long long>(1, (n + kThreads - 1) / kThreads));
+  s->point_grid = std::max(1, (Mt + kThreads - 1) / kThreads);
+  s->pose_grid = std::max(1, (Nt + kThreads - 1) / kThreads);
+  CUDA_TRY(s->d_cost_partials.alloc(s->cost_grid));
+  CUDA_TRY(s->d_point_partials.alloc(2 * (size_t)s->point_grid));
+  CUDA_TRY(s->d_pose_partials.alloc(2 * (size_t)s->pose_grid));
+  CUDA_TRY(s->d_scal.alloc(8));
+  CUDA_TRY(s->d_state.alloc(1));
+  CUDA_TRY(cudaMemsetAsync(s->d_state.p, 0, sizeof(LmState), st));
+  CUDA_TRY(cudaMemsetAsync(s->d_scal.p, 0, 8 * sizeof(double), st));
+  if (!s->h_state) CUDA_TRY(cudaMallocHost((void **)&s->h_state, sizeof(LmState)));
+  if (!s->h_scal) CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 8 * sizeof(double)));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  s->finalized = true;
+  return BA_OK;
+}
+
+int ba_update_parameters(ba_solver *s, const double *T_jw, const double *X) {
+  if (!s || !s->finalized) return BA_ERR_STATE;
+  CUDA_TRY(cudaSetDevice(s->device));
+  // the accepted parameters live in buffer `cur`; reset to buffer 0
+  if (T_jw) {
+    s->h_poses.assign(T_jw, T_jw + (size_t)s->N_total * 12);
+    CUDA_TRY(cudaMemcpyAsync(s->d_poses[0].p, T_jw, (size_t)s->N_total * 12 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_poses[1].p, s->d_poses[0].p, (size_t)s->N_total * 12 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  }
+  if (X) {
+    s->h_points.assign(X, X + (size_t)s->M_total * 3);
+    CUDA_TRY(cudaMemcpyAsync(s->d_points[0].p, X, (size_t)s->M_total * 3 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_points[1].p, s->d_points[0].p, (size_t)s->M_total * 3 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  }
+  CUDA_TRY(cudaMemsetAsync(s->d_state.p, 0, sizeof(LmState), s->stream));
+  return BA_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// iteration enqueue
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Phase { enum { Lin = 0, Schur, Solve, Backsub, Update, End, Count }; };
+
+static DecideArgs make_decide_args(ba_solver *s, const ba_options *opt) {
+  DecideArgs g;
+  g.cost_partials = s->d_cost_partials.p; g.n_cost = s->cost_grid;
+  g.point_partials = s->d_point_partials.p; g.n_point = s->point_grid;
+  g.pose_partials = s->d_pose_partials.p; g.n_pose = s->pose_grid;
+  g.scal = s->d_scal.p;
+  g.thr_step = (double)opt->threshold_step_size;
+  g.thr_cost = (double)opt->threshold_cost_change;
+  g.dec_ratio = (double)opt->decrease_ratio_lambda;
+  g.inc_ratio = (double)opt->increase_ratio_lambda;
+  g.inverse_scaler = opt->inverse_scaler;
+  const long long gM = s->global_M >= 0 ? s->global_M : s->M;
+  const long long gO = s->global_n_obs >= 0 ? s->global_n_obs : s->n_obs;
+  g.n_obs_global = (double)gO;
+  g.n_params_global = (double)(s->N + gM);
+  g.max_iteration = opt->max_num_iterations;
+  g.n_ranks = s->n_ranks;
+  return g;
+}
+
+// Enqueue the build (K1..K4) on the stream.  ev: optional events at phase boundaries.
+static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
+  cudaStream_t st = s->stream;
+  const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+  const double thres = (double)opt->threshold_huber_loss;
+  const LmState *dst = s->d_state.p;
+  const int ld = 6 * s->N + 1;
+  if (ev) cudaEventRecord(ev[Phase::Lin], st);
+  cudaMemsetAsync(s->d_Saug.p, 0, (size_t)ld * ld * sizeof(double), st);
+  if (s->n_split > 0 || (opt->b_accumulate && s->n_split_pairs > 0)) {
+    const int m = std::max(s->n_split, s->n_split_pairs);
+    k_zero_split<<<(m + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split, s->d_ptblk.p, s->Mp,
+                                                  s->d_split_pairs.p, s->n_split_pairs, s->d_Bsoa.p, s->Pp,
+                                                  opt->b_accumulate, dst);
+    s->launches++;
+  }
+  if (s->n_chunks > 0) {
+    if (opt->b_accumulate)
+      k_linearize_by_point<true><<<s->n_chunks, kThreads, 0, st>>>(
+          s->d_chunks.p, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p, s->d_obs_camflags.p, s->d_obs_pair.p,
+          prm, s->d_cams.p, thres, s->d_ptblk.p, s->Mp, s->d_Bsoa.p, s->Pp, dst);
+    else
+      k_linearize_by_point<false><<<s->n_chunks, kThreads, 0, st>>>(
+          s->d_chunks.p, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p, s->d_obs_camflags.p, s->d_obs_pair.p,
+          prm, s->d_cams.p, thres, s->d_ptblk.p, s->Mp, s->d_Bsoa.p, s->Pp, dst);
+    s->launches++;
+  }
+  if (s->n_split > 0) {
+    k_finish_split_points<<<(s->n_split + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split,
+                                                                    s->d_ptblk.p, s->Mp, dst);
+    s->launches++;
+  }
+  if (s->n_chunksA > 0) {
+    k_linearize_by_pose<<<s->n_chunksA, kThreads, 0, st>>>(s->d_chunksA.p, s->d_uvA.p, s->d_pointA.p,
+                                                           s->d_camA.p, s->d_poseidA.p, prm, s->d_cams.p, thres,
+                                                           s->d_partialsA.p, dst);
+    s->launches++;
+  }
+  if (s->N > 0) {
+    k_finish_poses<<<(s->N + 3) / 4, 128, 0, st>>>(s->d_pose_chunk_ptr.p, s->d_partialsA.p, s->N, s->d_A.p,
+                                                    s->d_a.p, s->d_Saug.p, ld, dst);
+    s->launches++;
+  }
+  if (ev) cudaEventRecord(ev[Phase::Schur], st);
+  if (s->P > 0) {
+    k_schur_pairs<<<(int)((s->P + 127) / 128), 128, 0, st>>>((int)s->P, s->d_pair_pose.p, s->d_pair_point.p,
+                                                             s->d_pair_end.p, s->d_Bsoa.p, s->Pp, s->d_ptblk.p,
+                                                             s->Mp, s->d_Saug.p, ld, dst);
+    s->launches++;
+  }
+  return BA_OK;
+}
+
+static int enqueue_allreduce_S(ba_solver *s) {
+  if (!s->comm) return BA_OK;
+  const size_t ld = (size_t)6 * s->N + 1;
+  ncclResult_t r = g_nccl.AllReduce(s->d_Saug.p, s->d_Saug.p, ld * ld, ncclDouble, ncclSum, s->comm, s->stream);
+  if (r != ncclSuccess) { s->err = "ncclAllReduce(S) failed"; return BA_ERR_NCCL; }
+  return BA_OK;
+}
+static int enqueue_allreduce_scal(ba_solver *s) {
+  if (!s->comm) return BA_OK;
+  ncclResult_t r = g_nccl.AllReduce(s->d_scal.p, s->d_scal.p, 5, ncclDouble, ncclSum, s->comm, s->stream);
+  if (r != ncclSuccess) { s->err = "ncclAllReduce(scalars) failed"; return BA_ERR_NCCL; }
+  return BA_OK;
+}
+
+static int enqueue_solve_backsub(ba_solver *s, cudaEvent_t *ev) {
+  cudaStream_t st = s->stream;
+  const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+  const ParamsW prw{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+  const LmState *dst = s->d_state.p;
+  const int n = 6 * s->N, ld = n + 1;
+  if (ev) cudaEventRecord(ev[Phase::Solve], st);
+  if (s->debug_keep && s->d_Scopy.p) {
+    cudaMemcpyAsync(s->d_Scopy.p, s->d_Saug.p, (size_t)ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  }
+  if (n > 0) cholesky_solve_enqueue(s->d_Saug.p, n, s->d_x.p, s->d_z.p, dst, st, &s->launches);
+  if (ev) cudaEventRecord(ev[Phase::Backsub], st);
+  if (s->n_split_pairs > 0) cudaMemsetAsync(s->d_Btx.p, 0, 3 * s->Mp * sizeof(double), st);
+  if (s->n_chunks > 0 && s->P > 0) {
+    k_backsub_pairs<<<s->n_chunks, kThreads, 0, st>>>(s->d_chunks.p, s->d_chunk_pair_count.p, s->d_pair_pose.p,
+                                                      s->d_pair_point.p, s->d_Bsoa.p, s->Pp, s->d_x.p,
+                                                      s->d_Btx.p, s->Mp, dst);
+    s->launches++;
+  }
+  k_backsub_points<<<s->point_grid, kThreads, 0, st>>>(s->M_total, s->d_point_has_pairs.p, s->d_point_free.p,
+                                                       s->d_ptblk.p, s->Mp, s->d_Btx.p, s->d_y.p, prm, prw,
+                                                       s->d_point_partials.p, dst);
+  s->launches++;
+  return BA_OK;
+}
+
+static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
+  cudaStream_t st = s->stream;
+  const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+  const ParamsW prw{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+  LmState *dst = s->d_state.p;
+  if (ev) cudaEventRecord(ev[Phase::Update], st);
+  k_update_poses<<<s->pose_grid, kThreads, 0, st>>>(s->N_total, s->d_pose_opt.p, s->d_x.p, s->d_A.p, s->d_a.p,
+                                                    prm, prw, s->d_pose_partials.p, dst);
+  k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                            s->d_obs_camflags.p, prm, 1, s->d_cams.p, s->d_cost_partials.p, 0, dst);
+  DecideArgs g = make_decide_args(s, opt);
+  k_reduce_scalars<<<1, kThreads, 0, st>>>(g, 0, dst);
+  s->launches += 3;
+  if (int rc = enqueue_allreduce_scal(s)) return rc;
+  k_decide<<<1, 1, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
+  s->launches++;
+  if (ev) cudaEventRecord(ev[Phase::End], st);
+  return BA_OK;
+}
+
+static int enqueue_iteration(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
+  if (int rc = enqueue_build(s, opt, ev)) return rc;
+  if (int rc = enqueue_allreduce_S(s)) return rc;
+  if (int rc = enqueue_solve_backsub(s, ev)) return rc;
+  return enqueue_update_decide(s, opt, ev);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ba_cost(ba_solver *s, double *cost) {
+  if (!s || !cost) return BA_ERR_INVALID;
+  if (int rc = ba_finalize(s)) return rc;
+  CUDA_TRY(cudaSetDevice(s->device));
+  const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+  k_cost<<<s->cost_grid, kThreads, 0, s->stream>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                                   s->d_obs_camflags.p, prm, 0, s->d_cams.p,
+                                                   s->d_cost_partials.p, 1, s->d_state.p);
+  ba_options o{};
+  o.max_num_iterations = 1;
+  DecideArgs g = make_decide_args(s, &o);
+  k_reduce_scalars<<<1, kThreads, 0, s->stream>>>(g, 1, s->d_state.p);
+  if (int rc = enqueue_allreduce_scal(s)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *cost = s->h_scal[0];
+  return BA_OK;
+}
+
+int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int cap, ba_result *result) {
+  if (!s || !opt_in) return BA_ERR_INVALID;
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  if (int rc = ba_finalize(s)) return rc;
+  CUDA_TRY(cudaSetDevice(s->device));
+  ba_options opt = *opt_in;
+  if (opt.inverse_scaler == 0.0) opt.inverse_scaler = 100.0;
+  if (opt.check_every <= 0) opt.check_every = 8;
+  const int max_it = opt.max_num_iterations;
+  cudaStream_t st = s->stream;
+  s->launches = 0;
+  CUDA_TRY(s->d_infos.alloc(std::max(1, max_it)));
+  // --- initial cost (:707) and state
+  {
+    const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+    k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                              s->d_obs_camflags.p, prm, 0, s->d_cams.p, s->d_cost_partials.p, 1,
+                                              s->d_state.p);
+    DecideArgs g = make_decide_args(s, &opt);
+    k_reduce_scalars<<<1, kThreads, 0, st>>>(g, 1, s->d_state.p);
+    if (int rc = enqueue_allreduce_scal(s)) return rc;
+    k_init_state<<<1, 1, 0, st>>>(s->d_state.p, s->d_scal.p, (double)opt.initial_lambda);
+    s->launches += 3;
+    CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  cudaEvent_t ev_begin, ev_end;
+  CUDA_TRY(cudaEventCreate(&ev_begin));
+  CUDA_TRY(cudaEventCreate(&ev_end));
+  CUDA_TRY(cudaEventRecord(ev_begin, st));
+  double phase_ms[Phase::Count] = {0};
+  int it_launched = 0;
+  int n_done = 0, converged = 0;
+  const bool use_graph = opt.use_graph != 0 && !s->profile && !s->comm;
+  if (s->debug_keep) {
+    const size_t ld = (size_t)6 * s->N + 1;
+    CUDA_TRY(s->d_Scopy.alloc(ld * ld));
+  }
+  if (use_graph && max_it > 0) {
+    ba_options key = opt;
+    key.check_every = 0;
+    if (!s->graph_exec || std::memcmp(&s->graph_opt, &key, sizeof(key)) != 0) {
+      destroy_graph(s);
+      cudaGraph_t graph;
+      const long long l0 = s->launches;
+      CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const int rc = enqueue_iteration(s, &opt, nullptr);
+      const cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc) return rc;
+      if (e != cudaSuccess) { s->err = std::string("graph capture: ") + cudaGetErrorString(e); return BA_ERR_CUDA; }
+      s->graph_nodes = s->launches - l0;
+      s->launches = l0;
+      CUDA_TRY(cudaGraphInstantiate(&s->graph_exec, graph, 0));
+      cudaGraphDestroy(graph);
+      s->graph_opt = key;
+    }
+  }
+  std::vector<cudaEvent_t> &evp = s->ev;
+  while (it_launched < max_it) {
+    const int batch = std::min(opt.check_every, max_it - it_launched);
+    for (int b = 0; b < batch; ++b) {
+      if (use_graph) {
+        CUDA_TRY(cudaGraphLaunch(s->graph_exec, st));
+      } else {
+        cudaEvent_t *ev = nullptr;
+        if (s->profile) {
+          const size_t need = (size_t)(it_launched + b + 1) * Phase::Count;
+          while (evp.size() < need) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); evp.push_back(e); }
+          ev = &evp[(size_t)(it_launched + b) * Phase::Count];
+        }
+        if (int rc = enqueue_iteration(s, &opt, ev)) return rc;
+      }
+    }
+    it_launched += batch;
+    CUDA_TRY(cudaMemcpyAsync(s->h_state, s->d_state.p, sizeof(LmState), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (s->h_state->done) break;
+  }
+  CUDA_TRY(cudaEventRecord(ev_end, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { s->err = std::string("kernel failure: ") + cudaGetErrorString(e); return BA_ERR_CUDA; }
+  }
+  if (max_it > 0) {
+    n_done = s->h_state->iteration;
+    converged = s->h_state->converged;
+  }
+  float dev_ms = 0.f;
+  cudaEventElapsedTime(&dev_ms, ev_begin, ev_end);
+  cudaEventDestroy(ev_begin);
+  cudaEventDestroy(ev_end);
+  if (use_graph) s->launches += s->graph_nodes * it_launched;
+  if (s->profile && !use_graph) {
+    for (int it = 0; it < std::min(n_done, it_launched); ++it) {
+      for (int ph = 0; ph < Phase::End; ++ph) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evp[(size_t)it * Phase::Count + ph], evp[(size_t)it * Phase::Count + ph + 1]);
+        phase_ms[ph] += ms;
+      }
+    }
+  }
+  std::vector<ba_iter_info> h_infos(std::max(1, n_done));
+  if (n_done > 0)
+    CUDA_TRY(cudaMemcpy(h_infos.data(), s->d_infos.p, (size_t)n_done * sizeof(ba_iter_info), cudaMemcpyDeviceToHost));
+  const double per_iter_ms = n_done > 0 ? dev_ms / n_done : 0.0;
+  for (int i = 0; i < n_done; ++i) h_infos[i].iter_time = per_iter_ms;
+  if (infos) for (int i = 0; i < std::min(n_done, cap); ++i) infos[i] = h_infos[i];
+  if (result) {
+    std::memset(result, 0, sizeof(*result));
+    result->n_iterations = n_done;
+    result->converged = converged;
+    result->initial_cost = s->h_scal[0];
+    result->final_cost = max_it > 0 ? s->h_state->prev_cost : s->h_scal[0];
+    result->device_time_ms = dev_ms;
+    result->t_linearize_ms = phase_ms[Phase::Lin];
+    result->t_schur_ms = phase_ms[Phase::Schur];
+    result->t_solve_ms = phase_ms[Phase::Solve];
+    result->t_backsub_ms = phase_ms[Phase::Backsub];
+    result->t_update_cost_ms = phase_ms[Phase::Update];
+    result->kernel_launches = s->launches;
+    result->total_time_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+  }
+  return BA_OK;
+}
+
+int ba_build_only(ba_solver *s, const ba_options *opt_in, double lambda, int do_solve) {
+  if (!s || !opt_in) return BA_ERR_INVALID;
+  if (int rc = ba_finalize(s)) return rc;
+  CUDA_TRY(cudaSetDevice(s->device));
+  ba_options opt = *opt_in;
+  cudaStream_t st = s->stream;
+  // state: keep `cur`, set lambda, not done
+  CUDA_TRY(cudaMemcpyAsync(s->h_state, s->d_state.p, sizeof(LmState), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  s->h_state->lambda = lambda;
+  s->h_state->done = 0;
+  CUDA_TRY(cudaMemcpyAsync(s->d_state.p, s->h_state, sizeof(LmState), cudaMemcpyHostToDevice, st));
+  if (s->debug_keep) {
+    const size_t ldc = (size_t)6 * s->N + 1;
+    CUDA_TRY(s->d_Scopy.alloc(ldc * ldc));
+  }
+  if (int rc = enqueue_build(s, &opt, nullptr)) return rc;
+  if (int rc = enqueue_allreduce_S(s)) return rc;
+  if (do_solve) {
+    if (int rc = enqueue_solve_backsub(s, nullptr)) return rc;
+  } else if (s->debug_keep) {
+    const size_t ld = (size_t)6 * s->N + 1;
+    CUDA_TRY(s->d_Scopy.alloc(ld * ld));
+    CUDA_TRY(cudaMemcpyAsync(s->d_Scopy.p, s->d_Saug.p, ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { s->err = std::string("kernel failure: ") + cudaGetErrorString(e); return BA_ERR_CUDA; }
+  return BA_OK;
+}
+
+static int current_buffer(ba_solver *s, int *cur) {
+  CUDA_TRY(cudaMemcpy(s->h_state, s->d_state.p, sizeof(LmState), cudaMemcpyDeviceToHost));
+  *cur = s->h_state->cur & 1;
+  return BA_OK;
+}
+
+int ba_get_poses(ba_solver *s, double *T_jw) {
+  if (!s || !s->finalized || !T_jw) return BA_ERR_STATE;
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  int cur;
+  if (int rc = current_buffer(s, &cur)) return rc;
+  CUDA_TRY(cudaMemcpy(T_jw, s->d_poses[cur].p, (size_t)s->N_total * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+  return BA_OK;
+}
+
+int ba_get_points(ba_solver *s, double *X) {
+  if (!s || !s->finalized || !X) return BA_ERR_STATE;
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  int cur;
+  if (int rc = current_buffer(s, &cur)) return rc;
+  CUDA_TRY(cudaMemcpy(X, s->d_points[cur].p, (size_t)s->M_total * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  return BA_OK;
+}
+
+int ba_get_sizes(ba_solver *s, long long *o) {
+  if (!s || !o) return BA_ERR_INVALID;
+  if (int rc = ba_finalize(s)) return rc;
+  o[0] = s->N; o[1] = s->M; o[2] = s->P; o[3] = s->n_obs; o[4] = s->N_total; o[5] = s->M_total;
+  return BA_OK;
+}
+
+long long ba_debug_dump(ba_solver *s, int which, double *buf) {
+  if (!s || !s->finalized) return BA_ERR_STATE;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  const int N = s->N, M = s->M, n = 6 * N, ld = n + 1;
+  const long long P = s->P;
+  auto fetch = [&](const double *d, size_t cnt) {
+    std::vector<double> h(cnt);
+    if (cnt) cudaMemcpy(h.data(), d, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+    return h;
+  };
+  switch (which) {
+    case 0: if (buf) { auto h = fetch(s->d_A.p, (size_t)N * 36); std::copy(h.begin(), h.end(), buf); } return (long long)N * 36;
+    case 1: if (buf) { auto h = fetch(s->d_a.p, (size_t)N * 6); std::copy(h.begin(), h.end(), buf); } return (long long)N * 6;
+    case 2: case 3: case 4: {
+      const int w = which == 3 ? 3 : 9;
+      if (buf) {
+        auto h = fetch(s->d_ptblk.p, kPtBlk * s->Mp);
+        const int sym[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+        for (int io = 0; io < M; ++io) {
+          const int i = s->h_opt_point[io];
+          if (which == 3) for (int k = 0; k < 3; ++k) buf[(size_t)io * 3 + k] = h[(PB_b + k) * s->Mp + i];
+          else {
+            const int base = which == 2 ? PB_Cd : PB_Cinv;
+            for (int k = 0; k < 9; ++k) buf[(size_t)io * 9 + k] = h[(base + sym[k]) * s->Mp + i];
+          }
+        }
+      }
+      return (long long)M * w;
+    }
+    case 5:
+      if (buf) {
+        auto h = fetch(s->d_Bsoa.p, 18 * s->Pp);
+        for (long long p = 0; p < P; ++p)
+          for (int k = 0; k < 18; ++k) buf[p * 18 + k] = h[(size_t)k * s->Pp + p];
+      }
+      return P * 18;
+    case 6: case 7: {
+      if (!s->d_Scopy.p) return BA_ERR_STATE;
+      if (buf) {
+        auto h = fetch(s->d_Scopy.p, (size_t)ld * ld);
+        if (which == 6) {
+          for (int r = 0; r < n; ++r)
+            for (int c = 0; c < n; ++c) {
+              const int a = std::min(r, c), b = std::max(r, c);
+              buf[(size_t)c * n + r] = h[(size_t)a * ld + b];  // symmetric; row-major upper is filled
+            }
+        } else {
+          for (int r = 0; r < n; ++r) buf[r] = h[(size_t)r * ld + n];
+        }
+      }
+      return which == 6 ? (long long)n * n : n;
+    }
+    case 8: if (buf) { auto h = fetch(s->d_x.p, (size_t)n); std::copy(h.begin(), h.end(), buf); } return n;
+    case 9:
+      if (buf) {
+        auto h = fetch(s->d_y.p, (size_t)s->M_total * 3);
+        for (int io = 0; io < M; ++io)
+          for (int k = 0; k < 3; ++k) buf[(size_t)io * 3 + k] = h[(size_t)s->h_opt_point[io] * 3 + k];
+      }
+      return (long long)M * 3;
+    case 10:
+      if (buf) {
+        LmState h;
+        cudaMemcpy(&h, s->d_state.p, sizeof(h), cudaMemcpyDeviceToHost);
+        buf[0] = 0.0; buf[1] = h.last_cost_new; buf[2] = h.last_model; buf[3] = h.last_rho; buf[4] = h.last_lambda;
+      }
+      return 5;
+    default: return BA_ERR_INVALID;
+  }
+}
+
+int ba_debug_pairs(ba_solver *s, int *pair_pose_id, int *pair_point_id) {
+  if (!s || !s->finalized) return BA_ERR_STATE;
+  for (long long p = 0; p < s->P; ++p) {
+    pair_pose_id[p] = s->h_opt_pose[s->h_pair_pose[p]];
+    pair_point_id[p] = s->h_pair_point[p];
+  }
+  return BA_OK;
+}
+
+int ba_comm_get_unique_id(void *id128) {
+  if (!id128) return BA_ERR_INVALID;
+  if (!g_nccl.load()) return BA_ERR_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return BA_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  std::memcpy(id128, &id, 128);
+  return BA_OK;
+}
+
+int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long long global_M,
+                 long long global_n_obs) {
+  if (!s || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return BA_ERR_INVALID;
+  if (!g_nccl.load()) { s->err = "libnccl.so.2 not found"; return BA_ERR_NCCL; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (int rc = ensure_stream(s)) return rc;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&s->comm, nranks, id, rank);
+  if (r != ncclSuccess) { s->err = "ncclCommInitRank failed"; s->comm = nullptr; return BA_ERR_NCCL; }
+  s->rank = rank; s->n_ranks = nranks; s->global_M = global_M; s->global_n_obs = global_n_obs;
+  destroy_graph(s);
+  return BA_OK;
+}
+
+int ba_comm_destroy(ba_solver *s) {
+  if (!s) return BA_ERR_INVALID;
+  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  s->comm = nullptr; s->rank = 0; s->n_ranks = 1; s->global_M = s->global_n_obs = -1;
+  return BA_OK;
+}
+
+}  // extern "C"

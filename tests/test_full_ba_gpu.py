@@ -1,0 +1,169 @@
+"""GPU parity tests of the full-BA device path against the CPU oracle, through the C-ABI.
+
+Tolerances (BASELINE.json north_star): Hessian/Schur blocks 1e-9 relative (FP64, reduction-order
+differences only), final cost 1e-6 relative, same convergence verdict, iterations within +-1.
+"""
+import numpy as np
+import pytest
+
+from bundle_adjustment_solver_b200 import scenes
+from helpers import S_block_view, blockwise_rel_err, load_engine, load_oracle, options_pair
+
+pytestmark = pytest.mark.gpu
+
+BLOCK_TOL = 1e-9
+
+
+def _compare_blocks(o, e, sizes, tol=BLOCK_TOL, check_S=True):
+    N = sizes["N"]
+    errs = {}
+    for name, blk in (("A", 36), ("a", 6), ("C", 9), ("b", 3), ("Cinv", 9), ("B", 18)):
+        errs[name] = blockwise_rel_err(e.dump(name), o.dump(name), blk)
+    if check_S:
+        errs["S"] = blockwise_rel_err(S_block_view(e.dump("S"), N), S_block_view(o.dump("S"), N), 36)
+        errs["rhs"] = blockwise_rel_err(e.dump("rhs"), o.dump("rhs"), 6)
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"block parity failed: {bad} (all: {errs})"
+    return errs
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("accum", [0, 1])
+def test_blocks_match_oracle_c1(seed, accum, oracle_mod, engine_lib):
+    sc = scenes.scene_test_ba(seed=seed)
+    o = load_oracle(sc)
+    o.build_only(thres_huber=1.0, lam=100.0, b_accumulate=accum, do_solve=True)
+    e = load_engine(sc, identical_internal=o.get_internal())
+    e.set_debug(True)
+    oo, eo = options_pair(b_accumulate=accum)
+    e.build_only(eo, 100.0, do_solve=True)
+    assert e.sizes() == o.sizes()
+    # same pair set, same order (sorted by point, pose)
+    assert all(np.array_equal(x, y) for x, y in zip(e.pairs(), o.pairs()))
+    _compare_blocks(o, e, o.sizes())
+    # reduced solve and back-substitution: x, y  (conditioning of S enters -> looser, stated)
+    assert blockwise_rel_err(e.dump("x"), o.dump("x"), 6) < 1e-6
+    assert blockwise_rel_err(e.dump("y"), o.dump("y"), 3) < 1e-6
+
+
+def test_initial_cost_matches(oracle_mod, engine_lib):
+    sc = scenes.scene_test_ba(seed=3)
+    o = load_oracle(sc)
+    o.sizes()
+    e = load_engine(sc, identical_internal=o.get_internal())
+    assert abs(e.cost() - o.cost()) <= 1e-12 * abs(o.cost())
+
+
+@pytest.mark.parametrize("seed,accum", [(0, 0), (1, 0), (2, 0), (0, 1)])
+def test_solve_c1_matches_oracle(seed, accum, oracle_mod, engine_lib):
+    sc = scenes.scene_test_ba(seed=seed)
+    kw = dict(max_num_iterations=300, threshold_cost_change=1e-6, threshold_step_size=1e-6, b_accumulate=accum)
+    oo, eo = options_pair(**kw)
+    o = load_oracle(sc)
+    infos_o, conv_o = o.solve(oo)
+    e = load_engine(sc, identical_internal=None)
+    from bundle_adjustment_solver_b200.solver import Summary
+    summ = Summary()
+    e.solve(eo, summ)
+    infos_e = summ.optimization_info_list
+    assert summ.convergence_status == conv_o
+    assert abs(len(infos_e) - len(infos_o)) <= 1, (len(infos_e), len(infos_o))
+    fo, fe = infos_o[-1].cost, infos_e[-1].cost
+    assert abs(fe - fo) <= 1e-6 * abs(fo), (fe, fo)
+    # the first iterations must agree tightly (same trajectory)
+    for k in range(min(5, len(infos_o), len(infos_e))):
+        assert abs(infos_e[k].cost - infos_o[k].cost) <= 1e-9 * abs(infos_o[k].cost)
+        assert infos_e[k].iteration_status == infos_o[k].iteration_status
+        assert abs(infos_e[k].damping_term - infos_o[k].damping_term) <= 1e-12 * infos_o[k].damping_term
+    # poses / points: stated tolerance 1e-6 m (user units), free parameters written back
+    Po, Xo = o.get_poses(), o.get_points()
+    Pe, Xe = e.get_poses(), e.get_points()
+    assert np.abs(Pe - Po).max() < 1e-6
+    assert np.abs(Xe - Xo).max() < 1e-6
+    # fixed poses untouched
+    assert np.array_equal(Pe[:5], sc.poses_init[:5])
+    print(summ.brief_report()[-600:])
+
+
+def test_fixed_points_and_split_point(oracle_mod, engine_lib):
+    """Edge cases: fixed landmarks, landmarks seen only by fixed poses, and one landmark with more
+    observations than a 256-observation chunk (split path with atomics)."""
+    sc = scenes.scene_trajectory(160, 400, 10, stereo=True, seed=5, n_fixed=3)
+    # a landmark seen by every pose in both cameras: 320 observations
+    rng = np.random.default_rng(0)
+    Xbig = np.array([16.0, 0.2, 30.0])
+    M = len(sc.points_true)
+    sc.points_true = np.vstack([sc.points_true, Xbig])
+    sc.points_init = np.vstack([sc.points_init, Xbig + 0.2])
+    T_cw = scenes.inv_T(sc.poses_true)
+    cams, poses, pts, uvs = [], [], [], []
+    for j in range(len(sc.poses_true)):
+        for c in range(2):
+            Xb = T_cw[j, :3, :3] @ Xbig + T_cw[j, :3, 3]
+            Xc = sc.cam_T[c][:3, :3] @ Xb + sc.cam_T[c][:3, 3]
+            uvs.append([sc.cam_intr[c, 0] * Xc[0] / Xc[2] + sc.cam_intr[c, 2],
+                        sc.cam_intr[c, 1] * Xc[1] / Xc[2] + sc.cam_intr[c, 3]])
+            cams.append(c); poses.append(j); pts.append(M)
+    sc.obs_cam = np.concatenate([sc.obs_cam, np.array(cams, dtype=np.int32)])
+    sc.obs_pose = np.concatenate([sc.obs_pose, np.array(poses, dtype=np.int32)])
+    sc.obs_point = np.concatenate([sc.obs_point, np.array(pts, dtype=np.int32)])
+    sc.obs_uv = np.vstack([sc.obs_uv, np.array(uvs)])
+    sc.fixed_points = np.array([1, 7, 50])
+    for accum in (0, 1):
+        o = load_oracle(sc)
+        o.build_only(thres_huber=1.0, lam=3.0, b_accumulate=accum, do_solve=True)
+        e = load_engine(sc, identical_internal=o.get_internal())
+        e.set_debug(True)
+        oo, eo = options_pair(b_accumulate=accum)
+        e.build_only(eo, 3.0, do_solve=True)
+        assert e.sizes() == o.sizes()
+        _compare_blocks(o, e, o.sizes())
+        assert blockwise_rel_err(e.dump("y"), o.dump("y"), 3) < 1e-6
+    # and a short solve agrees
+    oo, eo = options_pair(max_num_iterations=6)
+    o = load_oracle(sc)
+    infos_o, _ = o.solve(oo)
+    e = load_engine(sc)
+    from bundle_adjustment_solver_b200.solver import Summary
+    summ = Summary()
+    e.solve(eo, summ)
+    assert len(summ.optimization_info_list) == len(infos_o)
+    assert abs(summ.optimization_info_list[-1].cost - infos_o[-1].cost) <= 1e-6 * abs(infos_o[-1].cost)
+
+
+def test_graph_and_plain_launch_agree(oracle_mod, engine_lib):
+    sc = scenes.scene_test_ba(seed=4)
+    from bundle_adjustment_solver_b200.solver import Summary
+    outs = []
+    for use_graph in (1, 0):
+        _, eo = options_pair(max_num_iterations=12, use_graph=use_graph, check_every=5)
+        e = load_engine(sc)
+        summ = Summary()
+        e.solve(eo, summ)
+        outs.append([i.cost for i in summ.optimization_info_list])
+    assert len(outs[0]) == len(outs[1]) == 12
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-10)
+
+
+def test_c3_scaled_blocks_and_iterations(oracle_mod, engine_lib):
+    """Config C3 shape at 1/5 scale (40 poses x 10k landmarks would change the structure; keep 200
+    poses, 10k landmarks): block parity + 3 LM iterations."""
+    sc = scenes.scene_trajectory(200, 10_000, 10, stereo=True, seed=0, name="C3_fifth")
+    o = load_oracle(sc)
+    o.build_only(thres_huber=1.0, lam=100.0, b_accumulate=0, do_solve=True)
+    e = load_engine(sc, identical_internal=o.get_internal())
+    e.set_debug(True)
+    oo, eo = options_pair()
+    e.build_only(eo, 100.0, do_solve=True)
+    _compare_blocks(o, e, o.sizes())
+    assert blockwise_rel_err(e.dump("x"), o.dump("x"), 6) < 1e-6
+    oo, eo = options_pair(max_num_iterations=3)
+    o = load_oracle(sc)
+    infos_o, _ = o.solve(oo)
+    e = load_engine(sc)
+    from bundle_adjustment_solver_b200.solver import Summary
+    summ = Summary()
+    e.solve(eo, summ)
+    for a, b in zip(summ.optimization_info_list, infos_o):
+        assert abs(a.cost - b.cost) <= 1e-8 * abs(b.cost)
+        assert a.iteration_status == b.iteration_status
