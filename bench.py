@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 bundle-adjustment engine.
+
+Metric (BASELINE.json): LM iters/s & Schur-build obs/s.  One "step" = one full Levenberg-Marquardt
+iteration (linearise, Schur complement, reduced solve, back-substitution, trial cost, accept/lambda)
+over the workload's observations.  `value` = observations x LM iterations per second (whole job, all
+ranks), device-resident; `lm_iters_per_s` and `schur_build_obs_per_s` are reported beside it.
+Workload at N=1: config C3 "stereo full BA, 200 poses / 50k landmarks / ~1M observations on 1 B200".
+N>1 (weak scaling): every rank holds all 200 poses and its own 50k landmarks (+~1M observations);
+[S | rhs] and the LM scalars are all-reduced over NCCL every iteration.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # the reference's algorithm on host cores (oracle)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LM-iteration observation throughput (observations x LM iters/s; full iteration: linearise, Schur, solve, back-substitute, cost/accept)"
+UNIT = "obs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_scene(workload, rank, scale):
+    from bundle_adjustment_solver_b200 import scenes
+    if workload == "c3":
+        return scenes.scene_c3(seed=100 + rank, scale=scale, pose_noise_seed=7)
+    if workload == "c1":
+        return scenes.scene_test_ba(seed=rank)
+    if workload == "c4":
+        return scenes.scene_c4(seed=100 + rank, scale=scale)
+    if workload == "c5":
+        return scenes.scene_c5(seed=100 + rank, scale=scale)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+WORKLOAD_NAMES = {
+    "c1": "C1 test_ba.cpp stereo full BA (60 poses / 660 landmarks / 34,019 observations)",
+    "c3": "C3 stereo full BA, 200 poses / 50k landmarks / ~1M observations",
+    "c4": "C4 stereo full BA, 2000 poses / 1M landmarks / ~8M observations",
+    "c5": "C5 BAL-Venice-shaped mono full BA (1778 poses / ~1M points / ~5M observations)",
+}
+
+
+def algorithmic_bytes(sz, n_obs_free_pose):
+    """Algorithmic bytes per LM iteration of the implemented design (DESIGN.md 'Kernels')."""
+    O, Nt, Mt, N, M, P = sz["n_obs"], sz["N_total"], sz["M_total"], sz["N"], sz["M"], sz["P"]
+    n = 6 * N
+    b = {}
+    b["linearize"] = (32 * O + 96 * Nt + 24 * Mt + 144 * M + 144 * P          # K1: obs, params, point blocks, B
+                      + 28 * n_obs_free_pose + 24 * Mt + 96 * N + 2 * 336 * N  # K2: obs (pose order), A/a + S diag
+                      + 8 * (n + 1) * (n + 1))                                 # S memset
+    b["schur"] = 144 * P + 12 * P + 72 * M + 8 * n * (n + 1) // 2 * 2 + 16 * n  # K4: B, pair ids, Cinv/Cinv_b, S r/w
+    b["backsub"] = 144 * P + 8 * P + 48 * N + 24 * M + (144 + 24 + 24 + 24 + 24) * Mt
+    b["update_cost"] = 28 * O + 96 * Nt * 2 + 24 * Mt
+    b["solve_flops"] = n ** 3 / 3.0 + 2.0 * n * n
+    return b
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, loaded = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                loaded.append(float(f[7]) > 0)
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        under = [s for s, l in zip(sm, loaded) if l] or sm
+        return {"sm_mhz": float(np.median(under)) if under else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "samples_under_load": int(sum(loaded))}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own algorithm on the host cores.  The reference cannot be
+    compiled here (no Eigen/Ceres/OpenCV), so this is the oracle port (kind 'port'), single thread like
+    the reference (it has no threads), on a bounded number of LM iterations of the same workload."""
+    if rank != 0:
+        return
+    import oracle
+    from bundle_adjustment_solver_b200 import solver as S
+    sc = make_scene(args.workload, 0, args.scale)
+    o = S.load_scene(oracle.FullBAOracle(), sc)
+    o.sizes()
+    iters = max(1, min(args.steps, args.cpu_iters))
+    warm = 1 if args.warmup > 0 else 0
+    opt = oracle.default_full_options(max_num_iterations=max(1, warm), threshold_cost_change=0.0,
+                                      threshold_step_size=0.0)
+    if warm:
+        o.solve(opt)
+    opt.max_num_iterations = iters
+    t0 = time.perf_counter()
+    infos, _ = o.solve(opt)
+    dt = time.perf_counter() - t0
+    value = sc.n_obs * len(infos) / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(infos),
+        "warmup": warm, "ms_per_step": 1e3 * dt / len(infos), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "n_obs": sc.n_obs, "scale": args.scale},
+        "lm_iters_per_s": len(infos) / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{len(infos)} LM iterations of the same workload, oracle/ba_oracle.cpp -O2, "
+                                   f"host has {os.cpu_count()} cores; the reference is single-threaded"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOAD_NAMES))
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cpu-iters", type=int, default=4, help="LM iterations of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.steps = max(1, args.steps)
+    args.warmup = max(3, args.warmup)
+
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from bundle_adjustment_solver_b200 import capi
+    from bundle_adjustment_solver_b200 import solver as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+
+    sc = make_scene(args.workload, rank, args.scale)
+    L = capi.lib()
+
+    def new_solver():
+        s = S.FullBundleAdjustmentSolver(device=local_rank, stream=stream.cuda_stream)
+        S.load_scene(s, sc)
+        return s
+
+    def join_comm(s, sz):
+        if world == 1:
+            return
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            assert L.ba_comm_get_unique_id(raw) == 0
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.to(dev)
+        dist.broadcast(idbuf, 0)
+        tot = torch.tensor([sz["M"], sz["n_obs"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        rc = L.ba_comm_init(s.h, raw, rank, world, int(tot[0]), int(tot[1]))
+        if rc != 0:
+            raise SystemExit(f"ba_comm_init failed: {L.ba_last_error(s.h)}")
+
+    with torch.cuda.stream(stream):
+        s = new_solver()
+        s._upload()
+        sz = s.sizes()
+        join_comm(s, sz)
+        T12_0, X_0 = s.internal_parameters()
+        n_obs_free_pose = int(np.count_nonzero(~np.isin(sc.obs_pose, sc.fixed_poses)))
+
+        def solve_n(n_it, check_every=None, profile=False):
+            s.set_profile(profile)
+            opt = capi.default_options(max_num_iterations=n_it, threshold_cost_change=0.0, threshold_step_size=0.0,
+                                       check_every=check_every or n_it)
+            res = capi.Result()
+            rc = L.ba_solve(s.h, C.byref(opt), None, 0, C.byref(res))
+            if rc != 0:
+                raise SystemExit(f"ba_solve failed: {L.ba_last_error(s.h)}")
+            assert res.n_iterations == n_it, (res.n_iterations, n_it)
+            return res
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        # ---- warm-up (untimed): W steps, then keep the GPU busy ~1 s so the clock samples see load
+        solve_n(args.warmup)
+        t_w = time.perf_counter()
+        while time.perf_counter() - t_w < 1.0:
+            solve_n(args.steps)
+        # ---- timed: exactly K steps from the initial guess
+        s.update_parameters_internal(T12_0, X_0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        res = solve_n(args.steps)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = int(res.kernel_launches)
+        clocks = sampler.stop() if rank == 0 else None
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        nobs_all = torch.tensor([sz["n_obs"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nobs_all)
+        ms = float(tmax[0])
+        total_obs = float(nobs_all[0])
+        value = total_obs * args.steps / (ms * 1e-3)
+
+        # ---- per-phase device times (CUDA events on the launching stream, plain launches)
+        s.update_parameters_internal(T12_0, X_0)
+        solve_n(args.warmup, profile=True)
+        s.update_parameters_internal(T12_0, X_0)
+        resp = solve_n(args.steps, profile=True)
+        s.set_profile(False)
+        ph = {"linearize": resp.t_linearize_ms / args.steps, "schur": resp.t_schur_ms / args.steps,
+              "solve": resp.t_solve_ms / args.steps, "backsub": resp.t_backsub_ms / args.steps,
+              "update_cost": resp.t_update_cost_ms / args.steps}
+
+        # ---- end to end through the C-ABI from host buffers: register + finalize (H2D pack) +
+        #      solve to convergence + read back.  Per-step bytes = totals / LM iterations.
+        e2e = None
+        if not args.no_e2e:
+            s2 = S.FullBundleAdjustmentSolver(device=local_rank, stream=stream.cuda_stream)
+            join_comm_needed = world > 1
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            S.load_scene(s2, sc)
+            s2._upload()
+            if join_comm_needed:
+                join_comm(s2, sz)
+            opt = capi.default_options(max_num_iterations=50, threshold_cost_change=1e-6, threshold_step_size=1e-6)
+            summ = S.Summary()
+            s2.solve(opt, summ)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            it = len(summ.optimization_info_list)
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+            h2d = sc.n_obs * (16 + 16 + 12 + 12) + sz["N_total"] * 96 * 2 + sz["M_total"] * 24 * 2 + sz["P"] * 12
+            d2h = sz["N_total"] * 96 + sz["M_total"] * 24 + it * 64
+            e2e = {"value": total_obs * it / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(it, 1)),
+                   "d2h_bytes_per_step": int(d2h / max(it, 1)), "lm_iterations": it, "converged": bool(summ.convergence_status),
+                   "wall_s": dt, "final_cost": summ.optimization_info_list[-1].cost if it else None,
+                   "includes": "host registration, FinalizeParameters (sorts, H2D pack), LM loop to convergence, D2H write-back"}
+            del s2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    ab = algorithmic_bytes(sz, n_obs_free_pose)
+    phases = {}
+    for k in ("linearize", "schur", "backsub", "update_cost"):
+        gbs = ab[k] / (ph[k] * 1e-3) / 1e9 if ph[k] > 0 else 0.0
+        phases[k] = {"ms": ph[k], "algorithmic_bytes": ab[k], "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak}
+    phases["solve"] = {"ms": ph["solve"], "algorithmic_flops": ab["solve_flops"],
+                       "achieved_tflops": ab["solve_flops"] / (ph["solve"] * 1e-3) / 1e12 if ph["solve"] > 0 else 0.0}
+    t_build = ph["linearize"] + ph["schur"]
+    dom = max(("linearize", "schur", "backsub", "update_cost"), key=lambda k: ph[k])
+    roofline = {"bound": "hbm", "kernel": {"linearize": "k_linearize_by_point+k_linearize_by_pose", "schur": "k_schur_pairs",
+                                           "backsub": "k_backsub_pairs+k_backsub_points", "update_cost": "k_cost+k_update_poses"}[dom],
+                "achieved": phases[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": phases[dom]["frac_hbm"],
+                "traffic": None, "peak_source": peak_src,
+                "note": "dominant memory-bound phase of the step; per-phase table in 'phases' (the Cholesky phase is FP64-compute bound, see phases.solve)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        o = S.load_scene(oracle.FullBAOracle(), sc)
+        o.sizes()
+        it_cpu = max(1, args.cpu_iters)
+        oo = oracle.default_full_options(max_num_iterations=it_cpu, threshold_cost_change=0.0, threshold_step_size=0.0)
+        t0 = time.perf_counter()
+        infos, _ = o.solve(oo)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": sc.n_obs * len(infos) / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{len(infos)} LM iterations of the same workload on 1 of {os.cpu_count()} host cores "
+                         f"(oracle/ba_oracle.cpp; the reference is single-threaded), {dtc:.1f} s",
+               "ms_per_step": 1e3 * dtc / len(infos)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "per_gpu": {k: sz[k] for k in ("N", "M", "P", "n_obs")},
+                   "scale": args.scale, "parallelism": f"landmark-sharded x{world}, S all-reduce" if world > 1 else "single GPU",
+                   "l2": "no flush: per-iteration working set %.0f MB exceeds the 126 MB L2" % (
+                       (ab["linearize"] + ab["schur"] + ab["backsub"] + ab["update_cost"]) / 1e6),
+                   "cuda_graph": world == 1},
+        "lm_iters_per_s": args.steps / (ms * 1e-3),
+        "schur_build_obs_per_s": total_obs / (t_build * 1e-3) if t_build > 0 else None,
+        "phases": phases, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

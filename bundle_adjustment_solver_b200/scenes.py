@@ -142,7 +142,7 @@ def scene_test_ba(seed=0, pixel_sigma=0.0, num_total_poses=60, num_fixed_poses=5
 
 def scene_trajectory(n_poses, n_points, mean_track, stereo=True, seed=0, n_fixed=2, pixel_sigma=0.0,
                      heavy_tail=False, loop_fraction=0.0, point_error_level=0.5,
-                     pose_translation_error_level=0.1, name="traj"):
+                     pose_translation_error_level=0.1, name="traj", pose_noise_seed=None):
     """Configs C3/C4/C5: poses on a smooth trajectory, each landmark seen by a run of
     consecutive poses (in both cameras when stereo).  heavy_tail draws the track length from a
     geometric distribution clipped to [2, 100] (Venice-like); loop_fraction adds far-away
@@ -208,7 +208,9 @@ def scene_trajectory(n_poses, n_points, mean_track, stereo=True, seed=0, n_fixed
         uv = uv + rng.normal(0, pixel_sigma, uv.shape)
     poses_init = poses_true.copy()
     lvl = pose_translation_error_level
-    poses_init[n_fixed:, :3, 3] += rng.uniform(-lvl, lvl, (n_poses - n_fixed, 3))
+    # pose_noise_seed: landmark shards of one problem (multi-GPU) must share the same initial poses
+    prng = rng if pose_noise_seed is None else np.random.default_rng(pose_noise_seed)
+    poses_init[n_fixed:, :3, 3] += prng.uniform(-lvl, lvl, (n_poses - n_fixed, 3))
     points_init = points_true + rng.uniform(-point_error_level, point_error_level, (n_points, 3))
     return FullScene(
         cam_ids=cam_ids, cam_intr=intr, cam_T=cam_T, poses_true=poses_true, poses_init=poses_init,
@@ -218,10 +220,10 @@ def scene_trajectory(n_poses, n_points, mean_track, stereo=True, seed=0, n_fixed
         name=name, meta=dict(seed=seed, pixel_sigma=pixel_sigma, mean_track=mean_track))
 
 
-def scene_c3(seed=0, pixel_sigma=0.0, scale=1.0):
+def scene_c3(seed=0, pixel_sigma=0.0, scale=1.0, pose_noise_seed=None):
     """stereo full BA, 200 poses / 50k landmarks / ~1M observations."""
     return scene_trajectory(200, int(50_000 * scale), 10, stereo=True, seed=seed, pixel_sigma=pixel_sigma,
-                            name="C3_200p_50k_1M")
+                            name="C3_200p_50k_1M", pose_noise_seed=pose_noise_seed)
 
 
 def scene_c4(seed=0, pixel_sigma=0.0, scale=1.0):

@@ -118,7 +118,7 @@ def lib():
         L.orc_se3_exp_f64.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_poseonly_solve.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 11 + [
             C.POINTER(PoseOnlyOptions), C.POINTER(PoseOnlyResult)] + [C.c_void_p] * 3
-        L.orc_poseonly_solve_batched.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 13 + [
+        L.orc_poseonly_solve_batched.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 12 + [
             C.POINTER(PoseOnlyOptions), C.c_void_p]
         _lib = L
     return _lib

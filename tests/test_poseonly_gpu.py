@@ -1,0 +1,96 @@
+"""GPU parity of the batched pose-only kernels (FP32) against the float oracle, through the C-ABI.
+
+Tolerance: the reference arithmetic is float32 and the device sums the per-point terms in a different
+order (warp tree instead of sequential), so parity is float-level: optimised pose within 2e-4 (abs,
+R entries and metres), iteration count within +-1, identical convergence verdict, inlier masks equal
+except for points whose L1 residual sits within 1e-3 px of the rejection threshold.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from bundle_adjustment_solver_b200 import capi, scenes
+from bundle_adjustment_solver_b200 import solver as S
+
+pytestmark = pytest.mark.gpu
+
+OPT = (1e-6, 1e-6, 1.5, 2.5, 100)
+
+
+def _both(pb, opt=OPT, hist=False):
+    po = S.PoseOnlyBundleAdjustmentSolver(device=0)
+    out = po.solve_batched(pb.kind, pb.offsets, pb.points, pb.px_left, pb.px_right, pb.intr_left, pb.intr_right,
+                           pb.poses_init, capi.PoseOnlyOptions(*opt), left_to_right=pb.left_to_right,
+                           base_to_camera=pb.base_to_camera, world_to_last=pb.world_to_last, want_history=hist)
+    ref = oracle.poseonly_solve_batched(pb.kind, pb.offsets, pb.points, pb.px_left, pb.px_right, pb.intr_left,
+                                        pb.intr_right, pb.poses_init, oracle.PoseOnlyOptions(*opt),
+                                        left_to_right=pb.left_to_right, base_to_camera=pb.base_to_camera,
+                                        world_to_last=pb.world_to_last)
+    return out, ref
+
+
+def _check(out, ref, pb, pose_tol=2e-4):
+    nf = pb.n_frames
+    assert np.abs(out["poses"] - ref["poses"]).max() < pose_tol
+    for f in range(nf):
+        a, b = out["results"][f], ref["results"][f]
+        assert a.success == b.success == 1
+        assert a.converged == b.converged
+        assert abs(a.n_iterations - b.n_iterations) <= 1, (f, a.n_iterations, b.n_iterations)
+    for k in ("mask_left", "mask_right"):
+        diff = np.count_nonzero(out[k] != ref[k])
+        assert diff <= max(2, 1e-4 * out[k].size), (k, diff)
+
+
+@pytest.mark.parametrize("stereo", [True, False])
+@pytest.mark.parametrize("sigma", [0.0, 0.5])
+def test_6dof_batch_matches_oracle(stereo, sigma):
+    pb = scenes.scene_poseonly_batch(n_frames=96, n_points=300, seed=3, pixel_sigma=sigma, stereo=stereo)
+    out, ref = _both(pb)
+    _check(out, ref, pb)
+    if sigma == 0.0:
+        assert np.abs(out["poses"] - pb.poses_true).max() < 1e-3
+
+
+def test_6dof_ragged_and_invalid_right_pixels():
+    pb = scenes.scene_poseonly_batch(n_frames=64, n_points=300, seed=5, pixel_sigma=0.3, stereo=True,
+                                     right_invalid_fraction=0.2, ragged=True)
+    out, ref = _both(pb)
+    _check(out, ref, pb)
+
+
+@pytest.mark.parametrize("stereo", [True, False])
+def test_planar3dof_batch_matches_oracle(stereo):
+    pb = scenes.scene_poseonly_planar_batch(n_frames=48, n_points=300, seed=2, pixel_sigma=0.2, stereo=stereo)
+    out, ref = _both(pb)
+    _check(out, ref, pb)
+    assert np.abs(out["poses"] - pb.poses_true).max() < 5e-2
+
+
+def test_single_frame_large_uses_cta_path_and_debug_poses():
+    """test_compare_ceres_vs_native.cpp shape (one frame, many points): CTA-per-frame path."""
+    pb = scenes.scene_poseonly_batch(n_frames=1, n_points=20000, seed=9, pixel_sigma=0.0, stereo=False)
+    po = S.PoseOnlyBundleAdjustmentSolver(device=0)
+    r = po.solve(pb.kind, pb.points, pb.px_left, None, pb.intr_left, None, pb.poses_init[0],
+                 capi.PoseOnlyOptions(*OPT))
+    ref = oracle.poseonly_solve(pb.kind, pb.points, pb.px_left, None, pb.intr_left, None, pb.poses_init[0],
+                                oracle.PoseOnlyOptions(*OPT), want_history=True)
+    assert r["success"]
+    assert np.abs(r["pose"] - ref["pose"]).max() < 5e-4
+    assert abs(r["result"].n_iterations - ref["result"].n_iterations) <= 1
+    dbg = po.get_debug_poses()
+    assert len(dbg) == r["result"].n_iterations
+    n = min(len(dbg), len(ref["debug_poses"]))
+    assert np.abs(dbg[:n] - ref["debug_poses"][:n]).max() < 5e-3
+    assert np.abs(dbg[-1] - r["pose"]).max() < 1e-6
+
+
+def test_full_size_c2_properties():
+    """Config C2 at full size (4096 frames x 300 points): every frame converges to its true pose."""
+    pb = scenes.scene_poseonly_batch(n_frames=4096, n_points=300, seed=0, pixel_sigma=0.0, stereo=True)
+    po = S.PoseOnlyBundleAdjustmentSolver(device=0)
+    out = po.solve_batched(pb.kind, pb.offsets, pb.points, pb.px_left, pb.px_right, pb.intr_left, pb.intr_right,
+                           pb.poses_init, capi.PoseOnlyOptions(*OPT), left_to_right=pb.left_to_right)
+    assert all(r.success and r.converged for r in out["results"])
+    assert np.abs(out["poses"] - pb.poses_true).max() < 2e-3
+    assert max(r.n_iterations for r in out["results"]) <= 15
