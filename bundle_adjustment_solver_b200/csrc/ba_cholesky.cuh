@@ -8,8 +8,9 @@
 // n -- turns that row into z^T = (L^-1 rhs)^T, so the forward substitution is free.  The backward
 // substitution L^T x = z runs as a right-looking blocked sweep.
 //
-// v1: blocked right-looking, NB = 64, three kernels per panel (diag POTRF in one CTA, row-parallel
-// TRSM, shared-memory tiled SYRK/GEMM trailing update on CUDA-core FP64).
+// v2: blocked right-looking, NB = 64, three kernels per panel: diagonal-block Cholesky + explicit
+// triangular inverse in one CTA, panel TRSM as a tiled GEMM with that inverse, shared-memory tiled
+// SYRK/GEMM trailing update on CUDA-core FP64.  The backward sweep reuses the block inverses.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -18,67 +19,150 @@
 namespace ba {
 
 constexpr int kNB = 64;
+constexpr size_t kCholDiagSmem = (3 * kNB * (kNB + 1) + 3 * kNB) * sizeof(double);
 
-// ---- diagonal block: unblocked Cholesky of an nb x nb block in shared memory ---------------
-__global__ void __launch_bounds__(kNB) k_potrf_diag(double *__restrict__ A, int ld, int k0, int nb,
-                                                    const LmState *st) {
+// ---- diagonal block: Cholesky of an nb x nb block + its triangular inverse, one CTA of 1024 --------
+// The 2080 lower-triangle entries live in registers (<= 3 per thread) for the whole elimination;
+// only the current column travels through a double-buffered shared-memory vector, so each of the 64
+// column steps costs one barrier:  a_rc -= a_rj a_cj / d_j  (columns stay unscaled until the end,
+// then L = A D^-1/2).  L^-1 is then built by recursive doubling (X21 = -X22 L21 X11, block sizes
+// 1,2,..,32: 12 barriers instead of 64 substitution steps).  Linv (row-major 64x64, lower) lets the
+// panel TRSM and the backward substitution run as small GEMMs / GEMVs.
+__global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int ld, int k0, int nb,
+                                                    double *__restrict__ Linv_out, const LmState *st) {
   if (st->done) return;
-  __shared__ double L[kNB][kNB + 1];
+  extern __shared__ double chol_smem[];  // kCholDiagSmem bytes (opt-in > 48 KB)
+  double (*L)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(chol_smem);
+  double (*X)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(chol_smem + kNB * (kNB + 1));
+  double (*T)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(chol_smem + 2 * kNB * (kNB + 1));
+  double *colbuf = chol_smem + 3 * kNB * (kNB + 1);  // [2][kNB]
+  double *dinv = colbuf + 2 * kNB;                   // 1/sqrt(d)
   const int t = threadIdx.x;
-  // load lower triangle; pad with identity
-  for (int c = 0; c < kNB; ++c) {
-    double v = (t == c) ? 1.0 : 0.0;
-    if (t < nb && c < nb && t >= c) v = A[(size_t)(k0 + c) * ld + k0 + t];
-    L[t][c] = v;
+  constexpr int NE = kNB * (kNB + 1) / 2;  // 2080
+  int er[3], ec[3];
+  double v[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int e = t + 1024 * q;
+    int r = -1, c = -1;
+    double val = 0.0;
+    if (e < NE) {
+      r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while (r * (r + 1) / 2 > e) --r;
+      while ((r + 1) * (r + 2) / 2 <= e) ++r;
+      c = e - r * (r + 1) / 2;
+      val = (r == c) ? 1.0 : 0.0;  // identity padding
+      if (r < nb && c < nb) val = A[(size_t)(k0 + c) * ld + k0 + r];
+    }
+    er[q] = r; ec[q] = c; v[q] = val;
+  }
+  for (int j = 0; j < kNB; ++j) {
+    double *cb = colbuf + (j & 1) * kNB;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (ec[q] == j) cb[er[q]] = v[q];
+    __syncthreads();
+    const double d = cb[j];
+    // non-positive pivot (e.g. a pose without observations): emulate LDLT's D^+ = 0
+    const double di = (d > 0.0) ? 1.0 / d : 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (ec[q] > j) v[q] -= cb[er[q]] * di * cb[ec[q]];
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    if (er[q] >= 0 && er[q] == ec[q]) dinv[er[q]] = (v[q] > 0.0) ? 1.0 / sqrt(v[q]) : 0.0;
+  __syncthreads();
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int r = er[q], c = ec[q];
+    if (r < 0) continue;
+    const double l = (r == c) ? ((dinv[r] > 0.0) ? 1.0 / dinv[r] : kInf) : v[q] * dinv[c];
+    L[r][c] = l;
+    X[r][c] = (r == c) ? dinv[r] : 0.0;
+    if (r < nb && c < nb) A[(size_t)(k0 + c) * ld + k0 + r] = l;
   }
   __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    // left-looking column j: L[t][j] = (A[t][j] - sum_{m<j} L[t][m] L[j][m]) / L[j][j]
-    double acc = L[t][j];
-    if (t >= j) {
-      for (int m = 0; m < j; ++m) acc -= L[t][m] * L[j][m];
+  // recursive doubling: block b of size 2m: rows R = b*2m+m.., cols C = b*2m..
+  for (int m = 1; m < kNB; m <<= 1) {
+    const int per_level = (kNB / (2 * m)) * m * m;  // outputs of this level (<= 1024)
+    int bi = 0, i = 0, k = 0;
+    if (t < per_level) {
+      bi = t / (m * m);
+      i = (t / m) % m;
+      k = t % m;
+    }
+    const int R0 = bi * 2 * m + m, C0 = bi * 2 * m;
+    if (t < per_level) {
+      // T[i][k] = sum_q L[R0+i][C0+q] X[C0+q][C0+k], q >= k (X11 lower)
+      double acc = 0.0;
+      for (int q = k; q < m; ++q) acc += L[R0 + i][C0 + q] * X[C0 + q][C0 + k];
+      T[R0 + i][C0 + k] = acc;
     }
     __syncthreads();
-    // non-positive pivot (e.g. a pose without observations): emulate LDLT's D^+ = 0 by an
-    // infinite diagonal, which zeroes the column and the solution component
-    if (t == j) L[j][j] = (acc > 0.0) ? sqrt(acc) : __longlong_as_double(0x7ff0000000000000LL);
-    __syncthreads();
-    if (t > j) L[t][j] = acc / L[j][j];
+    if (t < per_level) {
+      // X21[i][k] = - sum_q X[R0+i][R0+q] T[q][k], q <= i (X22 lower)
+      double acc = 0.0;
+      for (int q = 0; q <= i; ++q) acc += X[R0 + i][R0 + q] * T[R0 + q][C0 + k];
+      X[R0 + i][C0 + k] = -acc;
+    }
     __syncthreads();
   }
-  if (t < nb)
-    for (int c = 0; c <= t; ++c) A[(size_t)(k0 + c) * ld + k0 + t] = L[t][c];
+  for (int e = t; e < kNB * kNB; e += 1024) {
+    const int r = e / kNB, c = e % kNB;
+    Linv_out[e] = (r >= c) ? X[r][c] : 0.0;
+  }
 }
 
-// ---- panel: rows r in (k0+nb, n] : A[r, k0:k0+nb] <- A[r, k0:k0+nb] L_kk^-T --------------------
-__global__ void __launch_bounds__(128) k_trsm_panel(double *__restrict__ A, int ld, int n_rows, int k0,
-                                                    int nb, const LmState *st) {
+// ---- panel: rows below the diagonal block: A[r, k0:k0+nb] <- A[r, k0:k0+nb] Linv^T (64-row tiles)
+__global__ void __launch_bounds__(256) k_chol_trsm(double *__restrict__ A, int ld, int n_rows, int k0, int nb,
+                                                   const double *__restrict__ Linv, const LmState *st) {
   if (st->done) return;
-  __shared__ double L[kNB][kNB + 1];
-  __shared__ double invd[kNB];
-  for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-    const int r = e % kNB, c = e / kNB;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < nb && c < nb && r >= c) v = A[(size_t)(k0 + c) * ld + k0 + r];
-    L[r][c] = v;
-    if (r == c) invd[r] = 1.0 / v;
+  constexpr int KH = 32;
+  __shared__ double At[KH][64 + 1];   // [m][row]   panel entries A[row][k0+m]
+  __shared__ double Lt[KH][64 + 1];   // [m][col]   Linv[col][m]
+  const int r0 = k0 + nb + blockIdx.x * 64;
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int mh = 0; mh < kNB; mh += KH) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < KH * 64; e += 256) {
+      const int i = e % 64, m = mh + e / 64;
+      const int rr = r0 + i;
+      At[e / 64][i] = (m < nb && rr < n_rows) ? A[(size_t)(k0 + m) * ld + rr] : 0.0;
+    }
+    for (int e = threadIdx.x; e < KH * 64; e += 256) {
+      const int m = mh + e % KH, c = e / KH;
+      Lt[e % KH][c] = Linv[c * kNB + m];  // X[c][m], zero for m > c
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int m = 0; m < KH; ++m) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = At[m][tx + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Lt[m][ty + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
   }
-  __syncthreads();
-  const int r = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rows) return;
-  double x[kNB];
 #pragma unroll
-  for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? A[(size_t)(k0 + c) * ld + r] : 0.0;
+  for (int j = 0; j < 4; ++j) {
+    const int c = ty + 16 * j;
 #pragma unroll
-  for (int c = 0; c < kNB; ++c) {
-    double acc = x[c];
-#pragma unroll
-    for (int m = 0; m < c; ++m) acc -= x[m] * L[c][m];
-    x[c] = acc * invd[c];
+    for (int i = 0; i < 4; ++i) {
+      const int rr = r0 + tx + 16 * i;
+      if (rr < n_rows && c < nb) A[(size_t)(k0 + c) * ld + rr] = acc[i][j];
+    }
   }
-#pragma unroll
-  for (int c = 0; c < kNB; ++c)
-    if (c < nb) A[(size_t)(k0 + c) * ld + r] = x[c];
 }
 
 // ---- trailing update: A[r, c] -= sum_m P[r, m] P[c, m], r >= c, both in (k0+nb, n_rows) ------
@@ -132,46 +216,59 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *__restrict__ A, int
   }
 }
 
-// ---- backward substitution L^T x = z, z = row n of the factor; single CTA (v1) -------------------
-// x_out[0..n).  Right-looking: after block k is solved, z[0:k0] -= L[k0:k0+nb, 0:k0]^T x_k.
+// ---- backward substitution L^T x = z, z = row n of the factor; single CTA, 1024 threads ---------
+// Right-looking over 64-blocks from the bottom: x_k = Linv_k^T z_k, then z[0:k0] -= L[k0:k0+nb,0:k0]^T x_k.
 __global__ void __launch_bounds__(1024) k_backward_solve(const double *__restrict__ A, int ld, int n,
+                                                         const double *__restrict__ Linv_all,
                                                          double *__restrict__ x_out, double *__restrict__ zbuf,
                                                          const LmState *st) {
   if (st->done) return;
   __shared__ double xk[kNB];
-  __shared__ double Ld[kNB][kNB + 1];
+  __shared__ double zk[kNB];
   const int t = threadIdx.x;
   for (int i = t; i < n; i += blockDim.x) zbuf[i] = A[(size_t)i * ld + n];
   __syncthreads();
   const int nblk = (n + kNB - 1) / kNB;
+  const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
   for (int kb = nblk - 1; kb >= 0; --kb) {
     const int k0 = kb * kNB, nb = min(kNB, n - k0);
-    for (int e = t; e < kNB * kNB; e += blockDim.x) {
-      const int r = e % kNB, c = e / kNB;
-      Ld[r][c] = (r < nb && c < nb && r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : ((r == c) ? 1.0 : 0.0);
-    }
-    if (t < kNB) xk[t] = (t < nb) ? zbuf[k0 + t] : 0.0;
+    const double *Xi = Linv_all + (size_t)kb * kNB * kNB;  // row-major X = L_kk^-1 (lower)
+    if (t < kNB) zk[t] = (t < nb) ? zbuf[k0 + t] : 0.0;
     __syncthreads();
-    if (t < 32) {
-      // solve L_kk^T x = z backwards; lane owns entries t and t+32
-      for (int j = nb - 1; j >= 0; --j) {
-        const double xj = xk[j] / Ld[j][j];
-        __syncwarp();
-        if (t == 0) xk[j] = xj;
-        for (int i = t; i < j; i += 32) xk[i] -= Ld[j][i] * xj;
-        __syncwarp();
-      }
+    // x_k[c] = sum_{r>=c} X[r][c] z_k[r]   (X^T z) ; warps over c, lanes over r
+    for (int c = warp; c < kNB; c += nwarps) {
+      double acc = 0.0;
+      for (int r = c + lane; r < kNB; r += 32) acc += Xi[r * kNB + c] * zk[r];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+      if (lane == 0) xk[c] = acc;
     }
     __syncthreads();
     if (t < nb) x_out[k0 + t] = xk[t];
-    // z[c] -= sum_r L[k0+r, c] * x_k[r], c < k0 ; warp per column, lanes over rows
-    const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
-    for (int c = warp; c < k0; c += nwarps) {
-      double acc = 0.0;
-      for (int r = lane; r < nb; r += 32) acc += A[(size_t)c * ld + k0 + r] * xk[r];
+    // z[c] -= sum_r L[k0+r, c] * x_k[r], c < k0 ; a warp takes 4 columns per trip (8 independent loads
+    // per lane in flight), lanes over the 64 contiguous rows
+    const double xa = xk[lane], xb = xk[lane + 32];
+    for (int c = warp * 4; c < k0; c += nwarps * 4) {
+      double acc[4];
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-      if (lane == 0) zbuf[c] -= acc;
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c + u;
+        double a0 = 0.0, a1 = 0.0;
+        if (cc < k0) {
+          const double *col = A + (size_t)cc * ld + k0;
+          a0 = (lane < nb) ? col[lane] : 0.0;
+          a1 = (lane + 32 < nb) ? col[lane + 32] : 0.0;
+        }
+        acc[u] = a0 * xa + a1 * xb;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __shfl_down_sync(0xffffffffu, acc[u], d);
+      if (lane == 0)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c + u < k0) zbuf[c + u] -= acc[u];
     }
     __syncthreads();
   }
@@ -182,23 +279,32 @@ struct CholeskyPlan {
 };
 
 // Enqueue factor + solve on `stream`.  Saug: (n+1)^2 doubles, ld = n+1.  x: n doubles.  zbuf: n.
-inline void cholesky_solve_enqueue(double *Saug, int n, double *x, double *zbuf, const LmState *st,
+// linv: ceil(n/64) * 64*64 doubles (inverses of the diagonal blocks).
+inline size_t cholesky_linv_doubles(int n) { return (size_t)((n + kNB - 1) / kNB) * kNB * kNB; }
+
+inline void cholesky_solve_enqueue(double *Saug, int n, double *x, double *zbuf, double *linv, const LmState *st,
                                    cudaStream_t stream, long long *launches) {
   const int ld = n + 1, n_rows = n + 1;
-  for (int k0 = 0; k0 < n; k0 += kNB) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem);
+    attr_set = true;
+  }
+  for (int k0 = 0, kb = 0; k0 < n; k0 += kNB, ++kb) {
     const int nb = (n - k0 < kNB) ? (n - k0) : kNB;
-    k_potrf_diag<<<1, kNB, 0, stream>>>(Saug, ld, k0, nb, st);
+    double *Li = linv + (size_t)kb * kNB * kNB;
+    k_chol_diag<<<1, 1024, kCholDiagSmem, stream>>>(Saug, ld, k0, nb, Li, st);
     const int rows_below = n_rows - (k0 + nb);
     if (rows_below > 0) {
-      k_trsm_panel<<<(rows_below + 127) / 128, 128, 0, stream>>>(Saug, ld, n_rows, k0, nb, st);
       const int tiles = (rows_below + 63) / 64;
+      k_chol_trsm<<<tiles, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, Li, st);
       dim3 g(tiles, tiles);
       k_syrk_update<<<g, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, st);
       if (launches) *launches += 2;
     }
     if (launches) *launches += 1;
   }
-  k_backward_solve<<<1, 1024, 0, stream>>>(Saug, ld, n, x, zbuf, st);
+  k_backward_solve<<<1, 1024, 0, stream>>>(Saug, ld, n, linv, x, zbuf, st);
   if (launches) *launches += 1;
 }
 

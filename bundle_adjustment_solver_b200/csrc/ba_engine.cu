@@ -309,16 +309,142 @@ __global__ void k_finish_poses(const int *__restrict__ pose_chunk_ptr, const dou
 }
 
 // ---------------------------------------------------------------------------
-// K4 (v1): Schur complement, one thread per pair p1; S -= E_p1 B_p2^T for p2 >= p1 of the same point.
+// K4: Schur complement  S -= sum_i E_ji B_ki^T (j<=k), rhs_j -= E_ji b_i, E_ji = B_ji Cinv_i  (:858-888).
+//
+// k_schur_tiles: one CTA per "Schur chunk" = a run of consecutive landmarks whose observing poses all
+// fall inside one window of W consecutive free poses.  The chunk's W x W block tile of S (upper block
+// triangle, W(W+1)/2 blocks) is accumulated in REGISTERS: thread (s1,s2) owns one 6x6 block for the
+// whole chunk and adds E_{s1,i} B_{s2,i}^T for every landmark i that both poses see.  Landmarks are
+// staged eight at a time in shared memory (E and B blocks, transposed so reads are conflict-free /
+// broadcast).  Only the final flush touches global memory: one FP64 red per tile entry per chunk
+// instead of one per landmark.
+// k_schur_pairs_list: fallback for landmarks whose poses do not fit a window (wide baselines, loop
+// closures): one thread per pair, direct FP64 reds.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_schur_pairs(int P, const int *__restrict__ pair_pose, const int *__restrict__ pair_point,
-              const int *__restrict__ pair_end /*index one past the last pair of this pair's point*/,
+struct SchurChunk {
+  int pt_start;   // first index into the tile-eligible landmark list
+  int pt_count;
+  int jmin;       // first free pose (j_opt) of the window
+  int _pad;
+};
+
+constexpr int kSchurW = 16;                              // window (poses)
+constexpr int kSchurTasks = kSchurW * (kSchurW + 1) / 2; // 136
+constexpr int kSchurThreads = 160;
+constexpr int kSchurPB = 8;                              // landmarks staged per batch
+
+__global__ void __launch_bounds__(kSchurThreads)
+k_schur_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt_point /*orig point id*/,
+              const int *__restrict__ tpt_pair_start /*[2n]: first, end*/, const int *__restrict__ pair_pose,
               const double *__restrict__ Bsoa, size_t Pp, const double *__restrict__ ptblk, size_t Mp,
               double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
   if (st->done) return;
-  const int p1 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p1 >= P) return;
+  constexpr int W = kSchurW, PB = kSchurPB;
+  __shared__ double Es[PB][18][W];
+  __shared__ double Bs[PB][18][W];
+  __shared__ double bs[PB][4];
+  __shared__ int masks[PB];
+  const SchurChunk ch = chunks[blockIdx.x];
+  const int t = threadIdx.x;
+  // task -> (s1 <= s2)
+  int s1 = -1, s2 = -1;
+  if (t < kSchurTasks) {
+    int rem = t;
+    s1 = 0;
+    while (rem >= W - s1) { rem -= W - s1; ++s1; }
+    s2 = s1 + rem;
+  }
+  double acc[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+  double racc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  // staging role: landmark slot q = t / W, pair slot v = t % W  (PB * W = 128 staging threads)
+  const int q_st = t / W, v_st = t % W;
+  for (int base = 0; base < ch.pt_count; base += PB) {
+    const int nb = min(PB, ch.pt_count - base);
+    __syncthreads();  // previous batch fully consumed
+    if (t < PB) masks[t] = 0;
+    __syncthreads();
+    if (q_st < nb && t < PB * W) {
+      const int ti = ch.pt_start + base + q_st;
+      const int p0 = tpt_pair_start[2 * ti], p1 = tpt_pair_start[2 * ti + 1];
+      const int p = p0 + v_st;
+      if (p < p1) {
+        const int pt = tpt_point[ti];
+        const int slot = pair_pose[p] - ch.jmin;
+        double B[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) B[k] = Bsoa[(size_t)k * Pp + p];
+        double ci[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ci[k] = ptblk[(PB_Cinv + k) * Mp + pt];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double b0 = B[r * 3], b1 = B[r * 3 + 1], b2 = B[r * 3 + 2];
+          Es[q_st][r * 3 + 0][slot] = b0 * ci[0] + b1 * ci[1] + b2 * ci[2];   // E = B Cinv (:862)
+          Es[q_st][r * 3 + 1][slot] = b0 * ci[1] + b1 * ci[3] + b2 * ci[4];
+          Es[q_st][r * 3 + 2][slot] = b0 * ci[2] + b1 * ci[4] + b2 * ci[5];
+          Bs[q_st][r * 3 + 0][slot] = b0;
+          Bs[q_st][r * 3 + 1][slot] = b1;
+          Bs[q_st][r * 3 + 2][slot] = b2;
+        }
+        atomicOr(&masks[q_st], 1 << slot);
+        if (v_st == 0) {
+          bs[q_st][0] = ptblk[(PB_b + 0) * Mp + pt];
+          bs[q_st][1] = ptblk[(PB_b + 1) * Mp + pt];
+          bs[q_st][2] = ptblk[(PB_b + 2) * Mp + pt];
+        }
+      }
+    }
+    __syncthreads();
+    if (t < kSchurTasks) {
+      for (int q = 0; q < nb; ++q) {
+        const int m = masks[q];
+        if (!(((m >> s1) & (m >> s2)) & 1)) continue;
+        double B[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) B[k] = Bs[q][k][s2];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double e0 = Es[q][r * 3][s1], e1 = Es[q][r * 3 + 1][s1], e2 = Es[q][r * 3 + 2][s1];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[r * 6 + c] += e0 * B[c * 3] + e1 * B[c * 3 + 1] + e2 * B[c * 3 + 2];
+          if (s1 == s2) racc[r] += e0 * bs[q][0] + e1 * bs[q][1] + e2 * bs[q][2];  // BCinv b (:864)
+        }
+      }
+    }
+  }
+  if (t < kSchurTasks) {
+    const int j1 = ch.jmin + s1, j2 = ch.jmin + s2;
+    // windows at the end of the pose range may stick out; such tasks never accumulated anything
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) any = any || (acc[i] != 0.0);
+    if (any) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          if (s1 == s2 && c < r) continue;
+          atomicAdd(&Saug[(size_t)(6 * j1 + r) * ld + 6 * j2 + c], -acc[r * 6 + c]);
+        }
+      if (s1 == s2)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) atomicAdd(&Saug[(size_t)(6 * j1 + r) * ld + (ld - 1)], -racc[r]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_schur_pairs_list(int n_list, const int *__restrict__ list /*pair indices p1, or null = identity*/,
+                   const int *__restrict__ pair_pose, const int *__restrict__ pair_point,
+                   const int *__restrict__ pair_end /*index one past the last pair of this pair's point*/,
+                   const double *__restrict__ Bsoa, size_t Pp, const double *__restrict__ ptblk, size_t Mp,
+                   double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= n_list) return;
+  const int p1 = list ? list[li] : li;
   const int pt = pair_point[p1];
   const int j1 = pair_pose[p1];
   double B1[18];
@@ -329,7 +455,6 @@ k_schur_pairs(int P, const int *__restrict__ pair_pose, const int *__restrict__ 
   for (int i = 0; i < 6; ++i) ci[i] = ptblk[(PB_Cinv + i) * Mp + pt];
 #pragma unroll
   for (int i = 0; i < 3; ++i) cb[i] = ptblk[(PB_Cinvb + i) * Mp + pt];
-  // E = B Cinv (:862) ; Cinv symmetric-packed {00,01,02,11,12,22}
   double E[18];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
@@ -749,9 +874,13 @@ struct ba_solver {
   DevBuf<int> d_pose_chunk_ptr, d_pose_opt, d_pair_pose, d_pair_point, d_pair_end, d_point_has_pairs;
   DevBuf<uint8_t> d_point_free;
   DevBuf<int> d_split_points, d_split_pairs;
+  DevBuf<SchurChunk> d_schur_chunks;
+  DevBuf<int> d_tpt_point, d_tpt_pair_start, d_fallback_pairs;
+  int n_schur_chunks = 0, n_fallback_pairs = 0;
+  int schur_mode = 1;  // 1 = register-tiled windows + fallback, 0 = direct reds only
   // blocks
   size_t Mp = 0, Pp = 0;
-  DevBuf<double> d_ptblk, d_Bsoa, d_A, d_a, d_partialsA, d_Saug, d_Scopy, d_x, d_z, d_Btx, d_y;
+  DevBuf<double> d_ptblk, d_Bsoa, d_A, d_a, d_partialsA, d_Saug, d_Scopy, d_x, d_z, d_linv, d_Btx, d_y;
   DevBuf<double> d_cost_partials, d_point_partials, d_pose_partials, d_scal;
   DevBuf<LmState> d_state;
   DevBuf<ba_iter_info> d_infos;
@@ -818,9 +947,11 @@ static void free_device(ba_solver *s) {
   s->d_poseidA.release(); s->d_chunks.release(); s->d_chunk_pair_count.release(); s->d_chunksA.release();
   s->d_pose_chunk_ptr.release(); s->d_pose_opt.release(); s->d_pair_pose.release(); s->d_pair_point.release();
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
-  s->d_split_points.release(); s->d_split_pairs.release(); s->d_ptblk.release(); s->d_Bsoa.release();
+  s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
+  s->d_tpt_point.release(); s->d_tpt_pair_start.release(); s->d_fallback_pairs.release();
+  s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
-  s->d_x.release(); s->d_z.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
+  s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
   s->d_point_partials.release(); s->d_pose_partials.release(); s->d_scal.release(); s->d_state.release();
   s->d_infos.release();
 }
@@ -987,6 +1118,48 @@ int ba_finalize(ba_solver *s) {
   std::vector<int> pair_end(P);
   for (long long p = P - 1; p >= 0; --p)
     pair_end[p] = (p + 1 < P && s->h_pair_point[p + 1] == s->h_pair_point[p]) ? pair_end[p + 1] : (int)(p + 1);
+  // --- Schur chunks: runs of consecutive landmarks whose free poses fit one window of kSchurW poses
+  std::vector<SchurChunk> schur_chunks;
+  std::vector<int> tpt_point, tpt_pair_start, fallback_pairs;
+  {
+    struct Cand { int point, p0, p1, jmin, jmax; };
+    std::vector<Cand> cands;
+    for (long long p = 0; p < P;) {
+      const int e = pair_end[p];
+      // pairs of a point are ascending in j_opt (points sorted by (point, pose), j_opt monotone in id)
+      Cand c{s->h_pair_point[p], (int)p, e, s->h_pair_pose[p], s->h_pair_pose[e - 1]};
+      if (s->schur_mode == 1 && c.jmax - c.jmin + 1 <= kSchurW) cands.push_back(c);
+      else for (int q = (int)p; q < e; ++q) fallback_pairs.push_back(q);
+      p = e;
+    }
+    constexpr int kMinPts = 6, kMaxPts = 160;
+    size_t i = 0;
+    while (i < cands.size()) {
+      int lo = cands[i].jmin, hi = cands[i].jmax;
+      size_t e = i + 1;
+      while (e < cands.size() && (int)(e - i) < kMaxPts) {
+        const int nlo = std::min(lo, cands[e].jmin), nhi = std::max(hi, cands[e].jmax);
+        if (nhi - nlo + 1 > kSchurW) break;
+        lo = nlo; hi = nhi; ++e;
+      }
+      if ((int)(e - i) >= kMinPts) {
+        SchurChunk sc{(int)tpt_point.size(), (int)(e - i), lo, 0};
+        for (size_t k = i; k < e; ++k) {
+          tpt_point.push_back(cands[k].point);
+          tpt_pair_start.push_back(cands[k].p0);  // [2*ti] = first pair, [2*ti+1] = one past the last
+          tpt_pair_start.push_back(cands[k].p1);
+        }
+        schur_chunks.push_back(sc);
+      } else {
+        for (size_t k = i; k < e; ++k)
+          for (int q = cands[k].p0; q < cands[k].p1; ++q) fallback_pairs.push_back(q);
+      }
+      i = e;
+    }
+    std::sort(fallback_pairs.begin(), fallback_pairs.end());
+  }
+  s->n_schur_chunks = (int)schur_chunks.size();
+  s->n_fallback_pairs = (int)fallback_pairs.size();
   // --- chunks of whole points (<= kThreads observations); longer points are split
   std::vector<Chunk> chunks;
   std::vector<int> chunk_pair_count;
@@ -1110,6 +1283,10 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_pair_end.upload(pair_end, st));
   CUDA_TRY(s->d_point_has_pairs.upload(point_has_pairs, st));
   CUDA_TRY(s->d_point_free.upload(point_free, st));
+  CUDA_TRY(s->d_schur_chunks.upload(schur_chunks, st));
+  CUDA_TRY(s->d_tpt_point.upload(tpt_point, st));
+  CUDA_TRY(s->d_tpt_pair_start.upload(tpt_pair_start, st));
+  CUDA_TRY(s->d_fallback_pairs.upload(fallback_pairs, st));
   CUDA_TRY(s->d_split_points.upload(split_points, st));
   CUDA_TRY(s->d_split_pairs.upload(split_pairs, st));
   // --- block storage
@@ -1124,6 +1301,7 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_Saug.alloc(nS * nS));
   CUDA_TRY(s->d_x.alloc(std::max<size_t>(1, (size_t)6 * s->N)));
   CUDA_TRY(s->d_z.alloc(std::max<size_t>(1, (size_t)6 * s->N)));
+  CUDA_TRY(s->d_linv.alloc(std::max<size_t>(1, cholesky_linv_doubles(6 * s->N))));
   CUDA_TRY(s->d_Btx.alloc(std::max<size_t>(1, 3 * s->Mp)));
   CUDA_TRY(s->d_y.alloc(std::max<size_t>(1, (size_t)Mt * 3)));
   CUDA_TRY(cudaMemsetAsync(s->d_ptblk.p, 0, s->d_ptblk.n * sizeof(double), st));
@@ -1241,10 +1419,16 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
     s->launches++;
   }
   if (ev) cudaEventRecord(ev[Phase::Schur], st);
-  if (s->P > 0) {
-    k_schur_pairs<<<(int)((s->P + 127) / 128), 128, 0, st>>>((int)s->P, s->d_pair_pose.p, s->d_pair_point.p,
-                                                             s->d_pair_end.p, s->d_Bsoa.p, s->Pp, s->d_ptblk.p,
-                                                             s->Mp, s->d_Saug.p, ld, dst);
+  if (s->n_schur_chunks > 0) {
+    k_schur_tiles<<<s->n_schur_chunks, kSchurThreads, 0, st>>>(s->d_schur_chunks.p, s->d_tpt_point.p,
+                                                              s->d_tpt_pair_start.p, s->d_pair_pose.p, s->d_Bsoa.p,
+                                                              s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+    s->launches++;
+  }
+  if (s->n_fallback_pairs > 0) {
+    k_schur_pairs_list<<<(s->n_fallback_pairs + 127) / 128, 128, 0, st>>>(
+        s->n_fallback_pairs, s->d_fallback_pairs.p, s->d_pair_pose.p, s->d_pair_point.p, s->d_pair_end.p,
+        s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
     s->launches++;
   }
   return BA_OK;
@@ -1274,7 +1458,7 @@ static int enqueue_solve_backsub(ba_solver *s, cudaEvent_t *ev) {
   if (s->debug_keep && s->d_Scopy.p) {
     cudaMemcpyAsync(s->d_Scopy.p, s->d_Saug.p, (size_t)ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, st);
   }
-  if (n > 0) cholesky_solve_enqueue(s->d_Saug.p, n, s->d_x.p, s->d_z.p, dst, st, &s->launches);
+  if (n > 0) cholesky_solve_enqueue(s->d_Saug.p, n, s->d_x.p, s->d_z.p, s->d_linv.p, dst, st, &s->launches);
   if (ev) cudaEventRecord(ev[Phase::Backsub], st);
   if (s->n_split_pairs > 0) cudaMemsetAsync(s->d_Btx.p, 0, 3 * s->Mp * sizeof(double), st);
   if (s->n_chunks > 0 && s->P > 0) {
