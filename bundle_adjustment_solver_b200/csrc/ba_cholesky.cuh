@@ -14,12 +14,15 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "ba_device.cuh"
 
 namespace ba {
 
 constexpr int kNB = 64;
-constexpr size_t kCholDiagSmem = (3 * kNB * (kNB + 1) + 3 * kNB) * sizeof(double);
+constexpr size_t kCholDiagSmem = (3 * kNB * (kNB + 1) + 3 * kNB + 2) * sizeof(double);
 
 // ---- diagonal block: Cholesky of an nb x nb block + its triangular inverse, one CTA of 1024 --------
 // The 2080 lower-triangle entries live in registers (<= 3 per thread) for the whole elimination;
@@ -35,8 +38,8 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
   double (*L)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(chol_smem);
   double (*X)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(chol_smem + kNB * (kNB + 1));
   double (*T)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(chol_smem + 2 * kNB * (kNB + 1));
-  double *colbuf = chol_smem + 3 * kNB * (kNB + 1);  // [2][kNB]
-  double *dinv = colbuf + 2 * kNB;                   // 1/sqrt(d)
+  double *colbuf = chol_smem + 3 * kNB * (kNB + 1);  // [2][kNB + 1]: column j and 1/d_j
+  double *dinv = colbuf + 2 * (kNB + 1);             // 1/sqrt(d)
   const int t = threadIdx.x;
   constexpr int NE = kNB * (kNB + 1) / 2;  // 2080
   int er[3], ec[3];
@@ -57,14 +60,18 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
     er[q] = r; ec[q] = c; v[q] = val;
   }
   for (int j = 0; j < kNB; ++j) {
-    double *cb = colbuf + (j & 1) * kNB;
+    double *cb = colbuf + (j & 1) * (kNB + 1);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-      if (ec[q] == j) cb[er[q]] = v[q];
+      if (ec[q] == j) {
+        cb[er[q]] = v[q];
+        // the owner of the pivot alone pays for the FP64 reciprocal (32 warps doing it redundantly
+        // made this kernel issue-bound).  Non-positive pivot (e.g. a pose without observations):
+        // emulate LDLT's D^+ = 0.
+        if (er[q] == j) cb[kNB] = (v[q] > 0.0) ? 1.0 / v[q] : 0.0;
+      }
     __syncthreads();
-    const double d = cb[j];
-    // non-positive pivot (e.g. a pose without observations): emulate LDLT's D^+ = 0
-    const double di = (d > 0.0) ? 1.0 / d : 0.0;
+    const double di = cb[kNB];
 #pragma unroll
     for (int q = 0; q < 3; ++q)
       if (ec[q] > j) v[q] -= cb[er[q]] * di * cb[ec[q]];
@@ -117,12 +124,13 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
 
 // ---- panel: rows below the diagonal block: A[r, k0:k0+nb] <- A[r, k0:k0+nb] Linv^T (64-row tiles)
 __global__ void __launch_bounds__(256) k_chol_trsm(double *__restrict__ A, int ld, int n_rows, int k0, int nb,
-                                                   const double *__restrict__ Linv, const LmState *st) {
+                                                   const double *__restrict__ Linv,
+                                                   const int *__restrict__ row_tiles, const LmState *st) {
   if (st->done) return;
   constexpr int KH = 32;
   __shared__ double At[KH][64 + 1];   // [m][row]   panel entries A[row][k0+m]
   __shared__ double Lt[KH][64 + 1];   // [m][col]   Linv[col][m]
-  const int r0 = k0 + nb + blockIdx.x * 64;
+  const int r0 = row_tiles[blockIdx.x] * 64;  // tile rows inside the envelope of this panel
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
   double acc[4][4];
 #pragma unroll
@@ -165,18 +173,35 @@ __global__ void __launch_bounds__(256) k_chol_trsm(double *__restrict__ A, int l
   }
 }
 
+// ---- rhs row when it shares the (partial) last diagonal tile: z_k = rhs_k L_kk^-T for that tile ---
+__global__ void __launch_bounds__(64) k_chol_trsm_tail(double *__restrict__ A, int ld, int n_rows, int k0, int nb,
+                                                       const double *__restrict__ Linv, const LmState *st) {
+  if (st->done) return;
+  __shared__ double a[kNB];
+  const int c = threadIdx.x, r = n_rows - 1;
+  a[c] = (c < nb) ? A[(size_t)(k0 + c) * ld + r] : 0.0;
+  __syncthreads();
+  double acc = 0.0;
+  for (int m = 0; m <= c; ++m) acc += a[m] * Linv[c * kNB + m];
+  if (c < nb) A[(size_t)(k0 + c) * ld + r] = acc;
+}
+
 // ---- trailing update: A[r, c] -= sum_m P[r, m] P[c, m], r >= c, both in (k0+nb, n_rows) ------
 // 64 x 64 output tile per CTA, 256 threads, 4 x 4 per thread, K = nb <= 64 staged in smem.
 __global__ void __launch_bounds__(256) k_syrk_update(double *__restrict__ A, int ld, int n_rows, int k0,
-                                                     int nb, const LmState *st) {
+                                                     int nb, const int *__restrict__ row_tiles,
+                                                     const LmState *st) {
   if (st->done) return;
-  const int base = k0 + nb;
-  const int tr = blockIdx.y, tc = blockIdx.x;
-  if (tc > tr) return;
+  // blockIdx.x enumerates pairs (ia >= ib) of the panel's envelope row tiles
+  int ia = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while (ia * (ia + 1) / 2 > (int)blockIdx.x) --ia;
+  while ((ia + 1) * (ia + 2) / 2 <= (int)blockIdx.x) ++ia;
+  const int ib = blockIdx.x - ia * (ia + 1) / 2;
+  const int tr = row_tiles[ia], tc = row_tiles[ib];
   constexpr int KH = 32;                // K staged in halves to stay under the 48 KB static limit
   __shared__ double Pr[KH][64 + 1];     // [m][row]
   __shared__ double Pc[KH][64 + 1];     // [m][col]
-  const int r0 = base + tr * 64, c0 = base + tc * 64;
+  const int r0 = tr * 64, c0 = tc * 64;
   const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
   double acc[4][4];
 #pragma unroll
@@ -220,6 +245,7 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *__restrict__ A, int
 // Right-looking over 64-blocks from the bottom: x_k = Linv_k^T z_k, then z[0:k0] -= L[k0:k0+nb,0:k0]^T x_k.
 __global__ void __launch_bounds__(1024) k_backward_solve(const double *__restrict__ A, int ld, int n,
                                                          const double *__restrict__ Linv_all,
+                                                         const int *__restrict__ first_tile,
                                                          double *__restrict__ x_out, double *__restrict__ zbuf,
                                                          const LmState *st) {
   if (st->done) return;
@@ -248,7 +274,8 @@ __global__ void __launch_bounds__(1024) k_backward_solve(const double *__restric
     // z[c] -= sum_r L[k0+r, c] * x_k[r], c < k0 ; a warp takes 4 columns per trip (8 independent loads
     // per lane in flight), lanes over the 64 contiguous rows
     const double xa = xk[lane], xb = xk[lane + 32];
-    for (int c = warp * 4; c < k0; c += nwarps * 4) {
+    const int cbeg = first_tile[kb] * kNB;  // columns left of the envelope hold zeros
+    for (int c = cbeg + warp * 4; c < k0; c += nwarps * 4) {
       double acc[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -274,17 +301,51 @@ __global__ void __launch_bounds__(1024) k_backward_solve(const double *__restric
   }
 }
 
+// Tile-level row envelope (skyline) of S: Cholesky creates no fill left of a row's first non-zero, so
+// tiles (r, c) with c < first_tile[r] stay zero and are skipped by TRSM / SYRK / the backward sweep.
+// For a dense S (every pose co-visible with every other) first_tile is all zeros and nothing is skipped.
 struct CholeskyPlan {
-  int n = 0;
+  int n = 0, T = 0;                 // matrix order, tile rows over n+1 rows (the last holds the rhs row)
+  std::vector<int> first_tile;      // [T]
+  std::vector<int> rows_ptr, rows;  // per panel k: tile rows r > k with first_tile[r] <= k
+  int *d_first_tile = nullptr, *d_rows = nullptr;
+  double dense_fraction = 1.0;
 };
+
+inline void cholesky_make_plan(CholeskyPlan &pl, int n, const std::vector<int> &first_pose /*per free pose: first co-visible pose*/) {
+  pl.n = n;
+  pl.T = (n + 1 + kNB - 1) / kNB;
+  pl.first_tile.assign(pl.T, pl.T);
+  for (size_t j = 0; j < first_pose.size(); ++j) {
+    const int c_tile = (6 * first_pose[j]) / kNB;
+    for (int r = (int)(6 * j) / kNB; r <= (int)(6 * j + 5) / kNB; ++r) pl.first_tile[r] = std::min(pl.first_tile[r], c_tile);
+  }
+  for (int r = 0; r < pl.T; ++r) pl.first_tile[r] = std::min(pl.first_tile[r], r);
+  pl.first_tile[n / kNB] = 0;  // the tile row that holds the rhs row is dense
+  pl.rows_ptr.assign(pl.T + 1, 0);
+  pl.rows.clear();
+  long long used = 0;
+  for (int k = 0; k < pl.T; ++k) {
+    pl.rows_ptr[k] = (int)pl.rows.size();
+    for (int r = k + 1; r < pl.T; ++r)
+      if (pl.first_tile[r] <= k) pl.rows.push_back(r);
+    const long long m = (long long)pl.rows.size() - pl.rows_ptr[k];
+    used += m * (m + 1) / 2;
+  }
+  pl.rows_ptr[pl.T] = (int)pl.rows.size();
+  long long dense = 0;
+  for (int k = 0; k < pl.T; ++k) { const long long m = pl.T - 1 - k; dense += m * (m + 1) / 2; }
+  pl.dense_fraction = dense > 0 ? (double)used / (double)dense : 1.0;
+}
+
+inline size_t cholesky_linv_doubles(int n) { return (size_t)((n + kNB - 1) / kNB) * kNB * kNB; }
 
 // Enqueue factor + solve on `stream`.  Saug: (n+1)^2 doubles, ld = n+1.  x: n doubles.  zbuf: n.
 // linv: ceil(n/64) * 64*64 doubles (inverses of the diagonal blocks).
-inline size_t cholesky_linv_doubles(int n) { return (size_t)((n + kNB - 1) / kNB) * kNB * kNB; }
-
-inline void cholesky_solve_enqueue(double *Saug, int n, double *x, double *zbuf, double *linv, const LmState *st,
-                                   cudaStream_t stream, long long *launches) {
-  const int ld = n + 1, n_rows = n + 1;
+// parts: bit 0 diag, 1 trsm, 2 syrk, 3 backward (all by default; subsets are for in-situ timing only)
+inline void cholesky_solve_enqueue(const CholeskyPlan &pl, double *Saug, double *x, double *zbuf, double *linv,
+                                   const LmState *st, cudaStream_t stream, long long *launches, int parts = 15) {
+  const int n = pl.n, ld = n + 1, n_rows = n + 1;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem);
@@ -293,19 +354,29 @@ inline void cholesky_solve_enqueue(double *Saug, int n, double *x, double *zbuf,
   for (int k0 = 0, kb = 0; k0 < n; k0 += kNB, ++kb) {
     const int nb = (n - k0 < kNB) ? (n - k0) : kNB;
     double *Li = linv + (size_t)kb * kNB * kNB;
-    k_chol_diag<<<1, 1024, kCholDiagSmem, stream>>>(Saug, ld, k0, nb, Li, st);
-    const int rows_below = n_rows - (k0 + nb);
-    if (rows_below > 0) {
-      const int tiles = (rows_below + 63) / 64;
-      k_chol_trsm<<<tiles, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, Li, st);
-      dim3 g(tiles, tiles);
-      k_syrk_update<<<g, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, st);
-      if (launches) *launches += 2;
+    if (parts & 1) {
+      k_chol_diag<<<1, 1024, kCholDiagSmem, stream>>>(Saug, ld, k0, nb, Li, st);
+      if (launches) *launches += 1;
     }
+    // rows of the same tile below a partial last diagonal block (only the rhs row can be there)
+    const int m = pl.rows_ptr[kb + 1] - pl.rows_ptr[kb];
+    const bool tail_in_tile = (k0 + nb < n_rows) && (k0 + nb < k0 + kNB);
+    if (tail_in_tile && (parts & 2)) {
+      // the diagonal tile itself carries the rhs row: treat tile kb as one more row tile
+      k_chol_trsm_tail<<<1, 64, 0, stream>>>(Saug, ld, n_rows, k0, nb, Li, st);
+      if (launches) *launches += 1;
+    }
+    if (m > 0) {
+      const int *rows = pl.d_rows + pl.rows_ptr[kb];
+      if (parts & 2) k_chol_trsm<<<m, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, Li, rows, st);
+      if (parts & 4) k_syrk_update<<<m * (m + 1) / 2, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, rows, st);
+      if (launches) *launches += ((parts >> 1) & 1) + ((parts >> 2) & 1);
+    }
+  }
+  if (parts & 8) {
+    k_backward_solve<<<1, 1024, 0, stream>>>(Saug, ld, n, linv, pl.d_first_tile, x, zbuf, st);
     if (launches) *launches += 1;
   }
-  k_backward_solve<<<1, 1024, 0, stream>>>(Saug, ld, n, linv, x, zbuf, st);
-  if (launches) *launches += 1;
 }
 
 }  // namespace ba

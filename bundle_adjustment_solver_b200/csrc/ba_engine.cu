@@ -878,6 +878,8 @@ struct ba_solver {
   DevBuf<int> d_tpt_point, d_tpt_pair_start, d_fallback_pairs;
   int n_schur_chunks = 0, n_fallback_pairs = 0;
   int schur_mode = 1;  // 1 = register-tiled windows + fallback, 0 = direct reds only
+  CholeskyPlan chol;
+  DevBuf<int> d_chol_rows, d_chol_first;
   // blocks
   size_t Mp = 0, Pp = 0;
   DevBuf<double> d_ptblk, d_Bsoa, d_A, d_a, d_partialsA, d_Saug, d_Scopy, d_x, d_z, d_linv, d_Btx, d_y;
@@ -949,6 +951,7 @@ static void free_device(ba_solver *s) {
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
   s->d_tpt_point.release(); s->d_tpt_pair_start.release(); s->d_fallback_pairs.release();
+  s->d_chol_rows.release(); s->d_chol_first.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
@@ -1158,6 +1161,18 @@ int ba_finalize(ba_solver *s) {
     }
     std::sort(fallback_pairs.begin(), fallback_pairs.end());
   }
+  // --- Cholesky envelope plan from the co-visibility structure
+  {
+    std::vector<int> first_pose(s->N);
+    for (int j = 0; j < s->N; ++j) first_pose[j] = j;
+    for (long long p = 0; p < P;) {
+      const int e = pair_end[p];
+      const int jmin = s->h_pair_pose[p];
+      for (int q = (int)p; q < e; ++q) first_pose[s->h_pair_pose[q]] = std::min(first_pose[s->h_pair_pose[q]], jmin);
+      p = e;
+    }
+    cholesky_make_plan(s->chol, 6 * s->N, first_pose);
+  }
   s->n_schur_chunks = (int)schur_chunks.size();
   s->n_fallback_pairs = (int)fallback_pairs.size();
   // --- chunks of whole points (<= kThreads observations); longer points are split
@@ -1283,6 +1298,14 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_pair_end.upload(pair_end, st));
   CUDA_TRY(s->d_point_has_pairs.upload(point_has_pairs, st));
   CUDA_TRY(s->d_point_free.upload(point_free, st));
+  {
+    std::vector<int> rows = s->chol.rows;
+    rows.push_back(0);
+    CUDA_TRY(s->d_chol_rows.upload(rows, st));
+    CUDA_TRY(s->d_chol_first.upload(s->chol.first_tile, st));
+    s->chol.d_rows = s->d_chol_rows.p;
+    s->chol.d_first_tile = s->d_chol_first.p;
+  }
   CUDA_TRY(s->d_schur_chunks.upload(schur_chunks, st));
   CUDA_TRY(s->d_tpt_point.upload(tpt_point, st));
   CUDA_TRY(s->d_tpt_pair_start.upload(tpt_pair_start, st));
@@ -1458,7 +1481,7 @@ static int enqueue_solve_backsub(ba_solver *s, cudaEvent_t *ev) {
   if (s->debug_keep && s->d_Scopy.p) {
     cudaMemcpyAsync(s->d_Scopy.p, s->d_Saug.p, (size_t)ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, st);
   }
-  if (n > 0) cholesky_solve_enqueue(s->d_Saug.p, n, s->d_x.p, s->d_z.p, s->d_linv.p, dst, st, &s->launches);
+  if (n > 0) cholesky_solve_enqueue(s->chol, s->d_Saug.p, s->d_x.p, s->d_z.p, s->d_linv.p, dst, st, &s->launches);
   if (ev) cudaEventRecord(ev[Phase::Backsub], st);
   if (s->n_split_pairs > 0) cudaMemsetAsync(s->d_Btx.p, 0, 3 * s->Mp * sizeof(double), st);
   if (s->n_chunks > 0 && s->P > 0) {
@@ -1784,6 +1807,34 @@ long long ba_debug_dump(ba_solver *s, int which, double *buf) {
       return 5;
     default: return BA_ERR_INVALID;
   }
+}
+
+// In-situ timing of parts of the reduced solve on whatever S currently holds (numerically meaningless,
+// timing only): parts bit 0 diag, 1 trsm, 2 syrk, 3 backward.  Graph-replayed `reps` times.
+int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
+  if (!s || !s->finalized || !ms_per_rep) return BA_ERR_STATE;
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  CUDA_TRY(cudaMemsetAsync(s->d_state.p, 0, sizeof(LmState), st));
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  cholesky_solve_enqueue(s->chol, s->d_Saug.p, s->d_x.p, s->d_z.p, s->d_linv.p, s->d_state.p, st, nullptr, parts);
+  CUDA_TRY(cudaStreamEndCapture(st, &graph));
+  CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) cudaGraphLaunch(exec, st);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < reps; ++i) cudaGraphLaunch(exec, st);
+  cudaEventRecord(e1, st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_per_rep = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+  return BA_OK;
 }
 
 int ba_debug_pairs(ba_solver *s, int *pair_pose_id, int *pair_point_id) {

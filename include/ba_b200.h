@@ -133,6 +133,8 @@ int ba_get_sizes(ba_solver *s, long long *out6); /* N_opt, M_opt, P(pairs), n_ob
  * buf == NULL returns the element count.  Free blocks are indexed by free index in id order. */
 long long ba_debug_dump(ba_solver *s, int which, double *buf);
 int ba_debug_pairs(ba_solver *s, int *pair_pose_id, int *pair_point_id); /* original ids per pair */
+/* In-situ timing of parts of the reduced solve (bit 0 diag, 1 trsm, 2 syrk, 3 backward); timing only. */
+int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep);
 
 /* ---- multi-GPU (one process per GPU; landmarks sharded, S all-reduced) -- */
 /* 128-byte NCCL unique id; rank 0 creates it, the host distributes it (torch.distributed, MPI...). */
