@@ -1,0 +1,155 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol (no compute
+without a GPU), it fails loudly without a device, the registration semantics mirror the reference,
+landmark sharding is exact (world_size-2 gloo run), and the scene generators are deterministic."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from bundle_adjustment_solver_b200 import capi, scenes, sharding
+from bundle_adjustment_solver_b200 import solver as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(engine_lib):
+    hdr = open(os.path.join(ROOT, "include", "ba_b200.h")).read()
+    declared = set(re.findall(r"\b(ba_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"ba_last_error"} - set(capi.SYMBOLS)
+    assert declared, "no declarations parsed"
+    missing = [s for s in sorted(declared) if not hasattr(engine_lib, s)]
+    assert not missing, missing
+    assert sorted(declared) == sorted(set(capi.SYMBOLS)), (sorted(declared ^ set(capi.SYMBOLS)))
+    assert b"sm_100a" in engine_lib.ba_version()
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(capi.Options) == 64 - 8 or C.sizeof(capi.Options) == 56
+    assert C.sizeof(capi.IterInfo) == 64
+    assert C.sizeof(capi.PoseOnlyOptions) == 20 and C.sizeof(capi.PoseOnlyResult) == 24
+    assert C.sizeof(oracle.IterInfo) == C.sizeof(capi.IterInfo)
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure path")
+def test_engine_fails_loudly_without_gpu(engine_lib):
+    h = C.c_void_p()
+    assert engine_lib.ba_create(C.byref(h), 0) == -2       # BA_ERR_CUDA, no silent CPU fallback
+    with pytest.raises(capi.BaError):
+        S.FullBundleAdjustmentSolver(device=0)
+    pb = scenes.scene_poseonly_batch(n_frames=2, n_points=16, seed=0)
+    with pytest.raises(capi.BaError):
+        S.PoseOnlyBundleAdjustmentSolver().solve_batched(pb.kind, pb.offsets, pb.points, pb.px_left, pb.px_right,
+                                                         pb.intr_left, pb.intr_right, pb.poses_init,
+                                                         capi.PoseOnlyOptions(1e-6, 1e-6, 1.5, 2.5, 10),
+                                                         left_to_right=pb.left_to_right)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "bundle_adjustment_solver_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "ba_oracle" not in txt and "orc_" not in txt, f
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.isfile(p):
+            assert "oracle" not in open(p).read().lower().replace("oracle's layout", "")
+
+
+def test_scene_generators_are_deterministic():
+    a, b = scenes.scene_test_ba(seed=2), scenes.scene_test_ba(seed=2)
+    assert np.array_equal(a.obs_uv, b.obs_uv) and np.array_equal(a.points_init, b.points_init)
+    c = scenes.scene_c3(seed=1, scale=0.02)
+    d = scenes.scene_c3(seed=1, scale=0.02)
+    assert np.array_equal(c.obs_uv, d.obs_uv)
+    assert 0.8e6 * 0.02 < c.n_obs < 1.2e6 * 0.02
+    e = scenes.scene_c5(seed=0, scale=0.01)
+    assert len(e.cam_ids) == 1 and e.obs_cam.max() == 0
+    deg = np.bincount(e.obs_point)
+    assert deg.min() >= 2 and deg.max() > 3 * np.median(deg)   # heavy tail
+
+
+def test_landmark_ranges_balance_and_cover():
+    sc = scenes.scene_c3(seed=0, scale=0.05)
+    for world in (1, 2, 3, 8):
+        rg = sharding.landmark_ranges(sc.obs_point, len(sc.points_init), world)
+        assert rg[0][0] == 0 and rg[-1][1] == len(sc.points_init)
+        assert all(rg[k][1] == rg[k + 1][0] for k in range(world - 1))
+        cnt = [np.count_nonzero((sc.obs_point >= lo) & (sc.obs_point < hi)) for lo, hi in rg]
+        assert sum(cnt) == sc.n_obs
+        assert max(cnt) - min(cnt) <= 0.05 * sc.n_obs / world + 64
+    # ragged / empty edge cases
+    assert sharding.landmark_ranges(np.zeros(0, dtype=np.int64), 0, 2) == [(0, 0), (0, 0)]
+    assert sharding.landmark_ranges(np.array([0, 0, 0]), 1, 2)[-1][1] == 1
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["BA_ROOT"]); sys.path.insert(0, os.path.join(os.environ["BA_ROOT"], "tests"))
+import oracle
+from bundle_adjustment_solver_b200 import scenes, sharding
+from bundle_adjustment_solver_b200 import solver as S
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sc = scenes.scene_trajectory(24, 300, 6, stereo=True, seed=4, n_fixed=2)
+sh = sharding.shard_scene(sc, rank, world)
+o = S.load_scene(oracle.FullBAOracle(), sh)
+o.build_only(thres_huber=1.0, lam=10.0, b_accumulate=0, do_solve=False)
+n = 6 * o.sizes()["N"]
+buf = torch.from_numpy(np.concatenate([o.dump("S"), o.dump("rhs"), [o.cost(), float(o.sizes()["M"]), float(o.sizes()["n_obs"])]]))
+dist.all_reduce(buf)                       # the engine's per-iteration exchange: [S | rhs] and LM scalars
+if rank == 0:
+    full = S.load_scene(oracle.FullBAOracle(), sc)
+    full.build_only(thres_huber=1.0, lam=10.0, b_accumulate=0, do_solve=False)
+    ref = np.concatenate([full.dump("S"), full.dump("rhs"), [full.cost(), float(full.sizes()["M"]), float(full.sizes()["n_obs"])]])
+    err = np.abs(buf.numpy() - ref).max() / np.abs(ref).max()
+    assert err < 1e-12, err
+    # replicated reduced solve + local back-substitution == the single-rank solution
+    x_full = np.linalg.solve(ref[:n * n].reshape(n, n), ref[n * n:n * n + n])
+    x_sum = np.linalg.solve(buf.numpy()[:n * n].reshape(n, n), buf.numpy()[n * n:n * n + n])
+    assert np.abs(x_full - x_sum).max() < 1e-9 * np.abs(x_full).max()
+    print("GLOO_OK", err)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_partial_systems_sum_to_the_full_system_gloo(tmp_path):
+    """world_size-2 gloo run on CPU: every rank builds [S | rhs] from its landmark shard (all poses
+    replicated); the all-reduced system equals the single-rank system (the N>1 path of the engine)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, BA_ROOT=ROOT, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    port = 29500 + (os.getpid() % 1000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "GLOO_OK" in out.stdout
+
+
+def test_shard_scene_preserves_relative_insertion_order():
+    sc = scenes.scene_trajectory(12, 80, 5, stereo=True, seed=9)
+    parts = [sharding.shard_scene(sc, r, 3) for r in range(3)]
+    assert sum(p.n_obs for p in parts) == sc.n_obs
+    assert sum(len(p.points_init) for p in parts) == len(sc.points_init)
+    lo, hi = parts[1].meta["landmark_range"]
+    k = (sc.obs_point >= lo) & (sc.obs_point < hi)
+    assert np.array_equal(parts[1].obs_uv, sc.obs_uv[k])       # same relative order => same last-writer pairs
+    assert parts[1].obs_point.min() == 0
