@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libba_b200.so")
 SOURCES = ["ba_engine.cu", "ba_poseonly.cu"]
-HEADERS = ["ba_device.cuh", "ba_cholesky.cuh", os.path.join("..", "..", "include", "ba_b200.h")]
+HEADERS = [os.path.join("..", "..", "include", "ba_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -15,11 +15,9 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    for f in SOURCES + HEADERS:
-        p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps += [os.path.join(CSRC, f) for f in HEADERS]
+    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in deps)
 
 
 def build(force=False, verbose=False):

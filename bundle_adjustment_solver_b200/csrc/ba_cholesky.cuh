@@ -15,8 +15,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
+#include "ba_cholesky_cluster.cuh"
 #include "ba_device.cuh"
 
 namespace ba {
@@ -308,8 +311,10 @@ struct CholeskyPlan {
   int n = 0, T = 0;                 // matrix order, tile rows over n+1 rows (the last holds the rhs row)
   std::vector<int> first_tile;      // [T]
   std::vector<int> rows_ptr, rows;  // per panel k: tile rows r > k with first_tile[r] <= k
-  int *d_first_tile = nullptr, *d_rows = nullptr;
+  int *d_first_tile = nullptr, *d_rows = nullptr, *d_rows_ptr = nullptr;
   double dense_fraction = 1.0;
+  int max_rows = 0;       // largest number of envelope row tiles under any panel
+  int cluster_size = 0;   // > 0: run the single-launch cluster kernel (small / narrow-envelope systems)
 };
 
 inline void cholesky_make_plan(CholeskyPlan &pl, int n, const std::vector<int> &first_pose /*per free pose: first co-visible pose*/) {
@@ -333,6 +338,14 @@ inline void cholesky_make_plan(CholeskyPlan &pl, int n, const std::vector<int> &
     used += m * (m + 1) / 2;
   }
   pl.rows_ptr[pl.T] = (int)pl.rows.size();
+  pl.max_rows = 0;
+  for (int k = 0; k < pl.T; ++k) pl.max_rows = std::max(pl.max_rows, pl.rows_ptr[k + 1] - pl.rows_ptr[k]);
+  // cluster path: every panel's tile jobs fit a few rounds of a <=16-CTA cluster
+  pl.cluster_size = 0;
+  if (n > 0 && n <= kClusterMaxN && pl.max_rows <= 12) {
+    const int jobs = pl.max_rows * (pl.max_rows + 1) / 2;
+    pl.cluster_size = jobs <= 1 ? 1 : jobs <= 2 ? 2 : jobs <= 4 ? 4 : jobs <= 8 ? 8 : 16;
+  }
   long long dense = 0;
   for (int k = 0; k < pl.T; ++k) { const long long m = pl.T - 1 - k; dense += m * (m + 1) / 2; }
   pl.dense_fraction = dense > 0 ? (double)used / (double)dense : 1.0;
@@ -346,6 +359,16 @@ inline size_t cholesky_linv_doubles(int n) { return (size_t)((n + kNB - 1) / kNB
 inline void cholesky_solve_enqueue(const CholeskyPlan &pl, double *Saug, double *x, double *zbuf, double *linv,
                                    const LmState *st, cudaStream_t stream, long long *launches, int parts = 15) {
   const int n = pl.n, ld = n + 1, n_rows = n + 1;
+  static const bool verbose = getenv("BA_B200_VERBOSE") != nullptr;
+  if (verbose) fprintf(stderr, "[ba_b200] cholesky n=%d T=%d max_rows=%d cluster_size=%d dense_fraction=%.3f parts=%d\n", n, pl.T, pl.max_rows, pl.cluster_size, pl.dense_fraction, parts);
+  if (pl.cluster_size > 0 && parts == 15) {
+    if (cholesky_cluster_enqueue(Saug, n, pl.d_rows_ptr, pl.d_rows, pl.d_first_tile, x, st, stream, pl.cluster_size)) {
+      if (launches) *launches += 1;
+      return;
+    }
+    const cudaError_t ce = cudaGetLastError();  // cluster launch unavailable: fall through to the multi-kernel path
+    if (verbose) fprintf(stderr, "[ba_b200] cluster launch failed: %s\n", cudaGetErrorString(ce));
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem);

@@ -879,7 +879,8 @@ struct ba_solver {
   int n_schur_chunks = 0, n_fallback_pairs = 0;
   int schur_mode = 1;  // 1 = register-tiled windows + fallback, 0 = direct reds only
   CholeskyPlan chol;
-  DevBuf<int> d_chol_rows, d_chol_first;
+  DevBuf<int> d_chol_rows, d_chol_first, d_chol_rows_ptr;
+  int chol_mode = -1;  // -1 auto, 0 multi-kernel, 1 cluster
   // blocks
   size_t Mp = 0, Pp = 0;
   DevBuf<double> d_ptblk, d_Bsoa, d_A, d_a, d_partialsA, d_Saug, d_Scopy, d_x, d_z, d_linv, d_Btx, d_y;
@@ -951,7 +952,7 @@ static void free_device(ba_solver *s) {
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
   s->d_tpt_point.release(); s->d_tpt_pair_start.release(); s->d_fallback_pairs.release();
-  s->d_chol_rows.release(); s->d_chol_first.release();
+  s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
@@ -1303,8 +1304,12 @@ int ba_finalize(ba_solver *s) {
     rows.push_back(0);
     CUDA_TRY(s->d_chol_rows.upload(rows, st));
     CUDA_TRY(s->d_chol_first.upload(s->chol.first_tile, st));
+    CUDA_TRY(s->d_chol_rows_ptr.upload(s->chol.rows_ptr, st));
     s->chol.d_rows = s->d_chol_rows.p;
     s->chol.d_first_tile = s->d_chol_first.p;
+    s->chol.d_rows_ptr = s->d_chol_rows_ptr.p;
+    if (const char *e = getenv("BA_B200_CHOL_MODE")) s->chol_mode = atoi(e);
+    if (s->chol_mode == 0) s->chol.cluster_size = 0;
   }
   CUDA_TRY(s->d_schur_chunks.upload(schur_chunks, st));
   CUDA_TRY(s->d_tpt_point.upload(tpt_point, st));
@@ -1805,6 +1810,9 @@ long long ba_debug_dump(ba_solver *s, int which, double *buf) {
         buf[0] = 0.0; buf[1] = h.last_cost_new; buf[2] = h.last_model; buf[3] = h.last_rho; buf[4] = h.last_lambda;
       }
       return 5;
+    case 11:  // raw factor buffer after the last solve: (n+1)^2 doubles, column-major lower + z row
+      if (buf) { auto h = fetch(s->d_Saug.p, (size_t)ld * ld); std::copy(h.begin(), h.end(), buf); }
+      return (long long)ld * ld;
     default: return BA_ERR_INVALID;
   }
 }
@@ -1832,6 +1840,11 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   *ms_per_rep = ms / reps;
+  if (getenv("BA_B200_VERBOSE")) {
+    unsigned long long dbg[8];
+    cudaMemcpyFromSymbol(dbg, g_cl_dbg, sizeof(dbg));
+    fprintf(stderr, "[ba_b200] cluster ns: diag %llu sync %llu trsm %llu sync %llu syrk %llu sync %llu backward %llu\n", dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5], dbg[6]);
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
   return BA_OK;

@@ -321,7 +321,7 @@ class FullBundleAdjustmentSolver:
         return "\n".join(lines)
 
     # --- debug / parity helpers ---------------------------------------------------------------
-    DUMP = dict(A=0, a=1, C=2, b=3, Cinv=4, B=5, S=6, rhs=7, x=8, y=9, scalars=10)
+    DUMP = dict(A=0, a=1, C=2, b=3, Cinv=4, B=5, S=6, rhs=7, x=8, y=9, scalars=10, factor=11)
 
     def set_debug(self, keep=True):
         self.L.ba_set_debug(self.h, int(keep))
