@@ -86,41 +86,55 @@ __device__ __forceinline__ void finish_point(const double *Craw, const double *b
   ptblk[(PB_Cinvb + 2) * Mp + pt] = cb2;
 }
 
-template <bool ACCUM_B>
-__global__ void __launch_bounds__(kThreads)
-k_linearize_by_point(const Chunk *__restrict__ chunks, const double2 *__restrict__ obs_uv,
+struct ChunkPoint {  // one landmark inside a point-order chunk
+  int point;        // original landmark id
+  int local_start;  // first observation slot inside the chunk
+  int len;          // observations of the landmark inside the chunk
+  int free;         // landmark is optimised
+};
+
+constexpr int kValsLd = kThreads + 1;  // padded row of the per-observation staging in shared memory
+
+// 96-byte pose gather as six 16-byte loads
+__device__ __forceinline__ void load_pose(const double *__restrict__ Tp, double *T) {
+  const double2 *p2 = reinterpret_cast<const double2 *>(Tp);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double2 v = __ldg(p2 + i);
+    T[2 * i] = v.x;
+    T[2 * i + 1] = v.y;
+  }
+}
+
+// K1a: landmark side (C, b, then damping + inverse).  One thread per observation of a chunk of whole
+// landmarks; the 9 per-observation terms are staged in shared memory and summed per landmark by 9 threads
+// (one per component) walking the landmark's contiguous run.
+__global__ void __launch_bounds__(kThreads, 3)
+k_linearize_by_point(const Chunk *__restrict__ chunks, const int2 *__restrict__ chunk_pts /*first, count*/,
+                     const ChunkPoint *__restrict__ cpts, const double2 *__restrict__ obs_uv,
                      const int *__restrict__ obs_pose, const int *__restrict__ obs_point,
-                     const int *__restrict__ obs_camflags, const int *__restrict__ obs_pair,
-                     Params prm, const double *__restrict__ cams, double thres_huber,
-                     double *__restrict__ ptblk, size_t Mp, double *__restrict__ Bsoa, size_t Pp,
+                     const int *__restrict__ obs_camflags, Params prm, const double *__restrict__ cams,
+                     double thres_huber, double *__restrict__ ptblk, size_t Mp,
                      const LmState *__restrict__ st) {
   if (st->done) return;
-  __shared__ SegSmem<9, kWarps> sm9;
-  __shared__ SegSmem<18, kWarps> sm18;
+  __shared__ double vals[9][kValsLd];
+  __shared__ double sums[kThreads][9];  // a chunk holds at most kThreads landmarks
   const Chunk ch = chunks[blockIdx.x];
+  const int2 cp = chunk_pts[blockIdx.x];
   const int t = threadIdx.x;
-  const bool active = t < ch.obs_count;
   const int k = ch.obs_start + t;
   const double *poses = prm.poses[st->cur];
   const double *points = prm.points[st->cur];
   double v[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) v[i] = 0.0;
-  double Bv[18];
-#pragma unroll
-  for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
-  int pt = -1 - t, cf = 0, pair = -1, ps = -1;
-  if (active) {
-    pt = obs_point[k];
-    ps = obs_pose[k];
-    cf = obs_camflags[k];
-    pair = obs_pair[k];
+  if (t < ch.obs_count) {
+    const int cf = obs_camflags[k];
     if (cf & kFlagPointFree) {
+      const int pt = obs_point[k];
       const double2 uv = obs_uv[k];
       double T[12], X[3];
-      const double *Tp = poses + (size_t)ps * 12;
-#pragma unroll
-      for (int i = 0; i < 12; ++i) T[i] = __ldg(Tp + i);
+      load_pose(poses + (size_t)obs_pose[k] * 12, T);
       X[0] = __ldg(points + (size_t)pt * 3);
       X[1] = __ldg(points + (size_t)pt * 3 + 1);
       X[2] = __ldg(points + (size_t)pt * 3 + 2);
@@ -142,67 +156,91 @@ k_linearize_by_point(const Chunk *__restrict__ chunks, const double2 *__restrict
       v[6] = -(Rm[0] * wr0 + Rm[3] * wr1);
       v[7] = -(Rm[1] * wr0 + Rm[4] * wr1);
       v[8] = -(Rm[2] * wr0 + Rm[5] * wr1);
-      if (pair >= 0 && (ACCUM_B || (cf & kFlagLastOfPair))) {
-        double Q[12];
-        jac_Q(G, p.Xb, Q);
-        // B_ji = w Q^T Rm (:826), 6x3 row-major
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) Bv[r * 3 + c] = w * (Q[r] * Rm[c] + Q[6 + r] * Rm[3 + c]);
-      }
     }
   }
-  // segment heads / tails by point
-  const bool head = !active || t == 0 || obs_point[k - 1] != pt;
-  const bool tail = active && (t == ch.obs_count - 1 || obs_point[k + 1] != pt);
-  block_segmented_sum<9, kWarps>(v, head, tail, sm9);
-  if (tail && (cf & kFlagPointFree)) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) vals[i][t] = v[i];
+  __syncthreads();
+  // component sums: thread u -> (landmark p = u / 9, component c = u % 9)
+  for (int u = t; u < 9 * cp.y; u += kThreads) {
+    const int pidx = u / 9, c = u - 9 * pidx;
+    const ChunkPoint q = cpts[cp.x + pidx];
+    const double *row = &vals[c][q.local_start];
+    double acc = 0.0;
+    for (int i = 0; i < q.len; ++i) acc += row[i];
+    sums[pidx][c] = acc;
+  }
+  __syncthreads();
+  for (int pidx = t; pidx < cp.y; pidx += kThreads) {
+    const ChunkPoint q = cpts[cp.x + pidx];
+    if (!q.free) continue;
+    double w9[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w9[i] = sums[pidx][i];
     if (ch.flags & kChunkSplit) {
       // rare: a point with more observations than one chunk holds; raw sums are completed by
       // k_finish_split_points
 #pragma unroll
-      for (int i = 0; i < 6; ++i) atomicAdd(&ptblk[(PB_Cd + i) * Mp + pt], v[i]);
+      for (int i = 0; i < 6; ++i) atomicAdd(&ptblk[(PB_Cd + i) * Mp + q.point], w9[i]);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) atomicAdd(&ptblk[(PB_b + i) * Mp + pt], v[6 + i]);
+      for (int i = 0; i < 3; ++i) atomicAdd(&ptblk[(PB_b + i) * Mp + q.point], w9[6 + i]);
     } else {
-      finish_point(v, v + 6, st->lambda, ptblk, Mp, pt);
-    }
-  }
-  if (!ACCUM_B) {
-    if (active && pair >= 0 && (cf & kFlagLastOfPair)) {
-#pragma unroll
-      for (int i = 0; i < 18; ++i) Bsoa[(size_t)i * Pp + pair] = Bv[i];
-    }
-  } else {
-    // corrected mode: B_ji += over the observations of the pair (adjacent in this order)
-    const bool phead = !active || t == 0 || obs_pair[k - 1] != pair || pair < 0;
-    const bool ptail = active && pair >= 0 && (t == ch.obs_count - 1 || obs_pair[k + 1] != pair);
-    block_segmented_sum<18, kWarps>(Bv, phead, ptail, sm18);
-    if (ptail) {
-      if (ch.flags & kChunkSplit) {
-#pragma unroll
-        for (int i = 0; i < 18; ++i) atomicAdd(&Bsoa[(size_t)i * Pp + pair], Bv[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 18; ++i) Bsoa[(size_t)i * Pp + pair] = Bv[i];
-      }
+      finish_point(w9, w9 + 6, st->lambda, ptblk, Mp, q.point);
     }
   }
 }
 
+// K1b: off-diagonal blocks.  One thread per (pose, point) pair: B_ji = w Q^T Rm of the pair's LAST inserted
+// observation (reference-exact, full...cpp:826) or the sum over the pair's observations (corrected mode).
+// Every lane does useful work and consecutive pairs write consecutive slots of the component-major Bsoa.
+template <bool ACCUM_B>
+__global__ void __launch_bounds__(kThreads, ACCUM_B ? 2 : 3)
+k_pair_blocks(int P, const int2 *__restrict__ pair_obs /*first, last observation (point order)*/,
+              const double2 *__restrict__ obs_uv, const int *__restrict__ obs_pose,
+              const int *__restrict__ obs_point, const int *__restrict__ obs_camflags, Params prm,
+              const double *__restrict__ cams, double thres_huber, double *__restrict__ Bsoa, size_t Pp,
+              const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double *poses = prm.poses[st->cur];
+  const double *points = prm.points[st->cur];
+  const int2 po = pair_obs[p];
+  double Bv[18];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
+  double T[12], X[3];
+  load_pose(poses + (size_t)obs_pose[po.y] * 12, T);
+  const int pt = obs_point[po.y];
+  X[0] = __ldg(points + (size_t)pt * 3);
+  X[1] = __ldg(points + (size_t)pt * 3 + 1);
+  X[2] = __ldg(points + (size_t)pt * 3 + 2);
+  for (int k = ACCUM_B ? po.x : po.y; k <= po.y; ++k) {
+    const double2 uv = obs_uv[k];
+    const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
+    Proj pr;
+    project(T, X, cam, uv.x, uv.y, pr);
+    const double w = huber_weight(pr.r0, pr.r1, thres_huber);
+    double G[6], Rm[6], Q[12];
+    jac_G(pr, cam, G);
+    jac_R(G, T, Rm);
+    jac_Q(G, pr.Xb, Q);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Bv[r * 3 + c] += w * (Q[r] * Rm[c] + Q[6 + r] * Rm[3 + c]);
+  }
+#pragma unroll
+  for (int i = 0; i < 18; ++i) Bsoa[(size_t)i * Pp + p] = Bv[i];
+}
+
 __global__ void k_zero_split(const int *__restrict__ split_points, int n_split, double *__restrict__ ptblk,
-                             size_t Mp, const int *__restrict__ split_pairs, int n_split_pairs,
-                             double *__restrict__ Bsoa, size_t Pp, int accum_b, const LmState *st) {
+                             size_t Mp, const LmState *st) {
   if (st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_split) {
     const int pt = split_points[i];
     for (int k = 0; k < 9; ++k) ptblk[(size_t)k * Mp + pt] = 0.0;
-  }
-  if (accum_b && i < n_split_pairs) {
-    const int p = split_pairs[i];
-    for (int k = 0; k < 18; ++k) Bsoa[(size_t)k * Pp + p] = 0.0;
   }
 }
 
@@ -221,7 +259,7 @@ __global__ void k_finish_split_points(const int *__restrict__ split_points, int 
 // ---------------------------------------------------------------------------
 // K2: linearise in pose order -> per-chunk partial A (upper 21) and a (6).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_linearize_by_pose(const ChunkA *__restrict__ chunks, const double2 *__restrict__ uvA,
                     const int *__restrict__ pointA, const int *__restrict__ camA, const int *__restrict__ poseidA,
                     Params prm, const double *__restrict__ cams, double thres_huber,
@@ -325,7 +363,7 @@ struct SchurChunk {
   int pt_start;   // first index into the tile-eligible landmark list
   int pt_count;
   int jmin;       // first free pose (j_opt) of the window
-  int _pad;
+  int width;      // poses actually spanned by the chunk (<= kSchurW): tasks are the width(width+1)/2 pairs
 };
 
 constexpr int kSchurW = 16;                              // window (poses)
@@ -346,12 +384,14 @@ k_schur_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt
   __shared__ int masks[PB];
   const SchurChunk ch = chunks[blockIdx.x];
   const int t = threadIdx.x;
-  // task -> (s1 <= s2)
+  // task -> (s1 <= s2 < width): dense over the chunk's actual window, so lanes map to blocks that exist
+  const int Wc = ch.width;
+  const int ntasks = Wc * (Wc + 1) / 2;
   int s1 = -1, s2 = -1;
-  if (t < kSchurTasks) {
+  if (t < ntasks) {
     int rem = t;
     s1 = 0;
-    while (rem >= W - s1) { rem -= W - s1; ++s1; }
+    while (rem >= Wc - s1) { rem -= Wc - s1; ++s1; }
     s2 = s1 + rem;
   }
   double acc[36];
@@ -397,7 +437,7 @@ k_schur_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt
       }
     }
     __syncthreads();
-    if (t < kSchurTasks) {
+    if (t < ntasks) {
       for (int q = 0; q < nb; ++q) {
         const int m = masks[q];
         if (!(((m >> s1) & (m >> s2)) & 1)) continue;
@@ -414,7 +454,7 @@ k_schur_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt
       }
     }
   }
-  if (t < kSchurTasks) {
+  if (t < ntasks) {
     const int j1 = ch.jmin + s1, j2 = ch.jmin + s2;
     // windows at the end of the pose range may stick out; such tasks never accumulated anything
     bool any = false;
@@ -869,6 +909,8 @@ struct ba_solver {
   DevBuf<int> d_obs_pose, d_obs_point, d_obs_camflags, d_obs_pair;
   DevBuf<int> d_pointA, d_camA, d_poseidA;
   DevBuf<Chunk> d_chunks;
+  DevBuf<int2> d_chunk_pts, d_pair_obs;
+  DevBuf<ChunkPoint> d_cpts;
   DevBuf<int> d_chunk_pair_count;
   DevBuf<ChunkA> d_chunksA;
   DevBuf<int> d_pose_chunk_ptr, d_pose_opt, d_pair_pose, d_pair_point, d_pair_end, d_point_has_pairs;
@@ -947,7 +989,7 @@ static void free_device(ba_solver *s) {
   for (int i = 0; i < 2; ++i) { s->d_poses[i].release(); s->d_points[i].release(); }
   s->d_obs_uv.release(); s->d_uvA.release(); s->d_obs_pose.release(); s->d_obs_point.release();
   s->d_obs_camflags.release(); s->d_obs_pair.release(); s->d_pointA.release(); s->d_camA.release();
-  s->d_poseidA.release(); s->d_chunks.release(); s->d_chunk_pair_count.release(); s->d_chunksA.release();
+  s->d_poseidA.release(); s->d_chunks.release(); s->d_chunk_pts.release(); s->d_pair_obs.release(); s->d_cpts.release(); s->d_chunk_pair_count.release(); s->d_chunksA.release();
   s->d_pose_chunk_ptr.release(); s->d_pose_opt.release(); s->d_pair_pose.release(); s->d_pair_point.release();
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
@@ -1119,6 +1161,9 @@ int ba_finalize(ba_solver *s) {
   }
   s->P = (long long)s->h_pair_pose.size();
   const long long P = s->P;
+  std::vector<int2> pair_obs(P);
+  for (long long q = n - 1; q >= 0; --q) if (o_pair[q] >= 0) pair_obs[o_pair[q]].x = (int)q;   // first
+  for (long long q = 0; q < n; ++q) if (o_pair[q] >= 0) pair_obs[o_pair[q]].y = (int)q;        // last (= last inserted)
   std::vector<int> pair_end(P);
   for (long long p = P - 1; p >= 0; --p)
     pair_end[p] = (p + 1 < P && s->h_pair_point[p + 1] == s->h_pair_point[p]) ? pair_end[p + 1] : (int)(p + 1);
@@ -1136,7 +1181,10 @@ int ba_finalize(ba_solver *s) {
       else for (int q = (int)p; q < e; ++q) fallback_pairs.push_back(q);
       p = e;
     }
-    constexpr int kMinPts = 6, kMaxPts = 160;
+    // Greedy runs.  A run keeps growing while its pose window stays within kSchurW; once it holds enough
+    // landmarks to amortise the final flush it is also cut when the next landmark would WIDEN the window,
+    // so that most chunks are exactly as wide as their landmarks' tracks (dense register tiles).
+    constexpr int kMinPts = 6, kGoodPts = 48, kMaxPts = 256;
     size_t i = 0;
     while (i < cands.size()) {
       int lo = cands[i].jmin, hi = cands[i].jmax;
@@ -1144,10 +1192,11 @@ int ba_finalize(ba_solver *s) {
       while (e < cands.size() && (int)(e - i) < kMaxPts) {
         const int nlo = std::min(lo, cands[e].jmin), nhi = std::max(hi, cands[e].jmax);
         if (nhi - nlo + 1 > kSchurW) break;
+        if ((int)(e - i) >= kGoodPts && (nlo != lo || nhi != hi)) break;
         lo = nlo; hi = nhi; ++e;
       }
       if ((int)(e - i) >= kMinPts) {
-        SchurChunk sc{(int)tpt_point.size(), (int)(e - i), lo, 0};
+        SchurChunk sc{(int)tpt_point.size(), (int)(e - i), lo, hi - lo + 1};
         for (size_t k = i; k < e; ++k) {
           tpt_point.push_back(cands[k].point);
           tpt_pair_start.push_back(cands[k].p0);  // [2*ti] = first pair, [2*ti+1] = one past the last
@@ -1221,6 +1270,20 @@ int ba_finalize(ba_solver *s) {
     }
     flush();
   }
+  // landmarks of each chunk (runs of equal point id inside the chunk's observation range)
+  std::vector<int2> chunk_pts(chunks.size());
+  std::vector<ChunkPoint> cpts;
+  for (size_t c = 0; c < chunks.size(); ++c) {
+    chunk_pts[c].x = (int)cpts.size();
+    const long long a = chunks[c].obs_start, b = a + chunks[c].obs_count;
+    for (long long r = a; r < b;) {
+      long long e = r;
+      while (e < b && o_point[e] == o_point[r]) ++e;
+      cpts.push_back(ChunkPoint{o_point[r], (int)(r - a), (int)(e - r), s->h_point_opt[o_point[r]] >= 0 ? 1 : 0});
+      r = e;
+    }
+    chunk_pts[c].y = (int)cpts.size() - chunk_pts[c].x;
+  }
   s->n_chunks = (int)chunks.size();
   s->n_split = (int)split_points.size();
   s->n_split_pairs = (int)split_pairs.size();
@@ -1233,7 +1296,7 @@ int ba_finalize(ba_solver *s) {
     uvA.reserve(nA); pointA.reserve(nA); camA.reserve(nA); poseidA.reserve(nA);
     // chunk size adapts to observations per pose so that a pose yields only a few partials
     const long long per_pose = s->N > 0 ? (nA + s->N - 1) / s->N : 0;
-    int per_thread = (int)std::min<long long>(8, std::max<long long>(1, per_pose / (kThreads * 2)));
+    int per_thread = (int)std::min<long long>(4, std::max<long long>(1, per_pose / (kThreads * 4)));
     const long long chunk_cap = (long long)kThreads * per_thread;
     long long q = 0;
     while (q < n) {
@@ -1286,6 +1349,9 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_camA.upload(camA, st));
   CUDA_TRY(s->d_poseidA.upload(poseidA, st));
   CUDA_TRY(s->d_chunks.upload(chunks, st));
+  CUDA_TRY(s->d_chunk_pts.upload(chunk_pts, st));
+  CUDA_TRY(s->d_pair_obs.upload(pair_obs, st));
+  CUDA_TRY(s->d_cpts.upload(cpts, st));
   CUDA_TRY(s->d_chunk_pair_count.upload(chunk_pair_count, st));
   CUDA_TRY(s->d_chunksA.upload(chunksA, st));
   CUDA_TRY(s->d_pose_chunk_ptr.upload(pose_chunk_ptr, st));
@@ -1412,22 +1478,27 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   const int ld = 6 * s->N + 1;
   if (ev) cudaEventRecord(ev[Phase::Lin], st);
   cudaMemsetAsync(s->d_Saug.p, 0, (size_t)ld * ld * sizeof(double), st);
-  if (s->n_split > 0 || (opt->b_accumulate && s->n_split_pairs > 0)) {
-    const int m = std::max(s->n_split, s->n_split_pairs);
-    k_zero_split<<<(m + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split, s->d_ptblk.p, s->Mp,
-                                                  s->d_split_pairs.p, s->n_split_pairs, s->d_Bsoa.p, s->Pp,
-                                                  opt->b_accumulate, dst);
+  if (s->n_split > 0) {
+    k_zero_split<<<(s->n_split + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split, s->d_ptblk.p, s->Mp, dst);
     s->launches++;
   }
   if (s->n_chunks > 0) {
+    k_linearize_by_point<<<s->n_chunks, kThreads, 0, st>>>(s->d_chunks.p, s->d_chunk_pts.p, s->d_cpts.p,
+                                                           s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                                           s->d_obs_camflags.p, prm, s->d_cams.p, thres,
+                                                           s->d_ptblk.p, s->Mp, dst);
+    s->launches++;
+  }
+  if (s->P > 0) {
+    const int grid = (int)((s->P + kThreads - 1) / kThreads);
     if (opt->b_accumulate)
-      k_linearize_by_point<true><<<s->n_chunks, kThreads, 0, st>>>(
-          s->d_chunks.p, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p, s->d_obs_camflags.p, s->d_obs_pair.p,
-          prm, s->d_cams.p, thres, s->d_ptblk.p, s->Mp, s->d_Bsoa.p, s->Pp, dst);
+      k_pair_blocks<true><<<grid, kThreads, 0, st>>>((int)s->P, s->d_pair_obs.p, s->d_obs_uv.p, s->d_obs_pose.p,
+                                                     s->d_obs_point.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres,
+                                                     s->d_Bsoa.p, s->Pp, dst);
     else
-      k_linearize_by_point<false><<<s->n_chunks, kThreads, 0, st>>>(
-          s->d_chunks.p, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p, s->d_obs_camflags.p, s->d_obs_pair.p,
-          prm, s->d_cams.p, thres, s->d_ptblk.p, s->Mp, s->d_Bsoa.p, s->Pp, dst);
+      k_pair_blocks<false><<<grid, kThreads, 0, st>>>((int)s->P, s->d_pair_obs.p, s->d_obs_uv.p, s->d_obs_pose.p,
+                                                      s->d_obs_point.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres,
+                                                      s->d_Bsoa.p, s->Pp, dst);
     s->launches++;
   }
   if (s->n_split > 0) {
