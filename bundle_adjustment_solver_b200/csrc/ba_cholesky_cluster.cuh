@@ -18,17 +18,17 @@ namespace cg = cooperative_groups;
 constexpr int kCB = 64;          // block size (== kNB)
 constexpr int kCLD = kCB + 1;
 constexpr int kClusterThreads = 256;
-// shared memory (doubles): two staged operands [64][65] | column buffers [2][64] | di [2] | dinv/dval/dia [3][64]
-constexpr size_t kClusterSmem = (2 * kCB * kCLD + 8 * kCB) * sizeof(double);
+// shared memory (doubles): two staged operands [64][65] | scratch: column buffers [2][4][64], di [2], dval/dinv/invd [3][64]
+constexpr int kScratch = 16 * kCB;
+constexpr size_t kClusterSmem = (2 * kCB * kCLD + kScratch) * sizeof(double);
 constexpr int kClusterMaxN = kCB * kCLD;  // x is staged in the second operand buffer during the backward sweep
 
-// reciprocal off the slow division path: single-precision hardware approximation (2^-22) refined by two
-// Newton steps in double (2^-44, 2^-88 -> limited by rounding).  Out-of-float-range pivots take the slow path.
+// reciprocal off the slow division path (it sits on the per-column critical path of the sweep): hardware
+// approximation (~20 bits) refined by two Newton steps (-> ~1e-24 relative, i.e. limited by rounding); no
+// branches, no conversions.
 __device__ __forceinline__ double fast_rcp(double d) {
-  if (d < 1e-30 || d > 1e30) return 1.0 / d;
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d)));
-  double x = (double)r;
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
   double e = fma(-d, x, 1.0);
   x = fma(x, e, x);
   e = fma(-d, x, 1.0);
@@ -40,21 +40,25 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // the cluster) write the same locations between barriers, and a restrict-qualified pointer lets the compiler
 // reuse a value loaded two column steps earlier from the double-buffered column vector.
 
-// ---- diagonal block (256 threads as a 16 x 16 grid, 4 x 4 register slots each, 2-D cyclic) ------------
-// thread (ty, tx) owns elements (r = ty + 16a, c = tx + 16b).  Column step j (fully unrolled, so dead slot
-// groups are pruned at compile time): the owners of column j publish it (and the pivot reciprocal) through a
-// double-buffered shared vector, one barrier, then every thread applies the rank-1 update as a 4 x 4 outer
-// product (8 shared loads, 4 DMUL, <= 16 DFMA, no predicates: finished / upper slots are simply never read
-// again).  a_rc -= a_rj a_cj / d_j ; the unscaled columns are parked in shared memory and scaled at the end:
-// L = A D^-1/2.  Non-positive pivots (pose without observations) emulate LDLT's D^+ = 0.
-__device__ __forceinline__ void chol_diag_2d(double *A, int ld, int k0, int nb, double *sm) {
+// ---- tall panel (256 threads as a 16 x 16 grid, 2-D cyclic 4 x 4 register slots per 64 x 64 tile) --------
+// Factorises the diagonal block AND up to NT row tiles below it in the same column sweep: thread (ty, tx)
+// owns elements (r = ty + 16a, c = tx + 16b) of every tile.  Column step j (fully unrolled, dead slot groups
+// pruned at compile time): the owners of column j publish it for all tiles (plus the pivot reciprocal)
+// through a double-buffered shared vector, one barrier, then every thread applies the rank-1 update as 4 x 4
+// outer products.  a_rc -= a_rj a_cj / d_j ; columns stay unscaled in registers and are scaled once at the
+// end: L = A D^-1/2.  The panel rows thus cost no extra latency (no separate TRSM phase, no inverse).
+// Non-positive pivots (pose without observations) emulate LDLT's D^+ = 0.
+template <int NT>
+__device__ __forceinline__ void chol_panel_tall(double *A, int ld, int n_rows, int k0, int nb, const int *rw,
+                                                double *sm) {
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
-  double (*Lraw)[kCLD] = reinterpret_cast<double (*)[kCLD]>(sm);  // first operand buffer
-  double *cb = sm + 2 * kCB * kCLD;   // [2][64]
-  double *dib = cb + 2 * kCB;         // [2]
-  double *dia = cb + 3 * kCB;         // [64] 1/d_j
-  double *dval = cb + 4 * kCB;        // [64] d_j
+  double (*Ls)[kCLD] = reinterpret_cast<double (*)[kCLD]>(sm);  // scaled diagonal block (for the rhs tail)
+  double *cb = sm + 2 * kCB * kCLD;   // [2][4][64]
+  double *dib = cb + 8 * kCB;         // [2]
+  double *dval = cb + 9 * kCB;        // [64] d_j, then sqrt(d_j)
+  double *dinv = cb + 10 * kCB;       // [64] 1/sqrt(d_j)
   double v[4][4];
+  double p[NT > 0 ? NT : 1][4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -65,52 +69,108 @@ __device__ __forceinline__ void chol_diag_2d(double *A, int ld, int k0, int nb, 
       v[a][b] = val;
     }
 #pragma unroll
+  for (int q = 0; q < NT; ++q) {
+    const int r0 = rw[q] * kCB;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int r = r0 + ty + 16 * a, c = tx + 16 * b;
+        p[q][a][b] = (r < n_rows && c < nb) ? __ldcg(&A[(size_t)(k0 + c) * ld + r]) : 0.0;
+      }
+  }
+#ifdef BA_DIAG_TIMING
+  __syncthreads();
+  long long tt1 = clock64();
+#endif
+#pragma unroll
   for (int j = 0; j < kCB; ++j) {
-    const int par = (j & 1) * kCB, g = j >> 4, jm = j & 15;
+    const int par = (j & 1) * 4 * kCB, g = j >> 4, jm = j & 15;
     if (tx == jm) {
 #pragma unroll
-      for (int a = g; a < 4; ++a) {
-        const int r = ty + 16 * a;
-        if (r >= j) { cb[par + r] = v[a][g]; Lraw[r][j] = v[a][g]; }
-      }
+      for (int a = g; a < 4; ++a) cb[par + ty + 16 * a] = v[a][g];   // rows < j are stale but never read live
+#pragma unroll
+      for (int q = 0; q < NT; ++q)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) cb[par + (1 + q) * kCB + ty + 16 * a] = p[q][a][g];
       if (ty == jm) {
         const double d = v[g][g];
-        const double di = (d > 0.0) ? fast_rcp(d) : 0.0;
-        dib[j & 1] = di;
-        dia[j] = di;
+        const double r = fast_rcp(d);
+        dib[j & 1] = (d > 0.0) ? r : 0.0;
         dval[j] = d;
       }
     }
     __syncthreads();
     const double di = dib[j & 1];
-    double lr[4], lc[4];
-#pragma unroll
-    for (int a = g; a < 4; ++a) lr[a] = cb[par + ty + 16 * a] * di;
+    const bool own_live = tx > jm;  // in column group g only columns right of j are still live
+    double lc[4];
 #pragma unroll
     for (int b = g; b < 4; ++b) lc[b] = cb[par + tx + 16 * b];
+    {
+      double lr[4];
 #pragma unroll
-    for (int a = g; a < 4; ++a)
+      for (int a = g; a < 4; ++a) lr[a] = cb[par + ty + 16 * a] * di;
 #pragma unroll
-      for (int b = g; b <= a; ++b) v[a][b] -= lr[a] * lc[b];
-  }
-  __syncthreads();
-  if (t < kCB) {
-    const double s = sqrt(dia[t]);   // 1/sqrt(d)
-    dia[t] = s;
-    dval[t] = (s > 0.0) ? dval[t] * s : __longlong_as_double(0x7ff0000000000000LL);  // sqrt(d) or +inf
-  }
-  __syncthreads();
-  for (int e = t; e < kCB * kCB; e += kClusterThreads) {
-    const int r = e % kCB, c = e / kCB;
-    if (r >= c) {
-      const double l = (r == c) ? dval[c] : Lraw[r][c] * dia[c];
-      Lraw[r][c] = l;
-      if (r < nb && c < nb) A[(size_t)(k0 + c) * ld + k0 + r] = l;
-    } else {
-      Lraw[r][c] = 0.0;
+      for (int a = g; a < 4; ++a) {
+        if (own_live && g <= a) v[a][g] -= lr[a] * lc[g];
+#pragma unroll
+        for (int b = g + 1; b <= a; ++b) v[a][b] -= lr[a] * lc[b];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      double lr[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) lr[a] = cb[par + (1 + q) * kCB + ty + 16 * a] * di;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (own_live) p[q][a][g] -= lr[a] * lc[g];
+#pragma unroll
+        for (int b = g + 1; b < 4; ++b) p[q][a][b] -= lr[a] * lc[b];
+      }
     }
   }
+#ifdef BA_DIAG_TIMING
+  long long tt2 = clock64();
+#endif
   __syncthreads();
+  if (t < kCB) {
+    const double d = dval[t];
+    const double s = (d > 0.0) ? rsqrt(d) : 0.0;  // 1/sqrt(d)
+    dinv[t] = s;
+    dval[t] = (s > 0.0) ? d * s : __longlong_as_double(0x7ff0000000000000LL);  // sqrt(d) or +inf
+  }
+  __syncthreads();
+#ifdef BA_DIAG_TIMING
+  long long tt3 = clock64();
+#endif
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = ty + 16 * a, c = tx + 16 * b;
+      double l = 0.0;
+      if (r >= c) {
+        l = (r == c) ? dval[c] : v[a][b] * dinv[c];
+        if (r < nb) A[(size_t)(k0 + c) * ld + k0 + r] = l;
+      }
+      Ls[r][c] = l;
+    }
+#pragma unroll
+  for (int q = 0; q < NT; ++q) {
+    const int r0 = rw[q] * kCB;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int r = r0 + ty + 16 * a, c = tx + 16 * b;
+        if (r < n_rows && c < nb) A[(size_t)(k0 + c) * ld + r] = p[q][a][b] * dinv[c];
+      }
+  }
+  __syncthreads();
+#ifdef BA_DIAG_TIMING
+  if (t == 0) { g_t[1] = tt2 - tt1; g_t[2] = tt3 - tt2; g_t[3] = clock64() - tt3; }
+#endif
 }
 
 // ---- panel tile by substitution: X L_kk^T = A_tile.  4 threads per row (q = t%4 owns columns m = q + 4i in
@@ -119,7 +179,7 @@ __device__ __forceinline__ void chol_diag_2d(double *A, int ld, int k0, int nb, 
 __device__ __forceinline__ void job_trsm_subst(double *A, int ld, int n_rows, int k0, int nb, int r0,
                                                bool L_in_smem, double *sm) {
   double (*Ls)[kCLD] = reinterpret_cast<double (*)[kCLD]>(sm);
-  double *invd = sm + 2 * kCB * kCLD + 5 * kCB;
+  double *invd = sm + 2 * kCB * kCLD + 11 * kCB;
   const int t = threadIdx.x;
   if (!L_in_smem) {
     __syncthreads();
@@ -252,10 +312,17 @@ k_chol_cluster(double *A, int n, const int *__restrict__ rows_ptr, const int *__
     const int m = rows_ptr[kb + 1] - rows_ptr[kb];
     const int *rw = rows + rows_ptr[kb];
     unsigned long long t0 = timing ? gtime() : 0;
-    bool L_in_smem = false;
+    // Row tiles factorised together with the diagonal block.  Measured on B200: the extra FP64 work runs on
+    // ONE SM inside a barrier-per-column sweep (963 vs 294 cycles per column for 3 extra tiles), slower than
+    // handing the tiles to the other CTAs of the cluster, so the tall variant is kept for cluster size 1 only.
+    const int NTk = (ncta == 1) ? (m < 3 ? m : 3) : 0;
     if (rank == 0) {
-      chol_diag_2d(A, ld, k0, nb, csm);
-      L_in_smem = true;
+      switch (NTk) {
+        case 0: chol_panel_tall<0>(A, ld, n_rows, k0, nb, rw, csm); break;
+        case 1: chol_panel_tall<1>(A, ld, n_rows, k0, nb, rw, csm); break;
+        case 2: chol_panel_tall<2>(A, ld, n_rows, k0, nb, rw, csm); break;
+        default: chol_panel_tall<3>(A, ld, n_rows, k0, nb, rw, csm); break;
+      }
       if (nb < kCB) {
         // rhs row inside the partial last diagonal tile: z_k L_kk^T = rhs_k by substitution (thread 0..)
         double (*Ls)[kCLD] = reinterpret_cast<double (*)[kCLD]>(csm);
@@ -275,14 +342,12 @@ k_chol_cluster(double *A, int n, const int *__restrict__ rows_ptr, const int *__
     }
     if (m == 0) continue;  // uniform
     unsigned long long t1 = timing ? gtime() : 0;
-    // rank 0 keeps L_kk in shared memory and starts its panel tile without waiting for anyone
-    if (rank == 0 && m > 0) job_trsm_subst(A, ld, n_rows, k0, nb, rw[0] * kCB, true, csm);
     cluster.sync();
     unsigned long long t2 = timing ? gtime() : 0;
-    for (int job = rank; job < m; job += ncta)
-      if (job > 0 || rank != 0) job_trsm_subst(A, ld, n_rows, k0, nb, rw[job] * kCB, false, csm);
+    // row tiles beyond the tall panel (wide envelopes only): substitution jobs on all ranks
+    for (int job = NTk + rank; job < m; job += ncta) job_trsm_subst(A, ld, n_rows, k0, nb, rw[job] * kCB, false, csm);
     unsigned long long t3 = timing ? gtime() : 0;
-    cluster.sync();
+    if (m > NTk) cluster.sync();  // uniform
     unsigned long long t4 = timing ? gtime() : 0;
     const int npairs = m * (m + 1) / 2;
     for (int job = rank; job < npairs; job += ncta) {
@@ -305,7 +370,7 @@ k_chol_cluster(double *A, int n, const int *__restrict__ rows_ptr, const int *__
   __syncthreads();
   double *xs = csm + kCB * kCLD;             // x for all blocks (second operand buffer onwards is free here)
   double (*Ls)[kCLD] = reinterpret_cast<double (*)[kCLD]>(csm);
-  double *acc_s = csm + 2 * kCB * kCLD;       // [64]
+  double *acc_s = csm + 2 * kCB * kCLD + 12 * kCB;       // [64]
   const int warp = t >> 5, lane = t & 31;
   for (int kb = nblk - 1; kb >= 0; --kb) {
     const int k0 = kb * kCB, nb = min(kCB, n - k0);
@@ -324,7 +389,7 @@ k_chol_cluster(double *A, int n, const int *__restrict__ rows_ptr, const int *__
       }
     }
     __syncthreads();
-    double *invd = csm + 2 * kCB * kCLD + 5 * kCB;
+    double *invd = csm + 2 * kCB * kCLD + 11 * kCB;
     if (t < kCB) invd[t] = 1.0 / Ls[t][t];
     {
       // acc[c] = z[k0+c] - sum over envelope rows r >= k0+64 of L[r][k0+c] x[r];

@@ -166,27 +166,22 @@ k_linearize_by_point(const Chunk *__restrict__ chunks, const int2 *__restrict__ 
     const int pidx = u / 9, c = u - 9 * pidx;
     const ChunkPoint q = cpts[cp.x + pidx];
     const double *row = &vals[c][q.local_start];
-    double acc = 0.0;
-    for (int i = 0; i < q.len; ++i) acc += row[i];
-    sums[pidx][c] = acc;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = 0;
+    for (; i + 4 <= q.len; i += 4) { a0 += row[i]; a1 += row[i + 1]; a2 += row[i + 2]; a3 += row[i + 3]; }
+    for (; i < q.len; ++i) a0 += row[i];
+    sums[pidx][c] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
-  for (int pidx = t; pidx < cp.y; pidx += kThreads) {
+  // raw sums -> ptblk (Cd slots hold the un-damped C until k_finish_points runs); 9 consecutive threads
+  // write one landmark
+  for (int u = t; u < 9 * cp.y; u += kThreads) {
+    const int pidx = u / 9, c = u - 9 * pidx;
     const ChunkPoint q = cpts[cp.x + pidx];
     if (!q.free) continue;
-    double w9[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) w9[i] = sums[pidx][i];
-    if (ch.flags & kChunkSplit) {
-      // rare: a point with more observations than one chunk holds; raw sums are completed by
-      // k_finish_split_points
-#pragma unroll
-      for (int i = 0; i < 6; ++i) atomicAdd(&ptblk[(PB_Cd + i) * Mp + q.point], w9[i]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) atomicAdd(&ptblk[(PB_b + i) * Mp + q.point], w9[6 + i]);
-    } else {
-      finish_point(w9, w9 + 6, st->lambda, ptblk, Mp, q.point);
-    }
+    const int slot = c < 6 ? PB_Cd + c : PB_b + (c - 6);
+    if (ch.flags & kChunkSplit) atomicAdd(&ptblk[(size_t)slot * Mp + q.point], sums[pidx][c]);
+    else ptblk[(size_t)slot * Mp + q.point] = sums[pidx][c];
   }
 }
 
@@ -244,12 +239,13 @@ __global__ void k_zero_split(const int *__restrict__ split_points, int n_split, 
   }
 }
 
-__global__ void k_finish_split_points(const int *__restrict__ split_points, int n_split,
-                                      double *__restrict__ ptblk, size_t Mp, const LmState *st) {
+// K3: damping + 3x3 LDLT inverse + C^-1 b for every free landmark (one thread each, coalesced SoA rows)
+__global__ void __launch_bounds__(128)
+k_finish_points(int M_total, const uint8_t *__restrict__ point_free, double *__restrict__ ptblk, size_t Mp,
+                const LmState *st) {
   if (st->done) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_split) return;
-  const int pt = split_points[i];
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= M_total || !point_free[pt]) return;
   double c[6], b[3];
   for (int k = 0; k < 6; ++k) c[k] = ptblk[(PB_Cd + k) * Mp + pt];
   for (int k = 0; k < 3; ++k) b[k] = ptblk[(PB_b + k) * Mp + pt];
@@ -366,9 +362,9 @@ struct SchurChunk {
   int width;      // poses actually spanned by the chunk (<= kSchurW): tasks are the width(width+1)/2 pairs
 };
 
-constexpr int kSchurW = 16;                              // window (poses)
-constexpr int kSchurTasks = kSchurW * (kSchurW + 1) / 2; // 136
-constexpr int kSchurThreads = 160;
+constexpr int kSchurW = 15;                              // window (poses)
+constexpr int kSchurTasks = kSchurW * (kSchurW + 1) / 2; // 120
+constexpr int kSchurThreads = 128;
 constexpr int kSchurPB = 8;                              // landmarks staged per batch
 
 __global__ void __launch_bounds__(kSchurThreads)
@@ -378,21 +374,23 @@ k_schur_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt
               double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
   if (st->done) return;
   constexpr int W = kSchurW, PB = kSchurPB;
-  __shared__ double Es[PB][18][W];
-  __shared__ double Bs[PB][18][W];
+  __shared__ double Es[PB][18][W + 1];
+  __shared__ double Bs[PB][18][W + 1];
   __shared__ double bs[PB][4];
   __shared__ int masks[PB];
   const SchurChunk ch = chunks[blockIdx.x];
   const int t = threadIdx.x;
-  // task -> (s1 <= s2 < width): dense over the chunk's actual window, so lanes map to blocks that exist
+  // task -> (s1 <= s2 < width), enumerated column-major (s2 outer): a landmark whose poses are the first L
+  // slots of the window activates exactly the first L(L+1)/2 tasks, i.e. a dense prefix of the lanes, so
+  // warps beyond the prefix skip the landmark entirely and only one warp runs partially filled.
   const int Wc = ch.width;
   const int ntasks = Wc * (Wc + 1) / 2;
   int s1 = -1, s2 = -1;
   if (t < ntasks) {
+    s2 = 0;
     int rem = t;
-    s1 = 0;
-    while (rem >= Wc - s1) { rem -= Wc - s1; ++s1; }
-    s2 = s1 + rem;
+    while (rem > s2) { rem -= s2 + 1; ++s2; }
+    s1 = rem;
   }
   double acc[36];
 #pragma unroll
@@ -1184,7 +1182,7 @@ int ba_finalize(ba_solver *s) {
     // Greedy runs.  A run keeps growing while its pose window stays within kSchurW; once it holds enough
     // landmarks to amortise the final flush it is also cut when the next landmark would WIDEN the window,
     // so that most chunks are exactly as wide as their landmarks' tracks (dense register tiles).
-    constexpr int kMinPts = 6, kGoodPts = 48, kMaxPts = 256;
+    constexpr int kMinPts = 6, kMinStart = 24, kGoodPts = 48, kMaxPts = 192;
     size_t i = 0;
     while (i < cands.size()) {
       int lo = cands[i].jmin, hi = cands[i].jmax;
@@ -1193,6 +1191,7 @@ int ba_finalize(ba_solver *s) {
         const int nlo = std::min(lo, cands[e].jmin), nhi = std::max(hi, cands[e].jmax);
         if (nhi - nlo + 1 > kSchurW) break;
         if ((int)(e - i) >= kGoodPts && (nlo != lo || nhi != hi)) break;
+        if ((int)(e - i) >= kMinStart && cands[e].jmin != cands[i].jmin) break;  // keep a common first pose
         lo = nlo; hi = nhi; ++e;
       }
       if ((int)(e - i) >= kMinPts) {
@@ -1501,9 +1500,8 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
                                                       s->d_Bsoa.p, s->Pp, dst);
     s->launches++;
   }
-  if (s->n_split > 0) {
-    k_finish_split_points<<<(s->n_split + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split,
-                                                                    s->d_ptblk.p, s->Mp, dst);
+  if (s->M_total > 0) {
+    k_finish_points<<<(s->M_total + 127) / 128, 128, 0, st>>>(s->M_total, s->d_point_free.p, s->d_ptblk.p, s->Mp, dst);
     s->launches++;
   }
   if (s->n_chunksA > 0) {
