@@ -4,7 +4,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libba_b200.so")
+# BA_B200_LIB: alternative build of the same sources (A/B kernel experiments); product default is in-tree
+LIB = os.environ.get("BA_B200_LIB") or os.path.join(HERE, "libba_b200.so")
 SOURCES = ["ba_engine.cu", "ba_poseonly.cu"]
 HEADERS = [os.path.join("..", "..", "include", "ba_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

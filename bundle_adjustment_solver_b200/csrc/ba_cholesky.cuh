@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "ba_cholesky_banded.cuh"
 #include "ba_cholesky_cluster.cuh"
 #include "ba_device.cuh"
 
@@ -315,10 +316,16 @@ struct CholeskyPlan {
   double dense_fraction = 1.0;
   int max_rows = 0;       // largest number of envelope row tiles under any panel
   int cluster_size = 0;   // > 0: run the single-launch cluster kernel (small / narrow-envelope systems)
+  int bw = 0;             // scalar half-bandwidth of S: 6 (largest pose distance inside a track) + 5
+  bool banded = false;    // run the register-window banded kernel (ba_cholesky_banded.cuh)
 };
 
 inline void cholesky_make_plan(CholeskyPlan &pl, int n, const std::vector<int> &first_pose /*per free pose: first co-visible pose*/) {
   pl.n = n;
+  pl.bw = 0;
+  for (size_t j = 0; j < first_pose.size(); ++j) pl.bw = std::max(pl.bw, 6 * ((int)j - first_pose[j]) + 5);
+  pl.bw = std::min(pl.bw, std::max(0, n - 1));
+  pl.banded = cholesky_banded_supported(n, pl.bw) && n > kBandMaxW;
   pl.T = (n + 1 + kNB - 1) / kNB;
   pl.first_tile.assign(pl.T, pl.T);
   for (size_t j = 0; j < first_pose.size(); ++j) {
@@ -360,7 +367,13 @@ inline void cholesky_solve_enqueue(const CholeskyPlan &pl, double *Saug, double 
                                    const LmState *st, cudaStream_t stream, long long *launches, int parts = 15) {
   const int n = pl.n, ld = n + 1, n_rows = n + 1;
   static const bool verbose = getenv("BA_B200_VERBOSE") != nullptr;
-  if (verbose) fprintf(stderr, "[ba_b200] cholesky n=%d T=%d max_rows=%d cluster_size=%d dense_fraction=%.3f parts=%d\n", n, pl.T, pl.max_rows, pl.cluster_size, pl.dense_fraction, parts);
+  if (verbose) fprintf(stderr, "[ba_b200] cholesky n=%d T=%d max_rows=%d cluster_size=%d dense_fraction=%.3f bw=%d banded=%d parts=%d\n", n, pl.T, pl.max_rows, pl.cluster_size, pl.dense_fraction, pl.bw, (int)pl.banded, parts);
+  if (pl.banded && parts == 15) {
+    if (cholesky_banded_enqueue(Saug, n, pl.bw, x, linv, st, stream)) {
+      if (launches) *launches += 1;
+      return;
+    }
+  }
   if (pl.cluster_size > 0 && parts == 15) {
     if (cholesky_cluster_enqueue(Saug, n, pl.d_rows_ptr, pl.d_rows, pl.d_first_tile, x, st, stream, pl.cluster_size)) {
       if (launches) *launches += 1;

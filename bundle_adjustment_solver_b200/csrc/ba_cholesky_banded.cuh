@@ -1,0 +1,398 @@
+// ba_cholesky_banded.cuh -- K5 for BANDED reduced camera systems (sequential trajectories: every landmark
+// is seen by a short run of consecutive poses, so S has scalar half-bandwidth bw = 6 (track span) + 5).
+// Replaces `Am_BCinvBt_mat.ldlt().solve(am_BCinv_b_mat)` (core/full_bundle_adjustment_solver.cpp:890-908).
+//
+// The dependency chain of a Cholesky factorisation is n column steps long no matter how it is blocked; for a
+// band the work per step is only bw^2/2 FMAs, so the solve is bound by the LATENCY of one column step.  This
+// kernel therefore keeps the whole active window of the factorisation in the REGISTERS of one CTA and spends
+// exactly one __syncthreads per column:
+//
+//   * window = the W x W symmetric block rows/cols j .. j+W-1 (W >= bw+1, multiple of 16), stored FULL
+//     (both triangles, so the rank-1 update needs no predicates) in a 2-D cyclic layout: thread (ty, tx) of the
+//     16 x 16 CTA owns slots (ty + 16a, tx + 16b); matrix index i lives in slot i mod W.  The slot -> register
+//     mapping is static: the W column steps of one trip around the ring are fully unrolled.
+//   * step j: the owners of column j publish it (and the pivot reciprocal) through a double-buffered shared
+//     vector, barrier, every thread applies a_rc -= a_rj a_cj / d_j to its (W/16)^2 slots.  The slots of the
+//     NEXT column are updated first and published before the bulk of the update is issued, so the bulk overlaps
+//     the shared-memory round trip (software pipelining of the column chain).
+//   * after step j, ring slot j mod W is recycled for index j + W: the new row/column (original S values, they
+//     receive their first update at step j+1 at the earliest) was prefetched one 16-step group ahead.
+//   * columns stay unscaled in registers (L = A D^-1/2 is applied when a column is written out, off the
+//     critical path, by a rotating warp).  The rhs travels as one more window row, so z = L^-1 rhs falls out.
+//   * non-positive pivots (pose without observations) emulate Eigen LDLT's D^+ = 0.
+//
+// The backward sweep L^T x = z runs in the same launch: 16-column blocks from the bottom; the block's
+// off-diagonal part is a set of 16 dot products over <= bw rows (8 warps, shuffle reductions, L prefetched one
+// block ahead), the 16 x 16 triangle is solved inside one warp with shuffles.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <type_traits>
+
+#include "ba_cholesky_cluster.cuh"  // fast_rcp, gtime
+#include "ba_device.cuh"
+
+namespace ba {
+
+constexpr int kBandThreads = 256;
+constexpr int kBandMaxW = 112;
+
+template <int W>
+struct BandSmem {
+  union {
+    // factorisation: published columns of the current 16-step group (double-buffered by group parity):
+    // [pos < W] column entries by frame position, [W] rhs entry z_j (unscaled), [W + 1] 1 / d_j
+    double cb[2][16][W + 2];
+    // inverse pre-pass: per half-warp staging of a 16 x 16 diagonal block of L and its diagonal reciprocals
+    struct {
+      double lst[8][2][16][17];
+      double linvd[8][2][16];
+    } pre;
+  };
+  double xr[W + 32];     // ring of solved x entries (backward sweep), index r mod (W+32)
+  double acc[2][16];     // backward sweep: block right-hand side (double-buffered by block parity)
+  unsigned long long mbar;   // column-published barrier (one phase per column step, 8 warp arrivals)
+};
+
+// mbarrier wrappers (shared::cta): split arrive / wait so that the bulk of a column step's update is issued
+// between publishing the next column and waiting for everybody else's part of it
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "BA_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra BA_MBAR_DONE;\n"
+      "bra BA_MBAR_WAIT;\n"
+      "BA_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+__device__ unsigned long long g_band_dbg[4];
+
+// value of S(r, c) (r >= c) for the window, or the identity padding outside the matrix / zero outside the band
+__device__ __forceinline__ double band_load(const double *A, int ld, int n, int bw, int r, int c) {
+  if (r >= n) return (r == c) ? 1.0 : 0.0;
+  if (r - c > bw) return 0.0;
+  return __ldcg(A + (size_t)c * ld + r);
+}
+__device__ __forceinline__ double band_load_sym(const double *A, int ld, int n, int bw, int r, int c) {
+  return r >= c ? band_load(A, ld, n, bw, r, c) : band_load(A, ld, n, bw, c, r);
+}
+
+// Frame of group G (steps j = 16G .. 16G+15): slot (a, b) of thread (ty, tx) holds the window element
+// (16(G+a) + ty, 16(G+b) + tx); once step jm has retired index 16G + jm, the a == 0 slots of the threads
+// ty == jm (and the b == 0 slots of tx == jm) hold index 16G + jm + W instead.  After the group the slot
+// arrays are rotated by one so that the next group is again at a == b == 0: the 16-step body is the same code
+// for every group (it stays resident in the instruction cache).
+template <int W>
+__global__ void __launch_bounds__(kBandThreads, 1)
+k_chol_banded(double *A, int n, int bw, double *x_out, double *linv, int timing, const LmState *st) {
+  if (st->done) return;
+  constexpr int NS = W / 16;
+  __shared__ BandSmem<W> sm;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15, warp = t >> 5, lane = t & 31;
+  const int ld = n + 1;
+  unsigned long long t_begin = 0;
+  if (timing) t_begin = gtime();
+
+  double v[NS][NS];   // window slots
+  double zr[NS];      // rhs row entries of the column slots (replicated over ty)
+#pragma unroll
+  for (int a = 0; a < NS; ++a)
+#pragma unroll
+    for (int b = 0; b < NS; ++b) v[a][b] = band_load_sym(A, ld, n, bw, ty + 16 * a, tx + 16 * b);
+#pragma unroll
+  for (int b = 0; b < NS; ++b) {
+    const int c = tx + 16 * b;
+    zr[b] = (c < n) ? __ldcg(A + (size_t)c * ld + n) : 0.0;
+  }
+  // entries entering the window during group G: the row 16G + ty + W (held by threads ty, slots a == 0) and
+  // the column 16G + tx + W (threads tx, slots b == 0), in the frame of group G at the time they enter
+  double cur_row[NS], cur_col[NS], cur_z, nxt_row[NS], nxt_col[NS], nxt_z;
+  auto prefetch = [&](int G, double (&prow)[NS], double (&pcol)[NS], double &pz) {
+    const int qr = 16 * G + ty + W, qc = 16 * G + tx + W;
+#pragma unroll
+    for (int b = 0; b < NS; ++b) {
+      const int c = 16 * (G + b) + tx + ((b == 0 && tx <= ty) ? W : 0);
+      prow[b] = band_load_sym(A, ld, n, bw, qr, c);
+    }
+#pragma unroll
+    for (int a = 0; a < NS; ++a) {
+      const int r = 16 * (G + a) + ty + ((a == 0 && ty <= tx) ? W : 0);
+      pcol[a] = band_load_sym(A, ld, n, bw, r, qc);
+    }
+    pz = (qc < n) ? __ldcg(A + (size_t)qc * ld + n) : 0.0;
+  };
+  prefetch(0, cur_row, cur_col, cur_z);
+  if (t == 0) mbar_init(&sm.mbar, kBandThreads / 32);
+  __syncthreads();
+  unsigned phase = 0;
+  // column 0
+  if (tx == 0) {
+#pragma unroll
+    for (int a = 0; a < NS; ++a) sm.cb[0][0][ty + 16 * a] = v[a][0];
+    if (ty == 0) {
+      const double d = v[0][0];
+      const double r = fast_rcp(d);
+      sm.cb[0][0][W + 1] = (d > 0.0) ? r : 0.0;
+      sm.cb[0][0][W] = zr[0];
+    }
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&sm.mbar);
+  const int n_groups = (n + 15) / 16;
+#pragma unroll 1
+  for (int G = 0; G < n_groups; ++G) {
+    const int gp = G & 1;
+    // loads for the next group (consumed 16..31 steps from now)
+    prefetch(G + 1, nxt_row, nxt_col, nxt_z);
+    // one column step; GN = slot group of column j + 1 (0 inside the group, 1 for the last step, whose
+    // published column already uses the NEXT group's frame positions)
+    auto step = [&](auto gn_c, const int jm) {
+      constexpr int gn = decltype(gn_c)::value;
+      const int jm1 = (jm + 1) & 15;
+      const int np = gn ? (gp ^ 1) : gp;  // group parity of column j + 1
+      mbar_wait(&sm.mbar, phase);          // column j published by every warp
+      phase ^= 1;
+      const double *cbj = sm.cb[gp][jm];
+      const double di = cbj[W + 1];
+      double lc[NS], lr[NS];
+#pragma unroll
+      for (int b = 0; b < NS; ++b) lc[b] = cbj[tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < NS; ++a) lr[a] = cbj[ty + 16 * a] * di;
+      const double zl = cbj[W] * di;
+      // priority: the slots of column j + 1, recycle what that column needs, publish it
+#pragma unroll
+      for (int a = 0; a < NS; ++a) v[a][gn] -= lr[a] * lc[gn];
+      zr[gn] -= zl * lc[gn];
+      if (ty == jm) v[0][gn] = cur_row[gn];
+      if (tx == jm1) {
+        double *cbn = sm.cb[np][jm1];
+#pragma unroll
+        for (int a = 0; a < NS; ++a) cbn[ty + 16 * ((a + NS - gn) % NS)] = v[a][gn];
+        if (ty == jm1) {
+          const double d = v[gn][gn];
+          const double r = fast_rcp(d);
+          cbn[W + 1] = (d > 0.0) ? r : 0.0;
+        }
+        if (ty == 0) cbn[W] = zr[gn];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.mbar);  // this warp's part of column j + 1 is out
+      // bulk of the rank-1 update
+#pragma unroll
+      for (int b = 0; b < NS; ++b) {
+        if (b == gn) continue;
+#pragma unroll
+        for (int a = 0; a < NS; ++a) v[a][b] -= lr[a] * lc[b];
+        zr[b] -= zl * lc[b];
+      }
+      // recycle the slots of index j for index j + W
+      if (ty == jm) {
+#pragma unroll
+        for (int b = 0; b < NS; ++b)
+          if (b != gn) v[0][b] = cur_row[b];
+      }
+      if (tx == jm) {
+#pragma unroll
+        for (int a = 0; a < NS; ++a) v[a][0] = cur_col[a];
+        zr[0] = cur_z;
+      }
+    };
+#ifdef BA_BAND_UNROLL_ALL
+#pragma unroll
+#else
+#pragma unroll 3
+#endif
+    for (int jm = 0; jm < 15; ++jm) step(std::integral_constant<int, 0>{}, jm);
+    step(std::integral_constant<int, 1>{}, 15);
+    // the 16 finished columns of this group to global memory: L_rj = a_rj / sqrt(d_j) (and z_j); warp w
+    // writes columns w and w + 8.  cb[gp] is not written again before the next group's last step.
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int jm = warp + 8 * h, j = 16 * G + jm;
+      if (j < n) {
+        const double *cbj = sm.cb[gp][jm];
+        const double d = cbj[jm];
+        const double s = (d > 0.0) ? rsqrt(d) : 0.0;
+        double *col = A + (size_t)j * ld;
+#pragma unroll
+        for (int k = 0; k < (W + 31) / 32; ++k) {
+          const int rel = lane + 32 * k;
+          const int r = j + rel;
+          if (rel <= bw && r < n) {
+            int pos = jm + rel;
+            if (pos >= W) pos -= W;
+            double l = cbj[pos] * s;
+            if (rel == 0 && !(d > 0.0)) l = __longlong_as_double(0x7ff0000000000000LL);
+            col[r] = l;
+          }
+        }
+        if (lane == 0) col[n] = cbj[W] * s;
+      }
+    }
+    // rotate the frame by one group
+    {
+      double tmp[NS][NS], tz[NS];
+#pragma unroll
+      for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int b = 0; b < NS; ++b) tmp[a][b] = v[(a + 1) % NS][(b + 1) % NS];
+#pragma unroll
+      for (int b = 0; b < NS; ++b) tz[b] = zr[(b + 1) % NS];
+#pragma unroll
+      for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int b = 0; b < NS; ++b) v[a][b] = tmp[a][b];
+#pragma unroll
+      for (int b = 0; b < NS; ++b) { zr[b] = tz[b]; cur_row[b] = nxt_row[b]; cur_col[b] = nxt_col[b]; }
+      cur_z = nxt_z;
+    }
+  }
+  __syncthreads();
+  unsigned long long t_factor = 0;
+  if (timing) t_factor = gtime();
+
+  // ---- inverse pre-pass: X_k = L_kk^-1 for every 16 x 16 diagonal block (independent: all half-warps) ------
+  const int nblk = (n + 15) / 16;
+  {
+    const int h = lane >> 4, m = lane & 15;
+    double (*Ls)[17] = sm.pre.lst[warp][h];
+    double *idg = sm.pre.linvd[warp][h];
+#pragma unroll 1
+    for (int it = 0; it < (nblk + 15) / 16; ++it) {   // uniform trip count
+      const int kb = 16 * it + 2 * warp + h;
+      const bool live = kb < nblk;
+      const int j0 = kb * 16;
+      __syncwarp();
+      if (live) {
+        // lane m stages column m (rows m..15) of the block
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          double val = (r == m) ? 1.0 : 0.0;
+          if (r >= m && j0 + r < n) val = __ldcg(A + (size_t)(j0 + m) * ld + j0 + r);
+          Ls[r][m] = val;
+          if (r == m) idg[m] = 1.0 / val;   // +inf diagonal (zero pivot) -> 0
+        }
+      }
+      __syncwarp();
+      if (live) {
+        // lane c solves L x = e_c by right-looking substitution in registers
+        double xs[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) xs[r] = (r == m) ? 1.0 : 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          xs[r] *= idg[r];
+#pragma unroll
+          for (int q = r + 1; q < 16; ++q) xs[q] -= Ls[q][r] * xs[r];
+        }
+        double *out = linv + (size_t)kb * 256;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) out[r * 16 + m] = (r >= m) ? xs[r] : 0.0;   // X[r][c = m]
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- backward sweep L^T x = z ------------------------------------------------------------------
+  // blocks of 16 columns from the bottom.  Block [j0, j0+16):
+  //   acc_c = z_c - sum_{r >= j0+16, r <= c+bw} L_rc x_r      (8 warps x 2 columns, shuffle reductions)
+  //   x_c   = sum_{m >= c} X[m][c] acc_m  (X = L_kk^-1)       (every warp redundantly: one barrier per block)
+  constexpr int XR = W + 32;
+  constexpr int NSEG = (W + 31) / 32;
+  constexpr int D = 3;  // register prefetch distance (blocks)
+  double lo0[D][NSEG], lo1[D][NSEG], zc0[D], zc1[D], li[D][8];
+  auto load_block = [&](int kb, double (&l0)[NSEG], double (&l1)[NSEG], double &z0, double &z1, double (&lv)[8]) {
+    const int j0 = kb * 16;
+    const int c0 = j0 + warp, c1 = j0 + warp + 8;
+    const bool ok = kb >= 0;
+#pragma unroll
+    for (int k = 0; k < NSEG; ++k) {
+      const int r = j0 + 16 + lane + 32 * k;
+      l0[k] = (ok && c0 < n && r < n && r - c0 <= bw) ? __ldcg(A + (size_t)c0 * ld + r) : 0.0;
+      l1[k] = (ok && c1 < n && r < n && r - c1 <= bw) ? __ldcg(A + (size_t)c1 * ld + r) : 0.0;
+    }
+    z0 = (ok && lane == 0 && c0 < n) ? __ldcg(A + (size_t)c0 * ld + n) : 0.0;
+    z1 = (ok && lane == 0 && c1 < n) ? __ldcg(A + (size_t)c1 * ld + n) : 0.0;
+    // lane (h, c): X[m][c] for m = 8h .. 8h+7
+    const int h = lane >> 4, c = lane & 15;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lv[q] = ok ? __ldcg(linv + (size_t)kb * 256 + (8 * h + q) * 16 + c) : 0.0;
+  };
+#pragma unroll
+  for (int u = 0; u < D; ++u) load_block(nblk - 1 - u, lo0[u], lo1[u], zc0[u], zc1[u], li[u]);
+#pragma unroll 1
+  for (int kb0 = nblk - 1; kb0 >= 0; kb0 -= D) {
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      const int kb = kb0 - u;
+      if (kb < 0) break;  // uniform
+      const int j0 = kb * 16, bp = kb & 1;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NSEG; ++k) {
+        const int r = j0 + 16 + lane + 32 * k;
+        const double xv = (r < n) ? sm.xr[r % XR] : 0.0;
+        s0 += lo0[u][k] * xv;
+        s1 += lo1[u][k] * xv;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, d);
+        s1 += __shfl_down_sync(0xffffffffu, s1, d);
+      }
+      if (lane == 0) {
+        sm.acc[bp][warp] = zc0[u] - s0;
+        sm.acc[bp][warp + 8] = zc1[u] - s1;
+      }
+      __syncthreads();
+      {
+        const int h = lane >> 4, c = lane & 15;
+        double xa = 0.0, xb = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          xa += li[u][q] * sm.acc[bp][8 * h + q];
+          xb += li[u][q + 1] * sm.acc[bp][8 * h + q + 1];
+        }
+        double xc = xa + xb;
+        xc += __shfl_down_sync(0xffffffffu, xc, 16);
+        if (lane < 16 && j0 + c < n) {
+          sm.xr[(j0 + c) % XR] = xc;          // every warp writes the same value
+          if (warp == 0) x_out[j0 + c] = xc;
+        }
+      }
+      __syncwarp();
+      load_block(kb - D, lo0[u], lo1[u], zc0[u], zc1[u], li[u]);
+    }
+  }
+  if (timing && t == 0) {
+    g_band_dbg[0] = t_factor - t_begin;
+    g_band_dbg[1] = gtime() - t_factor;
+  }
+}
+
+inline bool cholesky_banded_supported(int n, int bw) { return n > 0 && bw + 1 <= kBandMaxW; }
+
+inline bool cholesky_banded_enqueue(double *Saug, int n, int bw, double *x, double *linv, const LmState *st,
+                                    cudaStream_t stream) {
+  static const int timing = getenv("BA_B200_VERBOSE") != nullptr;
+  if (bw + 1 <= 48) k_chol_banded<48><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
+  else if (bw + 1 <= 80) k_chol_banded<80><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
+  else if (bw + 1 <= 112) k_chol_banded<112><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
+  else return false;
+  return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace ba

@@ -1374,7 +1374,9 @@ int ba_finalize(ba_solver *s) {
     s->chol.d_first_tile = s->d_chol_first.p;
     s->chol.d_rows_ptr = s->d_chol_rows_ptr.p;
     if (const char *e = getenv("BA_B200_CHOL_MODE")) s->chol_mode = atoi(e);
-    if (s->chol_mode == 0) s->chol.cluster_size = 0;
+    // BA_B200_CHOL_MODE: -1 auto (banded > cluster > multi-kernel), 0 multi-kernel, 1 cluster, 2 banded
+    if (s->chol_mode == 0) { s->chol.cluster_size = 0; s->chol.banded = false; }
+    if (s->chol_mode == 1) s->chol.banded = false;
   }
   CUDA_TRY(s->d_schur_chunks.upload(schur_chunks, st));
   CUDA_TRY(s->d_tpt_point.upload(tpt_point, st));
@@ -1912,6 +1914,10 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
   if (getenv("BA_B200_VERBOSE")) {
     unsigned long long dbg[8];
     cudaMemcpyFromSymbol(dbg, g_cl_dbg, sizeof(dbg));
+    if (s->chol.banded) {
+      cudaMemcpyFromSymbol(dbg, g_band_dbg, 4 * sizeof(unsigned long long));
+      fprintf(stderr, "[ba_b200] banded ns: factor %llu backward %llu (n=%d bw=%d)\n", dbg[0], dbg[1], s->chol.n, s->chol.bw);
+    } else
     fprintf(stderr, "[ba_b200] cluster ns: diag %llu sync %llu trsm %llu sync %llu syrk %llu sync %llu backward %llu\n", dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5], dbg[6]);
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
