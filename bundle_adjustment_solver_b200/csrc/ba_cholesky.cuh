@@ -26,6 +26,7 @@
 namespace ba {
 
 constexpr int kNB = 64;
+constexpr int kGroup = 4;   // panels per group of the two-level trailing update
 constexpr size_t kCholDiagSmem = (3 * kNB * (kNB + 1) + 3 * kNB + 2) * sizeof(double);
 
 // ---- diagonal block: Cholesky of an nb x nb block + its triangular inverse, one CTA of 1024 --------
@@ -126,55 +127,70 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
   }
 }
 
-// ---- panel: rows below the diagonal block: A[r, k0:k0+nb] <- A[r, k0:k0+nb] Linv^T (64-row tiles)
+// ---- FP64 tensor-core tile product (DMMA, mma.sync.m8n8k4.f64; measured 37.1 TFLOP/s on B200 against 34.2 for
+// DFMA, at 1/8 of the issue slots and 1/5 of the shared-memory reads of a 4x4 register tile) ---------------
+// C(64 x 64) += X^T Y for operands staged in shared memory as X[m][row], Y[m][col] (row stride kLdT = 68:
+// stride = 4 mod 16 makes the 8 x 4 fragment reads conflict-free).  8 warps; warp w owns rows 16 (w % 4) + [0,16)
+// and columns 32 (w / 4) + [0,32): 2 x 4 DMMA tiles, accumulators acc[i][j][2] in the m8n8 C layout
+// (lane l: row l / 4, columns 2 (l % 4) + {0, 1}).
+constexpr int kLdT = 68;
+constexpr int kKH = 32;   // K staged per pass
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void tile_mac_dmma(const double (*X)[kLdT], const double (*Y)[kLdT], double (&acc)[2][4][2]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int rbase = 16 * (w & 3) + (lane >> 2), cbase = 32 * (w >> 2) + (lane >> 2), kq = lane & 3;
+#pragma unroll
+  for (int m0 = 0; m0 < kKH; m0 += 4) {
+    double a[2], b[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a[i] = X[m0 + kq][rbase + 8 * i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Y[m0 + kq][cbase + 8 * j];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// ---- panel: rows below the diagonal block: A[r, k0:k0+nb] <- A[r, k0:k0+nb] Linv^T (64-row tiles, DMMA)
 __global__ void __launch_bounds__(256) k_chol_trsm(double *__restrict__ A, int ld, int n_rows, int k0, int nb,
                                                    const double *__restrict__ Linv,
                                                    const int *__restrict__ row_tiles, const LmState *st) {
   if (st->done) return;
-  constexpr int KH = 32;
-  __shared__ double At[KH][64 + 1];   // [m][row]   panel entries A[row][k0+m]
-  __shared__ double Lt[KH][64 + 1];   // [m][col]   Linv[col][m]
+  __shared__ double At[kKH][kLdT];   // [m][row]   panel entries A[row][k0+m]
+  __shared__ double Lt[kKH][kLdT];   // [m][col]   Linv[col][m]
   const int r0 = row_tiles[blockIdx.x] * 64;  // tile rows inside the envelope of this panel
-  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
-  double acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int mh = 0; mh < kNB; mh += KH) {
+  double acc[2][4][2] = {};
+  for (int mh = 0; mh < kNB; mh += kKH) {
     __syncthreads();
-    for (int e = threadIdx.x; e < KH * 64; e += 256) {
+    for (int e = threadIdx.x; e < kKH * 64; e += 256) {
       const int i = e % 64, m = mh + e / 64;
       const int rr = r0 + i;
       At[e / 64][i] = (m < nb && rr < n_rows) ? A[(size_t)(k0 + m) * ld + rr] : 0.0;
     }
-    for (int e = threadIdx.x; e < KH * 64; e += 256) {
-      const int m = mh + e % KH, c = e / KH;
-      Lt[e % KH][c] = Linv[c * kNB + m];  // X[c][m], zero for m > c
+    for (int e = threadIdx.x; e < kKH * 64; e += 256) {
+      const int m = mh + e % kKH, c = e / kKH;
+      Lt[e % kKH][c] = Linv[c * kNB + m];  // X[c][m], zero for m > c
     }
     __syncthreads();
-#pragma unroll 8
-    for (int m = 0; m < KH; ++m) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = At[m][tx + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Lt[m][ty + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
+    tile_mac_dmma(At, Lt, acc);
   }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = ty + 16 * j;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = r0 + tx + 16 * i;
-      if (rr < n_rows && c < nb) A[(size_t)(k0 + c) * ld + rr] = acc[i][j];
-    }
-  }
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int rr = r0 + 16 * (w & 3) + 8 * i + (lane >> 2);
+        const int c = 32 * (w >> 2) + 8 * j + 2 * (lane & 3) + e;
+        if (rr < n_rows && c < nb) A[(size_t)(k0 + c) * ld + rr] = acc[i][j][e];
+      }
 }
 
 // ---- rhs row when it shares the (partial) last diagonal tile: z_k = rhs_k L_kk^-T for that tile ---
@@ -191,58 +207,52 @@ __global__ void __launch_bounds__(64) k_chol_trsm_tail(double *__restrict__ A, i
 }
 
 // ---- trailing update: A[r, c] -= sum_m P[r, m] P[c, m], r >= c, both in (k0+nb, n_rows) ------
-// 64 x 64 output tile per CTA, 256 threads, 4 x 4 per thread, K = nb <= 64 staged in smem.
+// 64 x 64 output tile per CTA, 8 warps of DMMA (2 x 4 m8n8k4 tiles per warp), K = nb <= 64 staged in halves.
+// n_cols == 0: blockIdx.x enumerates the pairs (ia >= ib) of row_tiles (triangular); n_cols > 0: rectangular,
+// rows x the first n_cols entries of the same list (two-level blocking: the columns inside a panel group).
+// K = nb may span several panels (k0 = first column of the group).
 __global__ void __launch_bounds__(256) k_syrk_update(double *__restrict__ A, int ld, int n_rows, int k0,
-                                                     int nb, const int *__restrict__ row_tiles,
+                                                     int nb, const int *__restrict__ row_tiles, int n_cols,
                                                      const LmState *st) {
   if (st->done) return;
-  // blockIdx.x enumerates pairs (ia >= ib) of the panel's envelope row tiles
-  int ia = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
-  while (ia * (ia + 1) / 2 > (int)blockIdx.x) --ia;
-  while ((ia + 1) * (ia + 2) / 2 <= (int)blockIdx.x) ++ia;
-  const int ib = blockIdx.x - ia * (ia + 1) / 2;
+  int ia, ib;
+  if (n_cols > 0) {
+    ia = blockIdx.x / n_cols;
+    ib = blockIdx.x - ia * n_cols;
+    if (ia < ib) return;
+  } else {
+    ia = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+    while (ia * (ia + 1) / 2 > (int)blockIdx.x) --ia;
+    while ((ia + 1) * (ia + 2) / 2 <= (int)blockIdx.x) ++ia;
+    ib = blockIdx.x - ia * (ia + 1) / 2;
+  }
   const int tr = row_tiles[ia], tc = row_tiles[ib];
-  constexpr int KH = 32;                // K staged in halves to stay under the 48 KB static limit
-  __shared__ double Pr[KH][64 + 1];     // [m][row]
-  __shared__ double Pc[KH][64 + 1];     // [m][col]
+  __shared__ double Pr[kKH][kLdT];     // [m][row]
+  __shared__ double Pc[kKH][kLdT];     // [m][col]
   const int r0 = tr * 64, c0 = tc * 64;
-  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
-  double acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int mh = 0; mh < nb; mh += KH) {
+  double acc[2][4][2] = {};
+  for (int mh = 0; mh < nb; mh += kKH) {
     __syncthreads();
-    for (int e = threadIdx.x; e < KH * 64; e += 256) {
+    for (int e = threadIdx.x; e < kKH * 64; e += 256) {
       const int i = e % 64, m = mh + e / 64;
       const int rr = r0 + i, cc = c0 + i;
       Pr[e / 64][i] = (m < nb && rr < n_rows) ? A[(size_t)(k0 + m) * ld + rr] : 0.0;
       Pc[e / 64][i] = (m < nb && cc < n_rows) ? A[(size_t)(k0 + m) * ld + cc] : 0.0;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int m = 0; m < KH; ++m) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Pr[m][tx + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Pc[m][ty + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
+    tile_mac_dmma(Pr, Pc, acc);
   }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int cc = c0 + ty + 16 * j;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = r0 + tx + 16 * i;
-      if (rr < n_rows && cc < n_rows - 1 && rr >= cc) A[(size_t)cc * ld + rr] -= acc[i][j];
-    }
-  }
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int rr = r0 + 16 * (w & 3) + 8 * i + (lane >> 2);
+        const int cc = c0 + 32 * (w >> 2) + 8 * j + 2 * (lane & 3) + e;
+        if (rr < n_rows && cc < n_rows - 1 && rr >= cc) A[(size_t)cc * ld + rr] -= acc[i][j][e];
+      }
 }
 
 // ---- backward substitution L^T x = z, z = row n of the factor; single CTA, 1024 threads ---------
@@ -305,6 +315,67 @@ __global__ void __launch_bounds__(1024) k_backward_solve(const double *__restric
   }
 }
 
+// ---- backward substitution for LARGE systems: one launch per 64-block from the bottom, many CTAs ---------
+// Every CTA recomputes x_k = Linv_k^T z_k (64 x 64 mat-vec, L2-resident operands) and then applies its share of
+// z[c] -= sum_r L[k0 + r][c] x_k[r] for the columns c < k0 inside the envelope (a warp takes 4 columns per trip,
+// lanes over the 64 contiguous rows of a column).  CTA 0 stores x_k.  z lives in zbuf (initialised from row n
+// of the factor by k_backward_init).
+constexpr int kBwdColsPerCta = 64;
+__global__ void __launch_bounds__(256) k_backward_init(const double *__restrict__ A, int ld, int n,
+                                                       double *__restrict__ zbuf, const LmState *st) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) zbuf[i] = A[(size_t)i * ld + n];
+}
+__global__ void __launch_bounds__(256) k_backward_block(const double *__restrict__ A, int ld, int n, int kb,
+                                                        const double *__restrict__ Linv_all, int cbeg,
+                                                        double *__restrict__ x_out, double *zbuf,
+                                                        const LmState *st) {
+  if (st->done) return;
+  __shared__ double zk[kNB];
+  __shared__ double xk[kNB];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int k0 = kb * kNB, nb = min(kNB, n - k0);
+  const double *Xi = Linv_all + (size_t)kb * kNB * kNB;  // row-major X = L_kk^-1 (lower)
+  if (t < kNB) zk[t] = (t < nb) ? zbuf[k0 + t] : 0.0;
+  __syncthreads();
+  // x_k[c] = sum_{r >= c} X[r][c] z_k[r]; 8 warps x 8 columns, lanes over r
+  for (int c = warp; c < kNB; c += 8) {
+    double acc = 0.0;
+    for (int r = c + lane; r < kNB; r += 32) acc += Xi[r * kNB + c] * zk[r];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (lane == 0) xk[c] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && t < nb) x_out[k0 + t] = xk[t];
+  const double xa = xk[lane], xb = xk[lane + 32];
+  const int c_lo = cbeg + blockIdx.x * kBwdColsPerCta;
+  const int c_hi = min(k0, c_lo + kBwdColsPerCta);
+  for (int c = c_lo + warp * 4; c < c_hi; c += 8 * 4) {
+    double acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int cc = c + u;
+      double a0 = 0.0, a1 = 0.0;
+      if (cc < c_hi) {
+        const double *col = A + (size_t)cc * ld + k0;
+        a0 = (lane < nb) ? col[lane] : 0.0;
+        a1 = (lane + 32 < nb) ? col[lane + 32] : 0.0;
+      }
+      acc[u] = a0 * xa + a1 * xb;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __shfl_down_sync(0xffffffffu, acc[u], d);
+    if (lane == 0)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + u < c_hi) zbuf[c + u] -= acc[u];
+  }
+}
+
 // Tile-level row envelope (skyline) of S: Cholesky creates no fill left of a row's first non-zero, so
 // tiles (r, c) with c < first_tile[r] stay zero and are skipped by TRSM / SYRK / the backward sweep.
 // For a dense S (every pose co-visible with every other) first_tile is all zeros and nothing is skipped.
@@ -316,6 +387,11 @@ struct CholeskyPlan {
   double dense_fraction = 1.0;
   int max_rows = 0;       // largest number of envelope row tiles under any panel
   int cluster_size = 0;   // > 0: run the single-launch cluster kernel (small / narrow-envelope systems)
+  // two-level blocking (large systems): panels are grouped by kGroup; inside a group the trailing update only
+  // touches the group's own column tiles (narrow_cnt[k] = leading entries of panel k's row list that lie inside
+  // the group); after the group one rank-(64 kGroup) update covers the rest (grp_off/grp_cnt index `rows`)
+  std::vector<int> narrow_cnt, grp_off, grp_cnt;
+  bool two_level = false;
   int bw = 0;             // scalar half-bandwidth of S: 6 (largest pose distance inside a track) + 5
   bool banded = false;    // run the register-window banded kernel (ba_cholesky_banded.cuh)
 };
@@ -345,6 +421,25 @@ inline void cholesky_make_plan(CholeskyPlan &pl, int n, const std::vector<int> &
     used += m * (m + 1) / 2;
   }
   pl.rows_ptr[pl.T] = (int)pl.rows.size();
+  // two-level plan
+  pl.two_level = n > 2048;
+  pl.narrow_cnt.assign(pl.T, 0);
+  pl.grp_off.clear(); pl.grp_cnt.clear();
+  if (pl.two_level) {
+    for (int g0 = 0; g0 < pl.T; g0 += kGroup) {
+      const int g1 = std::min(pl.T, g0 + kGroup);
+      for (int k = g0; k < g1; ++k) {
+        int c = 0;
+        for (int q = pl.rows_ptr[k]; q < pl.rows_ptr[k + 1] && pl.rows[q] < g1; ++q) ++c;
+        pl.narrow_cnt[k] = c;
+      }
+      pl.grp_off.push_back((int)pl.rows.size());
+      int cnt = 0;
+      for (int r = g1; r < pl.T; ++r)
+        if (pl.first_tile[r] < g1) { pl.rows.push_back(r); ++cnt; }
+      pl.grp_cnt.push_back(cnt);
+    }
+  }
   pl.max_rows = 0;
   for (int k = 0; k < pl.T; ++k) pl.max_rows = std::max(pl.max_rows, pl.rows_ptr[k + 1] - pl.rows_ptr[k]);
   // cluster path: every panel's tile jobs fit a few rounds of a <=16-CTA cluster
@@ -405,13 +500,38 @@ inline void cholesky_solve_enqueue(const CholeskyPlan &pl, double *Saug, double 
     if (m > 0) {
       const int *rows = pl.d_rows + pl.rows_ptr[kb];
       if (parts & 2) k_chol_trsm<<<m, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, Li, rows, st);
-      if (parts & 4) k_syrk_update<<<m * (m + 1) / 2, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, rows, st);
+      if (parts & 4) {
+        if (!pl.two_level) {
+          k_syrk_update<<<m * (m + 1) / 2, 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, rows, 0, st);
+        } else if (pl.narrow_cnt[kb] > 0) {
+          k_syrk_update<<<m * pl.narrow_cnt[kb], 256, 0, stream>>>(Saug, ld, n_rows, k0, nb, rows, pl.narrow_cnt[kb], st);
+        }
+      }
       if (launches) *launches += ((parts >> 1) & 1) + ((parts >> 2) & 1);
+    }
+    if (pl.two_level && (parts & 4) && ((kb + 1) % kGroup == 0 || k0 + kNB >= n)) {
+      const int g = kb / kGroup, mg = pl.grp_cnt[g];
+      if (mg > 0) {
+        const int kg0 = g * kGroup * kNB, kw = std::min(n, (kb + 1) * kNB) - kg0;
+        k_syrk_update<<<mg * (mg + 1) / 2, 256, 0, stream>>>(Saug, ld, n_rows, kg0, kw, pl.d_rows + pl.grp_off[g], 0, st);
+        if (launches) *launches += 1;
+      }
     }
   }
   if (parts & 8) {
-    k_backward_solve<<<1, 1024, 0, stream>>>(Saug, ld, n, linv, pl.d_first_tile, x, zbuf, st);
-    if (launches) *launches += 1;
+    if (n <= 2048) {
+      k_backward_solve<<<1, 1024, 0, stream>>>(Saug, ld, n, linv, pl.d_first_tile, x, zbuf, st);
+      if (launches) *launches += 1;
+    } else {
+      k_backward_init<<<(n + 255) / 256, 256, 0, stream>>>(Saug, ld, n, zbuf, st);
+      const int nblk = (n + kNB - 1) / kNB;
+      for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k0 = kb * kNB, cbeg = std::min(k0, pl.first_tile[kb] * kNB);
+        const int grid = std::max(1, (k0 - cbeg + kBwdColsPerCta - 1) / kBwdColsPerCta);
+        k_backward_block<<<grid, 256, 0, stream>>>(Saug, ld, n, kb, linv, cbeg, x, zbuf, st);
+      }
+      if (launches) *launches += 1 + nblk;
+    }
   }
 }
 
