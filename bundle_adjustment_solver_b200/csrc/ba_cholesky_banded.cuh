@@ -79,6 +79,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 
 __device__ unsigned long long g_band_dbg[4];
 
+__device__ __forceinline__ void dmma_884b(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
 // value of S(r, c) (r >= c) for the window, or the identity padding outside the matrix / zero outside the band
 __device__ __forceinline__ double band_load(const double *A, int ld, int n, int bw, int r, int c) {
   if (r >= n) return (r == c) ? 1.0 : 0.0;
@@ -87,6 +93,126 @@ __device__ __forceinline__ double band_load(const double *A, int ld, int n, int 
 }
 __device__ __forceinline__ double band_load_sym(const double *A, int ld, int n, int bw, int r, int c) {
   return r >= c ? band_load(A, ld, n, bw, r, c) : band_load(A, ld, n, bw, c, r);
+}
+
+// ---- backward sweep (shared by the banded kernels); runs on the first 256 threads of the CTA, named barrier 1
+template <int W, typename SM>
+__device__ __forceinline__ void band_backward(double *A, int n, int bw, double *x_out, double *linv, SM &sm) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int ld = n + 1;
+  // ---- inverse pre-pass: X_k = L_kk^-1 for every 16 x 16 diagonal block (independent: all half-warps) ------
+  const int nblk = (n + 15) / 16;
+  {
+    const int h = lane >> 4, m = lane & 15;
+    double (*Ls)[17] = sm.pre.lst[warp][h];
+    double *idg = sm.pre.linvd[warp][h];
+#pragma unroll 1
+    for (int it = 0; it < (nblk + 15) / 16; ++it) {   // uniform trip count
+      const int kb = 16 * it + 2 * warp + h;
+      const bool live = kb < nblk;
+      const int j0 = kb * 16;
+      __syncwarp();
+      if (live) {
+        // lane m stages column m (rows m..15) of the block
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          double val = (r == m) ? 1.0 : 0.0;
+          if (r >= m && j0 + r < n) val = __ldcg(A + (size_t)(j0 + m) * ld + j0 + r);
+          Ls[r][m] = val;
+          if (r == m) idg[m] = 1.0 / val;   // +inf diagonal (zero pivot) -> 0
+        }
+      }
+      __syncwarp();
+      if (live) {
+        // lane c solves L x = e_c by right-looking substitution in registers
+        double xs[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) xs[r] = (r == m) ? 1.0 : 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          xs[r] *= idg[r];
+#pragma unroll
+          for (int q = r + 1; q < 16; ++q) xs[q] -= Ls[q][r] * xs[r];
+        }
+        double *out = linv + (size_t)kb * 256;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) out[r * 16 + m] = (r >= m) ? xs[r] : 0.0;   // X[r][c = m]
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+
+  // ---- backward sweep L^T x = z ------------------------------------------------------------------
+  // blocks of 16 columns from the bottom.  Block [j0, j0+16):
+  //   acc_c = z_c - sum_{r >= j0+16, r <= c+bw} L_rc x_r      (8 warps x 2 columns, shuffle reductions)
+  //   x_c   = sum_{m >= c} X[m][c] acc_m  (X = L_kk^-1)       (every warp redundantly: one barrier per block)
+  constexpr int XR = W + 32;
+  constexpr int NSEG = (W + 31) / 32;
+  constexpr int D = 3;  // register prefetch distance (blocks)
+  double lo0[D][NSEG], lo1[D][NSEG], zc0[D], zc1[D], li[D][8];
+  auto load_block = [&](int kb, double (&l0)[NSEG], double (&l1)[NSEG], double &z0, double &z1, double (&lv)[8]) {
+    const int j0 = kb * 16;
+    const int c0 = j0 + warp, c1 = j0 + warp + 8;
+    const bool ok = kb >= 0;
+#pragma unroll
+    for (int k = 0; k < NSEG; ++k) {
+      const int r = j0 + 16 + lane + 32 * k;
+      l0[k] = (ok && c0 < n && r < n && r - c0 <= bw) ? __ldcg(A + (size_t)c0 * ld + r) : 0.0;
+      l1[k] = (ok && c1 < n && r < n && r - c1 <= bw) ? __ldcg(A + (size_t)c1 * ld + r) : 0.0;
+    }
+    z0 = (ok && lane == 0 && c0 < n) ? __ldcg(A + (size_t)c0 * ld + n) : 0.0;
+    z1 = (ok && lane == 0 && c1 < n) ? __ldcg(A + (size_t)c1 * ld + n) : 0.0;
+    // lane (h, c): X[m][c] for m = 8h .. 8h+7
+    const int h = lane >> 4, c = lane & 15;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lv[q] = ok ? __ldcg(linv + (size_t)kb * 256 + (8 * h + q) * 16 + c) : 0.0;
+  };
+#pragma unroll
+  for (int u = 0; u < D; ++u) load_block(nblk - 1 - u, lo0[u], lo1[u], zc0[u], zc1[u], li[u]);
+#pragma unroll 1
+  for (int kb0 = nblk - 1; kb0 >= 0; kb0 -= D) {
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+      const int kb = kb0 - u;
+      if (kb < 0) break;  // uniform
+      const int j0 = kb * 16, bp = kb & 1;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NSEG; ++k) {
+        const int r = j0 + 16 + lane + 32 * k;
+        const double xv = (r < n) ? sm.xr[r % XR] : 0.0;
+        s0 += lo0[u][k] * xv;
+        s1 += lo1[u][k] * xv;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, d);
+        s1 += __shfl_down_sync(0xffffffffu, s1, d);
+      }
+      if (lane == 0) {
+        sm.acc[bp][warp] = zc0[u] - s0;
+        sm.acc[bp][warp + 8] = zc1[u] - s1;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        const int h = lane >> 4, c = lane & 15;
+        double xa = 0.0, xb = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          xa += li[u][q] * sm.acc[bp][8 * h + q];
+          xb += li[u][q + 1] * sm.acc[bp][8 * h + q + 1];
+        }
+        double xc = xa + xb;
+        xc += __shfl_down_sync(0xffffffffu, xc, 16);
+        if (lane < 16 && j0 + c < n) {
+          sm.xr[(j0 + c) % XR] = xc;          // every warp writes the same value
+          if (warp == 0) x_out[j0 + c] = xc;
+        }
+      }
+      __syncwarp();
+      load_block(kb - D, lo0[u], lo1[u], zc0[u], zc1[u], li[u]);
+    }
+  }
 }
 
 // Frame of group G (steps j = 16G .. 16G+15): slot (a, b) of thread (ty, tx) holds the window element
@@ -264,130 +390,303 @@ k_chol_banded(double *A, int n, int bw, double *x_out, double *linv, int timing,
   unsigned long long t_factor = 0;
   if (timing) t_factor = gtime();
 
-  // ---- inverse pre-pass: X_k = L_kk^-1 for every 16 x 16 diagonal block (independent: all half-warps) ------
-  const int nblk = (n + 15) / 16;
-  {
-    const int h = lane >> 4, m = lane & 15;
-    double (*Ls)[17] = sm.pre.lst[warp][h];
-    double *idg = sm.pre.linvd[warp][h];
-#pragma unroll 1
-    for (int it = 0; it < (nblk + 15) / 16; ++it) {   // uniform trip count
-      const int kb = 16 * it + 2 * warp + h;
-      const bool live = kb < nblk;
-      const int j0 = kb * 16;
-      __syncwarp();
-      if (live) {
-        // lane m stages column m (rows m..15) of the block
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          double val = (r == m) ? 1.0 : 0.0;
-          if (r >= m && j0 + r < n) val = __ldcg(A + (size_t)(j0 + m) * ld + j0 + r);
-          Ls[r][m] = val;
-          if (r == m) idg[m] = 1.0 / val;   // +inf diagonal (zero pivot) -> 0
-        }
-      }
-      __syncwarp();
-      if (live) {
-        // lane c solves L x = e_c by right-looking substitution in registers
-        double xs[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) xs[r] = (r == m) ? 1.0 : 0.0;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          xs[r] *= idg[r];
-#pragma unroll
-          for (int q = r + 1; q < 16; ++q) xs[q] -= Ls[q][r] * xs[r];
-        }
-        double *out = linv + (size_t)kb * 256;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) out[r * 16 + m] = (r >= m) ? xs[r] : 0.0;   // X[r][c = m]
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- backward sweep L^T x = z ------------------------------------------------------------------
-  // blocks of 16 columns from the bottom.  Block [j0, j0+16):
-  //   acc_c = z_c - sum_{r >= j0+16, r <= c+bw} L_rc x_r      (8 warps x 2 columns, shuffle reductions)
-  //   x_c   = sum_{m >= c} X[m][c] acc_m  (X = L_kk^-1)       (every warp redundantly: one barrier per block)
-  constexpr int XR = W + 32;
-  constexpr int NSEG = (W + 31) / 32;
-  constexpr int D = 3;  // register prefetch distance (blocks)
-  double lo0[D][NSEG], lo1[D][NSEG], zc0[D], zc1[D], li[D][8];
-  auto load_block = [&](int kb, double (&l0)[NSEG], double (&l1)[NSEG], double &z0, double &z1, double (&lv)[8]) {
-    const int j0 = kb * 16;
-    const int c0 = j0 + warp, c1 = j0 + warp + 8;
-    const bool ok = kb >= 0;
-#pragma unroll
-    for (int k = 0; k < NSEG; ++k) {
-      const int r = j0 + 16 + lane + 32 * k;
-      l0[k] = (ok && c0 < n && r < n && r - c0 <= bw) ? __ldcg(A + (size_t)c0 * ld + r) : 0.0;
-      l1[k] = (ok && c1 < n && r < n && r - c1 <= bw) ? __ldcg(A + (size_t)c1 * ld + r) : 0.0;
-    }
-    z0 = (ok && lane == 0 && c0 < n) ? __ldcg(A + (size_t)c0 * ld + n) : 0.0;
-    z1 = (ok && lane == 0 && c1 < n) ? __ldcg(A + (size_t)c1 * ld + n) : 0.0;
-    // lane (h, c): X[m][c] for m = 8h .. 8h+7
-    const int h = lane >> 4, c = lane & 15;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) lv[q] = ok ? __ldcg(linv + (size_t)kb * 256 + (8 * h + q) * 16 + c) : 0.0;
-  };
-#pragma unroll
-  for (int u = 0; u < D; ++u) load_block(nblk - 1 - u, lo0[u], lo1[u], zc0[u], zc1[u], li[u]);
-#pragma unroll 1
-  for (int kb0 = nblk - 1; kb0 >= 0; kb0 -= D) {
-#pragma unroll
-    for (int u = 0; u < D; ++u) {
-      const int kb = kb0 - u;
-      if (kb < 0) break;  // uniform
-      const int j0 = kb * 16, bp = kb & 1;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int k = 0; k < NSEG; ++k) {
-        const int r = j0 + 16 + lane + 32 * k;
-        const double xv = (r < n) ? sm.xr[r % XR] : 0.0;
-        s0 += lo0[u][k] * xv;
-        s1 += lo1[u][k] * xv;
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        s0 += __shfl_down_sync(0xffffffffu, s0, d);
-        s1 += __shfl_down_sync(0xffffffffu, s1, d);
-      }
-      if (lane == 0) {
-        sm.acc[bp][warp] = zc0[u] - s0;
-        sm.acc[bp][warp + 8] = zc1[u] - s1;
-      }
-      __syncthreads();
-      {
-        const int h = lane >> 4, c = lane & 15;
-        double xa = 0.0, xb = 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; q += 2) {
-          xa += li[u][q] * sm.acc[bp][8 * h + q];
-          xb += li[u][q + 1] * sm.acc[bp][8 * h + q + 1];
-        }
-        double xc = xa + xb;
-        xc += __shfl_down_sync(0xffffffffu, xc, 16);
-        if (lane < 16 && j0 + c < n) {
-          sm.xr[(j0 + c) % XR] = xc;          // every warp writes the same value
-          if (warp == 0) x_out[j0 + c] = xc;
-        }
-      }
-      __syncwarp();
-      load_block(kb - D, lo0[u], lo1[u], zc0[u], zc1[u], li[u]);
-    }
-  }
+  band_backward<W>(A, n, bw, x_out, linv, sm);
   if (timing && t == 0) {
     g_band_dbg[0] = t_factor - t_begin;
     g_band_dbg[1] = gtime() - t_factor;
   }
 }
 
-inline bool cholesky_banded_supported(int n, int bw) { return n > 0 && bw + 1 <= kBandMaxW; }
+// =====================================================================================================
+// v3: 8-column block steps, FP64 tensor-core (DMMA) window update, dedicated panel warp.
+//
+// The chain of a blocked factorisation is one PANEL (8 columns) long per step instead of one column: a single
+// producer warp factors the 8 x 8 diagonal block redundantly in the registers of every lane (no shuffles, no
+// barriers inside the 8-pivot chain) and applies the triangular solve to the panel rows its lanes own, while
+// eight consumer warps keep the W x W window as m8n8 DMMA accumulator tiles (one of each symmetric pair, by
+// ring slot) and apply the rank-8 update with two mma.sync.m8n8k4.f64 per tile.  Hand-off through shared
+// memory and two pairs of mbarriers: consumers publish the NEXT panel (raw, after its priority update) before
+// they touch the rest of the window, so the producer's chain overlaps the bulk of the update.
+//   ring slot X holds absolute 8-row tile I with I = X (mod NT); slot s mod NT retires at step s and is
+//   recycled for tile s + NT (original S values, prefetched during the previous step).  Requires W >= bw + 8.
+// =====================================================================================================
+constexpr int kBand3Threads = 288;  // 8 consumer warps + 1 producer warp
+
+template <int W>
+struct Band3Smem {
+  union {
+    struct {
+      double raw[2][W + 1][8];    // published raw panel by ring position; row W = rhs entries z
+      double Lp[2][W + 1][12];    // factored panel (row stride 12: conflict-free 8 x 4 fragment reads)
+    } f;
+    struct {
+      double lst[8][2][16][17];
+      double linvd[8][2][16];
+    } pre;
+  };
+  double xr[W + 32];
+  double acc[2][16];
+  unsigned long long bar_raw[2], bar_L[2];
+};
+
+// reciprocal square root off the slow libm path: hardware approximation (2^-22) + two Newton steps
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kBand3Threads, 1)
+k_chol_banded_dmma(double *A, int n, int bw, double *x_out, double *linv, int timing, const LmState *st) {
+  if (st->done) return;
+  constexpr int NT = W / 8;
+  constexpr int NTILES = NT * (NT + 1) / 2;
+  constexpr int TPW = (NTILES + 7) / 8;        // tiles per consumer warp
+  constexpr int NSL = (W + 1 + 31) / 32;       // panel rows per producer lane
+  __shared__ Band3Smem<W> sm;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int ld = n + 1;
+  const int nsteps = (n + 7) / 8;
+  unsigned long long t_begin = 0;
+  if (timing) t_begin = gtime();
+  if (t == 0) {
+    mbar_init(&sm.bar_raw[0], 8); mbar_init(&sm.bar_raw[1], 8);
+    mbar_init(&sm.bar_L[0], 1);   mbar_init(&sm.bar_L[1], 1);
+  }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ------------------------------------------------ producer: panel factorisation ----------------
+    // Unscaled right-looking elimination (a_rc -= a_rk a_ck / d_k): the pivot chain needs one reciprocal per
+    // column; the square-root scaling L = A D^-1/2 is applied at the end, off the chain.
+    int P = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      const int par = s & 1;
+      mbar_wait(&sm.bar_raw[par], (s >> 1) & 1);
+      double a[NSL][8];
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        const int pos = lane + 32 * sl;
+        const double4 *src = reinterpret_cast<const double4 *>(&sm.f.raw[par][pos <= W ? pos : W][0]);
+        const double4 v0 = src[0], v1 = src[1];
+        a[sl][0] = v0.x; a[sl][1] = v0.y; a[sl][2] = v0.z; a[sl][3] = v0.w;
+        a[sl][4] = v1.x; a[sl][5] = v1.y; a[sl][6] = v1.z; a[sl][7] = v1.w;
+      }
+      double D[8][8], rs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) D[i][j] = sm.f.raw[par][8 * P + i][j];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double d = D[k][k];
+        const bool pos_def = d > 0.0;
+        const double rc = pos_def ? fast_rcp(d) : 0.0;       // non-positive pivot: LDLT's D^+ = 0
+        rs[k] = pos_def ? fast_rsqrt(d) : 0.0;
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) {
+          const double ti = D[i][k] * rc;
+#pragma unroll
+          for (int j = k + 1; j <= i; ++j) D[i][j] -= ti * D[j][k];
+        }
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+          const double u = a[sl][k] * rc;
+#pragma unroll
+          for (int m = k + 1; m < 8; ++m) a[sl][m] -= u * D[m][k];
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        const int pos = lane + 32 * sl;
+        if (pos <= W) {
+          double4 *dst = reinterpret_cast<double4 *>(&sm.f.Lp[par][pos][0]);
+          dst[0] = make_double4(a[sl][0] * rs[0], a[sl][1] * rs[1], a[sl][2] * rs[2], a[sl][3] * rs[3]);
+          dst[1] = make_double4(a[sl][4] * rs[4], a[sl][5] * rs[5], a[sl][6] * rs[6], a[sl][7] * rs[7]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bar_L[par]);
+      P = (P + 1 == NT) ? 0 : P + 1;
+    }
+  } else {
+    // ------------------------------------------------ consumers: window tiles -----------------------
+    const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
+    const int laneL = fr * 12 + kq;      // fragment offset inside an 8-row tile of Lp
+    const int lanePB = fr * 8 + fc;      // publish offset when the tile's column slot is the panel
+    const int lanePA = fc * 8 + fr;      // ... when its row slot is the panel (transposed)
+    int As[TPW], Bs[TPW];
+    double acc[TPW][2], pre[TPW][2];
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+      const int e = warp + 8 * i;   // enumeration of slot pairs As >= Bs
+      int ia = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while (ia * (ia + 1) / 2 > e) --ia;
+      while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
+      const bool live = e < NTILES;
+      As[i] = live ? ia : -1;
+      Bs[i] = live ? e - ia * (ia + 1) / 2 : -1;
+      acc[i][0] = acc[i][1] = pre[i][0] = pre[i][1] = 0.0;
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) acc[i][q] = band_load_sym(A, ld, n, bw, 8 * As[i] + fr, 8 * Bs[i] + fc + q);
+      }
+    }
+    double zv = (t < W && t < n) ? __ldcg(A + (size_t)t * ld + n) : 0.0, zpre = 0.0;
+    // loads for the tiles that ring slot X takes over when it retires at step sr (new absolute tile sr + NT;
+    // the other slot Y of a tile then holds tile sr + 1 + ((Y - X - 1) mod NT)); zero outside band / matrix
+    auto prefetch = [&](int X, int sr) {
+      const int Inew = sr + NT;
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        const bool tA = As[i] == X, tB = Bs[i] == X;
+        if (!(tA || tB)) continue;
+        const int Y = tA ? Bs[i] : As[i];
+        int d = Y - X - 1;
+        if (d < 0) d += NT;
+        const int Iy = (Y == X) ? Inew : sr + 1 + d;
+        const int r = 8 * (tA ? Inew : Iy) + fr, c0 = 8 * (tA ? Iy : Inew) + fc;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = c0 + q;
+          const int lo = min(r, c), hi = max(r, c);
+          pre[i][q] = (hi < n && hi - lo <= bw) ? __ldcg(A + (size_t)lo * ld + hi) : 0.0;
+        }
+      }
+      if (t >= 8 * X && t < 8 * X + 8) {
+        const int zc = 8 * Inew + (t - 8 * X);
+        zpre = (zc < n) ? __ldcg(A + (size_t)zc * ld + n) : 0.0;
+      }
+    };
+    // first panel
+#pragma unroll
+    for (int i = 0; i < TPW; ++i)
+      if (Bs[i] == 0) {
+        sm.f.raw[0][0][As[i] * 64 + lanePB] = acc[i][0];
+        sm.f.raw[0][0][As[i] * 64 + lanePB + 1] = acc[i][1];
+      }
+    if (t < 8) sm.f.raw[0][W][t] = zv;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.bar_raw[0]);
+    prefetch(0, 0);
+
+    int P = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      const int par = s & 1;
+      const int Pn = (P + 1 == NT) ? 0 : P + 1;
+      const double *Lp = &sm.f.Lp[par][0][0];
+      double *rawn = &sm.f.raw[par ^ 1][0][0];
+      mbar_wait(&sm.bar_L[par], (s >> 1) & 1);
+      const bool z_retire = (t >= 8 * P && t < 8 * P + 8);
+      const bool z_next = (t >= 8 * Pn && t < 8 * Pn + 8);
+      auto update_z = [&]() {
+        if (t < W) {
+          if (z_retire) zv = zpre;
+          else {
+            const double4 *lz = reinterpret_cast<const double4 *>(Lp + W * 12);
+            const double4 *lt = reinterpret_cast<const double4 *>(Lp + t * 12);
+            const double4 z0 = lz[0], z1 = lz[1], l0 = lt[0], l1 = lt[1];
+            zv -= z0.x * l0.x + z0.y * l0.y + z0.z * l0.z + z0.w * l0.w + z1.x * l1.x + z1.y * l1.y + z1.z * l1.z + z1.w * l1.w;
+          }
+        }
+      };
+      // priority: everything the next panel needs, published before the bulk
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        const bool nA = As[i] == Pn, nB = Bs[i] == Pn;
+        if (nA || nB) {
+          if (As[i] == P || Bs[i] == P) {
+            acc[i][0] = pre[i][0];
+            acc[i][1] = pre[i][1];
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              dmma_884b(acc[i][0], acc[i][1], -Lp[As[i] * 96 + laneL + 4 * h], Lp[Bs[i] * 96 + laneL + 4 * h]);
+          }
+          if (nB) {
+            rawn[As[i] * 64 + lanePB] = acc[i][0];
+            rawn[As[i] * 64 + lanePB + 1] = acc[i][1];
+          } else {
+            rawn[Bs[i] * 64 + lanePA] = acc[i][0];
+            rawn[Bs[i] * 64 + lanePA + 8] = acc[i][1];
+          }
+        }
+      }
+      if (z_next) {
+        update_z();
+        rawn[W * 8 + (t - 8 * Pn)] = zv;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.bar_raw[par ^ 1]);
+      // bulk
+#pragma unroll
+      for (int i = 0; i < TPW; ++i) {
+        if (As[i] < 0 || As[i] == Pn || Bs[i] == Pn) continue;
+        if (As[i] == P || Bs[i] == P) {
+          acc[i][0] = pre[i][0];
+          acc[i][1] = pre[i][1];
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            dmma_884b(acc[i][0], acc[i][1], -Lp[As[i] * 96 + laneL + 4 * h], Lp[Bs[i] * 96 + laneL + 4 * h]);
+        }
+      }
+      if (!z_next) update_z();
+      // finished panel to global memory: warp w writes column w (coalesced over rows)
+      {
+        const int c = 8 * s + warp;
+        if (c < n) {
+          double *col = A + (size_t)c * ld + 8 * s;
+#pragma unroll
+          for (int q = 0; q < (W + 31) / 32; ++q) {
+            const int pos = lane + 32 * q;
+            int rel = pos - 8 * P;
+            if (rel < 0) rel += W;
+            if (pos < W && rel >= warp && rel - warp <= bw && 8 * s + rel < n) {
+              double l = Lp[pos * 12 + warp];
+              if (rel == warp && !(l > 0.0)) l = __longlong_as_double(0x7ff0000000000000LL);
+              col[rel] = l;
+            }
+          }
+          if (lane == 0) A[(size_t)c * ld + n] = Lp[W * 12 + warp];
+        }
+      }
+      // loads for the slot that retires at the next step
+      prefetch(Pn, s + 1);
+      P = Pn;
+    }
+  }
+  __syncthreads();
+  unsigned long long t_factor = 0;
+  if (timing) t_factor = gtime();
+  if (warp < 8) band_backward<W>(A, n, bw, x_out, linv, sm);
+  if (timing && t == 0) {
+    g_band_dbg[0] = t_factor - t_begin;
+    g_band_dbg[1] = gtime() - t_factor;
+  }
+}
+
+inline bool cholesky_banded_supported(int n, int bw) { return n > 0 && bw + 8 <= kBandMaxW; }
 
 inline bool cholesky_banded_enqueue(double *Saug, int n, int bw, double *x, double *linv, const LmState *st,
                                     cudaStream_t stream) {
   static const int timing = getenv("BA_B200_VERBOSE") != nullptr;
+  static const int mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 3;
+  if (mode == 3) {   // DMMA block steps (needs W >= bw + 8)
+    if (bw + 8 <= 48) k_chol_banded_dmma<48><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
+    else if (bw + 8 <= 80) k_chol_banded_dmma<80><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
+    else if (bw + 8 <= 112) k_chol_banded_dmma<112><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
+    else return false;
+    return cudaGetLastError() == cudaSuccess;
+  }
   if (bw + 1 <= 48) k_chol_banded<48><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
   else if (bw + 1 <= 80) k_chol_banded<80><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
   else if (bw + 1 <= 112) k_chol_banded<112><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
