@@ -155,9 +155,12 @@ __device__ __forceinline__ void ldlt3_inverse(const double *c, double *inv) {
   if (fabs(a22) > best) { p0 = 2; }
   if (p0 == 1) { swapd(a00, a11); swapd(a20, a21); }
   else if (p0 == 2) { swapd(a00, a22); swapd(a10, a21); }
+  // one reciprocal per pivot instead of twelve divisions (differs from a true division by <= 1 ulp)
+  const double tol = 2.2250738585072014e-308;
   const double d0 = a00;
-  double l10 = a10, l20 = a20;
-  if (fabs(d0) > 0.0) { l10 /= d0; l20 /= d0; }
+  const double r0 = (fabs(d0) > 0.0) ? 1.0 / d0 : 1.0;
+  double l10 = a10 * r0, l20 = a20 * r0;
+  if (!(fabs(d0) > 0.0)) { l10 = a10; l20 = a20; }
   // k = 1: compares the not-yet-updated diagonals (Eigen's unblocked kernel is left-looking)
   int p1 = 1;
   if (fabs(a22) > fabs(a11)) p1 = 2;
@@ -165,11 +168,13 @@ __device__ __forceinline__ void ldlt3_inverse(const double *c, double *inv) {
   const double t0 = d0 * l10;
   const double d1 = a11 - l10 * t0;
   double l21 = a21 - l20 * t0;
-  if (fabs(d1) > 0.0) l21 /= d1;
+  const double r1 = (fabs(d1) > 0.0) ? 1.0 / d1 : 1.0;
+  l21 *= r1;
   // k = 2
   const double u0 = d0 * l20, u1 = d1 * l21;
   const double d2 = a22 - (l20 * u0 + l21 * u1);
-  const double tol = 2.2250738585072014e-308;
+  const double r2 = (fabs(d2) > 0.0) ? 1.0 / d2 : 1.0;
+  const double q0 = (fabs(d0) > tol) ? r0 : 0.0, q1 = (fabs(d1) > tol) ? r1 : 0.0, q2 = (fabs(d2) > tol) ? r2 : 0.0;
 #pragma unroll
   for (int col = 0; col < 3; ++col) {
     double v0 = (col == 0) ? 1.0 : 0.0, v1 = (col == 1) ? 1.0 : 0.0, v2 = (col == 2) ? 1.0 : 0.0;
@@ -181,9 +186,9 @@ __device__ __forceinline__ void ldlt3_inverse(const double *c, double *inv) {
     v2 -= l20 * v0;
     v2 -= l21 * v1;
     // D^+
-    v0 = (fabs(d0) > tol) ? v0 / d0 : 0.0;
-    v1 = (fabs(d1) > tol) ? v1 / d1 : 0.0;
-    v2 = (fabs(d2) > tol) ? v2 / d2 : 0.0;
+    v0 *= q0;
+    v1 *= q1;
+    v2 *= q2;
     // L^-T
     v1 -= l21 * v2;
     v0 -= l10 * v1 + l20 * v2;

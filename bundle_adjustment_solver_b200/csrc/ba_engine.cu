@@ -190,14 +190,16 @@ k_linearize_by_point(const Chunk *__restrict__ chunks, const int2 *__restrict__ 
 // Every lane does useful work and consecutive pairs write consecutive slots of the component-major Bsoa.
 template <bool ACCUM_B>
 __global__ void __launch_bounds__(kThreads, ACCUM_B ? 2 : 3)
-k_pair_blocks(int P, const int2 *__restrict__ pair_obs /*first, last observation (point order)*/,
+k_pair_blocks(int n_list, const int *__restrict__ list /*pair indices, or null = identity*/,
+              const int2 *__restrict__ pair_obs /*first, last observation (point order)*/,
               const double2 *__restrict__ obs_uv, const int *__restrict__ obs_pose,
               const int *__restrict__ obs_point, const int *__restrict__ obs_camflags, Params prm,
               const double *__restrict__ cams, double thres_huber, double *__restrict__ Bsoa, size_t Pp,
               const LmState *__restrict__ st) {
   if (st->done) return;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= n_list) return;
+  const int p = list ? list[li] : li;
   const double *poses = prm.poses[st->cur];
   const double *points = prm.points[st->cur];
   const int2 po = pair_obs[p];
@@ -241,11 +243,11 @@ __global__ void k_zero_split(const int *__restrict__ split_points, int n_split, 
 
 // K3: damping + 3x3 LDLT inverse + C^-1 b for every free landmark (one thread each, coalesced SoA rows)
 __global__ void __launch_bounds__(128)
-k_finish_points(int M_total, const uint8_t *__restrict__ point_free, double *__restrict__ ptblk, size_t Mp,
-                const LmState *st) {
+k_finish_points(int M_total, const uint8_t *__restrict__ point_fb /*free landmark on the by-point path*/,
+                double *__restrict__ ptblk, size_t Mp, const LmState *st) {
   if (st->done) return;
   const int pt = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pt >= M_total || !point_free[pt]) return;
+  if (pt >= M_total || !point_fb[pt]) return;
   double c[6], b[3];
   for (int k = 0; k < 6; ++k) c[k] = ptblk[(PB_Cd + k) * Mp + pt];
   for (int k = 0; k < 3; ++k) b[k] = ptblk[(PB_b + k) * Mp + pt];
@@ -345,15 +347,10 @@ __global__ void k_finish_poses(const int *__restrict__ pose_chunk_ptr, const dou
 // ---------------------------------------------------------------------------
 // K4: Schur complement  S -= sum_i E_ji B_ki^T (j<=k), rhs_j -= E_ji b_i, E_ji = B_ji Cinv_i  (:858-888).
 //
-// k_schur_tiles: one CTA per "Schur chunk" = a run of consecutive landmarks whose observing poses all
-// fall inside one window of W consecutive free poses.  The chunk's W x W block tile of S (upper block
-// triangle, W(W+1)/2 blocks) is accumulated in REGISTERS: thread (s1,s2) owns one 6x6 block for the
-// whole chunk and adds E_{s1,i} B_{s2,i}^T for every landmark i that both poses see.  Landmarks are
-// staged eight at a time in shared memory (E and B blocks, transposed so reads are conflict-free /
-// broadcast).  Only the final flush touches global memory: one FP64 red per tile entry per chunk
-// instead of one per landmark.
-// k_schur_pairs_list: fallback for landmarks whose poses do not fit a window (wide baselines, loop
-// closures): one thread per pair, direct FP64 reds.
+// k_build_tiles (below): landmarks whose observing poses fall inside one window of 16 consecutive free poses:
+// linearisation, C^-1 and the Schur products fused, the products as a DMMA GEMM over landmark batches.
+// k_schur_pairs_list: landmarks whose poses do not fit a window (wide baselines, loop closures, dense
+// co-visibility): one thread per pair, direct FP64 reds.
 // ---------------------------------------------------------------------------
 struct SchurChunk {
   int pt_start;   // first index into the tile-eligible landmark list
@@ -362,113 +359,272 @@ struct SchurChunk {
   int width;      // poses actually spanned by the chunk (<= kSchurW): tasks are the width(width+1)/2 pairs
 };
 
-constexpr int kSchurW = 15;                              // window (poses)
-constexpr int kSchurTasks = kSchurW * (kSchurW + 1) / 2; // 120
-constexpr int kSchurThreads = 128;
-constexpr int kSchurPB = 8;                              // landmarks staged per batch
+// ---------------------------------------------------------------------------
+// K1+K3+K4 fused for "tile" landmarks (all free poses of the landmark inside a window of <= 16 poses):
+// one CTA per Schur chunk.  Landmarks are processed in batches of 16:
+//   1. one thread per (pose, landmark) incidence: projection, residual, Huber weight, Rm, Q for its (1..n_cam)
+//      observations -> partial C (6) / b (3), and B = w Q^T Rm of the pair (last inserted observation, or the sum in
+//      corrected mode), written straight into the GEMM operand B_all and to Bsoa (kept for the back-substitution)
+//   2. one thread per landmark: C, b sums, damping, Eigen-style 3x3 LDLT inverse -> ptblk, rhs column of B_all
+//   3. incidence threads: E = B C^-1 -> GEMM operand E_all
+//   4. the chunk's window of S (<= 96 x 96 + rhs column) -= E_all B_all^T on the FP64 tensor cores: the batch's
+//      landmarks are stacked along K (K = 3 x 16), so the per-landmark outer products become ONE dense
+//      mma.sync.m8n8k4 GEMM whose accumulator tiles stay in registers for the whole chunk
+// and flushed once per chunk with FP64 reds into the upper triangle of S / the rhs column.
+// ---------------------------------------------------------------------------
+constexpr int kTileW = 16;          // window (poses)
+constexpr int kTileLB = 16;         // landmarks per batch
+constexpr int kTileK = 3 * kTileLB; // 48
+constexpr int kLdE = 100;           // E_all[k][row]  (96 rows; stride = 4 mod 16: conflict-free fragment reads)
+constexpr int kLdB = 116;           // B_all[k][col]  (96 cols + rhs tile)
+constexpr int kTileMaxInc = 20;     // incidences per landmark (free and fixed poses)
+constexpr int kTileIncCap = kTileLB * kTileMaxInc;
+constexpr int kTileTPW = 23;        // tiles per DMMA warp (12 x 13 upper tiles + 12 rhs tiles over 4 warps)
+constexpr int kRhsTile = 12;
+constexpr int kTileOperand = kTileK * kLdE + kTileK * kLdB;   // doubles per operand buffer
+constexpr size_t kTileSmem = (size_t)(2 * kTileOperand + 9 * kTileIncCap + kTileLB * 24) * sizeof(double);
+constexpr int kTileProd = 256;             // producer threads (8 warps)
+constexpr int kTileCons = 128;             // consumer threads (4 DMMA warps)
+constexpr int kTileThreads = kTileProd + kTileCons;
 
-__global__ void __launch_bounds__(kSchurThreads)
-k_schur_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt_point /*orig point id*/,
-              const int *__restrict__ tpt_pair_start /*[2n]: first, end*/, const int *__restrict__ pair_pose,
-              const double *__restrict__ Bsoa, size_t Pp, const double *__restrict__ ptblk, size_t Mp,
-              double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
+// non-volatile DMMA: ordered by its data dependencies only, so the scheduler may batch the fragment loads
+__device__ __forceinline__ void dmma_884nv(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// 3x3 symmetric inverse (Eigen LDLT semantics) of the damped block, results in registers
+__device__ __forceinline__ void damp_invert(const double *Craw, double lambda, double *cd, double *ci /*6 upper*/) {
+  const double lp1 = 1.0 + lambda;
+  cd[0] = Craw[0] * lp1; cd[1] = Craw[1]; cd[2] = Craw[2]; cd[3] = Craw[3] * lp1; cd[4] = Craw[4]; cd[5] = Craw[5] * lp1;
+  double inv[9];
+  ldlt3_inverse(cd, inv);
+  ci[0] = inv[0]; ci[1] = inv[1]; ci[2] = inv[2]; ci[3] = inv[4]; ci[4] = inv[5]; ci[5] = inv[8];
+}
+
+// Warps 0-7 (producers) linearise batch b + 1 into operand buffer (b + 1) & 1 while warps 8-11 (consumers) run the
+// DMMA GEMM of batch b; named barriers 1,2 = operands full, 3,4 = operands consumed, 5 = producer-internal.
+template <bool ACCUM_B>
+__global__ void __launch_bounds__(kTileThreads, 1)
+k_build_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt_point,
+              const int *__restrict__ tpt_inc_start, const int4 *__restrict__ inc_a /*obs_first, n_obs, pose, pair*/,
+              const int2 *__restrict__ inc_b /*slot (-1: fixed pose), tile landmark index*/,
+              const double2 *__restrict__ obs_uv, const int *__restrict__ obs_camflags, Params prm,
+              const double *__restrict__ cams, double thres_huber, double *__restrict__ Bsoa, size_t Pp,
+              double *__restrict__ ptblk, size_t Mp, double *__restrict__ Saug, int ld,
+              const LmState *__restrict__ st) {
   if (st->done) return;
-  constexpr int W = kSchurW, PB = kSchurPB;
-  __shared__ double Es[PB][18][W + 1];
-  __shared__ double Bs[PB][18][W + 1];
-  __shared__ double bs[PB][4];
-  __shared__ int masks[PB];
+  extern __shared__ double tsm[];
+  double *cpart = tsm + 2 * kTileOperand;                     // [9][kTileIncCap]
+  double *lmk = cpart + 9 * kTileIncCap;                      // [kTileLB][24]: raw sums (9) | Cinv (6) at +12
   const SchurChunk ch = chunks[blockIdx.x];
-  const int t = threadIdx.x;
-  // task -> (s1 <= s2 < width), enumerated column-major (s2 outer): a landmark whose poses are the first L
-  // slots of the window activates exactly the first L(L+1)/2 tasks, i.e. a dense prefix of the lanes, so
-  // warps beyond the prefix skip the landmark entirely and only one warp runs partially filled.
-  const int Wc = ch.width;
-  const int ntasks = Wc * (Wc + 1) / 2;
-  int s1 = -1, s2 = -1;
-  if (t < ntasks) {
-    s2 = 0;
-    int rem = t;
-    while (rem > s2) { rem -= s2 + 1; ++s2; }
-    s1 = rem;
-  }
-  double acc[36];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int n_batches = (ch.pt_count + kTileLB - 1) / kTileLB;
+  const int nrows = 6 * ch.width;
+
+  if (warp < kTileProd / 32) {
+    // ===================================================== producers =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+    const double *poses = prm.poses[st->cur];
+    const double *points = prm.points[st->cur];
+    const double lambda = st->lambda;
+    for (int bt = 0; bt < n_batches; ++bt) {
+      const int buf = bt & 1;
+      double (*Ea)[kLdE] = reinterpret_cast<double (*)[kLdE]>(tsm + buf * kTileOperand);
+      double (*Ba)[kLdB] = reinterpret_cast<double (*)[kLdB]>(tsm + buf * kTileOperand + kTileK * kLdE);
+      const int base = bt * kTileLB;
+      const int nb = min(kTileLB, ch.pt_count - base);
+      const int ti0 = ch.pt_start + base;
+      const int i0 = tpt_inc_start[ti0], ninc = tpt_inc_start[ti0 + nb] - i0;
+      if (bt >= 2) bar_sync(3 + buf, kTileThreads);   // consumers are done with this buffer
+      {
+        double2 *z = reinterpret_cast<double2 *>(tsm + buf * kTileOperand);
+        for (int e = t; e < kTileOperand / 2; e += kTileProd) z[e] = make_double2(0.0, 0.0);
+      }
+      bar_sync(5, kTileProd);
+      // ---- 1. incidences
+      for (int ii = t; ii < ninc; ii += kTileProd) {
+        const int4 ia = inc_a[i0 + ii];
+        const int2 ib = inc_b[i0 + ii];
+        const int li = ib.y - ti0, slot = ib.x;
+        const int pt = tpt_point[ib.y];
+        double T[12], X[3];
+        load_pose(poses + (size_t)ia.z * 12, T);
+        X[0] = __ldg(points + (size_t)pt * 3);
+        X[1] = __ldg(points + (size_t)pt * 3 + 1);
+        X[2] = __ldg(points + (size_t)pt * 3 + 2);
+        double cp[9], Bv[18];
 #pragma unroll
-  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-  double racc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  // staging role: landmark slot q = t / W, pair slot v = t % W  (PB * W = 128 staging threads)
-  const int q_st = t / W, v_st = t % W;
-  for (int base = 0; base < ch.pt_count; base += PB) {
-    const int nb = min(PB, ch.pt_count - base);
-    __syncthreads();  // previous batch fully consumed
-    if (t < PB) masks[t] = 0;
-    __syncthreads();
-    if (q_st < nb && t < PB * W) {
-      const int ti = ch.pt_start + base + q_st;
-      const int p0 = tpt_pair_start[2 * ti], p1 = tpt_pair_start[2 * ti + 1];
-      const int p = p0 + v_st;
-      if (p < p1) {
-        const int pt = tpt_point[ti];
-        const int slot = pair_pose[p] - ch.jmin;
-        double B[18];
+        for (int i = 0; i < 9; ++i) cp[i] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 18; ++k) B[k] = Bsoa[(size_t)k * Pp + p];
+        for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
+        for (int k = ia.x; k < ia.x + ia.y; ++k) {
+          const double2 uv = obs_uv[k];
+          const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
+          Proj pr;
+          project(T, X, cam, uv.x, uv.y, pr);
+          const double w = huber_weight(pr.r0, pr.r1, thres_huber);
+          const double wr0 = w * pr.r0, wr1 = w * pr.r1;
+          double G[6], Rm[6];
+          jac_G(pr, cam, G);
+          jac_R(G, T, Rm);
+          cp[0] += w * (Rm[0] * Rm[0] + Rm[3] * Rm[3]);
+          cp[1] += w * (Rm[0] * Rm[1] + Rm[3] * Rm[4]);
+          cp[2] += w * (Rm[0] * Rm[2] + Rm[3] * Rm[5]);
+          cp[3] += w * (Rm[1] * Rm[1] + Rm[4] * Rm[4]);
+          cp[4] += w * (Rm[1] * Rm[2] + Rm[4] * Rm[5]);
+          cp[5] += w * (Rm[2] * Rm[2] + Rm[5] * Rm[5]);
+          cp[6] -= Rm[0] * wr0 + Rm[3] * wr1;
+          cp[7] -= Rm[1] * wr0 + Rm[4] * wr1;
+          cp[8] -= Rm[2] * wr0 + Rm[5] * wr1;
+          if (slot >= 0 && (ACCUM_B || k == ia.x + ia.y - 1)) {
+            double Q[12];
+            jac_Q(G, pr.Xb, Q);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) Bv[r * 3 + c] += w * (Q[r] * Rm[c] + Q[6 + r] * Rm[3 + c]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cpart[i * kTileIncCap + ii] = cp[i];
+        if (slot >= 0) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              Ba[3 * li + c][6 * slot + r] = Bv[r * 3 + c];
+              Bsoa[(size_t)(r * 3 + c) * Pp + ia.w] = Bv[r * 3 + c];
+            }
+        }
+      }
+      bar_sync(5, kTileProd);
+      // ---- 2a. per-landmark sums of the 9 components: thread (landmark, component)
+      for (int u = t; u < 9 * nb; u += kTileProd) {
+        const int li = u / 9, c = u - 9 * li;
+        const int a = tpt_inc_start[ti0 + li] - i0, b = tpt_inc_start[ti0 + li + 1] - i0;
+        double sacc = 0.0;
+        for (int ii = a; ii < b; ++ii) sacc += cpart[c * kTileIncCap + ii];
+        lmk[li * 24 + c] = sacc;
+      }
+      bar_sync(5, kTileProd);
+      // ---- 2b. damping + inverse, one thread per landmark
+      if (t < nb) {
+        double c9[9], cd[6], ci[6];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c9[i] = lmk[t * 24 + i];
+        damp_invert(c9, lambda, cd, ci);
+        const int pt = tpt_point[ti0 + t];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) lmk[t * 24 + 12 + i] = ci[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ba[3 * t + c][8 * kRhsTile] = c9[6 + c];
+        ptblk[(PB_b + 0) * Mp + pt] = c9[6];
+        ptblk[(PB_b + 1) * Mp + pt] = c9[7];
+        ptblk[(PB_b + 2) * Mp + pt] = c9[8];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          ptblk[(PB_Cd + i) * Mp + pt] = cd[i];
+          ptblk[(PB_Cinv + i) * Mp + pt] = ci[i];
+        }
+        ptblk[(PB_Cinvb + 0) * Mp + pt] = ci[0] * c9[6] + ci[1] * c9[7] + ci[2] * c9[8];
+        ptblk[(PB_Cinvb + 1) * Mp + pt] = ci[1] * c9[6] + ci[3] * c9[7] + ci[4] * c9[8];
+        ptblk[(PB_Cinvb + 2) * Mp + pt] = ci[2] * c9[6] + ci[4] * c9[7] + ci[5] * c9[8];
+      }
+      bar_sync(5, kTileProd);
+      // ---- 3. E = B Cinv
+      for (int ii = t; ii < ninc; ii += kTileProd) {
+        const int2 ib = inc_b[i0 + ii];
+        const int li = ib.y - ti0, slot = ib.x;
+        if (slot < 0) continue;
         double ci[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) ci[k] = ptblk[(PB_Cinv + k) * Mp + pt];
+        for (int i = 0; i < 6; ++i) ci[i] = lmk[li * 24 + 12 + i];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-          const double b0 = B[r * 3], b1 = B[r * 3 + 1], b2 = B[r * 3 + 2];
-          Es[q_st][r * 3 + 0][slot] = b0 * ci[0] + b1 * ci[1] + b2 * ci[2];   // E = B Cinv (:862)
-          Es[q_st][r * 3 + 1][slot] = b0 * ci[1] + b1 * ci[3] + b2 * ci[4];
-          Es[q_st][r * 3 + 2][slot] = b0 * ci[2] + b1 * ci[4] + b2 * ci[5];
-          Bs[q_st][r * 3 + 0][slot] = b0;
-          Bs[q_st][r * 3 + 1][slot] = b1;
-          Bs[q_st][r * 3 + 2][slot] = b2;
-        }
-        atomicOr(&masks[q_st], 1 << slot);
-        if (v_st == 0) {
-          bs[q_st][0] = ptblk[(PB_b + 0) * Mp + pt];
-          bs[q_st][1] = ptblk[(PB_b + 1) * Mp + pt];
-          bs[q_st][2] = ptblk[(PB_b + 2) * Mp + pt];
+          const double b0 = Ba[3 * li][6 * slot + r], b1 = Ba[3 * li + 1][6 * slot + r], b2 = Ba[3 * li + 2][6 * slot + r];
+          // the operand holds -E so that the GEMM accumulates S -= E B^T directly
+          Ea[3 * li + 0][6 * slot + r] = -(b0 * ci[0] + b1 * ci[1] + b2 * ci[2]);
+          Ea[3 * li + 1][6 * slot + r] = -(b0 * ci[1] + b1 * ci[3] + b2 * ci[4]);
+          Ea[3 * li + 2][6 * slot + r] = -(b0 * ci[2] + b1 * ci[4] + b2 * ci[5]);
         }
       }
+      bar_arrive(1 + buf, kTileThreads);   // operands of batch bt are complete
     }
-    __syncthreads();
-    if (t < ntasks) {
-      for (int q = 0; q < nb; ++q) {
-        const int m = masks[q];
-        if (!(((m >> s1) & (m >> s2)) & 1)) continue;
-        double B[18];
+  } else {
+    // ===================================================== consumers =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int cw = warp - kTileProd / 32;
+    const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
+    // tiles of this warp: upper tiles (ti <= tj < nt) row-major, each row followed by its rhs tile
+    const int nt = (nrows + 7) >> 3;
+    const int ntile = nt * (nt + 1) / 2 + nt;
+    const int cnt = (ntile + 3) >> 2;
+    // per tile: shared-memory addresses of the lane's A / B fragment at k-step 0 of buffer 0; aoff < 0: no tile
+    int aoff[kTileTPW], boff[kTileTPW];
+    unsigned aadr[kTileTPW], badr[kTileTPW];
+    double acc[kTileTPW][2];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(tsm);
 #pragma unroll
-        for (int k = 0; k < 18; ++k) B[k] = Bs[q][k][s2];
+    for (int i = 0; i < kTileTPW; ++i) {
+      int e = cw * cnt + i, ti = 0, len = nt + 1;
+      const bool live = i < cnt && e < ntile;
+      if (live) {
+        while (e >= len) { e -= len; ++ti; --len; }
+      }
+      const int tj = (ti + e == nt) ? kRhsTile : ti + e;
+      aoff[i] = live ? 8 * ti : -1;
+      boff[i] = live ? 8 * tj : 0;
+      aadr[i] = sbase + 8u * (unsigned)(kq * kLdE + fr + (live ? 8 * ti : 0));
+      badr[i] = sbase + 8u * (unsigned)(kTileK * kLdE + kq * kLdB + fr + (live ? 8 * tj : 0));
+      acc[i][0] = acc[i][1] = 0.0;
+    }
+    for (int bt = 0; bt < n_batches; ++bt) {
+      const int buf = bt & 1;
+      const unsigned boffs = buf ? 8u * kTileOperand : 0u;
+      const int nb = min(kTileLB, ch.pt_count - bt * kTileLB);
+      bar_sync(1 + buf, kTileThreads);
+      // window += (-E_all) B_all^T  (K = 3 nb, zero padded); k-steps unrolled so that the fragment loads use
+      // immediate offsets and can be issued in batches ahead of the DMMAs
+      const int ksteps = (3 * nb + 3) >> 2;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double e0 = Es[q][r * 3][s1], e1 = Es[q][r * 3 + 1][s1], e2 = Es[q][r * 3 + 2][s1];
+      for (int ks = 0; ks < kTileK / 4; ++ks) {
+        if (ks >= ksteps) break;   // uniform
 #pragma unroll
-          for (int c = 0; c < 6; ++c) acc[r * 6 + c] += e0 * B[c * 3] + e1 * B[c * 3 + 1] + e2 * B[c * 3 + 2];
-          if (s1 == s2) racc[r] += e0 * bs[q][0] + e1 * bs[q][1] + e2 * bs[q][2];  // BCinv b (:864)
+        for (int g0 = 0; g0 < kTileTPW; g0 += 8) {
+          if (g0 >= cnt) break;   // uniform
+          double af[8], bf[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (g0 + i < kTileTPW) {
+              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(af[i]) : "r"(aadr[g0 + i] + boffs + (unsigned)(ks * 4 * kLdE * 8)));
+              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bf[i]) : "r"(badr[g0 + i] + boffs + (unsigned)(ks * 4 * kLdB * 8)));
+            }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (g0 + i < kTileTPW) dmma_884(acc[g0 + i][0], acc[g0 + i][1], af[i], bf[i]);
         }
       }
+      bar_arrive(3 + buf, kTileThreads);
     }
-  }
-  if (t < ntasks) {
-    const int j1 = ch.jmin + s1, j2 = ch.jmin + s2;
-    // windows at the end of the pose range may stick out; such tasks never accumulated anything
-    bool any = false;
+    // ---- flush: upper triangle of S (row-major) and the rhs column
+    const int row0 = 6 * ch.jmin;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) any = any || (acc[i] != 0.0);
-    if (any) {
+    for (int i = 0; i < kTileTPW; ++i) {
+      if (aoff[i] < 0) continue;
+      const int lr = aoff[i] + fr, tj8 = boff[i];
+      if (lr >= nrows) continue;
+      const size_t grow = (size_t)(row0 + lr) * ld;
+      if (tj8 == 8 * kRhsTile) {
+        if (fc == 0 && acc[i][0] != 0.0) atomicAdd(&Saug[grow + (ld - 1)], acc[i][0]);
+      } else {
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          if (s1 == s2 && c < r) continue;
-          atomicAdd(&Saug[(size_t)(6 * j1 + r) * ld + 6 * j2 + c], -acc[r * 6 + c]);
+        for (int e = 0; e < 2; ++e) {
+          const int lc = tj8 + fc + e;
+          if (lc < nrows && lc >= lr && acc[i][e] != 0.0) atomicAdd(&Saug[grow + row0 + lc], acc[i][e]);
         }
-      if (s1 == s2)
-#pragma unroll
-        for (int r = 0; r < 6; ++r) atomicAdd(&Saug[(size_t)(6 * j1 + r) * ld + (ld - 1)], -racc[r]);
+      }
     }
   }
 }
@@ -915,7 +1071,14 @@ struct ba_solver {
   DevBuf<uint8_t> d_point_free;
   DevBuf<int> d_split_points, d_split_pairs;
   DevBuf<SchurChunk> d_schur_chunks;
-  DevBuf<int> d_tpt_point, d_tpt_pair_start, d_fallback_pairs;
+  DevBuf<int> d_tpt_point, d_tpt_inc_start, d_fallback_pairs;
+  DevBuf<int4> d_inc_a;
+  DevBuf<int2> d_inc_b;
+  DevBuf<Chunk> d_chunks_fb;
+  DevBuf<int2> d_chunk_pts_fb;
+  DevBuf<ChunkPoint> d_cpts_fb;
+  DevBuf<uint8_t> d_point_fb;
+  int n_chunks_fb = 0;
   int n_schur_chunks = 0, n_fallback_pairs = 0;
   int schur_mode = 1;  // 1 = register-tiled windows + fallback, 0 = direct reds only
   CholeskyPlan chol;
@@ -991,7 +1154,8 @@ static void free_device(ba_solver *s) {
   s->d_pose_chunk_ptr.release(); s->d_pose_opt.release(); s->d_pair_pose.release(); s->d_pair_point.release();
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
-  s->d_tpt_point.release(); s->d_tpt_pair_start.release(); s->d_fallback_pairs.release();
+  s->d_tpt_point.release(); s->d_tpt_inc_start.release(); s->d_fallback_pairs.release();
+  s->d_inc_a.release(); s->d_inc_b.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
   s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
@@ -1165,9 +1329,16 @@ int ba_finalize(ba_solver *s) {
   std::vector<int> pair_end(P);
   for (long long p = P - 1; p >= 0; --p)
     pair_end[p] = (p + 1 < P && s->h_pair_point[p + 1] == s->h_pair_point[p]) ? pair_end[p + 1] : (int)(p + 1);
-  // --- Schur chunks: runs of consecutive landmarks whose free poses fit one window of kSchurW poses
+  // --- observation range of every landmark in point order
+  std::vector<long long> pt_q0(Mt + 1, 0);
+  for (long long q = 0; q < n; ++q) pt_q0[o_point[q] + 1]++;
+  for (int i = 0; i < Mt; ++i) pt_q0[i + 1] += pt_q0[i];
+  // --- tile chunks: runs of consecutive landmarks whose free poses fit one window of kTileW poses
   std::vector<SchurChunk> schur_chunks;
-  std::vector<int> tpt_point, tpt_pair_start, fallback_pairs;
+  std::vector<int> tpt_point, tpt_inc_start, fallback_pairs;
+  std::vector<int4> inc_a;
+  std::vector<int2> inc_b;
+  std::vector<uint8_t> is_tile_point(Mt, 0);
   {
     struct Cand { int point, p0, p1, jmin, jmax; };
     std::vector<Cand> cands;
@@ -1175,21 +1346,25 @@ int ba_finalize(ba_solver *s) {
       const int e = pair_end[p];
       // pairs of a point are ascending in j_opt (points sorted by (point, pose), j_opt monotone in id)
       Cand c{s->h_pair_point[p], (int)p, e, s->h_pair_pose[p], s->h_pair_pose[e - 1]};
-      if (s->schur_mode == 1 && c.jmax - c.jmin + 1 <= kSchurW) cands.push_back(c);
+      // incidences = distinct poses (free or fixed) observing the landmark
+      int n_inc = 0, prev = -1;
+      for (long long q = pt_q0[c.point]; q < pt_q0[c.point + 1]; ++q)
+        if (o_pose[q] != prev) { ++n_inc; prev = o_pose[q]; }
+      if (s->schur_mode == 1 && c.jmax - c.jmin + 1 <= kTileW && n_inc <= kTileMaxInc) cands.push_back(c);
       else for (int q = (int)p; q < e; ++q) fallback_pairs.push_back(q);
       p = e;
     }
-    // Greedy runs.  A run keeps growing while its pose window stays within kSchurW; once it holds enough
+    // Greedy runs.  A run keeps growing while its pose window stays within kTileW; once it holds enough
     // landmarks to amortise the final flush it is also cut when the next landmark would WIDEN the window,
-    // so that most chunks are exactly as wide as their landmarks' tracks (dense register tiles).
-    constexpr int kMinPts = 6, kMinStart = 24, kGoodPts = 48, kMaxPts = 192;
+    // so that most chunks are exactly as wide as their landmarks' tracks (dense GEMM operands).
+    constexpr int kMinPts = 6, kMinStart = 32, kGoodPts = 64, kMaxPts = 128;
     size_t i = 0;
     while (i < cands.size()) {
       int lo = cands[i].jmin, hi = cands[i].jmax;
       size_t e = i + 1;
       while (e < cands.size() && (int)(e - i) < kMaxPts) {
         const int nlo = std::min(lo, cands[e].jmin), nhi = std::max(hi, cands[e].jmax);
-        if (nhi - nlo + 1 > kSchurW) break;
+        if (nhi - nlo + 1 > kTileW) break;
         if ((int)(e - i) >= kGoodPts && (nlo != lo || nhi != hi)) break;
         if ((int)(e - i) >= kMinStart && cands[e].jmin != cands[i].jmin) break;  // keep a common first pose
         lo = nlo; hi = nhi; ++e;
@@ -1197,9 +1372,18 @@ int ba_finalize(ba_solver *s) {
       if ((int)(e - i) >= kMinPts) {
         SchurChunk sc{(int)tpt_point.size(), (int)(e - i), lo, hi - lo + 1};
         for (size_t k = i; k < e; ++k) {
-          tpt_point.push_back(cands[k].point);
-          tpt_pair_start.push_back(cands[k].p0);  // [2*ti] = first pair, [2*ti+1] = one past the last
-          tpt_pair_start.push_back(cands[k].p1);
+          const int pt = cands[k].point, ti = (int)tpt_point.size();
+          is_tile_point[pt] = 1;
+          tpt_point.push_back(pt);
+          tpt_inc_start.push_back((int)inc_a.size());
+          for (long long q = pt_q0[pt]; q < pt_q0[pt + 1];) {
+            long long r = q;
+            while (r < pt_q0[pt + 1] && o_pose[r] == o_pose[q]) ++r;
+            const int pair = o_pair[q];
+            inc_a.push_back(make_int4((int)q, (int)(r - q), o_pose[q], pair));
+            inc_b.push_back(make_int2(pair >= 0 ? s->h_pair_pose[pair] - lo : -1, ti));
+            q = r;
+          }
         }
         schur_chunks.push_back(sc);
       } else {
@@ -1208,6 +1392,7 @@ int ba_finalize(ba_solver *s) {
       }
       i = e;
     }
+    tpt_inc_start.push_back((int)inc_a.size());
     std::sort(fallback_pairs.begin(), fallback_pairs.end());
   }
   // --- Cholesky envelope plan from the co-visibility structure
@@ -1224,25 +1409,32 @@ int ba_finalize(ba_solver *s) {
   }
   s->n_schur_chunks = (int)schur_chunks.size();
   s->n_fallback_pairs = (int)fallback_pairs.size();
-  // --- chunks of whole points (<= kThreads observations); longer points are split
-  std::vector<Chunk> chunks;
-  std::vector<int> chunk_pair_count;
-  std::vector<int> split_points, split_pairs;
-  {
+  // --- chunks of whole points (<= kThreads observations); longer points are split.  Built twice: over all
+  //     landmarks (back-substitution, cost) and over the landmarks of the by-point path only (linearisation)
+  struct PointChunks {
+    std::vector<Chunk> chunks;
+    std::vector<int> chunk_pair_count, split_points, split_pairs;
+    std::vector<int2> chunk_pts;
+    std::vector<ChunkPoint> cpts;
+  };
+  auto build_point_chunks = [&](bool skip_tile_points) {
+    PointChunks pc;
     long long q = 0;
     Chunk cur{0, 0, 0, 0};
     int cur_pairs_first = -1, cur_pairs_last = -1;
+    long long cur_end = 0;
     auto flush = [&]() {
       if (cur.obs_count == 0) return;
       cur.pair_start = cur_pairs_first < 0 ? 0 : cur_pairs_first;
-      chunks.push_back(cur);
-      chunk_pair_count.push_back(cur_pairs_first < 0 ? 0 : cur_pairs_last - cur_pairs_first + 1);
+      pc.chunks.push_back(cur);
+      pc.chunk_pair_count.push_back(cur_pairs_first < 0 ? 0 : cur_pairs_last - cur_pairs_first + 1);
       cur = Chunk{0, 0, 0, 0};
       cur_pairs_first = cur_pairs_last = -1;
     };
     auto add_range = [&](long long a, long long b) {  // obs [a,b) appended to the current chunk
       if (cur.obs_count == 0) cur.obs_start = (int)a;
       cur.obs_count += (int)(b - a);
+      cur_end = b;
       for (long long r = a; r < b; ++r)
         if (o_pair[r] >= 0 && (o_cf[r] & kFlagLastOfPair)) { if (cur_pairs_first < 0) cur_pairs_first = o_pair[r]; cur_pairs_last = o_pair[r]; }
     };
@@ -1250,9 +1442,10 @@ int ba_finalize(ba_solver *s) {
       long long e = q;
       while (e < n && o_point[e] == o_point[q]) ++e;
       const long long len = e - q;
+      if (skip_tile_points && is_tile_point[o_point[q]]) { flush(); q = e; continue; }
       if (len > kThreads) {
         flush();
-        if (s->h_point_opt[o_point[q]] >= 0) split_points.push_back(o_point[q]);
+        if (s->h_point_opt[o_point[q]] >= 0) pc.split_points.push_back(o_point[q]);
         for (long long a = q; a < e; a += kThreads) {
           const long long b = std::min(e, a + kThreads);
           add_range(a, b);
@@ -1260,30 +1453,39 @@ int ba_finalize(ba_solver *s) {
           flush();
         }
         for (long long r = q; r < e; ++r)
-          if (o_pair[r] >= 0 && (split_pairs.empty() || split_pairs.back() != o_pair[r])) split_pairs.push_back(o_pair[r]);
+          if (o_pair[r] >= 0 && (pc.split_pairs.empty() || pc.split_pairs.back() != o_pair[r])) pc.split_pairs.push_back(o_pair[r]);
       } else {
-        if (cur.obs_count + len > kThreads) flush();
+        // a chunk is a CONTIGUOUS observation range: close it when skipped landmarks lie in between
+        if (cur.obs_count + len > kThreads || (cur.obs_count > 0 && cur_end != q)) flush();
         add_range(q, e);
       }
       q = e;
     }
     flush();
-  }
-  // landmarks of each chunk (runs of equal point id inside the chunk's observation range)
-  std::vector<int2> chunk_pts(chunks.size());
-  std::vector<ChunkPoint> cpts;
-  for (size_t c = 0; c < chunks.size(); ++c) {
-    chunk_pts[c].x = (int)cpts.size();
-    const long long a = chunks[c].obs_start, b = a + chunks[c].obs_count;
-    for (long long r = a; r < b;) {
-      long long e = r;
-      while (e < b && o_point[e] == o_point[r]) ++e;
-      cpts.push_back(ChunkPoint{o_point[r], (int)(r - a), (int)(e - r), s->h_point_opt[o_point[r]] >= 0 ? 1 : 0});
-      r = e;
+    // landmarks of each chunk (runs of equal point id inside the chunk's observation range)
+    pc.chunk_pts.resize(pc.chunks.size());
+    for (size_t c = 0; c < pc.chunks.size(); ++c) {
+      pc.chunk_pts[c].x = (int)pc.cpts.size();
+      const long long a = pc.chunks[c].obs_start, b = a + pc.chunks[c].obs_count;
+      for (long long r = a; r < b;) {
+        long long e = r;
+        while (e < b && o_point[e] == o_point[r]) ++e;
+        pc.cpts.push_back(ChunkPoint{o_point[r], (int)(r - a), (int)(e - r), s->h_point_opt[o_point[r]] >= 0 ? 1 : 0});
+        r = e;
+      }
+      pc.chunk_pts[c].y = (int)pc.cpts.size() - pc.chunk_pts[c].x;
     }
-    chunk_pts[c].y = (int)cpts.size() - chunk_pts[c].x;
-  }
+    return pc;
+  };
+  PointChunks pc_all = build_point_chunks(false);
+  PointChunks pc_fb = build_point_chunks(true);
+  std::vector<Chunk> &chunks = pc_all.chunks;
+  std::vector<int> &chunk_pair_count = pc_all.chunk_pair_count;
+  std::vector<int> &split_points = pc_fb.split_points, &split_pairs = pc_all.split_pairs;
+  std::vector<int2> &chunk_pts = pc_all.chunk_pts;
+  std::vector<ChunkPoint> &cpts = pc_all.cpts;
   s->n_chunks = (int)chunks.size();
+  s->n_chunks_fb = (int)pc_fb.chunks.size();
   s->n_split = (int)split_points.size();
   s->n_split_pairs = (int)split_pairs.size();
   // --- pose-ordered arrays (free poses only) and their chunks
@@ -1380,7 +1582,17 @@ int ba_finalize(ba_solver *s) {
   }
   CUDA_TRY(s->d_schur_chunks.upload(schur_chunks, st));
   CUDA_TRY(s->d_tpt_point.upload(tpt_point, st));
-  CUDA_TRY(s->d_tpt_pair_start.upload(tpt_pair_start, st));
+  CUDA_TRY(s->d_tpt_inc_start.upload(tpt_inc_start, st));
+  CUDA_TRY(s->d_inc_a.upload(inc_a, st));
+  CUDA_TRY(s->d_inc_b.upload(inc_b, st));
+  CUDA_TRY(s->d_chunks_fb.upload(pc_fb.chunks, st));
+  CUDA_TRY(s->d_chunk_pts_fb.upload(pc_fb.chunk_pts, st));
+  CUDA_TRY(s->d_cpts_fb.upload(pc_fb.cpts, st));
+  {
+    std::vector<uint8_t> point_fb(Mt);
+    for (int i = 0; i < Mt; ++i) point_fb[i] = (!s->h_point_fixed[i] && !is_tile_point[i]) ? 1 : 0;
+    CUDA_TRY(s->d_point_fb.upload(point_fb, st));
+  }
   CUDA_TRY(s->d_fallback_pairs.upload(fallback_pairs, st));
   CUDA_TRY(s->d_split_points.upload(split_points, st));
   CUDA_TRY(s->d_split_pairs.upload(split_pairs, st));
@@ -1483,29 +1695,7 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
     k_zero_split<<<(s->n_split + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split, s->d_ptblk.p, s->Mp, dst);
     s->launches++;
   }
-  if (s->n_chunks > 0) {
-    k_linearize_by_point<<<s->n_chunks, kThreads, 0, st>>>(s->d_chunks.p, s->d_chunk_pts.p, s->d_cpts.p,
-                                                           s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
-                                                           s->d_obs_camflags.p, prm, s->d_cams.p, thres,
-                                                           s->d_ptblk.p, s->Mp, dst);
-    s->launches++;
-  }
-  if (s->P > 0) {
-    const int grid = (int)((s->P + kThreads - 1) / kThreads);
-    if (opt->b_accumulate)
-      k_pair_blocks<true><<<grid, kThreads, 0, st>>>((int)s->P, s->d_pair_obs.p, s->d_obs_uv.p, s->d_obs_pose.p,
-                                                     s->d_obs_point.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres,
-                                                     s->d_Bsoa.p, s->Pp, dst);
-    else
-      k_pair_blocks<false><<<grid, kThreads, 0, st>>>((int)s->P, s->d_pair_obs.p, s->d_obs_uv.p, s->d_obs_pose.p,
-                                                      s->d_obs_point.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres,
-                                                      s->d_Bsoa.p, s->Pp, dst);
-    s->launches++;
-  }
-  if (s->M_total > 0) {
-    k_finish_points<<<(s->M_total + 127) / 128, 128, 0, st>>>(s->M_total, s->d_point_free.p, s->d_ptblk.p, s->Mp, dst);
-    s->launches++;
-  }
+  // pose side first: k_finish_poses STORES the damped diagonal blocks and the rhs, everything after it adds
   if (s->n_chunksA > 0) {
     k_linearize_by_pose<<<s->n_chunksA, kThreads, 0, st>>>(s->d_chunksA.p, s->d_uvA.p, s->d_pointA.p,
                                                            s->d_camA.p, s->d_poseidA.p, prm, s->d_cams.p, thres,
@@ -1517,11 +1707,47 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
                                                     s->d_a.p, s->d_Saug.p, ld, dst);
     s->launches++;
   }
+  // landmarks on the by-point path (poses do not fit a window, or not enough neighbours for a chunk)
+  if (s->n_chunks_fb > 0) {
+    k_linearize_by_point<<<s->n_chunks_fb, kThreads, 0, st>>>(s->d_chunks_fb.p, s->d_chunk_pts_fb.p, s->d_cpts_fb.p,
+                                                              s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                                              s->d_obs_camflags.p, prm, s->d_cams.p, thres,
+                                                              s->d_ptblk.p, s->Mp, dst);
+    s->launches++;
+  }
+  if (s->n_fallback_pairs > 0) {
+    const int grid = (s->n_fallback_pairs + kThreads - 1) / kThreads;
+    if (opt->b_accumulate)
+      k_pair_blocks<true><<<grid, kThreads, 0, st>>>(s->n_fallback_pairs, s->d_fallback_pairs.p, s->d_pair_obs.p,
+                                                     s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                                     s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p, s->Pp, dst);
+    else
+      k_pair_blocks<false><<<grid, kThreads, 0, st>>>(s->n_fallback_pairs, s->d_fallback_pairs.p, s->d_pair_obs.p,
+                                                      s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                                      s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p, s->Pp, dst);
+    s->launches++;
+  }
+  if (s->n_chunks_fb > 0) {
+    k_finish_points<<<(s->M_total + 127) / 128, 128, 0, st>>>(s->M_total, s->d_point_fb.p, s->d_ptblk.p, s->Mp, dst);
+    s->launches++;
+  }
   if (ev) cudaEventRecord(ev[Phase::Schur], st);
+  // tile landmarks: linearisation + C^-1 + Schur products fused (DMMA)
   if (s->n_schur_chunks > 0) {
-    k_schur_tiles<<<s->n_schur_chunks, kSchurThreads, 0, st>>>(s->d_schur_chunks.p, s->d_tpt_point.p,
-                                                              s->d_tpt_pair_start.p, s->d_pair_pose.p, s->d_Bsoa.p,
-                                                              s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_build_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+      cudaFuncSetAttribute(k_build_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+      attr_set = true;
+    }
+    if (opt->b_accumulate)
+      k_build_tiles<true><<<s->n_schur_chunks, kTileThreads, kTileSmem, st>>>(
+          s->d_schur_chunks.p, s->d_tpt_point.p, s->d_tpt_inc_start.p, s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p,
+          s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+    else
+      k_build_tiles<false><<<s->n_schur_chunks, kTileThreads, kTileSmem, st>>>(
+          s->d_schur_chunks.p, s->d_tpt_point.p, s->d_tpt_inc_start.p, s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p,
+          s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
     s->launches++;
   }
   if (s->n_fallback_pairs > 0) {
