@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=4, help="LM iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-max-iters", type=int, default=300,
+                    help="iteration cap of the end-to-end solve (SURVEY 8d: thresholds 1e-6f, max 300 iterations)")
     ap.add_argument("--quick", action="store_true", help="profiling run: no clock-settling loop, phases, e2e or CPU baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -304,14 +306,19 @@ def main():
                 dist.barrier()
             t0 = time.perf_counter()
             S.load_scene(s2, sc)
+            t_reg = time.perf_counter()
             s2._upload()
             if join_comm_needed:
                 join_comm(s2, sz)
-            opt = capi.default_options(max_num_iterations=50, threshold_cost_change=1e-6, threshold_step_size=1e-6)
+            t_fin = time.perf_counter()
+            opt = capi.default_options(max_num_iterations=args.e2e_max_iters, threshold_cost_change=1e-6,
+                                       threshold_step_size=1e-6)
             summ = S.Summary()
             s2.solve(opt, summ)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            stages = {"register_ms": 1e3 * (t_reg - t0), "finalize_h2d_ms": 1e3 * (t_fin - t_reg),
+                      "solve_writeback_ms": 1e3 * (t0 + dt - t_fin)}
             it = len(summ.optimization_info_list)
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             if world > 1:
@@ -321,7 +328,7 @@ def main():
             d2h = sz["N_total"] * 96 + sz["M_total"] * 24 + it * 64
             e2e = {"value": total_obs * it / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(it, 1)),
                    "d2h_bytes_per_step": int(d2h / max(it, 1)), "lm_iterations": it, "converged": bool(summ.convergence_status),
-                   "wall_s": dt, "final_cost": summ.optimization_info_list[-1].cost if it else None,
+                   "wall_s": dt, "stages_ms": stages, "final_cost": summ.optimization_info_list[-1].cost if it else None,
                    "includes": "host registration, FinalizeParameters (sorts, H2D pack), LM loop to convergence, D2H write-back"}
             del s2
 

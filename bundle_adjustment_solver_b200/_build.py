@@ -9,7 +9,7 @@ LIB = os.environ.get("BA_B200_LIB") or os.path.join(HERE, "libba_b200.so")
 SOURCES = ["ba_engine.cu", "ba_poseonly.cu"]
 HEADERS = [os.path.join("..", "..", "include", "ba_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
 
 
 def _stale():
@@ -27,6 +27,6 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl", "-lgomp"]
     subprocess.check_call(cmd)
     return LIB

@@ -1009,6 +1009,21 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+// Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync) with the release
+// threshold lifted, so the ~40 buffers of a problem cost a handful of driver allocations and a re-finalised or
+// second solver reuses what an earlier one returned.  g_alloc_stream: stream of the entry point in progress.
+thread_local cudaStream_t g_alloc_stream = nullptr;
+inline void pool_setup(int device) {
+  static bool done[64] = {};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[device] = true;
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -1018,7 +1033,7 @@ struct DevBuf {
     release();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc((void **)&p, count * sizeof(T));
+    return cudaMallocAsync((void **)&p, count * sizeof(T), g_alloc_stream);
   }
   cudaError_t upload(const std::vector<T> &h, cudaStream_t st) {
     cudaError_t e = alloc(h.size());
@@ -1026,7 +1041,7 @@ struct DevBuf {
     return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, g_alloc_stream);
     p = nullptr;
     n = 0;
   }
@@ -1114,6 +1129,8 @@ static int ensure_stream(ba_solver *s) {
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
   }
+  pool_setup(s->device);
+  g_alloc_stream = s->stream;
   return BA_OK;
 }
 
@@ -1168,7 +1185,9 @@ void ba_destroy(ba_solver *s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  g_alloc_stream = s->stream;
   free_device(s);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   for (auto e : s->ev) cudaEventDestroy(e);
   if (s->h_state) cudaFreeHost(s->h_state);
   if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -1241,6 +1260,34 @@ int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const 
   if (!s || n_obs < 0 || (n_obs > 0 && (!cam_id || !pose || !point || !uv))) return BA_ERR_INVALID;
   if (n_obs > 2000000000LL) { s->err = "too many observations for 32-bit indexing"; return BA_ERR_INVALID; }
   s->h_obs_cam.clear(); s->h_obs_pose.clear(); s->h_obs_point.clear(); s->h_obs_uv.clear();
+  // fast path: every row valid (the common case) -> bulk copies and a table look-up of the camera slot
+  {
+    int max_id = -1, min_id = 0;
+    for (auto &kv : s->cam_slot) { max_id = std::max(max_id, kv.first); min_id = std::min(min_id, kv.first); }
+    if (min_id >= 0 && max_id < 4096) {
+      std::vector<int> table(max_id + 1, -1);
+      for (auto &kv : s->cam_slot) table[kv.first] = kv.second;
+      const int Nt = s->N_total, Mt = s->M_total;
+      long long bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+      for (long long k = 0; k < n_obs; ++k) {
+        const int c = cam_id[k];
+        bad += (c < 0 || c > max_id || table[c] < 0 || pose[k] < 0 || pose[k] >= Nt || point[k] < 0 || point[k] >= Mt);
+      }
+      if (bad == 0) {
+        s->h_obs_cam.resize(n_obs);
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < n_obs; ++k) s->h_obs_cam[k] = table[cam_id[k]];
+        s->h_obs_pose.assign(pose, pose + n_obs);
+        s->h_obs_point.assign(point, point + n_obs);
+        s->h_obs_uv.assign(uv, uv + 2 * n_obs);
+        s->n_obs = n_obs;
+        if (n_kept) *n_kept = s->n_obs;
+        s->finalized = false;
+        return BA_OK;
+      }
+    }
+  }
   s->h_obs_cam.reserve(n_obs); s->h_obs_pose.reserve(n_obs); s->h_obs_point.reserve(n_obs);
   s->h_obs_uv.reserve(2 * n_obs);
   for (long long k = 0; k < n_obs; ++k) {
@@ -1267,6 +1314,14 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(cudaSetDevice(s->device));
   if (int rc = ensure_stream(s)) return rc;
   destroy_graph(s);
+  static const bool verbose = getenv("BA_B200_VERBOSE") != nullptr;
+  auto tp0 = std::chrono::high_resolution_clock::now();
+  auto lap = [&](const char *what) {
+    if (!verbose) return;
+    const auto now = std::chrono::high_resolution_clock::now();
+    fprintf(stderr, "[ba_b200] finalize %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tp0).count());
+    tp0 = now;
+  };
   const int Nt = s->N_total, Mt = s->M_total;
   const long long n = s->n_obs;
   // --- free indices in id order (FinalizeParameters :182-206; insertion order replaces hash order)
@@ -1288,22 +1343,27 @@ int ba_finalize(ba_solver *s) {
     for (int i = 0; i < Mt; ++i) cnt2[i + 1] += cnt2[i];
     for (long long q = 0; q < n; ++q) { const int k = by_pose[q]; by_point[cnt2[s->h_obs_point[k]]++] = k; }
   }
+  lap("counting sorts");
   // --- point-ordered observation arrays, pairs, last-writer flags
   std::vector<double2> uv(n);
   std::vector<int> o_pose(n), o_point(n), o_cf(n), o_pair(n);
   s->h_pair_pose.clear(); s->h_pair_point.clear();
   std::vector<int> point_has_pairs(Mt, 0);
   {
-    int prev_pt = -1, prev_ps = -1;
+#pragma omp parallel for schedule(static)
     for (long long q = 0; q < n; ++q) {
       const int k = by_point[q];
       const int ps = s->h_obs_pose[k], pt = s->h_obs_point[k];
       const bool pf = s->h_pose_opt[ps] >= 0, qf = s->h_point_opt[pt] >= 0;
       uv[q] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
       o_pose[q] = ps; o_point[q] = pt;
-      int cf = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
+      o_cf[q] = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
+    }
+    int prev_pt = -1, prev_ps = -1;
+    for (long long q = 0; q < n; ++q) {
+      const int ps = o_pose[q], pt = o_point[q];
       int pair = -1;
-      if (pf && qf) {
+      if ((o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree)) {
         if (pt != prev_pt || ps != prev_ps) {
           s->h_pair_pose.push_back(s->h_pose_opt[ps]);
           s->h_pair_point.push_back(pt);
@@ -1312,7 +1372,6 @@ int ba_finalize(ba_solver *s) {
         pair = (int)s->h_pair_pose.size() - 1;
       }
       o_pair[q] = pair;
-      o_cf[q] = cf;
       prev_pt = pt; prev_ps = ps;
     }
     // last observation of each (point,pose) run = last inserted of the pair (stable sort)
@@ -1329,6 +1388,7 @@ int ba_finalize(ba_solver *s) {
   std::vector<int> pair_end(P);
   for (long long p = P - 1; p >= 0; --p)
     pair_end[p] = (p + 1 < P && s->h_pair_point[p + 1] == s->h_pair_point[p]) ? pair_end[p + 1] : (int)(p + 1);
+  lap("point order, pairs");
   // --- observation range of every landmark in point order
   std::vector<long long> pt_q0(Mt + 1, 0);
   for (long long q = 0; q < n; ++q) pt_q0[o_point[q] + 1]++;
@@ -1395,6 +1455,7 @@ int ba_finalize(ba_solver *s) {
     tpt_inc_start.push_back((int)inc_a.size());
     std::sort(fallback_pairs.begin(), fallback_pairs.end());
   }
+  lap("tile chunks, incidences");
   // --- Cholesky envelope plan from the co-visibility structure
   {
     std::vector<int> first_pose(s->N);
@@ -1409,6 +1470,7 @@ int ba_finalize(ba_solver *s) {
   }
   s->n_schur_chunks = (int)schur_chunks.size();
   s->n_fallback_pairs = (int)fallback_pairs.size();
+  lap("cholesky plan");
   // --- chunks of whole points (<= kThreads observations); longer points are split.  Built twice: over all
   //     landmarks (back-substitution, cost) and over the landmarks of the by-point path only (linearisation)
   struct PointChunks {
@@ -1488,6 +1550,7 @@ int ba_finalize(ba_solver *s) {
   s->n_chunks_fb = (int)pc_fb.chunks.size();
   s->n_split = (int)split_points.size();
   s->n_split_pairs = (int)split_pairs.size();
+  lap("point chunks");
   // --- pose-ordered arrays (free poses only) and their chunks
   std::vector<double2> uvA; std::vector<int> pointA, camA, poseidA;
   std::vector<ChunkA> chunksA; std::vector<int> pose_chunk_ptr(s->N + 1, 0);
@@ -1528,6 +1591,7 @@ int ba_finalize(ba_solver *s) {
     for (int j = 0; j < s->N; ++j) pose_chunk_ptr[j + 1] = pose_chunk_ptr[j] + cnt[j];
   }
   s->n_chunksA = (int)chunksA.size();
+  lap("pose order");
   // --- upload
   cudaStream_t st = s->stream;
   std::vector<uint8_t> point_free(Mt);
@@ -1596,6 +1660,8 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_fallback_pairs.upload(fallback_pairs, st));
   CUDA_TRY(s->d_split_points.upload(split_points, st));
   CUDA_TRY(s->d_split_pairs.upload(split_pairs, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  lap("uploads");
   // --- block storage
   s->Mp = ((size_t)Mt + 31) / 32 * 32;
   s->Pp = ((size_t)P + 31) / 32 * 32;
@@ -1631,6 +1697,7 @@ int ba_finalize(ba_solver *s) {
   if (!s->h_state) CUDA_TRY(cudaMallocHost((void **)&s->h_state, sizeof(LmState)));
   if (!s->h_scal) CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 8 * sizeof(double)));
   CUDA_TRY(cudaStreamSynchronize(st));
+  lap("block storage");
   s->finalized = true;
   return BA_OK;
 }
@@ -1854,6 +1921,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   const auto t0 = std::chrono::high_resolution_clock::now();
   if (int rc = ba_finalize(s)) return rc;
   CUDA_TRY(cudaSetDevice(s->device));
+  if (int rc = ensure_stream(s)) return rc;
   ba_options opt = *opt_in;
   if (opt.inverse_scaler == 0.0) opt.inverse_scaler = 100.0;
   if (opt.check_every <= 0) opt.check_every = 8;
@@ -1979,6 +2047,7 @@ int ba_build_only(ba_solver *s, const ba_options *opt_in, double lambda, int do_
   if (!s || !opt_in) return BA_ERR_INVALID;
   if (int rc = ba_finalize(s)) return rc;
   CUDA_TRY(cudaSetDevice(s->device));
+  if (int rc = ensure_stream(s)) return rc;
   ba_options opt = *opt_in;
   cudaStream_t st = s->stream;
   // state: keep `cur`, set lambda, not done
