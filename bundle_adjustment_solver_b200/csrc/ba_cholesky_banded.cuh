@@ -77,7 +77,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       : "memory");
 }
 
-__device__ unsigned long long g_band_dbg[4];
+__device__ unsigned long long g_band_dbg[16];
 
 __device__ __forceinline__ void dmma_884b(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -674,13 +674,323 @@ k_chol_banded_dmma(double *A, int n, int bw, double *x_out, double *linv, int ti
   }
 }
 
+// =====================================================================================================
+// v4: same block-step scheme (8-column panels, DMMA update, dedicated panel warp), but the window lives in
+// SHARED memory as 8 x 8 tiles (lower triangle, ring slots).  Work is assigned by RELATIVE tile position, the
+// same for every step: the tiles of the next panel first (one per warp), then the rest; nothing is searched,
+// recycled through registers or published - the panel warp reads its panel straight out of the window.
+// Requires W >= bw + 16: the rows that enter the window during a step then only meet zeros in the next panel.
+// =====================================================================================================
+constexpr int kBand4Cons = 9;                        // consumer warps (sub-partitions 0-2)
+constexpr int kBand4Threads = 384;                   // 12 warps: 9 consumers, 1 producer (warp 3), 2 idle
+constexpr int kBand4Active = 32 * (kBand4Cons + 1);  // threads that take part in the hand-off barriers
+
+template <int W>
+struct Band4Smem {
+  union {
+    struct {
+      double win[(W / 8) * (W / 8)][64];   // tile (row slot, col slot), row-major 8 x 8
+      double Lp[2][W + 1][12];             // factored panel (row stride 12: conflict-free 8 x 4 fragment reads)
+      double zwin[W];                      // rhs entries of the window columns (ring position)
+    } f;
+    struct {
+      double lst[8][2][16][17];
+      double linvd[8][2][16];
+    } pre;
+  };
+  double xr[W + 32];
+  double acc[2][16];
+  unsigned long long bar_raw[2], bar_L[2];
+};
+
+template <int W>
+__global__ void __launch_bounds__(kBand4Threads, 1)
+k_chol_banded_smem(double *A, int n, int bw, double *x_out, double *linv, int timing, const LmState *st) {
+  if (st->done) return;
+  constexpr int NT = W / 8;
+  constexpr int T2 = (NT - 2) * (NT - 1) / 2;   // tiles outside the next panel: 2 <= rb <= ra <= NT - 1
+  constexpr int TP2 = (T2 + kBand4Cons - 1) / kBand4Cons;
+  constexpr int NSL = (W + 1 + 31) / 32;        // panel rows per producer lane
+  // Roles by scheduler: warp w runs on SM sub-partition w % 4.  DMMA and DFMA share the FP64 pipe of a
+  // sub-partition and a DMMA holds it for 16 cycles, so the latency-critical pivot chain of the panel warp
+  // gets a sub-partition without DMMA traffic: warp 3 is the producer, warps 7 and 11 stay idle, the nine
+  // warps on sub-partitions 0-2 are the consumers.
+  const bool is_producer = (threadIdx.x >> 5) == 3;
+  const bool is_idle = ((threadIdx.x >> 5) & 3) == 3 && !is_producer;
+  const int cwi = (threadIdx.x >> 5) - ((threadIdx.x >> 5) >> 2);   // consumer index 0..8 (warps 0,1,2,4,5,6,8,9,10)
+  const int ct = cwi * 32 + (threadIdx.x & 31);                     // consumer thread index 0..287
+  extern __shared__ unsigned char band4_raw[];
+  Band4Smem<W> &sm = *reinterpret_cast<Band4Smem<W> *>(band4_raw);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int ld = n + 1;
+  const int nsteps = (n + 7) / 8;
+  unsigned long long t_begin = 0;
+  if (timing) t_begin = gtime();
+  if (t == 0) {
+    mbar_init(&sm.bar_raw[0], 8); mbar_init(&sm.bar_raw[1], 8);
+    mbar_init(&sm.bar_L[0], 1);   mbar_init(&sm.bar_L[1], 1);
+  }
+  // initial window: tiles (I, J), I >= J (the upper ones are never read)
+  for (int e = t; e < NT * NT * 64; e += kBand4Threads) {
+    const int tile = e >> 6, i = (e >> 3) & 7, j = e & 7;
+    const int I = tile / NT, J = tile - I * NT;
+    sm.f.win[tile][8 * i + j] = (I >= J) ? band_load_sym(A, ld, n, bw, 8 * I + i, 8 * J + j) : 0.0;
+  }
+  for (int e = t; e < W; e += kBand4Threads) sm.f.zwin[e] = (e < n) ? __ldcg(A + (size_t)e * ld + n) : 0.0;
+  __syncthreads();
+
+  if (is_idle) {
+    // nothing: joins the block-wide barrier below
+  } else if (is_producer) {
+    // ------------------------------------------------ producer: panel factorisation ----------------
+    int P = 0;
+    long long tw = 0, tk = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      const int par = s & 1;
+      const long long c0 = timing ? clock64() : 0;
+      if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(5 + par), "n"(kBand4Active) : "memory");   // panel carries every earlier update
+      const long long c1 = timing ? clock64() : 0;
+      double a[NSL][8];
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        const int pos = lane + 32 * sl;
+        if (pos < W) {
+          const double4 *src = reinterpret_cast<const double4 *>(&sm.f.win[(pos >> 3) * NT + P][8 * (pos & 7)]);
+          const double4 v0 = src[0], v1 = src[1];
+          a[sl][0] = v0.x; a[sl][1] = v0.y; a[sl][2] = v0.z; a[sl][3] = v0.w;
+          a[sl][4] = v1.x; a[sl][5] = v1.y; a[sl][6] = v1.z; a[sl][7] = v1.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a[sl][k] = (pos == W) ? sm.f.zwin[8 * P + k] : 0.0;
+        }
+      }
+      double D[8][8], rs[8];
+      {
+        const double4 *dsrc = reinterpret_cast<const double4 *>(&sm.f.win[P * NT + P][0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double4 v0 = dsrc[2 * i], v1 = dsrc[2 * i + 1];
+          D[i][0] = v0.x; D[i][1] = v0.y; D[i][2] = v0.z; D[i][3] = v0.w;
+          D[i][4] = v1.x; D[i][5] = v1.y; D[i][6] = v1.z; D[i][7] = v1.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double d = D[k][k];
+        const bool pos_def = d > 0.0;
+        const double rc = pos_def ? fast_rcp(d) : 0.0;       // non-positive pivot: LDLT's D^+ = 0
+        rs[k] = pos_def ? fast_rsqrt(d) : 0.0;
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) {
+          const double ti = D[i][k] * rc;
+#pragma unroll
+          for (int j = k + 1; j <= i; ++j) D[i][j] -= ti * D[j][k];
+        }
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+          const double u = a[sl][k] * rc;
+#pragma unroll
+          for (int m = k + 1; m < 8; ++m) a[sl][m] -= u * D[m][k];
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        const int pos = lane + 32 * sl;
+        if (pos <= W) {
+          double4 *dst = reinterpret_cast<double4 *>(&sm.f.Lp[par][pos][0]);
+          dst[0] = make_double4(a[sl][0] * rs[0], a[sl][1] * rs[1], a[sl][2] * rs[2], a[sl][3] * rs[3]);
+          dst[1] = make_double4(a[sl][4] * rs[4], a[sl][5] * rs[5], a[sl][6] * rs[6], a[sl][7] * rs[7]);
+        }
+      }
+      asm volatile("bar.arrive %0, %1;" ::"r"(3 + par), "n"(kBand4Active) : "memory");
+      if (timing) { tw += c1 - c0; tk += clock64() - c1; }
+      P = (P + 1 == NT) ? 0 : P + 1;
+    }
+    if (timing && lane == 0) { g_band_dbg[2] = tw; g_band_dbg[3] = tk; }
+  } else {
+    // ------------------------------------------------ consumers -------------------------------------
+    const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
+    const int laneL = fr * 12 + kq, laneC = fr * 8 + fc;
+    // relative coordinates of this warp's bulk tiles (the same at every step)
+    int ra2[TP2], rb2[TP2];
+#pragma unroll
+    for (int i = 0; i < TP2; ++i) {
+      int e = cwi + kBand4Cons * i, ra = 2, len = 1;    // row ra holds rb = 2 .. ra: (ra - 1) tiles
+      const bool live = e < T2;
+      if (live) {
+        while (e >= len) { e -= len; ++ra; ++len; }
+      }
+      ra2[i] = live ? ra : -1;
+      rb2[i] = live ? 2 + e : 0;
+    }
+    auto tile_update = [&](const double *Lp, int sa, int sb) {
+      double *c = &sm.f.win[sa * NT + sb][laneC];
+      double2 v = *reinterpret_cast<double2 *>(c);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) dmma_884b(v.x, v.y, -Lp[sa * 96 + laneL + 4 * h], Lp[sb * 96 + laneL + 4 * h]);
+      *reinterpret_cast<double2 *>(c) = v;
+    };
+    // streams of the elements this thread reloads when ring slot P is recycled for tile row s + NT: element
+    // e = t + 256 q -> relative column tile rc = 1 + e / 64, (i, j) inside the tile; every step moves it by
+    // 8 rows and 8 columns.  In-band is a static property of (rc, i, j); only the matrix bound moves.
+    constexpr int NV = (NT * 64 + 32 * kBand4Cons - 1) / (32 * kBand4Cons);
+    const double *nvp[NV];
+    int nvhi[NV];
+    unsigned nvok = 0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int e = ct + 32 * kBand4Cons * q;
+      const int rc = 1 + (e >> 6), i = (e >> 3) & 7, j = e & 7;
+      const int r = 8 * NT + i, c = 8 * rc + j;          // step 0
+      const int lo = min(r, c), hi = max(r, c);
+      nvp[q] = A + (size_t)lo * ld + hi;
+      nvhi[q] = hi;
+      if (e < NT * 64 && rc >= 2 && hi - lo <= bw) nvok |= 1u << q;
+    }
+    const size_t nvstride = (size_t)8 * (ld + 1);
+    long long ctm[5] = {0, 0, 0, 0, 0};
+    int zc = 8 * NT + (ct & 7);      // column whose rhs entry the threads of the retiring slot load (t / 8 == P)
+    int P = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+      const int par = s & 1;
+      const int Pn = (P + 1 == NT) ? 0 : P + 1;
+      const double *Lp = &sm.f.Lp[par][0][0];
+      const long long c0 = timing ? clock64() : 0;
+      // new tile row (8 s + W ..): loads issued now, stored after the bulk update
+      double nv[NV];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        nv[q] = (((nvok >> q) & 1u) && nvhi[q] < n) ? __ldcg(nvp[q]) : 0.0;
+        nvp[q] += nvstride;
+        nvhi[q] += 8;
+      }
+      const bool z_retire = (ct >> 3) == P && ct < W;
+      double znew = 0.0;
+      if (z_retire) znew = (zc < n) ? __ldcg(A + (size_t)zc * ld + n) : 0.0;
+      zc += 8;
+      const long long c1 = timing ? clock64() : 0;
+      asm volatile("bar.sync %0, %1;" ::"r"(3 + par), "n"(kBand4Active) : "memory");
+      const long long c2 = timing ? clock64() : 0;
+      // ---- priority: the next panel = relative column 1
+      for (int ra = 1 + cwi; ra < NT; ra += kBand4Cons) {
+        int sa = P + ra;
+        if (sa >= NT) sa -= NT;
+        tile_update(Lp, sa, Pn);
+      }
+      if (cwi == 0) {   // tile (new row, next panel) lies outside the band (W >= bw + 16): zeros
+        *reinterpret_cast<double2 *>(&sm.f.win[P * NT + Pn][2 * lane]) = make_double2(0.0, 0.0);
+      }
+      const bool z_next = (ct >> 3) == Pn && ct < W;
+      auto z_update = [&]() {
+        const double4 *lz = reinterpret_cast<const double4 *>(Lp + W * 12);
+        const double4 *lt = reinterpret_cast<const double4 *>(Lp + ct * 12);
+        const double4 z0 = lz[0], z1 = lz[1], l0 = lt[0], l1 = lt[1];
+        sm.f.zwin[ct] -= z0.x * l0.x + z0.y * l0.y + z0.z * l0.z + z0.w * l0.w + z1.x * l1.x + z1.y * l1.y + z1.z * l1.z + z1.w * l1.w;
+      };
+      if (z_next) z_update();
+      asm volatile("bar.arrive %0, %1;" ::"r"(5 + (par ^ 1)), "n"(kBand4Active) : "memory");
+      const long long c3 = timing ? clock64() : 0;
+      // ---- bulk: operands of all tiles first, then the DMMAs (two dependent ones per tile), then the stores
+      if (ct < W && !z_retire && !z_next) z_update();
+      {
+        double2 cv[TP2];
+        double af[TP2][2], bf[TP2][2];
+        double *cp[TP2];
+#pragma unroll
+        for (int i = 0; i < TP2; ++i) {
+          int sa = P + max(ra2[i], 0), sb = P + rb2[i];
+          if (sa >= NT) sa -= NT;
+          if (sb >= NT) sb -= NT;
+          cp[i] = &sm.f.win[sa * NT + sb][laneC];
+          cv[i] = *reinterpret_cast<double2 *>(cp[i]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            af[i][h] = -Lp[sa * 96 + laneL + 4 * h];
+            bf[i][h] = Lp[sb * 96 + laneL + 4 * h];
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < TP2; ++i) dmma_884b(cv[i].x, cv[i].y, af[i][h], bf[i][h]);
+#pragma unroll
+        for (int i = 0; i < TP2; ++i)
+          if (ra2[i] >= 0) *reinterpret_cast<double2 *>(cp[i]) = cv[i];
+      }
+      // ---- finished panel to global memory: warp w writes column w (coalesced over rows)
+      {
+        const int c = 8 * s + cwi;
+        if (cwi < 8 && c < n) {
+          double *col = A + (size_t)c * ld + 8 * s;
+#pragma unroll
+          for (int q = 0; q < (W + 31) / 32; ++q) {
+            const int pos = lane + 32 * q;
+            int rel = pos - 8 * P;
+            if (rel < 0) rel += W;
+            if (pos < W && rel >= cwi && rel - cwi <= bw && 8 * s + rel < n) {
+              double l = Lp[pos * 12 + cwi];
+              if (rel == cwi && !(l > 0.0)) l = __longlong_as_double(0x7ff0000000000000LL);
+              col[rel] = l;
+            }
+          }
+          if (lane == 0) A[(size_t)c * ld + n] = Lp[W * 12 + cwi];
+        }
+      }
+      // ---- recycle ring slot P for tile row s + NT (columns s + 2 .. s + NT; s + 1 was zeroed above)
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        const int e = ct + 32 * kBand4Cons * q;
+        const int rc = 1 + (e >> 6);
+        if (e < NT * 64 && rc >= 2) {
+          int sb = P + rc;
+          if (sb >= NT) sb -= NT;
+          sm.f.win[P * NT + sb][e & 63] = nv[q];
+        }
+      }
+      if (z_retire) sm.f.zwin[ct] = znew;
+      const long long c4 = timing ? clock64() : 0;
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kBand4Cons) : "memory");   // tiles change hands between steps
+      if (timing) { ctm[0] += c1 - c0; ctm[1] += c2 - c1; ctm[2] += c3 - c2; ctm[3] += c4 - c3; ctm[4] += clock64() - c4; }
+      P = Pn;
+    }
+    if (timing && t == 0) { for (int i = 0; i < 5; ++i) g_band_dbg[4 + i] = ctm[i]; }
+  }
+  __syncthreads();
+  unsigned long long t_factor = 0;
+  if (timing) t_factor = gtime();
+  if (warp < 8) band_backward<W>(A, n, bw, x_out, linv, sm);
+  if (timing && t == 0) {
+    g_band_dbg[0] = t_factor - t_begin;
+    g_band_dbg[1] = gtime() - t_factor;
+  }
+}
+
+template <int W>
+inline bool launch_band4(double *Saug, int n, int bw, double *x, double *linv, int timing, const LmState *st,
+                         cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_chol_banded_smem<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band4Smem<W>));
+    attr_set = true;
+  }
+  k_chol_banded_smem<W><<<1, kBand4Threads, sizeof(Band4Smem<W>), stream>>>(Saug, n, bw, x, linv, timing, st);
+  return cudaGetLastError() == cudaSuccess;
+}
+
 inline bool cholesky_banded_supported(int n, int bw) { return n > 0 && bw + 8 <= kBandMaxW; }
 
 inline bool cholesky_banded_enqueue(double *Saug, int n, int bw, double *x, double *linv, const LmState *st,
                                     cudaStream_t stream) {
   static const int timing = getenv("BA_B200_VERBOSE") != nullptr;
-  static const int mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 3;
-  if (mode == 3) {   // DMMA block steps (needs W >= bw + 8)
+  static const int mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 4;
+  if (mode == 4 && bw + 16 <= 120) {   // DMMA block steps, window in shared memory (needs W >= bw + 16)
+    if (bw + 16 <= 56) return launch_band4<56>(Saug, n, bw, x, linv, timing, st, stream);
+    if (bw + 16 <= 88) return launch_band4<88>(Saug, n, bw, x, linv, timing, st, stream);
+    return launch_band4<120>(Saug, n, bw, x, linv, timing, st, stream);
+  }
+  if (mode >= 3) {   // DMMA block steps (needs W >= bw + 8)
     if (bw + 8 <= 48) k_chol_banded_dmma<48><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
     else if (bw + 8 <= 80) k_chol_banded_dmma<80><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
     else if (bw + 8 <= 112) k_chol_banded_dmma<112><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);

@@ -2210,8 +2210,10 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
     unsigned long long dbg[8];
     cudaMemcpyFromSymbol(dbg, g_cl_dbg, sizeof(dbg));
     if (s->chol.banded) {
-      cudaMemcpyFromSymbol(dbg, g_band_dbg, 4 * sizeof(unsigned long long));
-      fprintf(stderr, "[ba_b200] banded ns: factor %llu backward %llu (n=%d bw=%d)\n", dbg[0], dbg[1], s->chol.n, s->chol.bw);
+      unsigned long long d2[16];
+      cudaMemcpyFromSymbol(d2, g_band_dbg, 16 * sizeof(unsigned long long));
+      fprintf(stderr, "[ba_b200] banded ns: factor %llu backward %llu (n=%d bw=%d) | cycles: producer wait %llu work %llu | consumer0 loads %llu waitL %llu priority %llu bulk %llu endbar %llu\n",
+              d2[0], d2[1], s->chol.n, s->chol.bw, d2[2], d2[3], d2[4], d2[5], d2[6], d2[7], d2[8]);
     } else
     fprintf(stderr, "[ba_b200] cluster ns: diag %llu sync %llu trsm %llu sync %llu syrk %llu sync %llu backward %llu\n", dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5], dbg[6]);
   }
