@@ -59,18 +59,61 @@ WORKLOAD_NAMES = {
 
 
 def algorithmic_bytes(sz, n_obs_free_pose):
-    """Algorithmic bytes per LM iteration of the implemented design (DESIGN.md 'Kernels')."""
+    """Algorithmic bytes / flops per LM iteration of the implemented design (DESIGN.md 'Kernels').
+    pose side  (k_linearize_by_pose + k_finish_poses): 28 B/obs in pose order, A/a and the S diagonal
+    point side (k_build_tiles, fused K1+K3+K4): 20 B/obs (pixel, camera) + 24 B per (pose, landmark) incidence,
+               pose/point gathers, B written once (144 B/pair), per-landmark blocks (144 B), S tile flush
+    back-substitution: B read once (144 B/pair) + per-landmark blocks;   cost: 28 B/obs."""
     O, Nt, Mt, N, M, P = sz["n_obs"], sz["N_total"], sz["M_total"], sz["N"], sz["M"], sz["P"]
     n = 6 * N
     b = {}
-    b["linearize"] = (32 * O + 96 * Nt + 24 * Mt + 144 * M + 144 * P          # K1: obs, params, point blocks, B
-                      + 28 * n_obs_free_pose + 24 * Mt + 96 * N + 2 * 336 * N  # K2: obs (pose order), A/a + S diag
-                      + 8 * (n + 1) * (n + 1))                                 # S memset
-    b["schur"] = 144 * P + 12 * P + 72 * M + 8 * n * (n + 1) // 2 * 2 + 16 * n  # K4: B, pair ids, Cinv/Cinv_b, S r/w
+    b["linearize"] = 28 * n_obs_free_pose + 96 * Nt + 24 * Mt + 2 * 336 * N + 8 * (n + 1) * (n + 1)  # pose side + S memset
+    b["schur"] = 20 * O + 24 * P + 96 * Nt + 24 * Mt + 144 * P + 144 * M + 8 * n * (n + 1) // 2 + 8 * n
     b["backsub"] = 144 * P + 8 * P + 48 * N + 24 * M + (144 + 24 + 24 + 24 + 24) * Mt
     b["update_cost"] = 28 * O + 96 * Nt * 2 + 24 * Mt
     b["solve_flops"] = n ** 3 / 3.0 + 2.0 * n * n
+    # build flops: ~330 per observation (projection, weight, Jacobians, C/b/B) + Schur 216 per block pair
+    b["schur_flops"] = 330.0 * O
     return b
+
+
+def poseonly_c2(device, stream, frames=4096, points=300, reps=5):
+    """Config C2: batched 6-DoF stereo pose-only BA, `frames` independent frames x `points` observations,
+    device-resident (ba_poseonly_upload / ba_poseonly_run), timed with CUDA events on the launching stream."""
+    import ctypes as C
+    import torch
+    from bundle_adjustment_solver_b200 import capi, scenes
+    L = capi.lib()
+    pb = scenes.scene_poseonly_batch(n_frames=frames, n_points=points, seed=1)
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    off = np.ascontiguousarray(pb.offsets, dtype=np.int32)
+    arrs = [f32(pb.points), f32(pb.px_left), f32(pb.px_right), f32(pb.intr_left), f32(pb.intr_right),
+            f32(pb.left_to_right), None, None, f32(pb.poses_init)]
+    h = C.c_void_p()
+    rc = L.ba_poseonly_upload(C.byref(h), device, pb.kind, pb.n_frames, capi.ptr(off), *[capi.ptr(a) for a in arrs])
+    if rc != 0:
+        raise SystemExit("ba_poseonly_upload failed")
+    opt = capi.PoseOnlyOptions(1e-6, 1e-6, 1.5, 2.5, 100)
+    for _ in range(3):
+        L.ba_poseonly_run(h, C.byref(opt), C.c_void_p(stream.cuda_stream))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        L.ba_poseonly_run(h, C.byref(opt), C.c_void_p(stream.cuda_stream))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    res = (capi.PoseOnlyResult * pb.n_frames)()
+    poses = np.zeros((pb.n_frames, 12), dtype=np.float32)
+    L.ba_poseonly_download(h, capi.ptr(poses), None, None, res)
+    L.ba_poseonly_free(h)
+    iters = float(np.mean([res[k].n_iterations for k in range(pb.n_frames)]))
+    n_pts = int(off[-1])
+    return {"workload": f"C2 batched 6-DoF stereo pose-only BA, {frames} frames x {points} points (FP32)",
+            "ms_per_batch": ms, "frames_per_s": pb.n_frames / (ms * 1e-3),
+            "point_iterations_per_s": n_pts * iters / (ms * 1e-3), "mean_gn_iterations": iters,
+            "max_pose_err_vs_truth": float(np.abs(poses - pb.poses_true).max()),
+            "bytes_per_solve": int(28 * n_pts), "note": "one warp per frame, persistent over the GN iterations; working set is L2-resident"}
 
 
 class ClockSampler:
@@ -173,6 +216,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=4, help="LM iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-poseonly", action="store_true", help="skip the C2 pose-only sub-benchmark")
     ap.add_argument("--e2e-max-iters", type=int, default=300,
                     help="iteration cap of the end-to-end solve (SURVEY 8d: thresholds 1e-6f, max 300 iterations)")
     ap.add_argument("--quick", action="store_true", help="profiling run: no clock-settling loop, phases, e2e or CPU baseline")
@@ -332,6 +376,11 @@ def main():
                    "includes": "host registration, FinalizeParameters (sorts, H2D pack), LM loop to convergence, D2H write-back"}
             del s2
 
+    po2 = None
+    if world == 1 and not args.no_poseonly:
+        with torch.cuda.stream(stream):
+            po2 = poseonly_c2(local_rank, stream)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -346,12 +395,35 @@ def main():
     phases["solve"] = {"ms": ph["solve"], "algorithmic_flops": ab["solve_flops"],
                        "achieved_tflops": ab["solve_flops"] / (ph["solve"] * 1e-3) / 1e12 if ph["solve"] > 0 else 0.0}
     t_build = ph["linearize"] + ph["schur"]
-    dom = max(("linearize", "schur", "backsub", "update_cost"), key=lambda k: ph[k])
-    roofline = {"bound": "hbm", "kernel": {"linearize": "k_linearize_by_point+k_linearize_by_pose", "schur": "k_schur_pairs",
-                                           "backsub": "k_backsub_pairs+k_backsub_points", "update_cost": "k_cost+k_update_poses"}[dom],
-                "achieved": phases[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": phases[dom]["frac_hbm"],
-                "traffic": None, "peak_source": peak_src,
-                "note": "dominant memory-bound phase of the step; per-phase table in 'phases' (the Cholesky phase is FP64-compute bound, see phases.solve)"}
+    kernels = {"linearize": "k_linearize_by_pose+k_finish_poses", "schur": "k_build_tiles (linearise + C^-1 + Schur DMMA GEMM)",
+               "backsub": "k_backsub_pairs+k_backsub_points", "update_cost": "k_cost+k_update_poses",
+               "solve": "k_chol_banded_smem (DMMA window update; cluster / multi-kernel DMMA variants for other structures)"}
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the default C3 workload from the
+    # committed `ncu --set full` capture profiles/r01_ncu_full_c3_summary.md; None for any other workload
+    ncu_traffic = {"solve": 0.99e6, "schur": 34.66e6 + 27.96e6, "linearize": 25.38e6 + 0.25e6,
+                   "backsub": 76.02e6 + 2.67e6 + 9.86e6, "update_cost": 29.24e6 + 0.11e6}
+    traffic = (lambda k: ncu_traffic[k]) if (args.workload == "c3" and args.scale == 1.0 and world == 1) else (lambda k: None)
+    # the dominant kernel of the step by device time
+    dom = max(ph, key=lambda k: ph[k])
+    fp64_tensor_peak = 37.1   # TFLOP/s, measured on this pool's B200 with profiles/micro/dmma_peak.cu (m8n8k4 DMMA)
+    if dom == "solve":
+        roofline = {"bound": "tensor", "kernel": kernels[dom], "achieved": phases["solve"]["achieved_tflops"],
+                    "peak": fp64_tensor_peak, "unit": "TFLOP/s", "frac": phases["solve"]["achieved_tflops"] / fp64_tensor_peak,
+                    "traffic": traffic("solve"),
+                    "peak_source": "measured FP64 DMMA throughput (profiles/micro/dmma_peak.cu; MEASURED_PEAKS.json has no FP64 figure)",
+                    "note": "achieved = dense-equivalent n^3/3 + 2n^2 flops / solve time; the banded factorisation is bound by "
+                            "its chain of n/8 dependent panel steps (latency), not by FP64 throughput - see DESIGN.md 4 (K5)"}
+    else:
+        roofline = {"bound": "hbm", "kernel": kernels[dom], "achieved": phases[dom]["achieved_gbs"], "peak": hbm_peak,
+                    "unit": "GB/s", "frac": phases[dom]["frac_hbm"], "traffic": traffic(dom), "peak_source": peak_src}
+    # the Jacobian / Schur build (BASELINE metric "Schur-build obs/s"): both build phases together
+    build_bytes = ab["linearize"] + ab["schur"]
+    build_gbs = build_bytes / (t_build * 1e-3) / 1e9 if t_build > 0 else 0.0
+    roofline_build = {"bound": "hbm", "kernel": kernels["linearize"] + " ; " + kernels["schur"], "achieved": build_gbs,
+                      "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak, "algorithmic_bytes": build_bytes,
+                      "traffic": (traffic("linearize") + traffic("schur")) if traffic("schur") is not None else None,
+                      "peak_source": peak_src,
+                      "fp64_tflops": (ab["schur_flops"] / (t_build * 1e-3) / 1e12) if t_build > 0 else 0.0}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -379,7 +451,7 @@ def main():
                    "cuda_graph": world == 1},
         "lm_iters_per_s": args.steps / (ms * 1e-3),
         "schur_build_obs_per_s": total_obs / (t_build * 1e-3) if t_build > 0 else None,
-        "phases": phases, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "phases": phases, "roofline": roofline, "roofline_build": roofline_build, "poseonly_c2": po2, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks,
     }
     print(json.dumps(line))

@@ -167,3 +167,71 @@ def test_c3_scaled_blocks_and_iterations(oracle_mod, engine_lib):
     for a, b in zip(summ.optimization_info_list, infos_o):
         assert abs(a.cost - b.cost) <= 1e-8 * abs(b.cost)
         assert a.iteration_status == b.iteration_status
+
+
+def _solve_vs_numpy(sc, monkeypatch=None, chol_mode=None, band_mode=None):
+    """Build S, rhs on the device, solve with the engine's reduced solver, compare with numpy."""
+    import os
+    for k, v in (("BA_B200_CHOL_MODE", chol_mode), ("BA_B200_BAND_MODE", band_mode)):
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+    try:
+        e = load_engine(sc)
+        e.set_debug(True)
+        _, eo = options_pair()
+        e.build_only(eo, 100.0, do_solve=True)
+        n = 6 * e.sizes()["N"]
+        Sm = e.dump("S").reshape(n, n)
+        rhs = e.dump("rhs")
+        x = e.dump("x")
+    finally:
+        os.environ.pop("BA_B200_CHOL_MODE", None)
+        os.environ.pop("BA_B200_BAND_MODE", None)
+    xr = np.linalg.solve(Sm, rhs)
+    return float(np.abs(x - xr).max() / np.abs(xr).max()), n
+
+
+@pytest.mark.parametrize("n_poses,track,band_mode", [(100, 6, 4), (120, 10, 4), (150, 14, 4), (120, 10, 3), (120, 10, 1),
+                                                     (37, 10, 4)])
+def test_banded_reduced_solve_matches_numpy(n_poses, track, band_mode, engine_lib):
+    """K5 banded kernels (v4 shared-memory DMMA window, v3 register tiles, v1 scalar window) on sequential
+    trajectories of three bandwidths; x against numpy.linalg.solve of the device-built S, rhs."""
+    sc = scenes.scene_trajectory(n_poses, 40 * n_poses, track, stereo=True, seed=1, n_fixed=2)
+    err, n = _solve_vs_numpy(sc, band_mode=band_mode)
+    assert err < 1e-9, (err, n)
+
+
+@pytest.mark.parametrize("chol_mode", [0, 1])
+def test_multikernel_and_cluster_reduced_solve_match_numpy(chol_mode, engine_lib):
+    sc = scenes.scene_trajectory(120, 4800, 10, stereo=True, seed=2, n_fixed=2)
+    err, n = _solve_vs_numpy(sc, chol_mode=chol_mode)
+    assert err < 1e-9, (err, n)
+
+
+def test_dense_reduced_system_dmma_two_level(engine_lib):
+    """Loop closures make S dense: n = 2388 > 2048 takes the two-level blocked Cholesky with DMMA TRSM/SYRK
+    tiles and the multi-CTA backward sweep."""
+    sc = scenes.scene_trajectory(400, 40_000, 5, stereo=False, seed=3, heavy_tail=True, loop_fraction=0.05)
+    err, n = _solve_vs_numpy(sc)
+    assert n > 2048
+    assert err < 1e-8, (err, n)
+
+
+def test_tile_build_with_fixed_poses_points_and_wide_tracks(oracle_mod, engine_lib):
+    """Fused tile build next to the by-point path: fixed poses inside the tracks (C-only incidences), fixed
+    landmarks (A-only observations), heavy-tailed tracks (some exceed the 16-pose window) and loop closures."""
+    sc = scenes.scene_trajectory(120, 6000, 6, stereo=True, seed=5, n_fixed=3, heavy_tail=True, loop_fraction=0.03)
+    sc.fixed_poses = np.array([0, 1, 2, 40, 41, 77])
+    sc.fixed_points = np.arange(0, 6000, 97)
+    for accum in (0, 1):
+        o = load_oracle(sc)
+        o.build_only(thres_huber=1.0, lam=100.0, b_accumulate=accum, do_solve=True)
+        e = load_engine(sc, identical_internal=o.get_internal())
+        e.set_debug(True)
+        oo, eo = options_pair(b_accumulate=accum)
+        e.build_only(eo, 100.0, do_solve=True)
+        assert e.sizes() == o.sizes()
+        _compare_blocks(o, e, o.sizes())
+        assert blockwise_rel_err(e.dump("y"), o.dump("y"), 3) < 1e-6
