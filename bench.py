@@ -25,6 +25,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: library chatter written to fd 1 (e.g. NCCL's version banner) is sent
+# to stderr for the whole run and the result goes to the saved descriptor
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 METRIC = "LM-iteration observation throughput (observations x LM iters/s; full iteration: linearise, Schur, solve, back-substitute, cost/accept)"
 UNIT = "obs/s"
 
@@ -202,7 +213,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -325,7 +336,7 @@ def main():
 
         if args.quick:
             if rank == 0:
-                print(json.dumps({"quick": True, "ms_per_step": ms / args.steps, "value": value, "gpu_launches": launches}))
+                emit({"quick": True, "ms_per_step": ms / args.steps, "value": value, "gpu_launches": launches})
             if world > 1:
                 dist.destroy_process_group()
             return
@@ -454,7 +465,7 @@ def main():
         "phases": phases, "roofline": roofline, "roofline_build": roofline_build, "poseonly_c2": po2, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
