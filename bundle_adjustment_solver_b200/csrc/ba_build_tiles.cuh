@@ -1,0 +1,325 @@
+// ba_build_tiles.cuh -- K1b+K3+K4 fused for "tile" landmarks: persistent CTAs, barrier-free producers (included by
+// ba_engine.cu inside namespace ba, after Params / SchurChunk / load_pose / damp_invert / bar_* helpers).
+//
+// Same arithmetic as core/full_bundle_adjustment_solver.cpp:716-831 (point side), :846-856, :858-888.  Layout of the
+// work (what changed against the first fused kernel, k_build_tiles):
+//   * the tile chunks are cut into batches of 8 landmarks (K = 24 operand rows); the flat list of batches is split
+//     evenly over one persistent CTA per SM, so the producer/consumer pipeline never drains between chunks
+//     (a chunk that straddles two CTAs is simply flushed twice -- the flush is additive);
+//   * a landmark is owned by 4 adjacent lanes of one warp; lane `sub` linearises incidences sub, sub+4, ... of the
+//     landmark, the 9 C/b partials are combined with an xor-butterfly (bitwise identical on the 4 lanes, so each
+//     lane inverts the damped C redundantly and forms E = B C^-1 for its own incidences): no CTA barrier, no
+//     shared-memory staging of partials, no idle threads while one thread per landmark inverts;
+//   * every producer warp is its own group with its own operand buffer (G = 5..7 buffers, sized by the widest
+//     window of the launch: ldE = 8 nt + 4, ldB = 8 nt + 12, both = 4 or 12 mod 16 -> conflict-free DMMA fragment
+//     reads) and runs ahead on its own batch; the index records of the next batch are prefetched;
+//   * the four DMMA warps consume the buffers round-robin, clear the rows they just read (they have the idle issue
+//     slots) and hand the buffer back: full[g] / empty[g] named barriers, nothing else.
+#pragma once
+
+constexpr int kT2LB = 8;                  // landmarks per batch (one producer warp, 4 lanes per landmark)
+constexpr int kT2K = 3 * kT2LB;           // 24 operand rows
+constexpr int kT2ProdWarps = 8;           // warps 0..7 (two warpgroups for setmaxnreg); at most 7 of them produce
+constexpr int kT2MaxGroups = 7;           // named barriers: full 1..7, empty 8..14, consumer-internal 15
+constexpr int kT2Cons = 128;              // 4 DMMA warps
+constexpr int kT2Threads = kT2ProdWarps * 32 + kT2Cons;
+constexpr int kT2SmemBytes = 227 * 1024;  // everything an SM has: one CTA per SM
+constexpr int kT2SmemDoubles = kT2SmemBytes / 8;
+constexpr int kT2SPW = 7;                 // 2 x 2 super-tiles per DMMA warp at the widest window (27 over 4 warps)
+
+struct TileLaunch {   // uniform per launch, fixed at finalize
+  int nt_max;         // 8x8 tiles across the widest chunk window
+  int ldE, ldB;       // operand leading dimensions (doubles): whole 2 x 2 super-tiles, = 4 mod 16
+  int bufD;           // doubles per operand buffer
+  int G;              // buffers = producer warps in use
+  int n_cta;
+};
+
+__device__ __forceinline__ void dmma_884nv2(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool ACCUM_B>
+__global__ void __launch_bounds__(kT2Threads, 1)
+k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ batches /*ti0, nb, chunk, rhs column*/,
+               const int *__restrict__ cta_batch_ptr, TileLaunch tl, const int *__restrict__ tpt_point,
+               const int *__restrict__ tpt_inc_start, const int4 *__restrict__ inc_a /*obs_first, n_obs, pose, pair*/,
+               const int2 *__restrict__ inc_b /*slot (-1: fixed pose), tile landmark index*/,
+               const double2 *__restrict__ obs_uv, const int *__restrict__ obs_camflags, Params prm,
+               const double *__restrict__ cams, double thres_huber, double *__restrict__ Bsoa, size_t Pp,
+               double *__restrict__ ptblk, size_t Mp, double *__restrict__ Saug, int ld,
+               const LmState *__restrict__ st) {
+  if (st->done) return;
+  extern __shared__ double tsm[];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int b0 = cta_batch_ptr[blockIdx.x], b1 = cta_batch_ptr[blockIdx.x + 1];
+  const int ldE = tl.ldE, ldB = tl.ldB, bufD = tl.bufD, G = tl.G;
+  const int bar_cnt = 32 + kT2Cons;
+  {
+    double2 *z = reinterpret_cast<double2 *>(tsm);
+    for (int e = t; e < G * bufD / 2; e += kT2Threads) z[e] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+
+  if (warp < kT2ProdWarps) {
+    // ===================================================== producers =====================================
+    // register split: the consumers can only take what the producers gave back to the CTA pool
+    // (8 warps x (168 - 152) >= 4 warps x (200 - 168)); asking for more spins forever in TRY_ALLOC
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
+    const int grp = warp;
+    if (grp >= G) return;
+    const int sub = lane & 3;
+    const int li = lane >> 2;   // landmark of the batch
+    const double *poses = prm.poses[st->cur];
+    const double *points = prm.points[st->cur];
+    const double lambda = st->lambda;
+    double *Ebase = tsm + grp * bufD;
+    double *Bbase = Ebase + kT2K * ldE;
+    // software pipeline over the warp's batches: rec_n = record of the next batch, (a, b, pt, X) of the current one
+    int a = 0, b = 0, pt = 0;
+    double X[3] = {0.0, 0.0, 0.0};
+    bool live = false;
+    int rhs_n = 0;   // rhs column of the chunk's B operand = 8 nt (tile column right after the window)
+    auto load_landmark = [&](int4 rec) {
+      live = li < rec.y;
+      rhs_n = rec.w;
+      a = b = pt = 0;
+      if (live) {
+        const int ti = rec.x + li;
+        a = __ldg(tpt_inc_start + ti);
+        b = __ldg(tpt_inc_start + ti + 1);
+        pt = __ldg(tpt_point + ti);
+        X[0] = __ldg(points + (size_t)pt * 3);
+        X[1] = __ldg(points + (size_t)pt * 3 + 1);
+        X[2] = __ldg(points + (size_t)pt * 3 + 2);
+      }
+    };
+    int fb = b0 + grp;
+    int4 rec_n = make_int4(0, 0, 0, 0);
+    if (fb < b1) {
+      load_landmark(__ldg(batches + fb));
+      if (fb + G < b1) rec_n = __ldg(batches + fb + G);
+    }
+    for (; fb < b1; fb += G) {
+      const bool cur_live = live;
+      const int ca = a, cb = b, cpt = pt;
+      const int rhs_col = rhs_n;
+      const double X0 = X[0], X1 = X[1], X2 = X[2];
+      // first incidence record of the current landmark, then the next batch's landmark data (in flight during
+      // the whole batch)
+      int4 ia_n = make_int4(0, 0, 0, 0);
+      int slot_n = -1;
+      if (ca + sub < cb) { ia_n = __ldg(inc_a + ca + sub); slot_n = __ldg(inc_b + ca + sub).x; }
+      if (fb + G < b1) {
+        load_landmark(rec_n);
+        if (fb + 2 * G < b1) rec_n = __ldg(batches + fb + 2 * G);
+      }
+      if (fb - b0 >= G) bar_sync(8 + grp, bar_cnt);   // the consumers have read and cleared this buffer
+      double cp[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) cp[i] = 0.0;
+      const double Xc[3] = {X0, X1, X2};
+      // ---- 1. incidences sub, sub + 4, ... of the landmark
+      for (int ii = ca + sub; ii < cb; ii += 4) {
+        const int4 ia = ia_n;
+        const int slot = slot_n;
+        if (ii + 4 < cb) { ia_n = __ldg(inc_a + ii + 4); slot_n = __ldg(inc_b + ii + 4).x; }
+        double T[12];
+        load_pose(poses + (size_t)ia.z * 12, T);
+        double Bv[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
+        for (int k = ia.x; k < ia.x + ia.y; ++k) {
+          const double2 uv = obs_uv[k];
+          const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
+          Proj pr;
+          project(T, Xc, cam, uv.x, uv.y, pr);
+          const double w = huber_weight(pr.r0, pr.r1, thres_huber);
+          const double wr0 = w * pr.r0, wr1 = w * pr.r1;
+          double Gm[6], Rm[6];
+          jac_G(pr, cam, Gm);
+          jac_R(Gm, T, Rm);
+          cp[0] += w * (Rm[0] * Rm[0] + Rm[3] * Rm[3]);
+          cp[1] += w * (Rm[0] * Rm[1] + Rm[3] * Rm[4]);
+          cp[2] += w * (Rm[0] * Rm[2] + Rm[3] * Rm[5]);
+          cp[3] += w * (Rm[1] * Rm[1] + Rm[4] * Rm[4]);
+          cp[4] += w * (Rm[1] * Rm[2] + Rm[4] * Rm[5]);
+          cp[5] += w * (Rm[2] * Rm[2] + Rm[5] * Rm[5]);
+          cp[6] -= Rm[0] * wr0 + Rm[3] * wr1;
+          cp[7] -= Rm[1] * wr0 + Rm[4] * wr1;
+          cp[8] -= Rm[2] * wr0 + Rm[5] * wr1;
+          if (slot >= 0 && (ACCUM_B || k == ia.x + ia.y - 1)) {
+            double Q[12];
+            jac_Q(Gm, pr.Xb, Q);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) Bv[r * 3 + c] += w * (Q[r] * Rm[c] + Q[6 + r] * Rm[3 + c]);
+          }
+        }
+        if (slot >= 0) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              Bbase[(3 * li + c) * ldB + 6 * slot + r] = Bv[r * 3 + c];
+              Bsoa[(size_t)(r * 3 + c) * Pp + ia.w] = Bv[r * 3 + c];
+            }
+        }
+      }
+      // ---- 2. landmark sums over its 4 lanes: xor butterfly, bitwise identical on every lane of the landmark
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        cp[i] += __shfl_xor_sync(0xffffffffu, cp[i], 1);
+        cp[i] += __shfl_xor_sync(0xffffffffu, cp[i], 2);
+      }
+      if (cur_live) {
+        // ---- damping + Eigen-style pivoted 3x3 LDLT inverse, redundantly on the 4 lanes (:846-856)
+        double cd[6], ci[6];
+        damp_invert(cp, lambda, cd, ci);
+        // the 18 per-landmark values are spread over the 4 lanes of the landmark
+        if (sub == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            ptblk[(PB_b + c) * Mp + cpt] = cp[6 + c];
+            Bbase[(3 * li + c) * ldB + rhs_col] = cp[6 + c];
+          }
+          ptblk[(PB_Cd + 0) * Mp + cpt] = cd[0];
+          ptblk[(PB_Cd + 1) * Mp + cpt] = cd[1];
+        } else if (sub == 1) {
+#pragma unroll
+          for (int i = 2; i < 6; ++i) ptblk[(PB_Cd + i) * Mp + cpt] = cd[i];
+          ptblk[(PB_Cinv + 0) * Mp + cpt] = ci[0];
+        } else if (sub == 2) {
+#pragma unroll
+          for (int i = 1; i < 6; ++i) ptblk[(PB_Cinv + i) * Mp + cpt] = ci[i];
+        } else {
+          ptblk[(PB_Cinvb + 0) * Mp + cpt] = ci[0] * cp[6] + ci[1] * cp[7] + ci[2] * cp[8];
+          ptblk[(PB_Cinvb + 1) * Mp + cpt] = ci[1] * cp[6] + ci[3] * cp[7] + ci[4] * cp[8];
+          ptblk[(PB_Cinvb + 2) * Mp + cpt] = ci[2] * cp[6] + ci[4] * cp[7] + ci[5] * cp[8];
+        }
+        // ---- 3. E = B Cinv for the lane's own incidences (B read back from the operand the lane wrote); the
+        //         operand holds -E so that the GEMM accumulates S -= E B^T directly
+        for (int ii = ca + sub; ii < cb; ii += 4) {
+          const int slot = __ldg(inc_b + ii).x;
+          if (slot < 0) continue;
+          const double *Bc = Bbase + (3 * li) * ldB + 6 * slot;
+          double *Ec = Ebase + (3 * li) * ldE + 6 * slot;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const double v0 = Bc[r], v1 = Bc[ldB + r], v2 = Bc[2 * ldB + r];
+            Ec[r] = -(v0 * ci[0] + v1 * ci[1] + v2 * ci[2]);
+            Ec[ldE + r] = -(v0 * ci[1] + v1 * ci[3] + v2 * ci[4]);
+            Ec[2 * ldE + r] = -(v0 * ci[2] + v1 * ci[4] + v2 * ci[5]);
+          }
+        }
+      }
+      bar_arrive(1 + grp, bar_cnt);   // operands of this batch are complete
+    }
+  } else {
+    // ===================================================== consumers =====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int cw = warp - kT2ProdWarps;
+    const int ct = t - kT2ProdWarps * 32;
+    const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
+    const double *Afrag0 = tsm + kq * ldE + fr;                 // + 8 ti
+    const double *Bfrag0 = tsm + kT2K * ldE + kq * ldB + fr;    // + 8 tj
+    // The window is cut into 2 x 2 super-tiles (16 x 16 entries) so that every fragment read from shared memory
+    // feeds two DMMAs: super-tile (I, J), J >= I, holds tiles (2I + p, 2J + q); the rhs travels as tile column nt.
+    int sdesc[kT2SPW];               // I | J << 8 | diagonal << 16 of the warp's super-tiles; mycnt of them are live
+    int aofs[kT2SPW], bofs[kT2SPW];  // 16 I, 16 J
+    double acc[kT2SPW][4][2];
+    int mycnt = 0, cur_chunk = -1, nrows = 0, row0 = 0, nt = 0;
+    // flush: upper triangle of S (row-major) and the rhs column
+    auto flush = [&]() {
+#pragma unroll
+      for (int i = 0; i < kT2SPW; ++i) {
+        if (i >= mycnt) continue;
+        const int I = sdesc[i] & 0xff, J = (sdesc[i] >> 8) & 0xff;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int tj = 2 * J + q;
+            const int lr = 8 * (2 * I + p) + fr;
+            if (lr >= nrows || tj > nt) continue;
+            const size_t grow = (size_t)(row0 + lr) * ld;
+            if (tj == nt) {
+              if (fc == 0 && acc[i][2 * p + q][0] != 0.0) atomicAdd(&Saug[grow + (ld - 1)], acc[i][2 * p + q][0]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int lc = 8 * tj + fc + e;
+                const double v = acc[i][2 * p + q][e];
+                if (lc < nrows && lc >= lr && v != 0.0) atomicAdd(&Saug[grow + row0 + lc], v);
+              }
+            }
+          }
+      }
+    };
+    int4 rec = make_int4(0, 0, 0, 0);
+    if (b0 < b1) rec = __ldg(batches + b0);
+    int buf = 0;
+    for (int fb = b0; fb < b1; ++fb) {
+      const int4 rec_n = (fb + 1 < b1) ? __ldg(batches + fb + 1) : rec;
+      if (rec.z != cur_chunk) {
+        if (cur_chunk >= 0) flush();
+        cur_chunk = rec.z;
+        const SchurChunk ch = chunks[cur_chunk];
+        nrows = 6 * ch.width;
+        row0 = 6 * ch.jmin;
+        nt = (nrows + 7) >> 3;
+        const int nI = (nt + 1) >> 1, nJ = (nt + 2) >> 1;          // super-rows, super-columns (rhs included)
+        const int nst = nI * nJ - nI * (nI - 1) / 2;
+        const int cnt = (nst + 3) >> 2;
+        mycnt = max(0, min(cnt, nst - cw * cnt));
+#pragma unroll
+        for (int i = 0; i < kT2SPW; ++i) {
+          int e = cw * cnt + i, I = 0, len = nJ;
+          if (i < mycnt) {
+            while (e >= len) { e -= len; ++I; --len; }
+          } else {
+            e = 0;
+          }
+          const int J = I + e;
+          sdesc[i] = I | (J << 8) | ((I == J) ? (1 << 16) : 0);
+          aofs[i] = 16 * I;
+          bofs[i] = 16 * J;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[i][u][0] = acc[i][u][1] = 0.0;
+        }
+      }
+      const double *Ab = Afrag0 + buf * bufD, *Bb = Bfrag0 + buf * bufD;
+      bar_sync(1 + buf, bar_cnt);
+      // window += (-E_all) B_all^T  (K = 3 nb, zero padded)
+      const int ksteps = (3 * rec.y + 3) >> 2;
+#pragma unroll 2
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const double *Ak = Ab + ks * 4 * ldE, *Bk = Bb + ks * 4 * ldB;
+#pragma unroll
+        for (int i = 0; i < kT2SPW; ++i) {
+          if (i >= mycnt) break;   // uniform
+          const double *pa = Ak + aofs[i], *pb = Bk + bofs[i];
+          const double a0 = pa[0], a1 = pa[8], v0 = pb[0], v1 = pb[8];
+          dmma_884nv2(acc[i][0][0], acc[i][0][1], a0, v0);
+          dmma_884nv2(acc[i][1][0], acc[i][1][1], a0, v1);
+          if (!(sdesc[i] >> 16)) dmma_884nv2(acc[i][2][0], acc[i][2][1], a1, v0);   // below the diagonal: not needed
+          dmma_884nv2(acc[i][3][0], acc[i][3][1], a1, v1);
+        }
+      }
+      if (fb + G < b1) {
+        // clear the rows the batch used and hand the buffer back to its producer warp
+        bar_sync(15, kT2Cons);
+        double2 *ze = reinterpret_cast<double2 *>(tsm + buf * bufD);
+        double2 *zb = reinterpret_cast<double2 *>(tsm + buf * bufD + kT2K * ldE);
+        const int ne = 2 * ksteps * ldE, nbb = 2 * ksteps * ldB;   // double2 counts of 4 ksteps rows
+        for (int e = ct; e < ne; e += kT2Cons) ze[e] = make_double2(0.0, 0.0);
+        for (int e = ct; e < nbb; e += kT2Cons) zb[e] = make_double2(0.0, 0.0);
+        bar_arrive(8 + buf, bar_cnt);
+      }
+      buf = (buf + 1 == G) ? 0 : buf + 1;
+      rec = rec_n;
+    }
+    if (cur_chunk >= 0) flush();
+  }
+}

@@ -629,6 +629,8 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt
   }
 }
 
+#include "ba_build_tiles.cuh"
+
 __global__ void __launch_bounds__(128)
 k_schur_pairs_list(int n_list, const int *__restrict__ list /*pair indices p1, or null = identity*/,
                    const int *__restrict__ pair_pose, const int *__restrict__ pair_point,
@@ -1087,8 +1089,10 @@ struct ba_solver {
   DevBuf<int> d_split_points, d_split_pairs;
   DevBuf<SchurChunk> d_schur_chunks;
   DevBuf<int> d_tpt_point, d_tpt_inc_start, d_fallback_pairs;
-  DevBuf<int4> d_inc_a;
+  DevBuf<int4> d_inc_a, d_tile_batches;
   DevBuf<int2> d_inc_b;
+  DevBuf<int> d_cta_batch_ptr;
+  TileLaunch tile_launch{};
   DevBuf<Chunk> d_chunks_fb;
   DevBuf<int2> d_chunk_pts_fb;
   DevBuf<ChunkPoint> d_cpts_fb;
@@ -1172,7 +1176,7 @@ static void free_device(ba_solver *s) {
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
   s->d_tpt_point.release(); s->d_tpt_inc_start.release(); s->d_fallback_pairs.release();
-  s->d_inc_a.release(); s->d_inc_b.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
+  s->d_inc_a.release(); s->d_inc_b.release(); s->d_tile_batches.release(); s->d_cta_batch_ptr.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
   s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
@@ -1455,6 +1459,30 @@ int ba_finalize(ba_solver *s) {
     tpt_inc_start.push_back((int)inc_a.size());
     std::sort(fallback_pairs.begin(), fallback_pairs.end());
   }
+  // --- flat list of 8-landmark batches over the tile chunks, split evenly over one persistent CTA per SM
+  std::vector<int4> tile_batches;
+  std::vector<int> cta_batch_ptr;
+  {
+    int nt_max = 1;
+    for (size_t c = 0; c < schur_chunks.size(); ++c) {
+      const SchurChunk &sc = schur_chunks[c];
+      nt_max = std::max(nt_max, (6 * sc.width + 7) / 8);
+      for (int o = 0; o < sc.pt_count; o += kT2LB)
+        tile_batches.push_back(make_int4(sc.pt_start + o, std::min(kT2LB, sc.pt_count - o), (int)c, 8 * ((6 * sc.width + 7) / 8)));
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    TileLaunch &tl = s->tile_launch;
+    tl.nt_max = nt_max;
+    tl.ldE = 16 * ((nt_max + 1) / 2) + 4;   // whole super-tiles; 4 mod 16: conflict-free fragment reads
+    tl.ldB = 16 * ((nt_max + 2) / 2) + 4;   // window + rhs tile column
+    tl.bufD = kT2K * (tl.ldE + tl.ldB);
+    tl.G = std::min(kT2MaxGroups, kT2SmemDoubles / tl.bufD);
+    const long long nbt = (long long)tile_batches.size();
+    tl.n_cta = (int)std::min<long long>(sms, std::max<long long>(1, (nbt + tl.G - 1) / tl.G));
+    cta_batch_ptr.resize(tl.n_cta + 1);
+    for (int k = 0; k <= tl.n_cta; ++k) cta_batch_ptr[k] = (int)(nbt * k / tl.n_cta);
+  }
   lap("tile chunks, incidences");
   // --- Cholesky envelope plan from the co-visibility structure
   {
@@ -1649,6 +1677,8 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_tpt_inc_start.upload(tpt_inc_start, st));
   CUDA_TRY(s->d_inc_a.upload(inc_a, st));
   CUDA_TRY(s->d_inc_b.upload(inc_b, st));
+  CUDA_TRY(s->d_tile_batches.upload(tile_batches, st));
+  CUDA_TRY(s->d_cta_batch_ptr.upload(cta_batch_ptr, st));
   CUDA_TRY(s->d_chunks_fb.upload(pc_fb.chunks, st));
   CUDA_TRY(s->d_chunk_pts_fb.upload(pc_fb.chunk_pts, st));
   CUDA_TRY(s->d_cpts_fb.upload(pc_fb.cpts, st));
@@ -1802,12 +1832,29 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   // tile landmarks: linearisation + C^-1 + Schur products fused (DMMA)
   if (s->n_schur_chunks > 0) {
     static bool attr_set = false;
+    static int tiles_version = 2;   // BA_B200_TILES=1: first fused kernel (CTA-barrier producers), kept for A/B timing
     if (!attr_set) {
       cudaFuncSetAttribute(k_build_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
       cudaFuncSetAttribute(k_build_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+      cudaFuncSetAttribute(k_build_tiles2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
+      cudaFuncSetAttribute(k_build_tiles2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
+      if (const char *e = getenv("BA_B200_TILES")) tiles_version = atoi(e);
       attr_set = true;
     }
-    if (opt->b_accumulate)
+    if (tiles_version == 2) {
+      const TileLaunch &tl = s->tile_launch;
+      const size_t smem = (size_t)tl.G * tl.bufD * sizeof(double);
+      if (opt->b_accumulate)
+        k_build_tiles2<true><<<tl.n_cta, kT2Threads, smem, st>>>(
+            s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
+            s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
+            s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+      else
+        k_build_tiles2<false><<<tl.n_cta, kT2Threads, smem, st>>>(
+            s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
+            s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
+            s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+    } else if (opt->b_accumulate)
       k_build_tiles<true><<<s->n_schur_chunks, kTileThreads, kTileSmem, st>>>(
           s->d_schur_chunks.p, s->d_tpt_point.p, s->d_tpt_inc_start.p, s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p,
           s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
