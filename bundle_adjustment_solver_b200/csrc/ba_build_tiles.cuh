@@ -13,14 +13,15 @@
 //   * every producer warp is its own group with its own operand buffer (G = 5..7 buffers, sized by the widest
 //     window of the launch: ldE = 8 nt + 4, ldB = 8 nt + 12, both = 4 or 12 mod 16 -> conflict-free DMMA fragment
 //     reads) and runs ahead on its own batch; the index records of the next batch are prefetched;
-//   * the four DMMA warps consume the buffers round-robin, clear the rows they just read (they have the idle issue
-//     slots) and hand the buffer back: full[g] / empty[g] named barriers, nothing else.
+//   * the four DMMA warps consume the buffers round-robin and hand them back: full[g] / empty[g] named barriers,
+//     nothing else; a producer clears the few window slots its landmark does not cover instead of anybody
+//     clearing whole buffers.
 #pragma once
 
 constexpr int kT2LB = 8;                  // landmarks per batch (one producer warp, 4 lanes per landmark)
 constexpr int kT2K = 3 * kT2LB;           // 24 operand rows
 constexpr int kT2ProdWarps = 8;           // warps 0..7 (two warpgroups for setmaxnreg); at most 7 of them produce
-constexpr int kT2MaxGroups = 7;           // named barriers: full 1..7, empty 8..14, consumer-internal 15
+constexpr int kT2MaxGroups = 7;           // named barriers: full 1..7, empty 8..14
 constexpr int kT2Cons = 128;              // 4 DMMA warps
 constexpr int kT2Threads = kT2ProdWarps * 32 + kT2Cons;
 constexpr int kT2SmemBytes = 227 * 1024;  // everything an SM has: one CTA per SM
@@ -79,10 +80,11 @@ k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ b
     int a = 0, b = 0, pt = 0;
     double X[3] = {0.0, 0.0, 0.0};
     bool live = false;
-    int rhs_n = 0;   // rhs column of the chunk's B operand = 8 nt (tile column right after the window)
+    int rhs_n = 0, nb_n = 0;   // rec.w = rhs column of the chunk's B operand (8 nt) | window width << 16; rec.y = landmarks
     auto load_landmark = [&](int4 rec) {
       live = li < rec.y;
       rhs_n = rec.w;
+      nb_n = rec.y;
       a = b = pt = 0;
       if (live) {
         const int ti = rec.x + li;
@@ -103,7 +105,7 @@ k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ b
     for (; fb < b1; fb += G) {
       const bool cur_live = live;
       const int ca = a, cb = b, cpt = pt;
-      const int rhs_col = rhs_n;
+      const int rhs_col = rhs_n & 0xffff, W = rhs_n >> 16, cur_nb = nb_n;
       const double X0 = X[0], X1 = X[1], X2 = X[2];
       // first incidence record of the current landmark, then the next batch's landmark data (in flight during
       // the whole batch)
@@ -114,21 +116,26 @@ k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ b
         load_landmark(rec_n);
         if (fb + 2 * G < b1) rec_n = __ldg(batches + fb + 2 * G);
       }
-      if (fb - b0 >= G) bar_sync(8 + grp, bar_cnt);   // the consumers have read and cleared this buffer
       double cp[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) cp[i] = 0.0;
       const double Xc[3] = {X0, X1, X2};
-      // ---- 1. incidences sub, sub + 4, ... of the landmark
-      for (int ii = ca + sub; ii < cb; ii += 4) {
+      // ---- 1. incidences sub, sub + 4, ... of the landmark, in warp-uniform rounds.  The buffer is only needed
+      //         when the first round is stored: its loads and arithmetic run while the consumers still read it
+      const int rounds = __reduce_max_sync(0xffffffffu, (cb - ca + 3) >> 2);
+      unsigned covered = 0u;   // window slots of the landmark that receive a B / E block
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int ii = ca + sub + 4 * rd;
+        const bool act = ii < cb;
         const int4 ia = ia_n;
-        const int slot = slot_n;
+        const int slot = act ? slot_n : -1;
         if (ii + 4 < cb) { ia_n = __ldg(inc_a + ii + 4); slot_n = __ldg(inc_b + ii + 4).x; }
-        double T[12];
-        load_pose(poses + (size_t)ia.z * 12, T);
         double Bv[18];
 #pragma unroll
         for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
+        if (act) {
+        double T[12];
+        load_pose(poses + (size_t)ia.z * 12, T);
         for (int k = ia.x; k < ia.x + ia.y; ++k) {
           const double2 uv = obs_uv[k];
           const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
@@ -157,7 +164,10 @@ k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ b
               for (int c = 0; c < 3; ++c) Bv[r * 3 + c] += w * (Q[r] * Rm[c] + Q[6 + r] * Rm[3 + c]);
           }
         }
+        }
+        if (rd == 0 && fb - b0 >= G) bar_sync(8 + grp, bar_cnt);   // the consumers have read and cleared this buffer
         if (slot >= 0) {
+          covered |= 1u << slot;
 #pragma unroll
           for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -167,11 +177,36 @@ k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ b
             }
         }
       }
+      if (rounds == 0 && fb - b0 >= G) bar_sync(8 + grp, bar_cnt);
       // ---- 2. landmark sums over its 4 lanes: xor butterfly, bitwise identical on every lane of the landmark
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         cp[i] += __shfl_xor_sync(0xffffffffu, cp[i], 1);
         cp[i] += __shfl_xor_sync(0xffffffffu, cp[i], 2);
+      }
+      // ---- the buffer still holds the previous batch: clear the window slots this landmark does not cover (few:
+      //      chunks group landmarks of the same window) and, on a partial batch, the rows of the first unused
+      //      landmark (the GEMM runs over whole k-steps of 4 rows); its rhs entries are cleared by the store below
+      covered |= __shfl_xor_sync(0xffffffffu, covered, 1);
+      covered |= __shfl_xor_sync(0xffffffffu, covered, 2);
+      const bool zrow = cur_live || li == cur_nb;
+      if (zrow) {
+        for (int sl = sub; sl < W; sl += 4) {
+          if ((covered >> sl) & 1u) continue;
+          double *Bz = Bbase + (3 * li) * ldB + 6 * sl;
+          double *Ez = Ebase + (3 * li) * ldE + 6 * sl;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 6; r += 2) {
+              *reinterpret_cast<double2 *>(Bz + c * ldB + r) = make_double2(0.0, 0.0);
+              *reinterpret_cast<double2 *>(Ez + c * ldE + r) = make_double2(0.0, 0.0);
+            }
+        }
+        if (!cur_live && sub == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Bbase[(3 * li + c) * ldB + rhs_col] = 0.0;
+        }
       }
       if (cur_live) {
         // ---- damping + Eigen-style pivoted 3x3 LDLT inverse, redundantly on the 4 lanes (:846-856)
@@ -220,7 +255,6 @@ k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ b
     // ===================================================== consumers =====================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const int cw = warp - kT2ProdWarps;
-    const int ct = t - kT2ProdWarps * 32;
     const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
     const double *Afrag0 = tsm + kq * ldE + fr;                 // + 8 ti
     const double *Bfrag0 = tsm + kT2K * ldE + kq * ldB + fr;    // + 8 tj
@@ -307,16 +341,7 @@ k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ b
           dmma_884nv2(acc[i][3][0], acc[i][3][1], a1, v1);
         }
       }
-      if (fb + G < b1) {
-        // clear the rows the batch used and hand the buffer back to its producer warp
-        bar_sync(15, kT2Cons);
-        double2 *ze = reinterpret_cast<double2 *>(tsm + buf * bufD);
-        double2 *zb = reinterpret_cast<double2 *>(tsm + buf * bufD + kT2K * ldE);
-        const int ne = 2 * ksteps * ldE, nbb = 2 * ksteps * ldB;   // double2 counts of 4 ksteps rows
-        for (int e = ct; e < ne; e += kT2Cons) ze[e] = make_double2(0.0, 0.0);
-        for (int e = ct; e < nbb; e += kT2Cons) zb[e] = make_double2(0.0, 0.0);
-        bar_arrive(8 + buf, bar_cnt);
-      }
+      if (fb + G < b1) bar_arrive(8 + buf, bar_cnt);   // hand the buffer back to its producer warp
       buf = (buf + 1 == G) ? 0 : buf + 1;
       rec = rec_n;
     }

@@ -1418,6 +1418,12 @@ int ba_finalize(ba_solver *s) {
       else for (int q = (int)p; q < e; ++q) fallback_pairs.push_back(q);
       p = e;
     }
+    // Landmarks are grouped by (first pose, last pose) rather than by id: consecutive landmarks then share their
+    // window, so a chunk's window is as narrow as its tracks and the GEMM operands are dense (mixed track lengths
+    // in id order would widen every chunk to the longest track in it)
+    std::stable_sort(cands.begin(), cands.end(), [](const Cand &x, const Cand &y) {
+      return x.jmin != y.jmin ? x.jmin < y.jmin : x.jmax < y.jmax;
+    });
     // Greedy runs.  A run keeps growing while its pose window stays within kTileW; once it holds enough
     // landmarks to amortise the final flush it is also cut when the next landmark would WIDEN the window,
     // so that most chunks are exactly as wide as their landmarks' tracks (dense GEMM operands).
@@ -1468,7 +1474,7 @@ int ba_finalize(ba_solver *s) {
       const SchurChunk &sc = schur_chunks[c];
       nt_max = std::max(nt_max, (6 * sc.width + 7) / 8);
       for (int o = 0; o < sc.pt_count; o += kT2LB)
-        tile_batches.push_back(make_int4(sc.pt_start + o, std::min(kT2LB, sc.pt_count - o), (int)c, 8 * ((6 * sc.width + 7) / 8)));
+        tile_batches.push_back(make_int4(sc.pt_start + o, std::min(kT2LB, sc.pt_count - o), (int)c, (8 * ((6 * sc.width + 7) / 8)) | (sc.width << 16)));
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
