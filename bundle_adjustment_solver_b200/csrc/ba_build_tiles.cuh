@@ -2,7 +2,7 @@
 // ba_engine.cu inside namespace ba, after Params / SchurChunk / load_pose / damp_invert / bar_* helpers).
 //
 // Same arithmetic as core/full_bundle_adjustment_solver.cpp:716-831 (point side), :846-856, :858-888.  Layout of the
-// work (what changed against the first fused kernel, k_build_tiles):
+// work:
 //   * the tile chunks are cut into batches of 8 landmarks (K = 24 operand rows); the flat list of batches is split
 //     evenly over one persistent CTA per SM, so the producer/consumer pipeline never drains between chunks
 //     (a chunk that straddles two CTAs is simply flushed twice -- the flush is additive);
@@ -42,7 +42,7 @@ __device__ __forceinline__ void dmma_884nv2(double &c0, double &c1, double a, do
 
 template <bool ACCUM_B>
 __global__ void __launch_bounds__(kT2Threads, 1)
-k_build_tiles2(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ batches /*ti0, nb, chunk, rhs column*/,
+k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ batches /*ti0, nb, chunk, rhs column*/,
                const int *__restrict__ cta_batch_ptr, TileLaunch tl, const int *__restrict__ tpt_point,
                const int *__restrict__ tpt_inc_start, const int4 *__restrict__ inc_a /*obs_first, n_obs, pose, pair*/,
                const int2 *__restrict__ inc_b /*slot (-1: fixed pose), tile landmark index*/,

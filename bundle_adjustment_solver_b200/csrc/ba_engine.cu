@@ -359,38 +359,9 @@ struct SchurChunk {
   int width;      // poses actually spanned by the chunk (<= kSchurW): tasks are the width(width+1)/2 pairs
 };
 
-// ---------------------------------------------------------------------------
-// K1+K3+K4 fused for "tile" landmarks (all free poses of the landmark inside a window of <= 16 poses):
-// one CTA per Schur chunk.  Landmarks are processed in batches of 16:
-//   1. one thread per (pose, landmark) incidence: projection, residual, Huber weight, Rm, Q for its (1..n_cam)
-//      observations -> partial C (6) / b (3), and B = w Q^T Rm of the pair (last inserted observation, or the sum in
-//      corrected mode), written straight into the GEMM operand B_all and to Bsoa (kept for the back-substitution)
-//   2. one thread per landmark: C, b sums, damping, Eigen-style 3x3 LDLT inverse -> ptblk, rhs column of B_all
-//   3. incidence threads: E = B C^-1 -> GEMM operand E_all
-//   4. the chunk's window of S (<= 96 x 96 + rhs column) -= E_all B_all^T on the FP64 tensor cores: the batch's
-//      landmarks are stacked along K (K = 3 x 16), so the per-landmark outer products become ONE dense
-//      mma.sync.m8n8k4 GEMM whose accumulator tiles stay in registers for the whole chunk
-// and flushed once per chunk with FP64 reds into the upper triangle of S / the rhs column.
-// ---------------------------------------------------------------------------
-constexpr int kTileW = 16;          // window (poses)
-constexpr int kTileLB = 16;         // landmarks per batch
-constexpr int kTileK = 3 * kTileLB; // 48
-constexpr int kLdE = 100;           // E_all[k][row]  (96 rows; stride = 4 mod 16: conflict-free fragment reads)
-constexpr int kLdB = 116;           // B_all[k][col]  (96 cols + rhs tile)
-constexpr int kTileMaxInc = 20;     // incidences per landmark (free and fixed poses)
-constexpr int kTileIncCap = kTileLB * kTileMaxInc;
-constexpr int kTileTPW = 23;        // tiles per DMMA warp (12 x 13 upper tiles + 12 rhs tiles over 4 warps)
-constexpr int kRhsTile = 12;
-constexpr int kTileOperand = kTileK * kLdE + kTileK * kLdB;   // doubles per operand buffer
-constexpr size_t kTileSmem = (size_t)(2 * kTileOperand + 9 * kTileIncCap + kTileLB * 24) * sizeof(double);
-constexpr int kTileProd = 256;             // producer threads (8 warps)
-constexpr int kTileCons = 128;             // consumer threads (4 DMMA warps)
-constexpr int kTileThreads = kTileProd + kTileCons;
+constexpr int kTileW = 16;          // widest window (free poses) a tile landmark may span
+constexpr int kTileMaxInc = 20;     // incidences per tile landmark (free and fixed poses)
 
-// non-volatile DMMA: ordered by its data dependencies only, so the scheduler may batch the fragment loads
-__device__ __forceinline__ void dmma_884nv(double &c0, double &c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -401,232 +372,6 @@ __device__ __forceinline__ void damp_invert(const double *Craw, double lambda, d
   double inv[9];
   ldlt3_inverse(cd, inv);
   ci[0] = inv[0]; ci[1] = inv[1]; ci[2] = inv[2]; ci[3] = inv[4]; ci[4] = inv[5]; ci[5] = inv[8];
-}
-
-// Warps 0-7 (producers) linearise batch b + 1 into operand buffer (b + 1) & 1 while warps 8-11 (consumers) run the
-// DMMA GEMM of batch b; named barriers 1,2 = operands full, 3,4 = operands consumed, 5 = producer-internal.
-template <bool ACCUM_B>
-__global__ void __launch_bounds__(kTileThreads, 1)
-k_build_tiles(const SchurChunk *__restrict__ chunks, const int *__restrict__ tpt_point,
-              const int *__restrict__ tpt_inc_start, const int4 *__restrict__ inc_a /*obs_first, n_obs, pose, pair*/,
-              const int2 *__restrict__ inc_b /*slot (-1: fixed pose), tile landmark index*/,
-              const double2 *__restrict__ obs_uv, const int *__restrict__ obs_camflags, Params prm,
-              const double *__restrict__ cams, double thres_huber, double *__restrict__ Bsoa, size_t Pp,
-              double *__restrict__ ptblk, size_t Mp, double *__restrict__ Saug, int ld,
-              const LmState *__restrict__ st) {
-  if (st->done) return;
-  extern __shared__ double tsm[];
-  double *cpart = tsm + 2 * kTileOperand;                     // [9][kTileIncCap]
-  double *lmk = cpart + 9 * kTileIncCap;                      // [kTileLB][24]: raw sums (9) | Cinv (6) at +12
-  const SchurChunk ch = chunks[blockIdx.x];
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int n_batches = (ch.pt_count + kTileLB - 1) / kTileLB;
-  const int nrows = 6 * ch.width;
-
-  if (warp < kTileProd / 32) {
-    // ===================================================== producers =====================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
-    const double *poses = prm.poses[st->cur];
-    const double *points = prm.points[st->cur];
-    const double lambda = st->lambda;
-    for (int bt = 0; bt < n_batches; ++bt) {
-      const int buf = bt & 1;
-      double (*Ea)[kLdE] = reinterpret_cast<double (*)[kLdE]>(tsm + buf * kTileOperand);
-      double (*Ba)[kLdB] = reinterpret_cast<double (*)[kLdB]>(tsm + buf * kTileOperand + kTileK * kLdE);
-      const int base = bt * kTileLB;
-      const int nb = min(kTileLB, ch.pt_count - base);
-      const int ti0 = ch.pt_start + base;
-      const int i0 = tpt_inc_start[ti0], ninc = tpt_inc_start[ti0 + nb] - i0;
-      if (bt >= 2) bar_sync(3 + buf, kTileThreads);   // consumers are done with this buffer
-      {
-        double2 *z = reinterpret_cast<double2 *>(tsm + buf * kTileOperand);
-        for (int e = t; e < kTileOperand / 2; e += kTileProd) z[e] = make_double2(0.0, 0.0);
-      }
-      bar_sync(5, kTileProd);
-      // ---- 1. incidences
-      for (int ii = t; ii < ninc; ii += kTileProd) {
-        const int4 ia = inc_a[i0 + ii];
-        const int2 ib = inc_b[i0 + ii];
-        const int li = ib.y - ti0, slot = ib.x;
-        const int pt = tpt_point[ib.y];
-        double T[12], X[3];
-        load_pose(poses + (size_t)ia.z * 12, T);
-        X[0] = __ldg(points + (size_t)pt * 3);
-        X[1] = __ldg(points + (size_t)pt * 3 + 1);
-        X[2] = __ldg(points + (size_t)pt * 3 + 2);
-        double cp[9], Bv[18];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cp[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
-        for (int k = ia.x; k < ia.x + ia.y; ++k) {
-          const double2 uv = obs_uv[k];
-          const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
-          Proj pr;
-          project(T, X, cam, uv.x, uv.y, pr);
-          const double w = huber_weight(pr.r0, pr.r1, thres_huber);
-          const double wr0 = w * pr.r0, wr1 = w * pr.r1;
-          double G[6], Rm[6];
-          jac_G(pr, cam, G);
-          jac_R(G, T, Rm);
-          cp[0] += w * (Rm[0] * Rm[0] + Rm[3] * Rm[3]);
-          cp[1] += w * (Rm[0] * Rm[1] + Rm[3] * Rm[4]);
-          cp[2] += w * (Rm[0] * Rm[2] + Rm[3] * Rm[5]);
-          cp[3] += w * (Rm[1] * Rm[1] + Rm[4] * Rm[4]);
-          cp[4] += w * (Rm[1] * Rm[2] + Rm[4] * Rm[5]);
-          cp[5] += w * (Rm[2] * Rm[2] + Rm[5] * Rm[5]);
-          cp[6] -= Rm[0] * wr0 + Rm[3] * wr1;
-          cp[7] -= Rm[1] * wr0 + Rm[4] * wr1;
-          cp[8] -= Rm[2] * wr0 + Rm[5] * wr1;
-          if (slot >= 0 && (ACCUM_B || k == ia.x + ia.y - 1)) {
-            double Q[12];
-            jac_Q(G, pr.Xb, Q);
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) Bv[r * 3 + c] += w * (Q[r] * Rm[c] + Q[6 + r] * Rm[3 + c]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cpart[i * kTileIncCap + ii] = cp[i];
-        if (slot >= 0) {
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              Ba[3 * li + c][6 * slot + r] = Bv[r * 3 + c];
-              Bsoa[(size_t)(r * 3 + c) * Pp + ia.w] = Bv[r * 3 + c];
-            }
-        }
-      }
-      bar_sync(5, kTileProd);
-      // ---- 2a. per-landmark sums of the 9 components: thread (landmark, component)
-      for (int u = t; u < 9 * nb; u += kTileProd) {
-        const int li = u / 9, c = u - 9 * li;
-        const int a = tpt_inc_start[ti0 + li] - i0, b = tpt_inc_start[ti0 + li + 1] - i0;
-        double sacc = 0.0;
-        for (int ii = a; ii < b; ++ii) sacc += cpart[c * kTileIncCap + ii];
-        lmk[li * 24 + c] = sacc;
-      }
-      bar_sync(5, kTileProd);
-      // ---- 2b. damping + inverse, one thread per landmark
-      if (t < nb) {
-        double c9[9], cd[6], ci[6];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) c9[i] = lmk[t * 24 + i];
-        damp_invert(c9, lambda, cd, ci);
-        const int pt = tpt_point[ti0 + t];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) lmk[t * 24 + 12 + i] = ci[i];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Ba[3 * t + c][8 * kRhsTile] = c9[6 + c];
-        ptblk[(PB_b + 0) * Mp + pt] = c9[6];
-        ptblk[(PB_b + 1) * Mp + pt] = c9[7];
-        ptblk[(PB_b + 2) * Mp + pt] = c9[8];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          ptblk[(PB_Cd + i) * Mp + pt] = cd[i];
-          ptblk[(PB_Cinv + i) * Mp + pt] = ci[i];
-        }
-        ptblk[(PB_Cinvb + 0) * Mp + pt] = ci[0] * c9[6] + ci[1] * c9[7] + ci[2] * c9[8];
-        ptblk[(PB_Cinvb + 1) * Mp + pt] = ci[1] * c9[6] + ci[3] * c9[7] + ci[4] * c9[8];
-        ptblk[(PB_Cinvb + 2) * Mp + pt] = ci[2] * c9[6] + ci[4] * c9[7] + ci[5] * c9[8];
-      }
-      bar_sync(5, kTileProd);
-      // ---- 3. E = B Cinv
-      for (int ii = t; ii < ninc; ii += kTileProd) {
-        const int2 ib = inc_b[i0 + ii];
-        const int li = ib.y - ti0, slot = ib.x;
-        if (slot < 0) continue;
-        double ci[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ci[i] = lmk[li * 24 + 12 + i];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double b0 = Ba[3 * li][6 * slot + r], b1 = Ba[3 * li + 1][6 * slot + r], b2 = Ba[3 * li + 2][6 * slot + r];
-          // the operand holds -E so that the GEMM accumulates S -= E B^T directly
-          Ea[3 * li + 0][6 * slot + r] = -(b0 * ci[0] + b1 * ci[1] + b2 * ci[2]);
-          Ea[3 * li + 1][6 * slot + r] = -(b0 * ci[1] + b1 * ci[3] + b2 * ci[4]);
-          Ea[3 * li + 2][6 * slot + r] = -(b0 * ci[2] + b1 * ci[4] + b2 * ci[5]);
-        }
-      }
-      bar_arrive(1 + buf, kTileThreads);   // operands of batch bt are complete
-    }
-  } else {
-    // ===================================================== consumers =====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int cw = warp - kTileProd / 32;
-    const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
-    // tiles of this warp: upper tiles (ti <= tj < nt) row-major, each row followed by its rhs tile
-    const int nt = (nrows + 7) >> 3;
-    const int ntile = nt * (nt + 1) / 2 + nt;
-    const int cnt = (ntile + 3) >> 2;
-    // per tile: shared-memory addresses of the lane's A / B fragment at k-step 0 of buffer 0; aoff < 0: no tile
-    int aoff[kTileTPW], boff[kTileTPW];
-    unsigned aadr[kTileTPW], badr[kTileTPW];
-    double acc[kTileTPW][2];
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(tsm);
-#pragma unroll
-    for (int i = 0; i < kTileTPW; ++i) {
-      int e = cw * cnt + i, ti = 0, len = nt + 1;
-      const bool live = i < cnt && e < ntile;
-      if (live) {
-        while (e >= len) { e -= len; ++ti; --len; }
-      }
-      const int tj = (ti + e == nt) ? kRhsTile : ti + e;
-      aoff[i] = live ? 8 * ti : -1;
-      boff[i] = live ? 8 * tj : 0;
-      aadr[i] = sbase + 8u * (unsigned)(kq * kLdE + fr + (live ? 8 * ti : 0));
-      badr[i] = sbase + 8u * (unsigned)(kTileK * kLdE + kq * kLdB + fr + (live ? 8 * tj : 0));
-      acc[i][0] = acc[i][1] = 0.0;
-    }
-    for (int bt = 0; bt < n_batches; ++bt) {
-      const int buf = bt & 1;
-      const unsigned boffs = buf ? 8u * kTileOperand : 0u;
-      const int nb = min(kTileLB, ch.pt_count - bt * kTileLB);
-      bar_sync(1 + buf, kTileThreads);
-      // window += (-E_all) B_all^T  (K = 3 nb, zero padded); k-steps unrolled so that the fragment loads use
-      // immediate offsets and can be issued in batches ahead of the DMMAs
-      const int ksteps = (3 * nb + 3) >> 2;
-#pragma unroll
-      for (int ks = 0; ks < kTileK / 4; ++ks) {
-        if (ks >= ksteps) break;   // uniform
-#pragma unroll
-        for (int g0 = 0; g0 < kTileTPW; g0 += 8) {
-          if (g0 >= cnt) break;   // uniform
-          double af[8], bf[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (g0 + i < kTileTPW) {
-              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(af[i]) : "r"(aadr[g0 + i] + boffs + (unsigned)(ks * 4 * kLdE * 8)));
-              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bf[i]) : "r"(badr[g0 + i] + boffs + (unsigned)(ks * 4 * kLdB * 8)));
-            }
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (g0 + i < kTileTPW) dmma_884(acc[g0 + i][0], acc[g0 + i][1], af[i], bf[i]);
-        }
-      }
-      bar_arrive(3 + buf, kTileThreads);
-    }
-    // ---- flush: upper triangle of S (row-major) and the rhs column
-    const int row0 = 6 * ch.jmin;
-#pragma unroll
-    for (int i = 0; i < kTileTPW; ++i) {
-      if (aoff[i] < 0) continue;
-      const int lr = aoff[i] + fr, tj8 = boff[i];
-      if (lr >= nrows) continue;
-      const size_t grow = (size_t)(row0 + lr) * ld;
-      if (tj8 == 8 * kRhsTile) {
-        if (fc == 0 && acc[i][0] != 0.0) atomicAdd(&Saug[grow + (ld - 1)], acc[i][0]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int lc = tj8 + fc + e;
-          if (lc < nrows && lc >= lr && acc[i][e] != 0.0) atomicAdd(&Saug[grow + row0 + lc], acc[i][e]);
-        }
-      }
-    }
-  }
 }
 
 #include "ba_build_tiles.cuh"
@@ -1838,36 +1583,23 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   // tile landmarks: linearisation + C^-1 + Schur products fused (DMMA)
   if (s->n_schur_chunks > 0) {
     static bool attr_set = false;
-    static int tiles_version = 2;   // BA_B200_TILES=1: first fused kernel (CTA-barrier producers), kept for A/B timing
     if (!attr_set) {
-      cudaFuncSetAttribute(k_build_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
-      cudaFuncSetAttribute(k_build_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
-      cudaFuncSetAttribute(k_build_tiles2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
-      cudaFuncSetAttribute(k_build_tiles2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
-      if (const char *e = getenv("BA_B200_TILES")) tiles_version = atoi(e);
+      cudaFuncSetAttribute(k_build_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
+      cudaFuncSetAttribute(k_build_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
       attr_set = true;
     }
-    if (tiles_version == 2) {
-      const TileLaunch &tl = s->tile_launch;
-      const size_t smem = (size_t)tl.G * tl.bufD * sizeof(double);
-      if (opt->b_accumulate)
-        k_build_tiles2<true><<<tl.n_cta, kT2Threads, smem, st>>>(
-            s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
-            s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
-            s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
-      else
-        k_build_tiles2<false><<<tl.n_cta, kT2Threads, smem, st>>>(
-            s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
-            s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
-            s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
-    } else if (opt->b_accumulate)
-      k_build_tiles<true><<<s->n_schur_chunks, kTileThreads, kTileSmem, st>>>(
-          s->d_schur_chunks.p, s->d_tpt_point.p, s->d_tpt_inc_start.p, s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p,
-          s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+    const TileLaunch &tl = s->tile_launch;
+    const size_t smem = (size_t)tl.G * tl.bufD * sizeof(double);
+    if (opt->b_accumulate)
+      k_build_tiles<true><<<tl.n_cta, kT2Threads, smem, st>>>(
+          s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
+          s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
+          s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
     else
-      k_build_tiles<false><<<s->n_schur_chunks, kTileThreads, kTileSmem, st>>>(
-          s->d_schur_chunks.p, s->d_tpt_point.p, s->d_tpt_inc_start.p, s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p,
-          s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+      k_build_tiles<false><<<tl.n_cta, kT2Threads, smem, st>>>(
+          s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
+          s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
+          s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
     s->launches++;
   }
   if (s->n_fallback_pairs > 0) {
