@@ -31,11 +31,12 @@ class Options(C.Structure):
         ("inverse_scaler", C.c_double),
         ("check_every", C.c_int),
         ("use_graph", C.c_int),
+        ("method", C.c_int),   # BA_METHOD_*: 0 LM, 1 Gauss-Newton (refactor class), 2 gradient descent
     ]
 
 
 def default_options(**kw):
-    o = Options(1, 1e-5, 1e-5, 1.0, 2.0, 50, 100.0, 0.33, 3.0, 0, 100.0, 0, 1)
+    o = Options(1, 1e-5, 1e-5, 1.0, 2.0, 50, 100.0, 0.33, 3.0, 0, 100.0, 0, 1, 0)
     for k, v in kw.items():
         setattr(o, k, v)
     return o

@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(kThreads)
 k_backsub_points(int M_total, const int *__restrict__ point_has_pairs, const uint8_t *__restrict__ point_free,
                  const double *__restrict__ ptblk, size_t Mp, const double *__restrict__ Btx,
                  double *__restrict__ y /*[M_total][3]*/, Params prm, ParamsW prw,
-                 double *__restrict__ partials /*[grid][2]*/, const LmState *__restrict__ st) {
+                 double *__restrict__ partials /*[grid][2]*/, int method, const LmState *__restrict__ st) {
   if (st->done) return;
   __shared__ double sm[kWarps][2];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -486,7 +486,19 @@ k_backsub_points(int M_total, const int *__restrict__ point_has_pairs, const uin
     const double *Xc = prm.points[st->cur] + (size_t)i * 3;
     double *Xt = prw.points[st->cur ^ 1] + (size_t)i * 3;
     double yv[3] = {0.0, 0.0, 0.0};
-    if (point_free[i]) {
+    if (point_free[i] && method == BA_METHOD_GRADIENT_DESCENT) {
+      // SolveByGradientDescent (full_bundle_adjustment_solver_refactor.cpp:1277-1283): the step is the gradient
+      // block b_i itself, clipped to max_point_step = 0.001
+#pragma unroll
+      for (int k = 0; k < 3; ++k) yv[k] = ptblk[(PB_b + k) * Mp + i];
+      const double nrm = sqrt(yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
+      if (nrm > 0.001) {
+        const double sc = 0.001 / nrm;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) yv[k] = yv[k] * sc;
+      }
+      acc[1] = sqrt(yv[0] * yv[0] + yv[1] * yv[1] + yv[2] * yv[2]);
+    } else if (point_free[i]) {
       double b[3], cd[6], ci[6], cb[3], bx[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int k = 0; k < 3; ++k) b[k] = ptblk[(PB_b + k) * Mp + i];
@@ -524,6 +536,21 @@ k_backsub_points(int M_total, const int *__restrict__ point_has_pairs, const uin
     partials[(size_t)blockIdx.x * 2] = acc[0];
     partials[(size_t)blockIdx.x * 2 + 1] = acc[1];
   }
+}
+
+// SolveByGradientDescent, pose side (full_bundle_adjustment_solver_refactor.cpp:1274-1276): x_j = a_j clipped to
+// max_pose_step = 0.001
+__global__ void k_gd_poses(int N, const double *__restrict__ a, double *__restrict__ x, const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  double v[6], s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { v[k] = a[(size_t)j * 6 + k]; s2 += v[k] * v[k]; }
+  const double nrm = sqrt(s2);
+  const double sc = (nrm > 0.001) ? 0.001 / nrm : 1.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) x[(size_t)j * 6 + k] = (nrm > 0.001) ? v[k] * sc : v[k];
 }
 
 // ---------------------------------------------------------------------------
@@ -617,6 +644,7 @@ struct DecideArgs {
   double n_obs_global, n_params_global;  // num_observations ; N_opt + M_opt
   int max_iteration;
   int n_ranks;
+  int method;   // BA_METHOD_*
 };
 
 // ordered (deterministic) sums of the per-block partials into scal[]
@@ -670,21 +698,29 @@ __global__ void k_decide(DecideArgs g, LmState *st, ba_iter_info *infos, int cap
   st->last_rho = rho;
   st->last_lambda = lambda;
   int status;
-  if (rho > 0.25) {
-    status = 0;       // UPDATE: trial buffer becomes current
+  if (g.method != BA_METHOD_LEVENBERG_MARQUARDT) {
+    // Gauss-Newton branch of the refactor class (full_bundle_adjustment_solver_refactor.cpp:976-982) and
+    // SolveByGradientDescent (:1285-1289): the step is always kept, lambda stays where it is
+    status = 0;
     st->cur ^= 1;
   } else {
-    status = 2;       // SKIPPED: keep current (RevertToReservedParameters)
-  }
-  if (rho > 0.5) {
-    lambda = fmax(1e-10, lambda * g.dec_ratio);
-    status = 1;       // UPDATE_TRUST_MORE
-  } else if (rho <= 0.25) {
-    lambda = fmin(100.0, lambda * g.inc_ratio);
+    if (rho > 0.25) {
+      status = 0;       // UPDATE: trial buffer becomes current
+      st->cur ^= 1;
+    } else {
+      status = 2;       // SKIPPED: keep current (RevertToReservedParameters)
+    }
+    if (rho > 0.5) {
+      lambda = fmax(1e-10, lambda * g.dec_ratio);
+      status = 1;       // UPDATE_TRUST_MORE
+    } else if (rho <= 0.25) {
+      lambda = fmin(100.0, lambda * g.inc_ratio);
+    }
   }
   const double average_error = current_cost / g.n_obs_global;
   const double cost_change = fabs(current_cost - previous_cost);
-  const double total_step = g.scal[2] + g.scal[4];
+  // gradient descent starts both step sums at 0.01 (refactor.cpp:1296-1297)
+  const double total_step = g.scal[2] + g.scal[4] + (g.method == BA_METHOD_GRADIENT_DESCENT ? 0.02 : 0.0);
   const double avg_step = total_step / g.n_params_global;
   bool converged = (avg_step < g.thr_step) || (cost_change < g.thr_cost);
   const int iteration = st->iteration;
@@ -1527,6 +1563,7 @@ static DecideArgs make_decide_args(ba_solver *s, const ba_options *opt) {
   g.n_params_global = (double)(s->N + gM);
   g.max_iteration = opt->max_num_iterations;
   g.n_ranks = s->n_ranks;
+  g.method = opt->method;
   return g;
 }
 
@@ -1625,7 +1662,7 @@ static int enqueue_allreduce_scal(ba_solver *s) {
   return BA_OK;
 }
 
-static int enqueue_solve_backsub(ba_solver *s, cudaEvent_t *ev) {
+static int enqueue_solve_backsub(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   cudaStream_t st = s->stream;
   const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
   const ParamsW prw{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
@@ -1635,10 +1672,15 @@ static int enqueue_solve_backsub(ba_solver *s, cudaEvent_t *ev) {
   if (s->debug_keep && s->d_Scopy.p) {
     cudaMemcpyAsync(s->d_Scopy.p, s->d_Saug.p, (size_t)ld * ld * sizeof(double), cudaMemcpyDeviceToDevice, st);
   }
-  if (n > 0) cholesky_solve_enqueue(s->chol, s->d_Saug.p, s->d_x.p, s->d_z.p, s->d_linv.p, dst, st, &s->launches);
+  const bool gd = opt->method == BA_METHOD_GRADIENT_DESCENT;
+  if (gd) {
+    if (s->N > 0) { k_gd_poses<<<(s->N + 127) / 128, 128, 0, st>>>(s->N, s->d_a.p, s->d_x.p, dst); s->launches++; }
+  } else if (n > 0) {
+    cholesky_solve_enqueue(s->chol, s->d_Saug.p, s->d_x.p, s->d_z.p, s->d_linv.p, dst, st, &s->launches);
+  }
   if (ev) cudaEventRecord(ev[Phase::Backsub], st);
-  if (s->n_split_pairs > 0) cudaMemsetAsync(s->d_Btx.p, 0, 3 * s->Mp * sizeof(double), st);
-  if (s->n_chunks > 0 && s->P > 0) {
+  if (!gd && s->n_split_pairs > 0) cudaMemsetAsync(s->d_Btx.p, 0, 3 * s->Mp * sizeof(double), st);
+  if (!gd && s->n_chunks > 0 && s->P > 0) {
     k_backsub_pairs<<<s->n_chunks, kThreads, 0, st>>>(s->d_chunks.p, s->d_chunk_pair_count.p, s->d_pair_pose.p,
                                                       s->d_pair_point.p, s->d_Bsoa.p, s->Pp, s->d_x.p,
                                                       s->d_Btx.p, s->Mp, dst);
@@ -1646,7 +1688,7 @@ static int enqueue_solve_backsub(ba_solver *s, cudaEvent_t *ev) {
   }
   k_backsub_points<<<s->point_grid, kThreads, 0, st>>>(s->M_total, s->d_point_has_pairs.p, s->d_point_free.p,
                                                        s->d_ptblk.p, s->Mp, s->d_Btx.p, s->d_y.p, prm, prw,
-                                                       s->d_point_partials.p, dst);
+                                                       s->d_point_partials.p, opt->method, dst);
   s->launches++;
   return BA_OK;
 }
@@ -1674,7 +1716,7 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
 static int enqueue_iteration(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   if (int rc = enqueue_build(s, opt, ev)) return rc;
   if (int rc = enqueue_allreduce_S(s)) return rc;
-  if (int rc = enqueue_solve_backsub(s, ev)) return rc;
+  if (int rc = enqueue_solve_backsub(s, opt, ev)) return rc;
   return enqueue_update_decide(s, opt, ev);
 }
 
@@ -1710,6 +1752,8 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   ba_options opt = *opt_in;
   if (opt.inverse_scaler == 0.0) opt.inverse_scaler = 100.0;
   if (opt.check_every <= 0) opt.check_every = 8;
+  if (opt.method < 0 || opt.method > BA_METHOD_GRADIENT_DESCENT) { s->err = "unknown ba_options.method"; return BA_ERR_INVALID; }
+  if (opt.method == BA_METHOD_GRADIENT_DESCENT && s->comm) { s->err = "gradient descent is single-GPU only"; return BA_ERR_STATE; }
   const int max_it = opt.max_num_iterations;
   cudaStream_t st = s->stream;
   s->launches = 0;
@@ -1848,7 +1892,7 @@ int ba_build_only(ba_solver *s, const ba_options *opt_in, double lambda, int do_
   if (int rc = enqueue_build(s, &opt, nullptr)) return rc;
   if (int rc = enqueue_allreduce_S(s)) return rc;
   if (do_solve) {
-    if (int rc = enqueue_solve_backsub(s, nullptr)) return rc;
+    if (int rc = enqueue_solve_backsub(s, &opt, nullptr)) return rc;
   } else if (s->debug_keep) {
     const size_t ld = (size_t)6 * s->N + 1;
     CUDA_TRY(s->d_Scopy.alloc(ld * ld));

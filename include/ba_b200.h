@@ -51,7 +51,17 @@ typedef struct ba_options {
   int check_every;               /* host polls the device convergence flag every this many LM
                                     iterations (device decides; extra iterations are no-ops). 0 = default */
   int use_graph;                 /* 1 = replay one LM iteration as a CUDA graph (default), 0 = plain launches */
+  int method;                    /* BA_METHOD_*: which loop of the reference ba_solve runs (0 = the default) */
 } ba_options;
+
+/* ba_options.method.  FullBundleAdjustmentSolver::Solve is always Levenberg-Marquardt (it ignores
+ * Options::solver_type, full_bundle_adjustment_solver.cpp:630-1044); FullBundleAdjustmentSolverRefactor::Solve
+ * switches on it (full_bundle_adjustment_solver_refactor.cpp:944-982) and adds SolveByGradientDescent (:1075-1367). */
+#define BA_METHOD_LEVENBERG_MARQUARDT 0 /* trial step, rho test, lambda update */
+#define BA_METHOD_GAUSS_NEWTON 1        /* refactor.cpp:976-982: same damped system (lambda stays initial_lambda),
+                                           the step is always kept */
+#define BA_METHOD_GRADIENT_DESCENT 2    /* refactor.cpp:1159-1330: step = the gradient blocks a_j, b_i clipped to a
+                                           norm of 0.001, always kept; single GPU only */
 
 /* Mirrors OptimizationInfo (core/solver_option_and_summary.h:37-46). */
 typedef struct ba_iter_info {

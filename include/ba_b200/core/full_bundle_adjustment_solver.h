@@ -166,7 +166,14 @@ class FullBundleAdjustmentSolver {
   // :182-206.  Public + idempotent here; only freezes the parameter set (observations may still be added).
   void FinalizeParameters() { is_parameter_finalized_ = true; }
 
-  bool Solve(Options options, Summary *summary = nullptr) {  // :630-1044
+  bool Solve(Options options, Summary *summary = nullptr) {  // :630-1044 (always LM: solver_type is not read)
+    return SolveWithMethod(options, summary, BA_METHOD_LEVENBERG_MARQUARDT);
+  }
+
+ protected:
+  // one Solve of the device engine with the loop selected by `method` (BA_METHOD_*); shared with the refactor
+  // front-end (core/full_bundle_adjustment_solver_refactor.h)
+  bool SolveWithMethod(Options options, Summary *summary, int method) {
     const auto t_start = std::chrono::high_resolution_clock::now();
     if (summary != nullptr) {
       summary->max_iteration_ = options.iteration_handle.max_num_iterations;
@@ -201,6 +208,7 @@ class FullBundleAdjustmentSolver {
     o.inverse_scaler = inverse_scaler_;
     o.check_every = 0;
     o.use_graph = 1;
+    o.method = method;
     const int cap = o.max_num_iterations > 0 ? o.max_num_iterations : 1;
     std::vector<ba_iter_info> infos(cap);
     ba_result result{};
@@ -248,6 +256,7 @@ class FullBundleAdjustmentSolver {
     return true;  // always (:666,1043)
   }
 
+ public:
   std::string GetSolverStatistics() const {  // :208-239 (prints; returns an empty string like the reference)
     std::stringstream ss;
     int n_opt_poses = 0, n_opt_points = 0;
@@ -275,6 +284,13 @@ class FullBundleAdjustmentSolver {
   const ba_result &last_result() const { return last_result_; }
   ba_solver *native_handle() { EnsureHandle(); return handle_; }
   void SetDevice(int device) { device_ = device; }
+
+ protected:
+  bool is_finalized() const { return is_parameter_finalized_; }
+  bool has_camera(int id) const { return camera_slot_.count(id) > 0; }
+  bool has_pose(_BA_Pose *p) const { return pose_index_.count(p) > 0; }
+  bool has_point(_BA_Point *p) const { return point_index_.count(p) > 0; }
+  long long num_observations() const { return static_cast<long long>(obs_cam_.size()); }
 
  private:
   static void PushPose12(const _BA_Pose &T, double t_scale, std::vector<double> *out) {

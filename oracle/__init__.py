@@ -34,11 +34,12 @@ class FullOptions(C.Structure):
         ("decrease_ratio_lambda", C.c_float),
         ("increase_ratio_lambda", C.c_float),
         ("b_accumulate", C.c_int),
+        ("method", C.c_int),   # 0 LM (Solve), 1 Gauss-Newton / 2 gradient descent of the refactor class
     ]
 
 
 def default_full_options(**kw):
-    o = FullOptions(1, 1e-5, 1e-5, 1.0, 2.0, 50, 100.0, 0.33, 3.0, 0)
+    o = FullOptions(1, 1e-5, 1e-5, 1.0, 2.0, 50, 100.0, 0.33, 3.0, 0, 0)
     for k, v in kw.items():
         setattr(o, k, v)
     return o

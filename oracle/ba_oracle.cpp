@@ -6,7 +6,9 @@
 // CPU restatement (plain C++17, single thread, no Eigen) of the reference's
 // analytic bundle-adjustment hot path:
 //   full BA   : core/full_bundle_adjustment_solver.cpp:72-206, 381-500, 503-628,
-//               630-1044, 1046-1082
+//               630-1044, 1046-1082; the Gauss-Newton branch and SolveByGradientDescent of
+//               core/full_bundle_adjustment_solver_refactor.cpp:944-982, 1075-1367 (same
+//               linearisation, different step / acceptance)
 //   pose-only : core/pose_only_bundle_adjustment_solver.cpp:8-399 (6-DoF),
 //               401-900 (planar 3-DoF), 907-1278 (JtJ helpers), 1280-1316 (se3
 //               exp), 1338-1583 (warp, Jacobians, gradient/Hessian)
@@ -254,6 +256,8 @@ struct FullOptions {  // mirrors Options (solver_option_and_summary.h:55-71), fl
   int max_num_iterations;
   float initial_lambda, decrease_ratio_lambda, increase_ratio_lambda;
   int b_accumulate;  // 0 = reference-exact (B assignment, last writer wins), 1 = corrected (B +=)
+  int method;        // 0 = Solve (LM); FullBundleAdjustmentSolverRefactor: 1 = Gauss-Newton branch of Solve
+                     // (full_bundle_adjustment_solver_refactor.cpp:976-982), 2 = SolveByGradientDescent (:1075-1367)
 };
 
 struct FullBA {
@@ -592,9 +596,28 @@ struct FullBA {
     std::vector<double> reserved_points((size_t)M * 3);
     for (int iteration = 0; iteration < max_iteration; ++iteration) {
       linearize(THRES_HUBER, opt.b_accumulate);
-      damp_and_invert(lambda);
-      schur();
-      solve_reduced();
+      if (opt.method == 2) {
+        // SolveByGradientDescent (refactor.cpp:1271-1283): the step is the gradient itself, every block clipped
+        // to a norm of 0.001
+        x.assign((size_t)N * 6, 0.0);
+        y.assign((size_t)M * 3, 0.0);
+        for (int j = 0; j < N; ++j) {
+          double s2 = 0;
+          for (int r = 0; r < 6; ++r) { x[(size_t)j * 6 + r] = a[(size_t)j * 6 + r]; s2 += x[(size_t)j * 6 + r] * x[(size_t)j * 6 + r]; }
+          const double nrm = std::sqrt(s2);
+          if (nrm > 0.001) for (int r = 0; r < 6; ++r) x[(size_t)j * 6 + r] = x[(size_t)j * 6 + r] * (0.001 / nrm);
+        }
+        for (int i = 0; i < M; ++i) {
+          double s2 = 0;
+          for (int r = 0; r < 3; ++r) { y[(size_t)i * 3 + r] = b[(size_t)i * 3 + r]; s2 += y[(size_t)i * 3 + r] * y[(size_t)i * 3 + r]; }
+          const double nrm = std::sqrt(s2);
+          if (nrm > 0.001) for (int r = 0; r < 3; ++r) y[(size_t)i * 3 + r] = y[(size_t)i * 3 + r] * (0.001 / nrm);
+        }
+      } else {
+        damp_and_invert(lambda);
+        schur();
+        solve_reduced();
+      }
       // reserve (:457-469) / update (:484-500)
       for (int j = 0; j < N; ++j) reserved_poses[j] = T_jw[opt_pose[j]];
       for (int i = 0; i < M; ++i)
@@ -607,13 +630,15 @@ struct FullBA {
         for (int c = 0; c < 3; ++c) X[(size_t)opt_point[i] * 3 + c] += y[(size_t)i * 3 + c];
 
       const double current_cost = evaluate_current_cost();
-      const double changed_error_by_model = model_change();
+      const double changed_error_by_model = (opt.method == 2) ? 1.0 : model_change();
       const double rho = (current_cost - previous_cost) * inverse_scaler / changed_error_by_model;
       last_cost_prev = previous_cost; last_cost_new = current_cost;
       last_model = changed_error_by_model; last_rho = rho; last_lambda = lambda;
 
       int iter_status;
-      if (rho > 0.25) {
+      if (opt.method != 0) {
+        iter_status = 0;  // refactor.cpp:976-982 / 1285-1289: the step is always kept, lambda untouched
+      } else if (rho > 0.25) {
         iter_status = 0;  // UPDATE
       } else {
         for (int j = 0; j < N; ++j) T_jw[opt_pose[j]] = reserved_poses[j];
@@ -621,7 +646,8 @@ struct FullBA {
           for (int c = 0; c < 3; ++c) X[(size_t)opt_point[i] * 3 + c] = reserved_points[(size_t)i * 3 + c];
         iter_status = 2;  // SKIPPED
       }
-      if (rho > 0.5) {
+      if (opt.method != 0) {
+      } else if (rho > 0.5) {
         lambda = std::max(1e-10, static_cast<double>(lambda * opt.decrease_ratio_lambda));
         iter_status = 1;  // UPDATE_TRUST_MORE
       } else if (rho <= 0.25) {
@@ -629,7 +655,8 @@ struct FullBA {
       }
       const double average_error = current_cost / num_observations;
       const double cost_change = std::fabs(current_cost - previous_cost);
-      double step_pose = 0.0, step_point = 0.0;
+      // gradient descent starts both sums at 0.01 (refactor.cpp:1296-1297)
+      double step_pose = (opt.method == 2) ? 0.01 : 0.0, step_point = (opt.method == 2) ? 0.01 : 0.0;
       for (int j = 0; j < N; ++j) {
         double s = 0;
         for (int r = 0; r < 6; ++r) s += x[(size_t)j * 6 + r] * x[(size_t)j * 6 + r];

@@ -85,6 +85,40 @@ def test_solve_c1_matches_oracle(seed, accum, oracle_mod, engine_lib):
     print(summ.brief_report()[-600:])
 
 
+@pytest.mark.parametrize("scene", ["c1", "trajectory"])
+@pytest.mark.parametrize("method,iters", [(1, 40), (2, 25)])
+def test_refactor_methods_match_oracle(scene, method, iters, oracle_mod, engine_lib):
+    """ba_options.method: the Gauss-Newton branch of FullBundleAdjustmentSolverRefactor::Solve
+    (full_bundle_adjustment_solver_refactor.cpp:976-982) and SolveByGradientDescent (:1075-1367) against the
+    oracle's restatement: every iteration kept (status UPDATE), lambda untouched, same cost trajectory."""
+    sc = scenes.scene_test_ba(seed=4) if scene == "c1" else scenes.scene_trajectory(60, 3000, 8, stereo=True, seed=9, n_fixed=2)
+    kw = dict(max_num_iterations=iters, threshold_cost_change=1e-9, threshold_step_size=1e-9, method=method)
+    oo, eo = options_pair(**kw)
+    o = load_oracle(sc)
+    infos_o, conv_o = o.solve(oo)
+    e = load_engine(sc, identical_internal=o_internal(sc))
+    from bundle_adjustment_solver_b200.solver import Summary
+    summ = Summary()
+    e.solve(eo, summ)
+    infos_e = summ.optimization_info_list
+    assert summ.convergence_status == conv_o and len(infos_e) == len(infos_o)
+    for ie, io in zip(infos_e, infos_o):
+        assert ie.iteration_status == 0 and io.iteration_status == 0
+        assert ie.damping_term == io.damping_term == 100.0
+        assert abs(ie.cost - io.cost) <= 1e-8 * abs(io.cost), (ie.cost, io.cost)
+        assert abs(ie.abs_step - io.abs_step) <= 1e-8 * abs(io.abs_step)
+    if method == 2:   # clipped gradient steps: each block moves by at most 0.001 (scaled units) per iteration
+        assert infos_e[-1].abs_step <= 0.001 + 0.02 / (sum(1 for _ in sc.points_init) + 1)
+    assert np.abs(e.get_poses() - o.get_poses()).max() < 1e-6
+    assert np.abs(e.get_points() - o.get_points()).max() < 1e-6
+
+
+def o_internal(sc):
+    o = load_oracle(sc)
+    o.sizes()
+    return o.get_internal()
+
+
 def test_fixed_points_and_split_point(oracle_mod, engine_lib):
     """Edge cases: fixed landmarks, landmarks seen only by fixed poses, and one landmark with more
     observations than a 256-observation chunk (split path with atomics)."""

@@ -28,8 +28,18 @@ def test_library_exports_every_declared_symbol(engine_lib):
     assert b"sm_100a" in engine_lib.ba_version()
 
 
-def test_struct_layouts_match_header():
-    assert C.sizeof(capi.Options) == 64 - 8 or C.sizeof(capi.Options) == 56
+def test_struct_layouts_match_header(tmp_path):
+    # the ctypes mirrors against the C compiler's view of include/ba_b200.h
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ba_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(ba_options), offsetof(ba_options, inverse_scaler),'
+                   ' offsetof(ba_options, method), sizeof(ba_iter_info));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    size, off_inv, off_method, size_info = map(int, subprocess.check_output([str(exe)]).split())
+    assert C.sizeof(capi.Options) == size == 64
+    assert capi.Options.inverse_scaler.offset == off_inv and capi.Options.method.offset == off_method
+    assert C.sizeof(capi.IterInfo) == size_info
     assert C.sizeof(capi.IterInfo) == 64
     assert C.sizeof(capi.PoseOnlyOptions) == 20 and C.sizeof(capi.PoseOnlyResult) == 24
     assert C.sizeof(oracle.IterInfo) == C.sizeof(capi.IterInfo)

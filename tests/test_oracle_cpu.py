@@ -330,3 +330,28 @@ def test_poseonly_oracle_recovers_true_pose_and_quirks():
     c = oracle.poseonly_solve(0, pb.points[:300], pb.px_left[:300], None, pb.intr_left, None, pb.poses_init[0],
                               oracle.PoseOnlyOptions(0.0, 0.0, 1.5, 2.5, 4))
     assert c["result"].n_iterations == 4 and not c["result"].converged
+
+
+def test_refactor_gauss_newton_and_gradient_descent_branches(oracle_mod):
+    """Oracle restatement of FullBundleAdjustmentSolverRefactor (refactor.cpp:944-982, 1075-1367): Gauss-Newton keeps
+    every step with lambda untouched (it stays a damped step with initial_lambda) and, lightly damped, reaches the LM
+    minimum on a well-posed scene; gradient descent moves every block by at most 0.001 (scaled units) per iteration
+    and never rejects."""
+    import oracle
+    from bundle_adjustment_solver_b200 import scenes
+    from bundle_adjustment_solver_b200 import solver as S
+    sc = scenes.scene_trajectory(12, 200, 6, stereo=True, seed=3, n_fixed=2)
+    res = {}
+    for method, iters, lam in ((0, 300, 100.0), (1, 300, 1e-3), (2, 15, 100.0)):
+        o = S.load_scene(oracle.FullBAOracle(), sc)
+        infos, conv = o.solve(oracle.default_full_options(max_num_iterations=iters, threshold_cost_change=1e-6,
+                                                          threshold_step_size=1e-6, method=method, initial_lambda=lam))
+        res[method] = (infos, conv)
+    lm, gn, gd = res[0][0], res[1][0], res[2][0]
+    assert all(i.iteration_status == 0 and abs(i.damping_term - 1e-3) < 1e-9 for i in gn)
+    assert all(i.iteration_status == 0 and i.damping_term == 100.0 for i in gd)
+    assert gn[-1].cost <= 1.01 * lm[-1].cost + 1e-6, (gn[-1].cost, lm[-1].cost)
+    n_blocks = 10 + 200
+    assert all(i.abs_step <= (0.02 + 0.001 * n_blocks) / n_blocks * (1 + 1e-12) for i in gd)
+    assert gd[-1].cost < 0.5 * gd[0].cost                        # clipped steps along the negative gradient
+    assert len(gd) == 15 and not res[2][1]      # max iterations reached -> convergence flag forced false
