@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <omp.h>
 #include <stdint.h>
 
 #include <algorithm>
@@ -24,6 +25,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -750,6 +752,30 @@ __global__ void k_decide(DecideArgs g, LmState *st, ba_iter_info *infos, int cap
   if (converged || iteration + 1 >= g.max_iteration) st->done = 1;
 }
 
+// Multi-GPU, banded reduced system: only the band of S (row r: columns r .. r + bw of the upper triangle, what the
+// build writes and the banded factorisation reads) and the rhs column take part in the all-reduce.
+__global__ void k_band_pack(const double *__restrict__ S, int n, int ld, int bw, double *__restrict__ packed,
+                            const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int r = blockIdx.x, w = bw + 2;
+  for (int t = threadIdx.x; t < w; t += blockDim.x) {
+    double v = 0.0;
+    if (t <= bw) { if (r + t < n) v = S[(size_t)r * ld + r + t]; }
+    else v = S[(size_t)r * ld + (ld - 1)];
+    packed[(size_t)r * w + t] = v;
+  }
+}
+__global__ void k_band_unpack(double *__restrict__ S, int n, int ld, int bw, const double *__restrict__ packed,
+                              const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int r = blockIdx.x, w = bw + 2;
+  for (int t = threadIdx.x; t < w; t += blockDim.x) {
+    const double v = packed[(size_t)r * w + t];
+    if (t <= bw) { if (r + t < n) S[(size_t)r * ld + r + t] = v; }
+    else S[(size_t)r * ld + (ld - 1)] = v;
+  }
+}
+
 }  // namespace ba
 
 // =============================================================================
@@ -807,6 +833,50 @@ inline void pool_setup(int device) {
   done[device] = true;
 }
 
+// exclusive prefix sum of v[0..n) in place (v has n + 1 entries; v[n] and the return value = total), OpenMP two-pass
+static long long exclusive_scan_inplace(int *v, long long n) {
+  int nth = 1;
+#pragma omp parallel
+  {
+#pragma omp single
+    nth = omp_get_num_threads();
+  }
+  std::vector<long long> part(nth + 1, 0);
+#pragma omp parallel num_threads(nth)
+  {
+    const int t = omp_get_thread_num();
+    const long long lo = n * t / nth, hi = n * (t + 1) / nth;
+    long long sum = 0;
+    for (long long q = lo; q < hi; ++q) sum += v[q];
+    part[t + 1] = sum;
+#pragma omp barrier
+#pragma omp single
+    for (int k = 0; k < nth; ++k) part[k + 1] += part[k];
+    long long run = part[t];
+    for (long long q = lo; q < hi; ++q) { const int x = v[q]; v[q] = (int)run; run += x; }
+  }
+  v[n] = (int)part[nth];
+  return part[nth];
+}
+
+// Small pinned blocks (the 64-byte LM state / scalar read-backs) are recycled process-wide: cudaMallocHost costs
+// about a millisecond, a solver is often created per problem.
+static std::mutex g_pinned_mu;
+static std::vector<void *> g_pinned_free;
+constexpr size_t kPinnedBlock = 256;
+static cudaError_t pinned_get(void **p) {
+  {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    if (!g_pinned_free.empty()) { *p = g_pinned_free.back(); g_pinned_free.pop_back(); return cudaSuccess; }
+  }
+  return cudaMallocHost(p, kPinnedBlock);
+}
+static void pinned_put(void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned_free.push_back(p);
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -853,6 +923,7 @@ struct ba_solver {
   bool finalized = false;
   std::vector<int> h_pose_opt, h_point_opt, h_opt_pose, h_opt_point;
   std::vector<int> h_pair_pose, h_pair_point;  // j_opt, original point id
+  std::vector<int> h_first_pose;               // per free pose: first co-visible free pose (envelope of S)
   int n_chunks = 0, n_chunksA = 0, n_split = 0, n_split_pairs = 0;
 
   // device problem
@@ -883,6 +954,7 @@ struct ba_solver {
   int schur_mode = 1;  // 1 = register-tiled windows + fallback, 0 = direct reds only
   CholeskyPlan chol;
   DevBuf<int> d_chol_rows, d_chol_first, d_chol_rows_ptr;
+  DevBuf<double> d_band;   // multi-GPU, banded S: band rows + rhs packed for the all-reduce
   int chol_mode = -1;  // -1 auto, 0 multi-kernel, 1 cluster
   // blocks
   size_t Mp = 0, Pp = 0;
@@ -958,7 +1030,7 @@ static void free_device(ba_solver *s) {
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
   s->d_tpt_point.release(); s->d_tpt_inc_start.release(); s->d_fallback_pairs.release();
   s->d_inc_a.release(); s->d_inc_b.release(); s->d_tile_batches.release(); s->d_cta_batch_ptr.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
-  s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release();
+  s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release(); s->d_band.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
@@ -974,8 +1046,8 @@ void ba_destroy(ba_solver *s) {
   free_device(s);
   if (s->stream) cudaStreamSynchronize(s->stream);
   for (auto e : s->ev) cudaEventDestroy(e);
-  if (s->h_state) cudaFreeHost(s->h_state);
-  if (s->h_scal) cudaFreeHost(s->h_scal);
+  pinned_put(s->h_state);
+  pinned_put(s->h_scal);
   if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -1092,6 +1164,24 @@ int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const 
   return BA_OK;
 }
 
+// device copies of the envelope plan; again after ba_comm_init agreed on the global envelope
+static int upload_cholesky_plan(ba_solver *s) {
+  cudaStream_t st = s->stream;
+  std::vector<int> rows = s->chol.rows;
+  rows.push_back(0);
+  CUDA_TRY(s->d_chol_rows.upload(rows, st));
+  CUDA_TRY(s->d_chol_first.upload(s->chol.first_tile, st));
+  CUDA_TRY(s->d_chol_rows_ptr.upload(s->chol.rows_ptr, st));
+  s->chol.d_rows = s->d_chol_rows.p;
+  s->chol.d_first_tile = s->d_chol_first.p;
+  s->chol.d_rows_ptr = s->d_chol_rows_ptr.p;
+  if (const char *e = getenv("BA_B200_CHOL_MODE")) s->chol_mode = atoi(e);
+  // BA_B200_CHOL_MODE: -1 auto (banded > cluster > multi-kernel), 0 multi-kernel, 1 cluster, 2 banded
+  if (s->chol_mode == 0) { s->chol.cluster_size = 0; s->chol.banded = false; }
+  if (s->chol_mode == 1) s->chol.banded = false;
+  return BA_OK;
+}
+
 int ba_finalize(ba_solver *s) {
   if (!s) return BA_ERR_INVALID;
   if (s->finalized) return BA_OK;
@@ -1118,10 +1208,12 @@ int ba_finalize(ba_solver *s) {
   s->M = (int)s->h_opt_point.size();
   // --- stable counting sort by pose, then by point  => order (point, pose, insertion)
   std::vector<int> by_pose(n), by_point(n);
+  std::vector<long long> pose_begin(Nt + 1, 0);   // observation range of every pose in by_pose order
   {
     std::vector<long long> cnt(Nt + 1, 0);
     for (long long k = 0; k < n; ++k) cnt[s->h_obs_pose[k] + 1]++;
     for (int j = 0; j < Nt; ++j) cnt[j + 1] += cnt[j];
+    pose_begin = cnt;
     for (long long k = 0; k < n; ++k) by_pose[cnt[s->h_obs_pose[k]]++] = (int)k;
     std::vector<long long> cnt2(Mt + 1, 0);
     for (long long k = 0; k < n; ++k) cnt2[s->h_obs_point[k] + 1]++;
@@ -1144,35 +1236,49 @@ int ba_finalize(ba_solver *s) {
       o_pose[q] = ps; o_point[q] = pt;
       o_cf[q] = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
     }
-    int prev_pt = -1, prev_ps = -1;
+    // a pair starts at every free (pose, point) observation whose predecessor in point order belongs to another
+    // (point, pose): flags, exclusive scan, fill -- three parallel passes instead of one serial scan
+    std::vector<int> pair_rank(n + 1, 0);
+#pragma omp parallel for schedule(static)
     for (long long q = 0; q < n; ++q) {
-      const int ps = o_pose[q], pt = o_point[q];
-      int pair = -1;
-      if ((o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree)) {
-        if (pt != prev_pt || ps != prev_ps) {
-          s->h_pair_pose.push_back(s->h_pose_opt[ps]);
-          s->h_pair_point.push_back(pt);
-          point_has_pairs[pt] = 1;
-        }
-        pair = (int)s->h_pair_pose.size() - 1;
-      }
-      o_pair[q] = pair;
-      prev_pt = pt; prev_ps = ps;
+      const bool both = (o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree);
+      pair_rank[q] = (both && (q == 0 || o_point[q] != o_point[q - 1] || o_pose[q] != o_pose[q - 1])) ? 1 : 0;
     }
-    // last observation of each (point,pose) run = last inserted of the pair (stable sort)
+    const long long n_pairs = exclusive_scan_inplace(pair_rank.data(), n);
+    s->h_pair_pose.resize(n_pairs); s->h_pair_point.resize(n_pairs);
+#pragma omp parallel for schedule(static)
     for (long long q = 0; q < n; ++q) {
-      if (o_pair[q] < 0) continue;
-      if (q + 1 == n || o_pair[q + 1] != o_pair[q]) o_cf[q] |= kFlagLastOfPair;
+      const bool both = (o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree);
+      const bool is_new = (q + 1 < n ? pair_rank[q + 1] : (int)n_pairs) != pair_rank[q];
+      if (is_new) {
+        s->h_pair_pose[pair_rank[q]] = s->h_pose_opt[o_pose[q]];
+        s->h_pair_point[pair_rank[q]] = o_point[q];
+        point_has_pairs[o_point[q]] = 1;
+      }
+      // rank counts the pairs that started before q: an observation of a pair that started earlier has index rank - 1
+      o_pair[q] = both ? (is_new ? pair_rank[q] : pair_rank[q] - 1) : -1;
     }
   }
   s->P = (long long)s->h_pair_pose.size();
   const long long P = s->P;
   std::vector<int2> pair_obs(P);
-  for (long long q = n - 1; q >= 0; --q) if (o_pair[q] >= 0) pair_obs[o_pair[q]].x = (int)q;   // first
-  for (long long q = 0; q < n; ++q) if (o_pair[q] >= 0) pair_obs[o_pair[q]].y = (int)q;        // last (= last inserted)
-  std::vector<int> pair_end(P);
-  for (long long p = P - 1; p >= 0; --p)
-    pair_end[p] = (p + 1 < P && s->h_pair_point[p + 1] == s->h_pair_point[p]) ? pair_end[p + 1] : (int)(p + 1);
+  // first / last observation of every pair (last = last inserted: stable sort) and the last-writer flag
+#pragma omp parallel for schedule(static)
+  for (long long q = 0; q < n; ++q) {
+    const int pr = o_pair[q];
+    if (pr < 0) continue;
+    if (q == 0 || o_pair[q - 1] != pr) pair_obs[pr].x = (int)q;
+    if (q + 1 == n || o_pair[q + 1] != pr) { pair_obs[pr].y = (int)q; o_cf[q] |= kFlagLastOfPair; }
+  }
+  // pairs of one landmark are contiguous: group starts, then one past the last pair of the landmark for every pair
+  std::vector<int> pair_end(P), grp_start;
+  for (long long p = 0; p < P; ++p)
+    if (p == 0 || s->h_pair_point[p] != s->h_pair_point[p - 1]) grp_start.push_back((int)p);
+  grp_start.push_back((int)P);
+  const long long n_grp = (long long)grp_start.size() - 1;
+#pragma omp parallel for schedule(static)
+  for (long long g = 0; g < n_grp; ++g)
+    for (int p = grp_start[g]; p < grp_start[g + 1]; ++p) pair_end[p] = grp_start[g + 1];
   lap("point order, pairs");
   // --- observation range of every landmark in point order
   std::vector<long long> pt_q0(Mt + 1, 0);
@@ -1185,30 +1291,40 @@ int ba_finalize(ba_solver *s) {
   std::vector<int2> inc_b;
   std::vector<uint8_t> is_tile_point(Mt, 0);
   {
-    struct Cand { int point, p0, p1, jmin, jmax; };
-    std::vector<Cand> cands;
-    for (long long p = 0; p < P;) {
-      const int e = pair_end[p];
-      // pairs of a point are ascending in j_opt (points sorted by (point, pose), j_opt monotone in id)
-      Cand c{s->h_pair_point[p], (int)p, e, s->h_pair_pose[p], s->h_pair_pose[e - 1]};
-      // incidences = distinct poses (free or fixed) observing the landmark
-      int n_inc = 0, prev = -1;
+    struct Cand { int point, p0, p1, jmin, jmax, n_inc, ok; };
+    // one candidate per landmark with pairs (parallel): window of its free poses, incidences = distinct poses
+    // (free or fixed) observing it; pairs of a point are ascending in j_opt
+    std::vector<Cand> all(n_grp);
+#pragma omp parallel for schedule(static)
+    for (long long g = 0; g < n_grp; ++g) {
+      const int p0 = grp_start[g], p1 = grp_start[g + 1];
+      Cand c{s->h_pair_point[p0], p0, p1, s->h_pair_pose[p0], s->h_pair_pose[p1 - 1], 0, 0};
+      int prev = -1;
       for (long long q = pt_q0[c.point]; q < pt_q0[c.point + 1]; ++q)
-        if (o_pose[q] != prev) { ++n_inc; prev = o_pose[q]; }
-      if (s->schur_mode == 1 && c.jmax - c.jmin + 1 <= kTileW && n_inc <= kTileMaxInc) cands.push_back(c);
-      else for (int q = (int)p; q < e; ++q) fallback_pairs.push_back(q);
-      p = e;
+        if (o_pose[q] != prev) { ++c.n_inc; prev = o_pose[q]; }
+      c.ok = (s->schur_mode == 1 && c.jmax - c.jmin + 1 <= kTileW && c.n_inc <= kTileMaxInc) ? 1 : 0;
+      all[g] = c;
     }
     // Landmarks are grouped by (first pose, last pose) rather than by id: consecutive landmarks then share their
     // window, so a chunk's window is as narrow as its tracks and the GEMM operands are dense (mixed track lengths
-    // in id order would widen every chunk to the longest track in it)
-    std::stable_sort(cands.begin(), cands.end(), [](const Cand &x, const Cand &y) {
-      return x.jmin != y.jmin ? x.jmin < y.jmin : x.jmax < y.jmax;
-    });
+    // in id order would widen every chunk to the longest track in it).  Stable counting sort on jmin * W + span.
+    std::vector<Cand> cands;
+    {
+      std::vector<int> key_cnt((size_t)std::max(1, s->N) * kTileW + 1, 0);
+      for (const Cand &c : all) {
+        if (c.ok) key_cnt[(size_t)c.jmin * kTileW + (c.jmax - c.jmin) + 1]++;
+        else for (int q = c.p0; q < c.p1; ++q) fallback_pairs.push_back(q);
+      }
+      for (size_t k = 1; k < key_cnt.size(); ++k) key_cnt[k] += key_cnt[k - 1];
+      cands.resize(key_cnt.back());
+      for (const Cand &c : all)
+        if (c.ok) cands[key_cnt[(size_t)c.jmin * kTileW + (c.jmax - c.jmin)]++] = c;
+    }
     // Greedy runs.  A run keeps growing while its pose window stays within kTileW; once it holds enough
     // landmarks to amortise the final flush it is also cut when the next landmark would WIDEN the window,
     // so that most chunks are exactly as wide as their landmarks' tracks (dense GEMM operands).
     constexpr int kMinPts = 6, kMinStart = 32, kGoodPts = 64, kMaxPts = 128;
+    std::vector<int> tpt_cand, tpt_lo;   // candidate and window start of every tile landmark
     size_t i = 0;
     while (i < cands.size()) {
       int lo = cands[i].jmin, hi = cands[i].jmax;
@@ -1221,29 +1337,37 @@ int ba_finalize(ba_solver *s) {
         lo = nlo; hi = nhi; ++e;
       }
       if ((int)(e - i) >= kMinPts) {
-        SchurChunk sc{(int)tpt_point.size(), (int)(e - i), lo, hi - lo + 1};
-        for (size_t k = i; k < e; ++k) {
-          const int pt = cands[k].point, ti = (int)tpt_point.size();
-          is_tile_point[pt] = 1;
-          tpt_point.push_back(pt);
-          tpt_inc_start.push_back((int)inc_a.size());
-          for (long long q = pt_q0[pt]; q < pt_q0[pt + 1];) {
-            long long r = q;
-            while (r < pt_q0[pt + 1] && o_pose[r] == o_pose[q]) ++r;
-            const int pair = o_pair[q];
-            inc_a.push_back(make_int4((int)q, (int)(r - q), o_pose[q], pair));
-            inc_b.push_back(make_int2(pair >= 0 ? s->h_pair_pose[pair] - lo : -1, ti));
-            q = r;
-          }
-        }
-        schur_chunks.push_back(sc);
+        schur_chunks.push_back(SchurChunk{(int)tpt_cand.size(), (int)(e - i), lo, hi - lo + 1});
+        for (size_t k = i; k < e; ++k) { tpt_cand.push_back((int)k); tpt_lo.push_back(lo); }
       } else {
         for (size_t k = i; k < e; ++k)
           for (int q = cands[k].p0; q < cands[k].p1; ++q) fallback_pairs.push_back(q);
       }
       i = e;
     }
-    tpt_inc_start.push_back((int)inc_a.size());
+    // incidence records of the tile landmarks: offsets by a scan over the incidence counts, then a parallel fill
+    const long long n_tpt = (long long)tpt_cand.size();
+    tpt_point.resize(n_tpt);
+    tpt_inc_start.assign(n_tpt + 1, 0);
+    for (long long t = 0; t < n_tpt; ++t) tpt_inc_start[t + 1] = tpt_inc_start[t] + cands[tpt_cand[t]].n_inc;
+    inc_a.resize(tpt_inc_start[n_tpt]);
+    inc_b.resize(tpt_inc_start[n_tpt]);
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < n_tpt; ++t) {
+      const int pt = cands[tpt_cand[t]].point, lo = tpt_lo[t];
+      is_tile_point[pt] = 1;
+      tpt_point[t] = pt;
+      int w = tpt_inc_start[t];
+      for (long long q = pt_q0[pt]; q < pt_q0[pt + 1];) {
+        long long r = q;
+        while (r < pt_q0[pt + 1] && o_pose[r] == o_pose[q]) ++r;
+        const int pair = o_pair[q];
+        inc_a[w] = make_int4((int)q, (int)(r - q), o_pose[q], pair);
+        inc_b[w] = make_int2(pair >= 0 ? s->h_pair_pose[pair] - lo : -1, (int)t);
+        ++w;
+        q = r;
+      }
+    }
     std::sort(fallback_pairs.begin(), fallback_pairs.end());
   }
   // --- flat list of 8-landmark batches over the tile chunks, split evenly over one persistent CTA per SM
@@ -1271,15 +1395,14 @@ int ba_finalize(ba_solver *s) {
     for (int k = 0; k <= tl.n_cta; ++k) cta_batch_ptr[k] = (int)(nbt * k / tl.n_cta);
   }
   lap("tile chunks, incidences");
-  // --- Cholesky envelope plan from the co-visibility structure
+  // --- Cholesky envelope plan from the co-visibility structure (first co-visible pose of every free pose)
   {
-    std::vector<int> first_pose(s->N);
+    std::vector<int> &first_pose = s->h_first_pose;
+    first_pose.resize(s->N);
     for (int j = 0; j < s->N; ++j) first_pose[j] = j;
-    for (long long p = 0; p < P;) {
-      const int e = pair_end[p];
-      const int jmin = s->h_pair_pose[p];
-      for (int q = (int)p; q < e; ++q) first_pose[s->h_pair_pose[q]] = std::min(first_pose[s->h_pair_pose[q]], jmin);
-      p = e;
+    for (long long g = 0; g < n_grp; ++g) {
+      const int jmin = s->h_pair_pose[grp_start[g]];
+      for (int q = grp_start[g]; q < grp_start[g + 1]; ++q) first_pose[s->h_pair_pose[q]] = std::min(first_pose[s->h_pair_pose[q]], jmin);
     }
     cholesky_make_plan(s->chol, 6 * s->N, first_pose);
   }
@@ -1370,34 +1493,36 @@ int ba_finalize(ba_solver *s) {
   std::vector<double2> uvA; std::vector<int> pointA, camA, poseidA;
   std::vector<ChunkA> chunksA; std::vector<int> pose_chunk_ptr(s->N + 1, 0);
   {
-    long long nA = 0;
-    for (long long q = 0; q < n; ++q) if (s->h_pose_opt[s->h_obs_pose[by_pose[q]]] >= 0) ++nA;
-    uvA.reserve(nA); pointA.reserve(nA); camA.reserve(nA); poseidA.reserve(nA);
+    // A-order = the by_pose order restricted to free poses: offsets per pose, chunks per pose (serial over poses),
+    // then a parallel gather of the observations
+    std::vector<long long> a_begin(Nt + 1, 0);
+    for (int ps = 0; ps < Nt; ++ps)
+      a_begin[ps + 1] = a_begin[ps] + (s->h_pose_opt[ps] >= 0 ? pose_begin[ps + 1] - pose_begin[ps] : 0);
+    const long long nA = a_begin[Nt];
+    uvA.resize(nA); pointA.resize(nA); camA.resize(nA); poseidA.resize(nA);
     // chunk size adapts to observations per pose so that a pose yields only a few partials
     const long long per_pose = s->N > 0 ? (nA + s->N - 1) / s->N : 0;
     int per_thread = (int)std::min<long long>(4, std::max<long long>(1, per_pose / (kThreads * 4)));
     const long long chunk_cap = (long long)kThreads * per_thread;
-    long long q = 0;
-    while (q < n) {
-      const int ps = s->h_obs_pose[by_pose[q]];
-      long long e = q;
-      while (e < n && s->h_obs_pose[by_pose[e]] == ps) ++e;
+    for (int ps = 0; ps < Nt; ++ps) {
       const int j = s->h_pose_opt[ps];
-      if (j >= 0) {
-        pose_chunk_ptr[j] = (int)chunksA.size();
-        for (long long a = q; a < e; a += chunk_cap) {
-          const long long b = std::min(e, a + chunk_cap);
-          chunksA.push_back(ChunkA{(int)uvA.size(), (int)(b - a), j, 0});
-          for (long long r = a; r < b; ++r) {
-            const int k = by_pose[r];
-            uvA.push_back(make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]));
-            pointA.push_back(s->h_obs_point[k]);
-            camA.push_back(s->h_obs_cam[k]);
-            poseidA.push_back(ps);
-          }
-        }
+      if (j < 0 || a_begin[ps + 1] == a_begin[ps]) continue;
+      pose_chunk_ptr[j] = (int)chunksA.size();
+      for (long long a = a_begin[ps]; a < a_begin[ps + 1]; a += chunk_cap)
+        chunksA.push_back(ChunkA{(int)a, (int)(std::min(a_begin[ps + 1], a + chunk_cap) - a), j, 0});
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ps = 0; ps < Nt; ++ps) {
+      if (s->h_pose_opt[ps] < 0) continue;
+      const long long len = pose_begin[ps + 1] - pose_begin[ps];
+      for (long long r = 0; r < len; ++r) {
+        const int k = by_pose[pose_begin[ps] + r];
+        const long long w = a_begin[ps] + r;
+        uvA[w] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
+        pointA[w] = s->h_obs_point[k];
+        camA[w] = s->h_obs_cam[k];
+        poseidA[w] = ps;
       }
-      q = e;
     }
     // poses without observations keep an empty chunk range: fix up the CSR (chunks are in pose order)
     std::vector<int> cnt(s->N, 0);
@@ -1445,20 +1570,7 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_pair_end.upload(pair_end, st));
   CUDA_TRY(s->d_point_has_pairs.upload(point_has_pairs, st));
   CUDA_TRY(s->d_point_free.upload(point_free, st));
-  {
-    std::vector<int> rows = s->chol.rows;
-    rows.push_back(0);
-    CUDA_TRY(s->d_chol_rows.upload(rows, st));
-    CUDA_TRY(s->d_chol_first.upload(s->chol.first_tile, st));
-    CUDA_TRY(s->d_chol_rows_ptr.upload(s->chol.rows_ptr, st));
-    s->chol.d_rows = s->d_chol_rows.p;
-    s->chol.d_first_tile = s->d_chol_first.p;
-    s->chol.d_rows_ptr = s->d_chol_rows_ptr.p;
-    if (const char *e = getenv("BA_B200_CHOL_MODE")) s->chol_mode = atoi(e);
-    // BA_B200_CHOL_MODE: -1 auto (banded > cluster > multi-kernel), 0 multi-kernel, 1 cluster, 2 banded
-    if (s->chol_mode == 0) { s->chol.cluster_size = 0; s->chol.banded = false; }
-    if (s->chol_mode == 1) s->chol.banded = false;
-  }
+  if (int rc = upload_cholesky_plan(s)) return rc;
   CUDA_TRY(s->d_schur_chunks.upload(schur_chunks, st));
   CUDA_TRY(s->d_tpt_point.upload(tpt_point, st));
   CUDA_TRY(s->d_tpt_inc_start.upload(tpt_inc_start, st));
@@ -1511,8 +1623,10 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_state.alloc(1));
   CUDA_TRY(cudaMemsetAsync(s->d_state.p, 0, sizeof(LmState), st));
   CUDA_TRY(cudaMemsetAsync(s->d_scal.p, 0, 8 * sizeof(double), st));
-  if (!s->h_state) CUDA_TRY(cudaMallocHost((void **)&s->h_state, sizeof(LmState)));
-  if (!s->h_scal) CUDA_TRY(cudaMallocHost((void **)&s->h_scal, 8 * sizeof(double)));
+  static_assert(sizeof(LmState) <= kPinnedBlock, "pinned block");
+  lap("block storage: device");
+  if (!s->h_state) CUDA_TRY(pinned_get((void **)&s->h_state));
+  if (!s->h_scal) CUDA_TRY(pinned_get((void **)&s->h_scal));
   CUDA_TRY(cudaStreamSynchronize(st));
   lap("block storage");
   s->finalized = true;
@@ -1650,8 +1764,21 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
 
 static int enqueue_allreduce_S(ba_solver *s) {
   if (!s->comm) return BA_OK;
-  const size_t ld = (size_t)6 * s->N + 1;
-  ncclResult_t r = g_nccl.AllReduce(s->d_Saug.p, s->d_Saug.p, ld * ld, ncclDouble, ncclSum, s->comm, s->stream);
+  const int n = 6 * s->N;
+  const size_t ld = (size_t)n + 1;
+  ncclResult_t r;
+  if (s->chol.banded && n > 0) {
+    // every rank holds the same plan (ba_comm_init agreed on the global envelope): band + rhs only
+    const int bw = s->chol.bw;
+    const size_t count = (size_t)n * (bw + 2);
+    if (s->d_band.n < count) CUDA_TRY(s->d_band.alloc(count));
+    k_band_pack<<<n, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, bw, s->d_band.p, s->d_state.p);
+    r = g_nccl.AllReduce(s->d_band.p, s->d_band.p, count, ncclDouble, ncclSum, s->comm, s->stream);
+    k_band_unpack<<<n, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, bw, s->d_band.p, s->d_state.p);
+    s->launches += 2;
+  } else {
+    r = g_nccl.AllReduce(s->d_Saug.p, s->d_Saug.p, ld * ld, ncclDouble, ncclSum, s->comm, s->stream);
+  }
   if (r != ncclSuccess) { s->err = "ncclAllReduce(S) failed"; return BA_ERR_NCCL; }
   return BA_OK;
 }
@@ -2082,6 +2209,22 @@ int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long lon
   if (r != ncclSuccess) { s->err = "ncclCommInitRank failed"; s->comm = nullptr; return BA_ERR_NCCL; }
   s->rank = rank; s->n_ranks = nranks; s->global_M = global_M; s->global_n_obs = global_n_obs;
   destroy_graph(s);
+  if (s->finalized && s->N > 0) {
+    // The reduced solve is replicated: every rank must factor the all-reduced S with the SAME plan, built from
+    // the co-visibility of ALL landmarks, not of its shard: min over ranks of the first co-visible pose.
+    cudaStream_t st = s->stream;
+    g_alloc_stream = st;
+    DevBuf<int> d_fp;
+    CUDA_TRY(d_fp.upload(s->h_first_pose, st));
+    r = g_nccl.AllReduce(d_fp.p, d_fp.p, (size_t)s->N, ncclInt, ncclMin, s->comm, st);
+    if (r != ncclSuccess) { s->err = "ncclAllReduce(envelope) failed"; return BA_ERR_NCCL; }
+    CUDA_TRY(cudaMemcpyAsync(s->h_first_pose.data(), d_fp.p, (size_t)s->N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    d_fp.release();
+    cholesky_make_plan(s->chol, 6 * s->N, s->h_first_pose);
+    if (int rc = upload_cholesky_plan(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   return BA_OK;
 }
 

@@ -23,6 +23,13 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     L = capi.lib()
     sc = scenes.scene_trajectory(60, 3000, 8, stereo=True, seed=21, n_fixed=2)
+    if os.environ.get("BA_MGPU_HETERO") == "1":
+        # short tracks in the first half of the landmarks, long ones in the second: the shards see different
+        # co-visibility envelopes, so the ranks only agree on the banded plan through ba_comm_init
+        first = np.full(len(sc.points_init), 10 ** 9, dtype=np.int64)
+        np.minimum.at(first, sc.obs_point, sc.obs_pose)
+        keep = (sc.obs_point >= len(sc.points_init) // 2) | (sc.obs_pose - first[sc.obs_point] < 3)
+        sc.obs_cam, sc.obs_pose, sc.obs_point, sc.obs_uv = sc.obs_cam[keep], sc.obs_pose[keep], sc.obs_point[keep], sc.obs_uv[keep]
     sh = sharding.shard_scene(sc, rank, world)
     e = S.load_scene(S.FullBundleAdjustmentSolver(device=local), sh)
     e._upload()
