@@ -26,6 +26,13 @@ constexpr int kT2Cons = 128;              // 4 DMMA warps
 constexpr int kT2Threads = kT2ProdWarps * 32 + kT2Cons;
 constexpr int kT2SmemBytes = 227 * 1024;  // everything an SM has: one CTA per SM
 constexpr int kT2SmemDoubles = kT2SmemBytes / 8;
+#ifndef BA_T2_PROD_REGS
+#define BA_T2_PROD_REGS 152
+#endif
+// register split (setmaxnreg): the consumers can only take what the producers gave back to the CTA pool
+constexpr int kT2ProdRegs = BA_T2_PROD_REGS;
+constexpr int kT2ConsRegs = 168 + 2 * (168 - kT2ProdRegs);
+static_assert(kT2ProdWarps * (168 - kT2ProdRegs) >= 4 * (kT2ConsRegs - 168) && kT2ProdRegs % 8 == 0, "register pool");
 constexpr int kT2SPW = 7;                 // 2 x 2 super-tiles per DMMA warp at the widest window (27 over 4 warps)
 
 struct TileLaunch {   // uniform per launch, fixed at finalize
@@ -64,9 +71,8 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
 
   if (warp < kT2ProdWarps) {
     // ===================================================== producers =====================================
-    // register split: the consumers can only take what the producers gave back to the CTA pool
-    // (8 warps x (168 - 152) >= 4 warps x (200 - 168)); asking for more spins forever in TRY_ALLOC
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
+    // asking for more than the pool holds spins forever in TRY_ALLOC (static_assert above)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT2ProdRegs));
     const int grp = warp;
     if (grp >= G) return;
     const int sub = lane & 3;
@@ -253,7 +259,7 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
     }
   } else {
     // ===================================================== consumers =====================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kT2ConsRegs));
     const int cw = warp - kT2ProdWarps;
     const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
     const double *Afrag0 = tsm + kq * ldE + fr;                 // + 8 ti
