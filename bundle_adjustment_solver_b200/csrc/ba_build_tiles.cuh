@@ -12,7 +12,9 @@
 //     shared-memory staging of partials, no idle threads while one thread per landmark inverts;
 //   * every producer warp is its own group with its own operand buffer (G = 5..7 buffers, sized by the widest
 //     window of the launch: ldE = 8 nt + 4, ldB = 8 nt + 12, both = 4 or 12 mod 16 -> conflict-free DMMA fragment
-//     reads) and runs ahead on its own batch; the index records of the next batch are prefetched;
+//     reads) and runs ahead on its own batch; the index records of the next round / next batch are prefetched,
+//     the next batch's landmark data only after the observation loop (live across it, it would be spilled, and a
+//     spill waits for the load);
 //   * the four DMMA warps consume the buffers round-robin and hand them back: full[g] / empty[g] named barriers,
 //     nothing else; a producer clears the few window slots its landmark does not cover instead of anybody
 //     clearing whole buffers.
@@ -27,9 +29,10 @@ constexpr int kT2Threads = kT2ProdWarps * 32 + kT2Cons;
 constexpr int kT2SmemBytes = 227 * 1024;  // everything an SM has: one CTA per SM
 constexpr int kT2SmemDoubles = kT2SmemBytes / 8;
 #ifndef BA_T2_PROD_REGS
-#define BA_T2_PROD_REGS 152
+#define BA_T2_PROD_REGS 160
 #endif
-// register split (setmaxnreg): the consumers can only take what the producers gave back to the CTA pool
+// register split (setmaxnreg): the consumers can only take what the producers gave back to the CTA pool.
+// Measured (C3 / C4 tile kernel): 144/216 0.151 / 1.31 ms, 152/200 0.138 / 1.21, 160/184 0.125 / 1.09, 168/168 0.158 / 1.36
 constexpr int kT2ProdRegs = BA_T2_PROD_REGS;
 constexpr int kT2ConsRegs = 168 + 2 * (168 - kT2ProdRegs);
 static_assert(kT2ProdWarps * (168 - kT2ProdRegs) >= 4 * (kT2ConsRegs - 168) && kT2ProdRegs % 8 == 0, "register pool");
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ batches /*ti0, nb, chunk, rhs column*/,
                const int *__restrict__ cta_batch_ptr, TileLaunch tl, const int *__restrict__ tpt_point,
                const int *__restrict__ tpt_inc_start, const int4 *__restrict__ inc_a /*obs_first, n_obs, pose, pair*/,
-               const int2 *__restrict__ inc_b /*slot (-1: fixed pose), tile landmark index*/,
+               const int2 *__restrict__ inc_b /*slot (-1: fixed pose), camera slots of obs 0 | obs 1 << 8*/,
                const double2 *__restrict__ obs_uv, const int *__restrict__ obs_camflags, Params prm,
                const double *__restrict__ cams, double thres_huber, double *__restrict__ Bsoa, size_t Pp,
                double *__restrict__ ptblk, size_t Mp, double *__restrict__ Saug, int ld,
@@ -108,6 +111,9 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
       load_landmark(__ldg(batches + fb));
       if (fb + G < b1) rec_n = __ldg(batches + fb + G);
     }
+    int4 ia_b = make_int4(0, 0, 0, 0);   // first incidence record of the lane in the coming batch
+    int2 sc_b = make_int2(-1, 0);
+    if (a + sub < b) { ia_b = __ldg(inc_a + a + sub); sc_b = __ldg(inc_b + a + sub); }
     for (; fb < b1; fb += G) {
       const bool cur_live = live;
       const int ca = a, cb = b, cpt = pt;
@@ -115,13 +121,8 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
       const double X0 = X[0], X1 = X[1], X2 = X[2];
       // first incidence record of the current landmark, then the next batch's landmark data (in flight during
       // the whole batch)
-      int4 ia_n = make_int4(0, 0, 0, 0);
-      int slot_n = -1;
-      if (ca + sub < cb) { ia_n = __ldg(inc_a + ca + sub); slot_n = __ldg(inc_b + ca + sub).x; }
-      if (fb + G < b1) {
-        load_landmark(rec_n);
-        if (fb + 2 * G < b1) rec_n = __ldg(batches + fb + 2 * G);
-      }
+      int4 ia_n = ia_b;
+      int2 sc_n = sc_b;
       double cp[9];
 #pragma unroll
       for (int i = 0; i < 9; ++i) cp[i] = 0.0;
@@ -130,12 +131,14 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
       //         when the first round is stored: its loads and arithmetic run while the consumers still read it
       const int rounds = __reduce_max_sync(0xffffffffu, (cb - ca + 3) >> 2);
       unsigned covered = 0u;   // window slots of the landmark that receive a B / E block
+      unsigned slots = 0u;     // (slot + 1) of the lane's incidence in round rd, 5 bits each
       for (int rd = 0; rd < rounds; ++rd) {
         const int ii = ca + sub + 4 * rd;
         const bool act = ii < cb;
         const int4 ia = ia_n;
-        const int slot = act ? slot_n : -1;
-        if (ii + 4 < cb) { ia_n = __ldg(inc_a + ii + 4); slot_n = __ldg(inc_b + ii + 4).x; }
+        const int slot = act ? sc_n.x : -1;
+        const int cams01 = sc_n.y;
+        if (ii + 4 < cb) { ia_n = __ldg(inc_a + ii + 4); sc_n = __ldg(inc_b + ii + 4); }
         double Bv[18];
 #pragma unroll
         for (int i = 0; i < 18; ++i) Bv[i] = 0.0;
@@ -144,7 +147,9 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
         load_pose(poses + (size_t)ia.z * 12, T);
         for (int k = ia.x; k < ia.x + ia.y; ++k) {
           const double2 uv = obs_uv[k];
-          const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
+          const int kk = k - ia.x;
+          const int cid = (kk == 0) ? (cams01 & 0xff) : (kk == 1) ? (cams01 >> 8) : (obs_camflags[k] & kCamMask);
+          const double *cam = cams + cid * kCamStride;
           Proj pr;
           project(T, Xc, cam, uv.x, uv.y, pr);
           const double w = huber_weight(pr.r0, pr.r1, thres_huber);
@@ -174,6 +179,7 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
         if (rd == 0 && fb - b0 >= G) bar_sync(8 + grp, bar_cnt);   // the consumers have read and cleared this buffer
         if (slot >= 0) {
           covered |= 1u << slot;
+          slots |= (unsigned)(slot + 1) << (5 * rd);
 #pragma unroll
           for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -184,6 +190,12 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
         }
       }
       if (rounds == 0 && fb - b0 >= G) bar_sync(8 + grp, bar_cnt);
+      // the next batch's landmark data is requested only now: in flight during the sums / inverse / E phase, but
+      // not live across the observation loop above (where it would be spilled -- a spill waits for the load)
+      if (fb + G < b1) {
+        load_landmark(rec_n);
+        if (fb + 2 * G < b1) rec_n = __ldg(batches + fb + 2 * G);
+      }
       // ---- 2. landmark sums over its 4 lanes: xor butterfly, bitwise identical on every lane of the landmark
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
@@ -241,8 +253,8 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
         }
         // ---- 3. E = B Cinv for the lane's own incidences (B read back from the operand the lane wrote); the
         //         operand holds -E so that the GEMM accumulates S -= E B^T directly
-        for (int ii = ca + sub; ii < cb; ii += 4) {
-          const int slot = __ldg(inc_b + ii).x;
+        for (; slots != 0u; slots >>= 5) {
+          const int slot = (int)(slots & 31u) - 1;
           if (slot < 0) continue;
           const double *Bc = Bbase + (3 * li) * ldB + 6 * slot;
           double *Ec = Ebase + (3 * li) * ldE + 6 * slot;
@@ -255,6 +267,9 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
           }
         }
       }
+      ia_b = make_int4(0, 0, 0, 0);
+      sc_b = make_int2(-1, 0);
+      if (a + sub < b) { ia_b = __ldg(inc_a + a + sub); sc_b = __ldg(inc_b + a + sub); }   // round 0 of the next batch
       bar_arrive(1 + grp, bar_cnt);   // operands of this batch are complete
     }
   } else {

@@ -1363,7 +1363,10 @@ int ba_finalize(ba_solver *s) {
         while (r < pt_q0[pt + 1] && o_pose[r] == o_pose[q]) ++r;
         const int pair = o_pair[q];
         inc_a[w] = make_int4((int)q, (int)(r - q), o_pose[q], pair);
-        inc_b[w] = make_int2(pair >= 0 ? s->h_pair_pose[pair] - lo : -1, (int)t);
+        // .y: camera slots of the first two observations, so that the camera block can be fetched before the
+        // observation's own record arrives
+        inc_b[w] = make_int2(pair >= 0 ? s->h_pair_pose[pair] - lo : -1,
+                             (o_cf[q] & kCamMask) | ((r - q > 1 ? (o_cf[q + 1] & kCamMask) : 0) << 8));
         ++w;
         q = r;
       }
