@@ -17,16 +17,17 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
-#include <omp.h>
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -833,28 +834,39 @@ inline void pool_setup(int device) {
   done[device] = true;
 }
 
-// exclusive prefix sum of v[0..n) in place (v has n + 1 entries; v[n] and the return value = total), OpenMP two-pass
+// Host-side data-parallel loops of set_observations / finalize: plain threads that are joined at the end of the
+// loop (at most 8).  An OpenMP team would keep spinning on every core after each of the dozen short regions, which
+// starves the caller's own thread (and the driver's staging copies that follow) on hosts with a CPU quota.
+static int host_threads() {
+  static const int n = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  return n;
+}
+template <typename F>
+static void parallel_ranges(long long n, F &&fn /*(lo, hi, tid)*/, long long grain = 4096) {
+  const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, n / grain));
+  if (nth <= 1) { fn(0LL, n, 0); return; }
+  std::vector<std::thread> th;
+  th.reserve(nth - 1);
+  for (int t = 1; t < nth; ++t) th.emplace_back([&fn, n, nth, t] { fn(n * t / nth, n * (t + 1) / nth, t); });
+  fn(0LL, n / nth, 0);
+  for (auto &x : th) x.join();
+}
+
+// exclusive prefix sum of v[0..n) in place (v has n + 1 entries; v[n] and the return value = total), two passes
 static long long exclusive_scan_inplace(int *v, long long n) {
-  int nth = 1;
-#pragma omp parallel
-  {
-#pragma omp single
-    nth = omp_get_num_threads();
-  }
+  const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, n / 4096));
   std::vector<long long> part(nth + 1, 0);
-#pragma omp parallel num_threads(nth)
-  {
-    const int t = omp_get_thread_num();
-    const long long lo = n * t / nth, hi = n * (t + 1) / nth;
-    long long sum = 0;
-    for (long long q = lo; q < hi; ++q) sum += v[q];
-    part[t + 1] = sum;
-#pragma omp barrier
-#pragma omp single
-    for (int k = 0; k < nth; ++k) part[k + 1] += part[k];
-    long long run = part[t];
-    for (long long q = lo; q < hi; ++q) { const int x = v[q]; v[q] = (int)run; run += x; }
-  }
+  auto range = [&](int t, long long &lo, long long &hi) { lo = n * t / nth; hi = n * (t + 1) / nth; };
+  auto run = [&](auto &&body) {
+    if (nth <= 1) { body(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; ++t) th.emplace_back([&body, t] { body(t); });
+    body(0);
+    for (auto &x : th) x.join();
+  };
+  run([&](int t) { long long lo, hi; range(t, lo, hi); long long sum = 0; for (long long q = lo; q < hi; ++q) sum += v[q]; part[t + 1] = sum; });
+  for (int k = 0; k < nth; ++k) part[k + 1] += part[k];
+  run([&](int t) { long long lo, hi; range(t, lo, hi); long long acc = part[t]; for (long long q = lo; q < hi; ++q) { const int x = v[q]; v[q] = (int)acc; acc += x; } });
   v[n] = (int)part[nth];
   return part[nth];
 }
@@ -1126,15 +1138,21 @@ int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const 
       for (auto &kv : s->cam_slot) table[kv.first] = kv.second;
       const int Nt = s->N_total, Mt = s->M_total;
       long long bad = 0;
-#pragma omp parallel for reduction(+ : bad) schedule(static)
-      for (long long k = 0; k < n_obs; ++k) {
-        const int c = cam_id[k];
-        bad += (c < 0 || c > max_id || table[c] < 0 || pose[k] < 0 || pose[k] >= Nt || point[k] < 0 || point[k] >= Mt);
-      }
+      std::atomic<long long> bad_total{0};
+      parallel_ranges(n_obs, [&](long long lo_, long long hi_, int) {
+        long long bad = 0;
+        for (long long k = (long long)lo_; k < (long long)hi_; ++k) {
+          const int c = cam_id[k];
+          bad += (c < 0 || c > max_id || table[c] < 0 || pose[k] < 0 || pose[k] >= Nt || point[k] < 0 || point[k] >= Mt);
+        }
+        bad_total += bad;
+      });
+      bad = bad_total.load();
       if (bad == 0) {
         s->h_obs_cam.resize(n_obs);
-#pragma omp parallel for schedule(static)
-        for (long long k = 0; k < n_obs; ++k) s->h_obs_cam[k] = table[cam_id[k]];
+        parallel_ranges(n_obs, [&](long long lo_, long long hi_, int) {
+          for (long long k = (long long)lo_; k < (long long)hi_; ++k) s->h_obs_cam[k] = table[cam_id[k]];
+        });
         s->h_obs_pose.assign(pose, pose + n_obs);
         s->h_obs_point.assign(point, point + n_obs);
         s->h_obs_uv.assign(uv, uv + 2 * n_obs);
@@ -1227,58 +1245,63 @@ int ba_finalize(ba_solver *s) {
   s->h_pair_pose.clear(); s->h_pair_point.clear();
   std::vector<int> point_has_pairs(Mt, 0);
   {
-#pragma omp parallel for schedule(static)
-    for (long long q = 0; q < n; ++q) {
-      const int k = by_point[q];
-      const int ps = s->h_obs_pose[k], pt = s->h_obs_point[k];
-      const bool pf = s->h_pose_opt[ps] >= 0, qf = s->h_point_opt[pt] >= 0;
-      uv[q] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
-      o_pose[q] = ps; o_point[q] = pt;
-      o_cf[q] = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
-    }
+    parallel_ranges(n, [&](long long lo_, long long hi_, int) {
+      for (long long q = (long long)lo_; q < (long long)hi_; ++q) {
+        const int k = by_point[q];
+        const int ps = s->h_obs_pose[k], pt = s->h_obs_point[k];
+        const bool pf = s->h_pose_opt[ps] >= 0, qf = s->h_point_opt[pt] >= 0;
+        uv[q] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
+        o_pose[q] = ps; o_point[q] = pt;
+        o_cf[q] = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
+      }
+    });
     // a pair starts at every free (pose, point) observation whose predecessor in point order belongs to another
     // (point, pose): flags, exclusive scan, fill -- three parallel passes instead of one serial scan
     std::vector<int> pair_rank(n + 1, 0);
-#pragma omp parallel for schedule(static)
-    for (long long q = 0; q < n; ++q) {
-      const bool both = (o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree);
-      pair_rank[q] = (both && (q == 0 || o_point[q] != o_point[q - 1] || o_pose[q] != o_pose[q - 1])) ? 1 : 0;
-    }
+    parallel_ranges(n, [&](long long lo_, long long hi_, int) {
+      for (long long q = (long long)lo_; q < (long long)hi_; ++q) {
+        const bool both = (o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree);
+        pair_rank[q] = (both && (q == 0 || o_point[q] != o_point[q - 1] || o_pose[q] != o_pose[q - 1])) ? 1 : 0;
+      }
+    });
     const long long n_pairs = exclusive_scan_inplace(pair_rank.data(), n);
     s->h_pair_pose.resize(n_pairs); s->h_pair_point.resize(n_pairs);
-#pragma omp parallel for schedule(static)
-    for (long long q = 0; q < n; ++q) {
-      const bool both = (o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree);
-      const bool is_new = (q + 1 < n ? pair_rank[q + 1] : (int)n_pairs) != pair_rank[q];
-      if (is_new) {
-        s->h_pair_pose[pair_rank[q]] = s->h_pose_opt[o_pose[q]];
-        s->h_pair_point[pair_rank[q]] = o_point[q];
-        point_has_pairs[o_point[q]] = 1;
+    parallel_ranges(n, [&](long long lo_, long long hi_, int) {
+      for (long long q = (long long)lo_; q < (long long)hi_; ++q) {
+        const bool both = (o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree);
+        const bool is_new = (q + 1 < n ? pair_rank[q + 1] : (int)n_pairs) != pair_rank[q];
+        if (is_new) {
+          s->h_pair_pose[pair_rank[q]] = s->h_pose_opt[o_pose[q]];
+          s->h_pair_point[pair_rank[q]] = o_point[q];
+          point_has_pairs[o_point[q]] = 1;
+        }
+        // rank counts the pairs that started before q: an observation of a pair that started earlier has index rank - 1
+        o_pair[q] = both ? (is_new ? pair_rank[q] : pair_rank[q] - 1) : -1;
       }
-      // rank counts the pairs that started before q: an observation of a pair that started earlier has index rank - 1
-      o_pair[q] = both ? (is_new ? pair_rank[q] : pair_rank[q] - 1) : -1;
-    }
+    });
   }
   s->P = (long long)s->h_pair_pose.size();
   const long long P = s->P;
   std::vector<int2> pair_obs(P);
   // first / last observation of every pair (last = last inserted: stable sort) and the last-writer flag
-#pragma omp parallel for schedule(static)
-  for (long long q = 0; q < n; ++q) {
-    const int pr = o_pair[q];
-    if (pr < 0) continue;
-    if (q == 0 || o_pair[q - 1] != pr) pair_obs[pr].x = (int)q;
-    if (q + 1 == n || o_pair[q + 1] != pr) { pair_obs[pr].y = (int)q; o_cf[q] |= kFlagLastOfPair; }
-  }
+  parallel_ranges(n, [&](long long lo_, long long hi_, int) {
+    for (long long q = (long long)lo_; q < (long long)hi_; ++q) {
+      const int pr = o_pair[q];
+      if (pr < 0) continue;
+      if (q == 0 || o_pair[q - 1] != pr) pair_obs[pr].x = (int)q;
+      if (q + 1 == n || o_pair[q + 1] != pr) { pair_obs[pr].y = (int)q; o_cf[q] |= kFlagLastOfPair; }
+    }
+  });
   // pairs of one landmark are contiguous: group starts, then one past the last pair of the landmark for every pair
   std::vector<int> pair_end(P), grp_start;
   for (long long p = 0; p < P; ++p)
     if (p == 0 || s->h_pair_point[p] != s->h_pair_point[p - 1]) grp_start.push_back((int)p);
   grp_start.push_back((int)P);
   const long long n_grp = (long long)grp_start.size() - 1;
-#pragma omp parallel for schedule(static)
-  for (long long g = 0; g < n_grp; ++g)
-    for (int p = grp_start[g]; p < grp_start[g + 1]; ++p) pair_end[p] = grp_start[g + 1];
+  parallel_ranges(n_grp, [&](long long lo_, long long hi_, int) {
+    for (long long g = (long long)lo_; g < (long long)hi_; ++g)
+      for (int p = grp_start[g]; p < grp_start[g + 1]; ++p) pair_end[p] = grp_start[g + 1];
+  });
   lap("point order, pairs");
   // --- observation range of every landmark in point order
   std::vector<long long> pt_q0(Mt + 1, 0);
@@ -1295,16 +1318,17 @@ int ba_finalize(ba_solver *s) {
     // one candidate per landmark with pairs (parallel): window of its free poses, incidences = distinct poses
     // (free or fixed) observing it; pairs of a point are ascending in j_opt
     std::vector<Cand> all(n_grp);
-#pragma omp parallel for schedule(static)
-    for (long long g = 0; g < n_grp; ++g) {
-      const int p0 = grp_start[g], p1 = grp_start[g + 1];
-      Cand c{s->h_pair_point[p0], p0, p1, s->h_pair_pose[p0], s->h_pair_pose[p1 - 1], 0, 0};
-      int prev = -1;
-      for (long long q = pt_q0[c.point]; q < pt_q0[c.point + 1]; ++q)
-        if (o_pose[q] != prev) { ++c.n_inc; prev = o_pose[q]; }
-      c.ok = (s->schur_mode == 1 && c.jmax - c.jmin + 1 <= kTileW && c.n_inc <= kTileMaxInc) ? 1 : 0;
-      all[g] = c;
-    }
+    parallel_ranges(n_grp, [&](long long lo_, long long hi_, int) {
+      for (long long g = (long long)lo_; g < (long long)hi_; ++g) {
+        const int p0 = grp_start[g], p1 = grp_start[g + 1];
+        Cand c{s->h_pair_point[p0], p0, p1, s->h_pair_pose[p0], s->h_pair_pose[p1 - 1], 0, 0};
+        int prev = -1;
+        for (long long q = pt_q0[c.point]; q < pt_q0[c.point + 1]; ++q)
+          if (o_pose[q] != prev) { ++c.n_inc; prev = o_pose[q]; }
+        c.ok = (s->schur_mode == 1 && c.jmax - c.jmin + 1 <= kTileW && c.n_inc <= kTileMaxInc) ? 1 : 0;
+        all[g] = c;
+      }
+    });
     // Landmarks are grouped by (first pose, last pose) rather than by id: consecutive landmarks then share their
     // window, so a chunk's window is as narrow as its tracks and the GEMM operands are dense (mixed track lengths
     // in id order would widen every chunk to the longest track in it).  Stable counting sort on jmin * W + span.
@@ -1352,25 +1376,26 @@ int ba_finalize(ba_solver *s) {
     for (long long t = 0; t < n_tpt; ++t) tpt_inc_start[t + 1] = tpt_inc_start[t] + cands[tpt_cand[t]].n_inc;
     inc_a.resize(tpt_inc_start[n_tpt]);
     inc_b.resize(tpt_inc_start[n_tpt]);
-#pragma omp parallel for schedule(static)
-    for (long long t = 0; t < n_tpt; ++t) {
-      const int pt = cands[tpt_cand[t]].point, lo = tpt_lo[t];
-      is_tile_point[pt] = 1;
-      tpt_point[t] = pt;
-      int w = tpt_inc_start[t];
-      for (long long q = pt_q0[pt]; q < pt_q0[pt + 1];) {
-        long long r = q;
-        while (r < pt_q0[pt + 1] && o_pose[r] == o_pose[q]) ++r;
-        const int pair = o_pair[q];
-        inc_a[w] = make_int4((int)q, (int)(r - q), o_pose[q], pair);
-        // .y: camera slots of the first two observations, so that the camera block can be fetched before the
-        // observation's own record arrives
-        inc_b[w] = make_int2(pair >= 0 ? s->h_pair_pose[pair] - lo : -1,
-                             (o_cf[q] & kCamMask) | ((r - q > 1 ? (o_cf[q + 1] & kCamMask) : 0) << 8));
-        ++w;
-        q = r;
+    parallel_ranges(n_tpt, [&](long long lo_, long long hi_, int) {
+      for (long long t = (long long)lo_; t < (long long)hi_; ++t) {
+        const int pt = cands[tpt_cand[t]].point, lo = tpt_lo[t];
+        is_tile_point[pt] = 1;
+        tpt_point[t] = pt;
+        int w = tpt_inc_start[t];
+        for (long long q = pt_q0[pt]; q < pt_q0[pt + 1];) {
+          long long r = q;
+          while (r < pt_q0[pt + 1] && o_pose[r] == o_pose[q]) ++r;
+          const int pair = o_pair[q];
+          inc_a[w] = make_int4((int)q, (int)(r - q), o_pose[q], pair);
+          // .y: camera slots of the first two observations, so that the camera block can be fetched before the
+          // observation's own record arrives
+          inc_b[w] = make_int2(pair >= 0 ? s->h_pair_pose[pair] - lo : -1,
+                               (o_cf[q] & kCamMask) | ((r - q > 1 ? (o_cf[q + 1] & kCamMask) : 0) << 8));
+          ++w;
+          q = r;
+        }
       }
-    }
+    });
     std::sort(fallback_pairs.begin(), fallback_pairs.end());
   }
   // --- flat list of 8-landmark batches over the tile chunks, split evenly over one persistent CTA per SM
@@ -1522,19 +1547,20 @@ int ba_finalize(ba_solver *s) {
       for (long long a = a_begin[ps]; a < a_begin[ps + 1]; a += sz)
         chunksA.push_back(ChunkA{(int)a, (int)(std::min(a_begin[ps + 1], a + sz) - a), j, 0});
     }
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int ps = 0; ps < Nt; ++ps) {
-      if (s->h_pose_opt[ps] < 0) continue;
-      const long long len = pose_begin[ps + 1] - pose_begin[ps];
-      for (long long r = 0; r < len; ++r) {
-        const int k = by_pose[pose_begin[ps] + r];
-        const long long w = a_begin[ps] + r;
-        uvA[w] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
-        pointA[w] = s->h_obs_point[k];
-        camA[w] = s->h_obs_cam[k];
-        poseidA[w] = ps;
+    parallel_ranges(Nt, [&](long long lo_, long long hi_, int) {
+      for (int ps = (int)lo_; ps < (int)hi_; ++ps) {
+        if (s->h_pose_opt[ps] < 0) continue;
+        const long long len = pose_begin[ps + 1] - pose_begin[ps];
+        for (long long r = 0; r < len; ++r) {
+          const int k = by_pose[pose_begin[ps] + r];
+          const long long w = a_begin[ps] + r;
+          uvA[w] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
+          pointA[w] = s->h_obs_point[k];
+          camA[w] = s->h_obs_cam[k];
+          poseidA[w] = ps;
+        }
       }
-    }
+    }, 1);
     // poses without observations keep an empty chunk range: fix up the CSR (chunks are in pose order)
     std::vector<int> cnt(s->N, 0);
     for (auto &c : chunksA) cnt[c.j_opt]++;
