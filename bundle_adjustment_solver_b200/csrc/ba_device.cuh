@@ -121,7 +121,8 @@ __device__ __forceinline__ void se3_exp(const double *xi, double *out) {
     b = 0.5;
     g = 0.33333333333333333333333333;
   } else {
-    const double s = sin(theta), c = cos(theta);
+    double s, c;
+    sincos(theta, &s, &c);
     a = s / theta;
     b = (1.0 - c) / (theta * theta);
     g = (theta - s) / (theta * theta * theta);

@@ -689,8 +689,7 @@ __global__ void k_init_state(LmState *st, const double *scal, double lambda0) {
 }
 
 // trust-region decision (:930-1007), one thread.
-__global__ void k_decide(DecideArgs g, LmState *st, ba_iter_info *infos, int cap) {
-  if (st->done) return;
+__device__ __forceinline__ void decide(const DecideArgs &g, LmState *st, ba_iter_info *infos, int cap) {
   const double current_cost = g.scal[0];
   const double model = -(g.scal[3] + g.scal[1]);  // EvaluateCostChangeByQuadraticModel (:435-455)
   const double previous_cost = st->prev_cost;
@@ -751,6 +750,33 @@ __global__ void k_decide(DecideArgs g, LmState *st, ba_iter_info *infos, int cap
   st->iteration = iteration + 1;
   st->converged = converged ? 1 : 0;
   if (converged || iteration + 1 >= g.max_iteration) st->done = 1;
+}
+
+__global__ void k_decide(DecideArgs g, LmState *st, ba_iter_info *infos, int cap) {
+  if (st->done) return;
+  decide(g, st, infos, cap);
+}
+
+// single GPU: the ordered sums of k_reduce_scalars and the decision in one launch (no exchange in between)
+__global__ void __launch_bounds__(kThreads) k_reduce_decide(DecideArgs g, LmState *st, ba_iter_info *infos, int cap) {
+  if (st->done) return;
+  __shared__ double sm[kWarps][5];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < g.n_cost; i += kThreads) acc[0] += g.cost_partials[i];
+  for (int i = threadIdx.x; i < g.n_point; i += kThreads) {
+    acc[1] += g.point_partials[2 * i];
+    acc[2] += g.point_partials[2 * i + 1];
+  }
+  for (int i = threadIdx.x; i < g.n_pose; i += kThreads) {
+    acc[3] += g.pose_partials[2 * i];
+    acc[4] += g.pose_partials[2 * i + 1];
+  }
+  block_sum<5, kWarps>(acc, sm);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) g.scal[i] = acc[i];
+    decide(g, st, infos, cap);
+  }
 }
 
 // Multi-GPU, banded reduced system: only the band of S (row r: columns r .. r + bw of the upper triangle, what the
@@ -968,6 +994,7 @@ struct ba_solver {
   DevBuf<int> d_chol_rows, d_chol_first, d_chol_rows_ptr;
   DevBuf<double> d_band;   // multi-GPU, banded S: band rows + rhs packed for the all-reduce
   int chol_mode = -1;  // -1 auto, 0 multi-kernel, 1 cluster
+  bool S_clean_outside_band = false;   // Saug was fully cleared since it was allocated / the plan changed
   // blocks
   size_t Mp = 0, Pp = 0;
   DevBuf<double> d_ptblk, d_Bsoa, d_A, d_a, d_partialsA, d_Saug, d_Scopy, d_x, d_z, d_linv, d_Btx, d_y;
@@ -1185,6 +1212,7 @@ int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const 
 // device copies of the envelope plan; again after ba_comm_init agreed on the global envelope
 static int upload_cholesky_plan(ba_solver *s) {
   cudaStream_t st = s->stream;
+  s->S_clean_outside_band = false;
   std::vector<int> rows = s->chol.rows;
   rows.push_back(0);
   CUDA_TRY(s->d_chol_rows.upload(rows, st));
@@ -1638,6 +1666,7 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_a.alloc(std::max<size_t>(1, (size_t)s->N * 6)));
   CUDA_TRY(s->d_partialsA.alloc(std::max<size_t>(1, (size_t)s->n_chunksA * 27)));
   CUDA_TRY(s->d_Saug.alloc(nS * nS));
+  s->S_clean_outside_band = false;
   CUDA_TRY(s->d_x.alloc(std::max<size_t>(1, (size_t)6 * s->N)));
   CUDA_TRY(s->d_z.alloc(std::max<size_t>(1, (size_t)6 * s->N)));
   CUDA_TRY(s->d_linv.alloc(std::max<size_t>(1, cholesky_linv_doubles(6 * s->N))));
@@ -1718,6 +1747,16 @@ static DecideArgs make_decide_args(ba_solver *s, const ba_options *opt) {
   return g;
 }
 
+// Banded plans clear only the band of Saug per iteration (enqueue_build); everything else is cleared once here,
+// before the first iteration (and before the iteration is captured into a graph).
+static int ensure_S_clean(ba_solver *s) {
+  if (!s->chol.banded || s->S_clean_outside_band) return BA_OK;
+  const size_t ld = (size_t)6 * s->N + 1;
+  CUDA_TRY(cudaMemsetAsync(s->d_Saug.p, 0, ld * ld * sizeof(double), s->stream));
+  s->S_clean_outside_band = true;
+  return BA_OK;
+}
+
 // Enqueue the build (K1..K4) on the stream.  ev: optional events at phase boundaries.
 static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   cudaStream_t st = s->stream;
@@ -1726,7 +1765,15 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   const LmState *dst = s->d_state.p;
   const int ld = 6 * s->N + 1;
   if (ev) cudaEventRecord(ev[Phase::Lin], st);
-  cudaMemsetAsync(s->d_Saug.p, 0, (size_t)ld * ld * sizeof(double), st);
+  if (s->chol.banded && s->S_clean_outside_band && (size_t)ld * ld * sizeof(double) > ((size_t)64 << 20)) {
+    // large banded reduced system (C4: 1.15 GB dense; a small one is cleared faster by one linear memset): everything outside the band (and the rhs column) stays zero once cleared -- the
+    // build, the factorisation and the exchange only touch row r's columns r .. r + bw and the last column
+    const int n = 6 * s->N;
+    cudaMemset2DAsync(s->d_Saug.p, (size_t)(ld + 1) * sizeof(double), 0, (size_t)(s->chol.bw + 1) * sizeof(double), n, st);
+    cudaMemset2DAsync(s->d_Saug.p + (ld - 1), (size_t)ld * sizeof(double), 0, sizeof(double), n, st);
+  } else {
+    cudaMemsetAsync(s->d_Saug.p, 0, (size_t)ld * ld * sizeof(double), st);
+  }
   if (s->n_split > 0) {
     k_zero_split<<<(s->n_split + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split, s->d_ptblk.p, s->Mp, dst);
     s->launches++;
@@ -1868,11 +1915,16 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
   k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
                                             s->d_obs_camflags.p, prm, 1, s->d_cams.p, s->d_cost_partials.p, 0, dst);
   DecideArgs g = make_decide_args(s, opt);
-  k_reduce_scalars<<<1, kThreads, 0, st>>>(g, 0, dst);
-  s->launches += 3;
-  if (int rc = enqueue_allreduce_scal(s)) return rc;
-  k_decide<<<1, 1, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
-  s->launches++;
+  s->launches += 2;
+  if (!s->comm) {
+    k_reduce_decide<<<1, kThreads, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
+    s->launches++;
+  } else {
+    k_reduce_scalars<<<1, kThreads, 0, st>>>(g, 0, dst);
+    if (int rc = enqueue_allreduce_scal(s)) return rc;
+    k_decide<<<1, 1, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
+    s->launches += 2;
+  }
   if (ev) cudaEventRecord(ev[Phase::End], st);
   return BA_OK;
 }
@@ -1922,6 +1974,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   cudaStream_t st = s->stream;
   s->launches = 0;
   CUDA_TRY(s->d_infos.alloc(std::max(1, max_it)));
+  if (int rc = ensure_S_clean(s)) return rc;
   // --- initial cost (:707) and state
   {
     const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
@@ -2053,6 +2106,7 @@ int ba_build_only(ba_solver *s, const ba_options *opt_in, double lambda, int do_
     const size_t ldc = (size_t)6 * s->N + 1;
     CUDA_TRY(s->d_Scopy.alloc(ldc * ldc));
   }
+  if (int rc = ensure_S_clean(s)) return rc;
   if (int rc = enqueue_build(s, &opt, nullptr)) return rc;
   if (int rc = enqueue_allreduce_S(s)) return rc;
   if (do_solve) {
