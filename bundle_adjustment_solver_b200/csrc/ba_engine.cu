@@ -618,21 +618,29 @@ k_cost(long long n_obs, const double2 *__restrict__ obs_uv, const int *__restric
   const double *poses = prm.poses[buf];
   const double *points = prm.points[buf];
   double acc[1] = {0.0};
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_obs;
-       k += (long long)gridDim.x * blockDim.x) {
-    const double2 uv = obs_uv[k];
-    const int ps = obs_pose[k], pt = obs_point[k];
-    const double *cam = cams + (obs_camflags[k] & kCamMask) * kCamStride;
+  // grid-stride loop, software-pipelined: the index record of the next observation is requested before the pose /
+  // point gathers of the current one, so the two dependent round trips of consecutive iterations overlap
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double2 uv = make_double2(0.0, 0.0);
+  int ps = 0, pt = 0, cf = 0;
+  if (k < n_obs) { uv = obs_uv[k]; ps = obs_pose[k]; pt = obs_point[k]; cf = obs_camflags[k]; }
+  while (k < n_obs) {
+    const long long kn = k + stride;
+    double2 uv_n = uv;
+    int ps_n = ps, pt_n = pt, cf_n = cf;
+    if (kn < n_obs) { uv_n = obs_uv[kn]; ps_n = obs_pose[kn]; pt_n = obs_point[kn]; cf_n = obs_camflags[kn]; }
+    const double *cam = cams + (cf & kCamMask) * kCamStride;
     double T[12], X[3];
-    const double *Tp = poses + (size_t)ps * 12;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) T[i] = __ldg(Tp + i);
+    load_pose(poses + (size_t)ps * 12, T);
     X[0] = __ldg(points + (size_t)pt * 3);
     X[1] = __ldg(points + (size_t)pt * 3 + 1);
     X[2] = __ldg(points + (size_t)pt * 3 + 2);
     Proj p;
     project(T, X, cam, uv.x, uv.y, p);
     acc[0] += sqrt(p.r0 * p.r0 + p.r1 * p.r1);
+    uv = uv_n; ps = ps_n; pt = pt_n; cf = cf_n;
+    k = kn;
   }
   block_sum<1, kWarps>(acc, sm);
   if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
