@@ -646,6 +646,103 @@ k_cost(long long n_obs, const double2 *__restrict__ obs_uv, const int *__restric
   if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
 }
 
+// ---------------------------------------------------------------------------
+// K4 for by-point landmarks when the reduced system is SMALL (dense co-visibility such as the test_ba.cpp scene:
+// every landmark seen by half of the 55 free poses): S -= sum_i E_i B_i^T as a dense FP64 tensor-core GEMM instead
+// of one FP64 red per block entry per landmark.  One CTA per (64 x 64 upper output tile, K split): the operands
+// X[3 l + c][row] = -E_i(row, c), Y[3 l + c][col] = B_i(col, c) of 10 landmarks per pass are scattered into shared
+// memory from the pair blocks (zeros where a pose does not see the landmark), E = B C^-1 formed on the fly; the rhs
+// travels as column n = ld - 1 (Y = b_i).  One red per output entry per CTA at the end.  (:858-888)
+// ---------------------------------------------------------------------------
+constexpr int kDenseLm = 10;   // landmarks per pass: 30 of the kKH = 32 operand rows
+constexpr int kDenseMaxPoses = 128;   // free poses (a landmark has at most one pair per pose): 6 N + 1 <= 769
+__global__ void __launch_bounds__(256)
+k_schur_dense_gemm(const int2 *__restrict__ groups /*pair range [x, y) of one landmark*/, int n_groups, int split_k,
+                   const int *__restrict__ pair_pose, const int *__restrict__ pair_point,
+                   const double *__restrict__ Bsoa, size_t Pp, const double *__restrict__ ptblk, size_t Mp,
+                   double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
+  if (st->done) return;
+  __shared__ double X[kKH][kLdT];
+  __shared__ double Y[kKH][kLdT];
+  __shared__ int lm_first[kDenseLm + 1];   // prefix of the pair counts of the pass
+  __shared__ int sq[kDenseLm * kDenseMaxPoses];
+  __shared__ short sj[kDenseLm * kDenseMaxPoses];
+  __shared__ unsigned char sl[kDenseLm * kDenseMaxPoses];
+  const int n = ld - 1;
+  const int tile_pair = blockIdx.x / split_k, ks = blockIdx.x - tile_pair * split_k;
+  int ib = (int)((sqrt(8.0 * tile_pair + 1.0) - 1.0) * 0.5);
+  while (ib * (ib + 1) / 2 > tile_pair) --ib;
+  while ((ib + 1) * (ib + 2) / 2 <= tile_pair) ++ib;
+  const int ia = tile_pair - ib * (ib + 1) / 2;        // ia <= ib: upper triangle, rows of tile ia, columns of tile ib
+  const int r0 = 64 * ia, c0 = 64 * ib;
+  const int per = (n_groups + split_k - 1) / split_k;
+  const int g_begin = ks * per, g_end = min(n_groups, g_begin + per);
+  double acc[2][4][2] = {};
+  for (int g0 = g_begin; g0 < g_end; g0 += kDenseLm) {
+    const int nl = min(kDenseLm, g_end - g0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kKH * kLdT; e += 256) { (&X[0][0])[e] = 0.0; (&Y[0][0])[e] = 0.0; }
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int l = 0; l < nl; ++l) { lm_first[l] = run; run += groups[g0 + l].y - groups[g0 + l].x; }
+      lm_first[nl] = run;
+    }
+    __syncthreads();
+    const int np = lm_first[nl];
+    // stage the pass's pairs (global pair index, pose, landmark slot) so that the scatter below has ONE global
+    // round trip per item and no data-dependent control flow in front of its loads
+    for (int pl = threadIdx.x; pl < np; pl += 256) {
+      int l = 0;
+      while (pl >= lm_first[l + 1]) ++l;
+      const int q = groups[g0 + l].x + (pl - lm_first[l]);
+      sq[pl] = q;
+      sj[pl] = (short)pair_pose[q];
+      sl[pl] = (unsigned char)l;
+    }
+    __syncthreads();
+    // one thread per (pair, row r of its 6 x 3 block); pairs fastest: Bsoa is component-major, so consecutive
+    // threads read consecutive doubles.  Loads unconditional and unrolled (in flight together), stores predicated.
+    const int items = np * 6;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < items; e += 256) {
+      const int r = e / np, pl = e - r * np;
+      const int q = sq[pl], l = sl[pl];
+      const int row = 6 * sj[pl] + r;
+      const double b0 = Bsoa[(size_t)(r * 3 + 0) * Pp + q], b1 = Bsoa[(size_t)(r * 3 + 1) * Pp + q],
+                   b2 = Bsoa[(size_t)(r * 3 + 2) * Pp + q];
+      const bool in_r = row >= r0 && row < r0 + 64, in_c = row >= c0 && row < c0 + 64;
+      if (in_c) { Y[3 * l][row - c0] = b0; Y[3 * l + 1][row - c0] = b1; Y[3 * l + 2][row - c0] = b2; }
+      if (in_r) {
+        const int pt = pair_point[q];
+        double ci[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ci[k] = ptblk[(PB_Cinv + k) * Mp + pt];
+        X[3 * l][row - r0] = -(b0 * ci[0] + b1 * ci[1] + b2 * ci[2]);
+        X[3 * l + 1][row - r0] = -(b0 * ci[1] + b1 * ci[3] + b2 * ci[4]);
+        X[3 * l + 2][row - r0] = -(b0 * ci[2] + b1 * ci[4] + b2 * ci[5]);
+      }
+    }
+    if (n >= c0 && n < c0 + 64 && threadIdx.x < 3 * nl) {   // rhs column: Y = b_i
+      const int l = threadIdx.x / 3, c = threadIdx.x - 3 * l;
+      Y[3 * l + c][n - c0] = ptblk[(PB_b + c) * Mp + pair_point[groups[g0 + l].x]];
+    }
+    __syncthreads();
+    tile_mac_dmma(X, Y, acc);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int rr = r0 + 16 * (w & 3) + 8 * i + (lane >> 2);
+        const int cc = c0 + 32 * (w >> 2) + 8 * j + 2 * (lane & 3) + e;
+        const double v = acc[i][j][e];
+        if (rr < n && cc <= n && rr <= cc && v != 0.0) atomicAdd(&Saug[(size_t)rr * ld + cc], v);
+      }
+}
+
 struct DecideArgs {
   const double *cost_partials; int n_cost;
   const double *point_partials; int n_point;   // {model, step} per block
@@ -987,6 +1084,8 @@ struct ba_solver {
   DevBuf<int> d_split_points, d_split_pairs;
   DevBuf<SchurChunk> d_schur_chunks;
   DevBuf<int> d_tpt_point, d_tpt_inc_start, d_fallback_pairs;
+  DevBuf<int2> d_fb_groups;   // pair range of every by-point landmark (dense-GEMM Schur path of small systems)
+  int n_fb_groups = 0;
   DevBuf<int4> d_inc_a, d_tile_batches;
   DevBuf<int2> d_inc_b;
   DevBuf<int> d_cta_batch_ptr;
@@ -1075,7 +1174,7 @@ static void free_device(ba_solver *s) {
   s->d_pose_chunk_ptr.release(); s->d_pose_opt.release(); s->d_pair_pose.release(); s->d_pair_point.release();
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
-  s->d_tpt_point.release(); s->d_tpt_inc_start.release(); s->d_fallback_pairs.release();
+  s->d_tpt_point.release(); s->d_tpt_inc_start.release(); s->d_fallback_pairs.release(); s->d_fb_groups.release();
   s->d_inc_a.release(); s->d_inc_b.release(); s->d_tile_batches.release(); s->d_cta_batch_ptr.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
   s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release(); s->d_band.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
@@ -1380,6 +1479,14 @@ int ba_finalize(ba_solver *s) {
       for (const Cand &c : all)
         if (c.ok) cands[key_cnt[(size_t)c.jmin * kTileW + (c.jmax - c.jmin)]++] = c;
     }
+    // Small reduced system whose landmarks mostly do NOT fit a window (dense co-visibility, test_ba.cpp): the
+    // by-point path ends in one dense tensor-core GEMM (k_schur_dense_gemm) that takes the few window landmarks
+    // along for free, while a second, nearly empty persistent tile launch would cost its fixed 30 us
+    if (6 * s->N + 1 <= 6 * kDenseMaxPoses + 1 && 2 * (long long)cands.size() < n_grp) {
+      for (const Cand &c : cands)
+        for (int q = c.p0; q < c.p1; ++q) fallback_pairs.push_back(q);
+      cands.clear();
+    }
     // Greedy runs.  A run keeps growing while its pose window stays within kTileW; once it holds enough
     // landmarks to amortise the final flush it is also cut when the next landmark would WIDEN the window,
     // so that most chunks are exactly as wide as their landmarks' tracks (dense GEMM operands).
@@ -1660,6 +1767,19 @@ int ba_finalize(ba_solver *s) {
     CUDA_TRY(s->d_point_fb.upload(point_fb, st));
   }
   CUDA_TRY(s->d_fallback_pairs.upload(fallback_pairs, st));
+  {
+    // the pairs of a landmark are contiguous in the pair numbering: ranges of the sorted fallback list
+    std::vector<int2> fb_groups;
+    for (size_t k = 0; k < fallback_pairs.size();) {
+      size_t e = k + 1;
+      while (e < fallback_pairs.size() && fallback_pairs[e] == fallback_pairs[e - 1] + 1 &&
+             s->h_pair_point[fallback_pairs[e]] == s->h_pair_point[fallback_pairs[k]]) ++e;
+      fb_groups.push_back(make_int2(fallback_pairs[k], fallback_pairs[k] + (int)(e - k)));
+      k = e;
+    }
+    s->n_fb_groups = (int)fb_groups.size();
+    CUDA_TRY(s->d_fb_groups.upload(fb_groups, st));
+  }
   CUDA_TRY(s->d_split_points.upload(split_points, st));
   CUDA_TRY(s->d_split_pairs.upload(split_pairs, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -1845,7 +1965,16 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
           s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
     s->launches++;
   }
-  if (s->n_fallback_pairs > 0) {
+  static const int dense_max = getenv("BA_B200_DENSE_SCHUR_MAX") ? atoi(getenv("BA_B200_DENSE_SCHUR_MAX")) : 6 * kDenseMaxPoses + 1;
+  if (s->n_fallback_pairs > 0 && ld <= dense_max) {
+    // small reduced system (dense co-visibility): the products as a tensor-core GEMM over 64 x 64 tiles
+    const int nT = (ld + 63) / 64, tile_pairs = nT * (nT + 1) / 2;
+    const int split_k = std::max(1, std::min((s->n_fb_groups + kDenseLm - 1) / kDenseLm, (2 * 148 + tile_pairs - 1) / tile_pairs));
+    k_schur_dense_gemm<<<tile_pairs * split_k, 256, 0, st>>>(s->d_fb_groups.p, s->n_fb_groups, split_k, s->d_pair_pose.p,
+                                                           s->d_pair_point.p, s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp,
+                                                           s->d_Saug.p, ld, dst);
+    s->launches++;
+  } else if (s->n_fallback_pairs > 0) {
     k_schur_pairs_list<<<(s->n_fallback_pairs + 127) / 128, 128, 0, st>>>(
         s->n_fallback_pairs, s->d_fallback_pairs.p, s->d_pair_pose.p, s->d_pair_point.p, s->d_pair_end.p,
         s->d_Bsoa.p, s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);

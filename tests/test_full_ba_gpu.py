@@ -269,3 +269,55 @@ def test_tile_build_with_fixed_poses_points_and_wide_tracks(oracle_mod, engine_l
         assert e.sizes() == o.sizes()
         _compare_blocks(o, e, o.sizes())
         assert blockwise_rel_err(e.dump("y"), o.dump("y"), 3) < 1e-6
+
+
+def test_c3_full_size_normal_equations_and_convergence(engine_lib):
+    """BASELINE config C3 at full size (200 poses / 50k landmarks / 1.0 M observations), where the oracle is too slow to
+    be the checker: size-independent properties of one linearisation + solve -- the reduced system is symmetric and
+    solved, every block row of the damped normal equations [A B; B^T C][x; y] = [a; b] holds for the dumped blocks, C^-1
+    inverts C -- and the LM loop converges to a lower cost."""
+    sc = scenes.scene_c3(seed=100, pose_noise_seed=7)
+    e = load_engine(sc)
+    e.set_debug(True)
+    _, eo = options_pair()
+    e.build_only(eo, 100.0, do_solve=True)
+    sz = e.sizes()
+    N, M, P = sz["N"], sz["M"], sz["P"]
+    assert sz["n_obs"] > 900_000 and M == 50_000 and N >= 190
+    n = 6 * N
+    Sm = e.dump("S").reshape(n, n)
+    rhs, x = e.dump("rhs"), e.dump("x").reshape(N, 6)
+    assert np.abs(Sm - Sm.T).max() <= 1e-12 * np.abs(Sm).max()
+    assert np.linalg.norm(Sm @ x.reshape(-1) - rhs) <= 1e-9 * np.linalg.norm(Sm, 2) * np.linalg.norm(x)
+    A, a = e.dump("A").reshape(N, 6, 6), e.dump("a").reshape(N, 6)
+    Cd, b = e.dump("C").reshape(M, 3, 3), e.dump("b").reshape(M, 3)
+    Ci = e.dump("Cinv").reshape(M, 3, 3)
+    B = e.dump("B").reshape(P, 6, 3)
+    y = e.dump("y").reshape(-1, 3)[:M]
+    pj, pi = e.pairs()                                   # original ids; free poses / points numbered in id order
+    free_pose = np.setdiff1d(np.arange(sz["N_total"]), np.asarray(sc.fixed_poses))
+    j_of = np.full(sz["N_total"], -1)
+    j_of[free_pose] = np.arange(N)
+    pjo = j_of[pj]
+    assert pjo.min() >= 0 and M == sz["M_total"]
+    # C^-1 C = I
+    assert np.abs(np.einsum("mij,mjk->mik", Ci, Cd) - np.eye(3)).max() < 1e-9
+    # landmark rows: C_i y_i + sum_j B_ji^T x_j = b_i
+    r_pt = np.einsum("mij,mj->mi", Cd, y) - b
+    np.add.at(r_pt, pi, np.einsum("pkc,pk->pc", B, x[pjo]))
+    assert np.abs(r_pt).max() <= 1e-9 * max(np.abs(b).max(), 1e-30)
+    # pose rows: A_j x_j + sum_i B_ji y_i = a_j
+    r_ps = np.einsum("jkl,jl->jk", A, x) - a
+    np.add.at(r_ps, pjo, np.einsum("pkc,pc->pk", B, y[pi]))
+    assert np.abs(r_ps).max() <= 1e-8 * np.abs(a).max()
+    # the LM loop from the same start: converges, cost goes down, every recorded iteration is consistent
+    from bundle_adjustment_solver_b200.solver import Summary
+    e2 = load_engine(sc)
+    summ = Summary()
+    _, eo = options_pair(max_num_iterations=300, threshold_cost_change=1e-6, threshold_step_size=1e-6)
+    c0 = e2.cost()
+    e2.solve(eo, summ)
+    infos = summ.optimization_info_list
+    assert summ.convergence_status and 5 < len(infos) < 300
+    assert infos[-1].cost < 0.05 * c0
+    assert all(i.iteration_status in (0, 1, 2) and 1e-10 <= i.damping_term <= 100.0 for i in infos)
