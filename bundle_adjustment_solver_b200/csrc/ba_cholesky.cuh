@@ -36,7 +36,24 @@ constexpr size_t kCholDiagSmem = (3 * kNB * (kNB + 1) + 3 * kNB + 2) * sizeof(do
 // then L = A D^-1/2).  L^-1 is then built by recursive doubling (X21 = -X22 L21 X11, block sizes
 // 1,2,..,32: 12 barriers instead of 64 substitution steps).  Linv (row-major 64x64, lower) lets the
 // panel TRSM and the backward substitution run as small GEMMs / GEMVs.
-__global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int ld, int k0, int nb,
+// reciprocal off the slow IEEE division path (it sits on the chain of all 64 column steps): hardware approximation
+// + two Newton steps, full double precision up to the last bit
+__device__ __forceinline__ double diag_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+#ifndef BA_DIAG_THREADS
+#define BA_DIAG_THREADS 1024
+#endif
+constexpr int kDiagThreads = BA_DIAG_THREADS;            // a barrier per column step: fewer threads, cheaper barrier
+constexpr int kDiagNQ = (kNB * (kNB + 1) / 2 + kDiagThreads - 1) / kDiagThreads;   // lower-triangle entries per thread
+__global__ void __launch_bounds__(kDiagThreads) k_chol_diag(double *__restrict__ A, int ld, int k0, int nb,
                                                     double *__restrict__ Linv_out, const LmState *st) {
   if (st->done) return;
   extern __shared__ double chol_smem[];  // kCholDiagSmem bytes (opt-in > 48 KB)
@@ -47,11 +64,11 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
   double *dinv = colbuf + 2 * (kNB + 1);             // 1/sqrt(d)
   const int t = threadIdx.x;
   constexpr int NE = kNB * (kNB + 1) / 2;  // 2080
-  int er[3], ec[3];
-  double v[3];
+  int er[kDiagNQ], ec[kDiagNQ];
+  double v[kDiagNQ];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const int e = t + 1024 * q;
+  for (int q = 0; q < kDiagNQ; ++q) {
+    const int e = t + kDiagThreads * q;
     int r = -1, c = -1;
     double val = 0.0;
     if (e < NE) {
@@ -67,27 +84,27 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
   for (int j = 0; j < kNB; ++j) {
     double *cb = colbuf + (j & 1) * (kNB + 1);
 #pragma unroll
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < kDiagNQ; ++q)
       if (ec[q] == j) {
         cb[er[q]] = v[q];
         // the owner of the pivot alone pays for the FP64 reciprocal (32 warps doing it redundantly
         // made this kernel issue-bound).  Non-positive pivot (e.g. a pose without observations):
         // emulate LDLT's D^+ = 0.
-        if (er[q] == j) cb[kNB] = (v[q] > 0.0) ? 1.0 / v[q] : 0.0;
+        if (er[q] == j) cb[kNB] = (v[q] > 0.0) ? diag_rcp(v[q]) : 0.0;
       }
     __syncthreads();
     const double di = cb[kNB];
 #pragma unroll
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < kDiagNQ; ++q)
       if (ec[q] > j) v[q] -= cb[er[q]] * di * cb[ec[q]];
   }
 #pragma unroll
-  for (int q = 0; q < 3; ++q)
+  for (int q = 0; q < kDiagNQ; ++q)
     if (er[q] >= 0 && er[q] == ec[q]) dinv[er[q]] = (v[q] > 0.0) ? 1.0 / sqrt(v[q]) : 0.0;
   __syncthreads();
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
+  for (int q = 0; q < kDiagNQ; ++q) {
     const int r = er[q], c = ec[q];
     if (r < 0) continue;
     const double l = (r == c) ? ((dinv[r] > 0.0) ? 1.0 / dinv[r] : kInf) : v[q] * dinv[c];
@@ -99,21 +116,18 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
   // recursive doubling: block b of size 2m: rows R = b*2m+m.., cols C = b*2m..
   for (int m = 1; m < kNB; m <<= 1) {
     const int per_level = (kNB / (2 * m)) * m * m;  // outputs of this level (<= 1024)
-    int bi = 0, i = 0, k = 0;
-    if (t < per_level) {
-      bi = t / (m * m);
-      i = (t / m) % m;
-      k = t % m;
-    }
-    const int R0 = bi * 2 * m + m, C0 = bi * 2 * m;
-    if (t < per_level) {
+    for (int tt = t; tt < per_level; tt += kDiagThreads) {
+      const int bi = tt / (m * m), i = (tt / m) % m, k = tt % m;
+      const int R0 = bi * 2 * m + m, C0 = bi * 2 * m;
       // T[i][k] = sum_q L[R0+i][C0+q] X[C0+q][C0+k], q >= k (X11 lower)
       double acc = 0.0;
       for (int q = k; q < m; ++q) acc += L[R0 + i][C0 + q] * X[C0 + q][C0 + k];
       T[R0 + i][C0 + k] = acc;
     }
     __syncthreads();
-    if (t < per_level) {
+    for (int tt = t; tt < per_level; tt += kDiagThreads) {
+      const int bi = tt / (m * m), i = (tt / m) % m, k = tt % m;
+      const int R0 = bi * 2 * m + m, C0 = bi * 2 * m;
       // X21[i][k] = - sum_q X[R0+i][R0+q] T[q][k], q <= i (X22 lower)
       double acc = 0.0;
       for (int q = 0; q <= i; ++q) acc += X[R0 + i][R0 + q] * T[R0 + q][C0 + k];
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(1024) k_chol_diag(double *__restrict__ A, int 
     }
     __syncthreads();
   }
-  for (int e = t; e < kNB * kNB; e += 1024) {
+  for (int e = t; e < kNB * kNB; e += kDiagThreads) {
     const int r = e / kNB, c = e % kNB;
     Linv_out[e] = (r >= c) ? X[r][c] : 0.0;
   }
@@ -486,7 +500,7 @@ inline void cholesky_solve_enqueue(const CholeskyPlan &pl, double *Saug, double 
     const int nb = (n - k0 < kNB) ? (n - k0) : kNB;
     double *Li = linv + (size_t)kb * kNB * kNB;
     if (parts & 1) {
-      k_chol_diag<<<1, 1024, kCholDiagSmem, stream>>>(Saug, ld, k0, nb, Li, st);
+      k_chol_diag<<<1, kDiagThreads, kCholDiagSmem, stream>>>(Saug, ld, k0, nb, Li, st);
       if (launches) *launches += 1;
     }
     // rows of the same tile below a partial last diagonal block (only the rhs row can be there)
