@@ -1893,7 +1893,9 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   const LmState *dst = s->d_state.p;
   const int ld = 6 * s->N + 1;
   if (ev) cudaEventRecord(ev[Phase::Lin], st);
-  if (s->chol.banded && s->S_clean_outside_band && (size_t)ld * ld * sizeof(double) > ((size_t)64 << 20)) {
+  // BA_B200_BAND_CLEAR_MIN_MB: size of the dense buffer above which only the band is cleared (tests force 0)
+  static const size_t band_clear_min = (size_t)(getenv("BA_B200_BAND_CLEAR_MIN_MB") ? atoi(getenv("BA_B200_BAND_CLEAR_MIN_MB")) : 64) << 20;
+  if (s->chol.banded && s->S_clean_outside_band && (size_t)ld * ld * sizeof(double) > band_clear_min) {
     // large banded reduced system (C4: 1.15 GB dense; a small one is cleared faster by one linear memset): everything outside the band (and the rhs column) stays zero once cleared -- the
     // build, the factorisation and the exchange only touch row r's columns r .. r + bw and the last column
     const int n = 6 * s->N;
