@@ -11,11 +11,13 @@
 //     lane inverts the damped C redundantly and forms E = B C^-1 for its own incidences): no CTA barrier, no
 //     shared-memory staging of partials, no idle threads while one thread per landmark inverts;
 //   * every producer warp is its own group with its own operand buffer (G = 5..7 buffers, sized by the widest
-//     window of the launch: ldE = 8 nt + 4, ldB = 8 nt + 12, both = 4 or 12 mod 16 -> conflict-free DMMA fragment
-//     reads) and runs ahead on its own batch; the index records of the next round / next batch are prefetched,
+//     window of the launch in whole 2 x 2 super-tiles, leading dimensions = 4 mod 16 -> conflict-free DMMA fragment
+//     reads) and runs ahead on its own batch; the eighth warp owns no buffer and prefetches the batch list's
+//     gathers into L2; the index records of the next round / next batch are prefetched,
 //     the next batch's landmark data only after the observation loop (live across it, it would be spilled, and a
 //     spill waits for the load);
-//   * the four DMMA warps consume the buffers round-robin and hand them back: full[g] / empty[g] named barriers,
+//   * the four DMMA warps consume the buffers round-robin (2 x 2 super-tiles: every fragment read feeds two DMMAs,
+//     accumulators in registers across all batches of a chunk, FP64 reds when the chunk changes) and hand them back: full[g] / empty[g] named barriers,
 //     nothing else; a producer clears the few window slots its landmark does not cover instead of anybody
 //     clearing whole buffers.
 #pragma once

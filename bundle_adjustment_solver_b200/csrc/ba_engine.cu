@@ -1,18 +1,22 @@
 // ba_engine.cu -- B200 (sm_100a) full bundle-adjustment engine behind the C-ABI of include/ba_b200.h.
 //
 // Device pipeline of one LM iteration (reference: core/full_bundle_adjustment_solver.cpp:709-1008):
-//   K1 k_linearize_by_point : per-observation projection/residual/Huber weight/Jacobians, observations
-//                             sorted by (point,pose,insertion); warp-shuffle segmented sums -> C, b per
-//                             point, B per (pose,point) pair (last-writer flag), then damping + 3x3
-//                             LDLT inverse in registers (K3 fused) (:716-831 point side, :846-856)
-//   K2 k_linearize_by_pose  : same per-observation math in pose order -> per-chunk partial A (21) / a (6)
-//      k_finish_poses       : ordered sum of the partials, fill-lower, damping, S diagonal + rhs init
+//   K2 k_linearize_by_pose  : per-observation projection / residual / Huber weight / Jacobians in pose order ->
+//      k_finish_poses         per-chunk partial A (21) / a (6); ordered sum, fill-lower, damping, S diagonal + rhs
 //                             (:795-810, :833-844, diagonal of :878-888)
-//   K4 k_schur              : per point E = B C^-1, rhs -= E b, S -= E B^T for pose pairs j<=k (:858-888)
-//   K5 cholesky_solve       : dense FP64 Cholesky of S with rhs carried as an extra row (:890-908)
-//   K6 k_backsub_pairs/points: y = C^-1 b - C^-1 sum_j B^T x_j, model change, trial points (:910-917,:435-455)
-//   K7 k_update_poses, k_cost, k_decide : se3Exp update, trial cost, rho / accept / lambda / convergence
+//   K1b+K3+K4 k_build_tiles : landmarks whose poses fit a 16-pose window (ba_build_tiles.cuh): linearisation, C, b,
+//                             B (last-writer rule), damping + pivoted 3x3 LDLT inverse, E = B C^-1 and the Schur
+//                             products S -= E B^T as an FP64 tensor-core GEMM, fused (:716-831, :846-856, :858-888)
+//   K1a/K3/K4 by-point path : everything else -- k_linearize_by_point (C, b), k_pair_blocks (B), k_finish_points
+//                             (C^-1), then k_schur_dense_gemm (small reduced systems: dense DMMA GEMM) or
+//                             k_schur_pairs_list (FP64 reds)
+//   K5 cholesky_solve       : FP64 Cholesky of S with the rhs carried as an extra row: banded (one CTA, DMMA window
+//                             update), cluster (small dense) or multi-kernel blocked DMMA (large dense) (:890-908)
+//   K6 k_backsub_pairs/points: y = C^-1 b - C^-1 sum_j B^T x_j, model change, trial points (:910-917,:435-455);
+//                             gradient-descent variant for FullBundleAdjustmentSolverRefactor::SolveByGradientDescent
+//   K7 k_update_poses, k_cost, k_reduce_decide : se3Exp update, trial cost, rho / accept / lambda / convergence
 //                             on the device (:922-1007)
+// Multi-GPU: landmarks sharded, k_band_pack / ncclAllReduce / k_band_unpack on [S | rhs] per iteration.
 // There is no CPU fallback: every entry point that computes requires a CUDA device.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
