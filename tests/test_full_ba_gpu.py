@@ -356,3 +356,32 @@ def test_band_only_clearing_of_the_reduced_system_is_equivalent(tmp_path, engine
     assert len(outs[0]["COSTS"]) == len(outs[1]["COSTS"]) == 25
     np.testing.assert_allclose(outs[0]["COSTS"], outs[1]["COSTS"], rtol=1e-10)
     np.testing.assert_allclose(outs[0]["POSES"], outs[1]["POSES"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("workload", ["c4", "c5"])
+def test_c4_c5_full_size_properties(workload, engine_lib):
+    """BASELINE configs C4 (2000 poses / 1 M landmarks / 8.0 M observations, banded) and C5 (1778 / 1 M / 5.0 M, mono,
+    dense reduced system) at full size, where the oracle cannot be the checker: the cost is additive over a split
+    of the landmarks (two engines holding one half each), and the first LM iterations behave -- valid statuses,
+    lambda inside its bounds, every accepted step lowers the cost, parameters stay finite."""
+    from bundle_adjustment_solver_b200 import sharding
+    from bundle_adjustment_solver_b200.solver import Summary
+    sc = scenes.scene_c4(seed=100) if workload == "c4" else scenes.scene_c5(seed=100)
+    assert sc.n_obs > 4_500_000
+    e = load_engine(sc)
+    c_full = e.cost()
+    halves = [load_engine(sharding.shard_scene(sc, r, 2)).cost() for r in range(2)]
+    assert abs(c_full - sum(halves)) <= 1e-11 * c_full
+    summ = Summary()
+    _, eo = options_pair(max_num_iterations=4, threshold_cost_change=0.0, threshold_step_size=0.0)
+    e.solve(eo, summ)
+    infos = summ.optimization_info_list
+    assert len(infos) == 4 and not summ.convergence_status      # the last allowed iteration never reports convergence
+    prev = c_full
+    for i in infos:
+        assert i.iteration_status in (0, 1, 2) and 1e-10 <= i.damping_term <= 100.0
+        if i.iteration_status != 2:
+            assert i.cost < prev
+            prev = i.cost
+    assert infos[-1].cost < 0.9 * c_full
+    assert np.isfinite(e.get_poses()).all() and np.isfinite(e.get_points()).all()
