@@ -1367,15 +1367,35 @@ int ba_finalize(ba_solver *s) {
   std::vector<int> by_pose(n), by_point(n);
   std::vector<long long> pose_begin(Nt + 1, 0);   // observation range of every pose in by_pose order
   {
-    std::vector<long long> cnt(Nt + 1, 0);
-    for (long long k = 0; k < n; ++k) cnt[s->h_obs_pose[k] + 1]++;
-    for (int j = 0; j < Nt; ++j) cnt[j + 1] += cnt[j];
-    pose_begin = cnt;
-    for (long long k = 0; k < n; ++k) by_pose[cnt[s->h_obs_pose[k]]++] = (int)k;
-    std::vector<long long> cnt2(Mt + 1, 0);
-    for (long long k = 0; k < n; ++k) cnt2[s->h_obs_point[k] + 1]++;
-    for (int i = 0; i < Mt; ++i) cnt2[i + 1] += cnt2[i];
-    for (long long q = 0; q < n; ++q) { const int k = by_pose[q]; by_point[cnt2[s->h_obs_point[k]]++] = k; }
+    // both sorts: per-thread histograms over contiguous ranges of the input, bucket offsets per thread, parallel
+    // scatter -- stable because every thread's range is contiguous and the ranges are ordered
+    std::vector<long long> starts;
+    auto counting_sort = [&](long long count, int n_buckets, auto &&key_of /*(q) -> bucket*/, auto &&item_of /*(q) -> value*/,
+                             std::vector<int> &out) {
+      const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, count / 65536));
+      std::vector<std::vector<int>> hist(nth, std::vector<int>((size_t)n_buckets, 0));
+      parallel_ranges(nth, [&](long long t0, long long t1, int) {
+        for (long long t = t0; t < t1; ++t) {
+          std::vector<int> &h = hist[t];
+          for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) h[key_of(q)]++;
+        }
+      }, 1);
+      starts.assign((size_t)n_buckets + 1, 0);
+      for (int b = 0; b < n_buckets; ++b) {
+        long long run = starts[b];
+        for (int t = 0; t < nth; ++t) { const int c = hist[t][b]; hist[t][b] = (int)run; run += c; }
+        starts[b + 1] = run;
+      }
+      parallel_ranges(nth, [&](long long t0, long long t1, int) {
+        for (long long t = t0; t < t1; ++t) {
+          std::vector<int> &h = hist[t];
+          for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) out[h[key_of(q)]++] = item_of(q);
+        }
+      }, 1);
+    };
+    counting_sort(n, Nt, [&](long long k) { return s->h_obs_pose[k]; }, [&](long long k) { return (int)k; }, by_pose);
+    pose_begin = starts;
+    counting_sort(n, Mt, [&](long long q) { return s->h_obs_point[by_pose[q]]; }, [&](long long q) { return by_pose[q]; }, by_point);
   }
   lap("counting sorts");
   // --- point-ordered observation arrays, pairs, last-writer flags
