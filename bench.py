@@ -362,6 +362,11 @@ def main():
         #      solve to convergence + read back.  Per-step bytes = totals / LM iterations.
         e2e = None
         if not args.no_e2e:
+            # the timed solver above is done: release it, so that the end-to-end solve runs in the steady state of a
+            # process that solves one problem after another (device buffers come back from the stream-ordered pool
+            # instead of growing it next to a live 300 MB problem -- that growth alone varied between 10 and 150 ms)
+            del s
+            torch.cuda.synchronize()
             s2 = S.FullBundleAdjustmentSolver(device=local_rank, stream=stream.cuda_stream)
             join_comm_needed = world > 1
             torch.cuda.synchronize()
