@@ -377,7 +377,7 @@ def main():
             t_reg = time.perf_counter()
             s2._upload()
             if join_comm_needed:
-                join_comm(s2, sz)
+                join_comm(s2, sz)   # N > 1: communicator creation (NCCL set-up, ~0.5 s) is inside the timed region
             t_fin = time.perf_counter()
             opt = capi.default_options(max_num_iterations=args.e2e_max_iters, threshold_cost_change=1e-6,
                                        threshold_step_size=1e-6)

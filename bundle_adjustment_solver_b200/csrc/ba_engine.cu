@@ -1339,6 +1339,26 @@ static int upload_cholesky_plan(ba_solver *s) {
   return BA_OK;
 }
 
+// Multi-GPU: the reduced solve is replicated, so every rank must factor the all-reduced S with the SAME plan, built
+// from the co-visibility of ALL landmarks, not of its shard: min over ranks of the first co-visible pose.  Called by
+// whichever comes second, ba_comm_init or ba_finalize.
+static int agree_on_envelope(ba_solver *s) {
+  if (!s->comm || s->N <= 0) return BA_OK;
+  cudaStream_t st = s->stream;
+  g_alloc_stream = st;
+  DevBuf<int> d_fp;
+  CUDA_TRY(d_fp.upload(s->h_first_pose, st));
+  ncclResult_t r = g_nccl.AllReduce(d_fp.p, d_fp.p, (size_t)s->N, ncclInt, ncclMin, s->comm, st);
+  if (r != ncclSuccess) { s->err = "ncclAllReduce(envelope) failed"; return BA_ERR_NCCL; }
+  CUDA_TRY(cudaMemcpyAsync(s->h_first_pose.data(), d_fp.p, (size_t)s->N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  d_fp.release();
+  cholesky_make_plan(s->chol, 6 * s->N, s->h_first_pose);
+  if (int rc = upload_cholesky_plan(s)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return BA_OK;
+}
+
 int ba_finalize(ba_solver *s) {
   if (!s) return BA_ERR_INVALID;
   if (s->finalized) return BA_OK;
@@ -1848,7 +1868,7 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(cudaStreamSynchronize(st));
   lap("block storage");
   s->finalized = true;
-  return BA_OK;
+  return agree_on_envelope(s);   // no-op on a single GPU
 }
 
 int ba_update_parameters(ba_solver *s, const double *T_jw, const double *X) {
@@ -2463,22 +2483,7 @@ int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long lon
   if (r != ncclSuccess) { s->err = "ncclCommInitRank failed"; s->comm = nullptr; return BA_ERR_NCCL; }
   s->rank = rank; s->n_ranks = nranks; s->global_M = global_M; s->global_n_obs = global_n_obs;
   destroy_graph(s);
-  if (s->finalized && s->N > 0) {
-    // The reduced solve is replicated: every rank must factor the all-reduced S with the SAME plan, built from
-    // the co-visibility of ALL landmarks, not of its shard: min over ranks of the first co-visible pose.
-    cudaStream_t st = s->stream;
-    g_alloc_stream = st;
-    DevBuf<int> d_fp;
-    CUDA_TRY(d_fp.upload(s->h_first_pose, st));
-    r = g_nccl.AllReduce(d_fp.p, d_fp.p, (size_t)s->N, ncclInt, ncclMin, s->comm, st);
-    if (r != ncclSuccess) { s->err = "ncclAllReduce(envelope) failed"; return BA_ERR_NCCL; }
-    CUDA_TRY(cudaMemcpyAsync(s->h_first_pose.data(), d_fp.p, (size_t)s->N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    d_fp.release();
-    cholesky_make_plan(s->chol, 6 * s->N, s->h_first_pose);
-    if (int rc = upload_cholesky_plan(s)) return rc;
-    CUDA_TRY(cudaStreamSynchronize(st));
-  }
+  if (s->finalized) return agree_on_envelope(s);
   return BA_OK;
 }
 

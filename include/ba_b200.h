@@ -151,7 +151,9 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep);
 int ba_comm_get_unique_id(void *id128);
 /* Joins the communicator.  After this, ba_solve all-reduces [S | rhs] and the LM scalars over NCCL
  * every iteration; each rank must hold ALL poses and only ITS landmarks + their observations.
- * global_num_opt_points = sum over ranks of free points (for the step-size average, :968-970). */
+ * global_num_opt_points = sum over ranks of free points (for the step-size average, :968-970).
+ * May be called before or after ba_finalize: whichever comes second min-reduces the co-visibility envelope over the
+ * ranks, so that every rank factors the summed reduced system with the same (global) plan. */
 int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long long global_num_opt_points,
                  long long global_num_observations);
 int ba_comm_destroy(ba_solver *s);
