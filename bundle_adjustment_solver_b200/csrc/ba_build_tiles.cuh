@@ -83,7 +83,7 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
     const int grp = warp;
     if (grp >= G) {
       // The last producer warp never owns a buffer (named barriers allow 7 groups): it walks the CTA's batch list
-      // ahead of the others and pulls what they will gather -- incidence records, pixels, camera flags, points --
+      // ahead of the others and pulls what they will gather -- incidence records, pixels, points --
       // into L2, so that their dependent round trips hit L2 instead of DRAM.  Hints only: no synchronisation.
       // (C3 / C4 / C5 tile kernel -1.6 / -4 / -3 %; prefetching into L1 instead measured the same.)
       if (warp == kT2ProdWarps - 1) {
@@ -148,8 +148,7 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
       const int ca = a, cb = b, cpt = pt;
       const int rhs_col = rhs_n & 0xffff, W = rhs_n >> 16, cur_nb = nb_n;
       const double X0 = X[0], X1 = X[1], X2 = X[2];
-      // first incidence record of the current landmark, then the next batch's landmark data (in flight during
-      // the whole batch)
+      // the lane's first incidence record was requested at the end of the previous batch
       int4 ia_n = ia_b;
       int2 sc_n = sc_b;
       double cp[9];
@@ -205,7 +204,7 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
           }
         }
         }
-        if (rd == 0 && fb - b0 >= G) bar_sync(8 + grp, bar_cnt);   // the consumers have read and cleared this buffer
+        if (rd == 0 && fb - b0 >= G) bar_sync(8 + grp, bar_cnt);   // the consumers have read this buffer
         if (slot >= 0) {
           covered |= 1u << slot;
           slots |= (unsigned)(slot + 1) << (5 * rd);
