@@ -21,18 +21,13 @@ namespace analytic_solver {
 enum class SolverType { UNDEFINED = -1, GRADIENT_DESCENT = 0, GAUSS_NEWTON = 1, LEVENBERG_MARQUARDT = 2 };
 enum class IterationStatus { UNDEFINED = -1, UPDATE = 0, UPDATE_TRUST_MORE = 1, SKIPPED = 2 };
 
-struct OptimizationInfo {
-  double cost{-1.0};
-  double cost_change{-1.0};
-  double average_reprojection_error{-1.0};
-  double abs_gradient{-1.0};
-  double abs_step{-1.0};
-  double damping_term{-1.0};
-  double iter_time{-1.0};
+struct OptimizationInfo {   // reference :37-46: one row per LM / GN iteration, every field starts at -1
+  double cost{-1.0}, cost_change{-1.0}, average_reprojection_error{-1.0};
+  double abs_gradient{-1.0}, abs_step{-1.0}, damping_term{-1.0}, iter_time{-1.0};
   IterationStatus iteration_status{IterationStatus::UNDEFINED};
 };
 
-class Options {
+class Options {   // reference :47-72: float thresholds / ratios on purpose (they are promoted in comparisons)
   friend class PoseOnlyBundleAdjustmentSolver;
   friend class FullBundleAdjustmentSolver;
 
@@ -40,23 +35,11 @@ class Options {
   Options() {}
   ~Options() {}
 
-  SolverType solver_type{SolverType::GAUSS_NEWTON};
-  struct {
-    float threshold_step_size{1e-5};
-    float threshold_cost_change{1e-5};
-  } convergence_handle;
-  struct {
-    float threshold_huber_loss{1.0};
-    float threshold_outlier_rejection{2.0};
-  } outlier_handle;
-  struct {
-    int max_num_iterations{50};
-  } iteration_handle;
-  struct {
-    float initial_lambda{100.0};
-    float decrease_ratio_lambda{0.33f};
-    float increase_ratio_lambda{3.0f};
-  } trust_region_handle;
+  SolverType solver_type{SolverType::GAUSS_NEWTON};   // read by FullBundleAdjustmentSolverRefactor::Solve only
+  struct { float threshold_step_size{1e-5}, threshold_cost_change{1e-5}; } convergence_handle;
+  struct { float threshold_huber_loss{1.0}, threshold_outlier_rejection{2.0}; } outlier_handle;
+  struct { int max_num_iterations{50}; } iteration_handle;
+  struct { float initial_lambda{100.0}, decrease_ratio_lambda{0.33f}, increase_ratio_lambda{3.0f}; } trust_region_handle;
   // Extension (not in the reference): false = reference-exact B_ji assignment (last observation of a
   // (pose, point) pair wins, full_bundle_adjustment_solver.cpp:826); true = accumulate (`+=`).
   bool accumulate_offdiagonal_blocks{false};
@@ -117,12 +100,10 @@ class Summary {
   const std::vector<OptimizationInfo> &optimization_info_list() const { return optimization_info_list_; }
   bool convergence_status() const { return convergence_status_; }
 
- protected:
+ protected:   // reference :86-92, filled by the friend solvers
   std::vector<OptimizationInfo> optimization_info_list_;
   int max_iteration_{0};
-  double total_time_in_millisecond_{0.0};
-  double threshold_step_size_{0.0};
-  double threshold_cost_change_{0.0};
+  double total_time_in_millisecond_{0.0}, threshold_step_size_{0.0}, threshold_cost_change_{0.0};
   bool convergence_status_{true};
 };
 
