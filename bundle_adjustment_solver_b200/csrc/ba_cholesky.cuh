@@ -21,6 +21,7 @@
 
 #include "ba_cholesky_banded.cuh"
 #include "ba_cholesky_cluster.cuh"
+#include "ba_cholesky_nd.cuh"
 #include "ba_device.cuh"
 
 namespace ba {
@@ -407,7 +408,9 @@ struct CholeskyPlan {
   std::vector<int> narrow_cnt, grp_off, grp_cnt;
   bool two_level = false;
   int bw = 0;             // scalar half-bandwidth of S: 6 (largest pose distance inside a track) + 5
-  bool banded = false;    // run the register-window banded kernel (ba_cholesky_banded.cuh)
+  bool banded = false;    // banded reduced system: serial window kernel (ba_cholesky_banded.cuh) or the partition below
+  NdPlan nd;              // partitioned banded solve (ba_cholesky_nd.cuh); nd.valid: preferred over the serial kernel
+  NdDevice nd_dev;
 };
 
 inline void cholesky_make_plan(CholeskyPlan &pl, int n, const std::vector<int> &first_pose /*per free pose: first co-visible pose*/) {
@@ -416,6 +419,13 @@ inline void cholesky_make_plan(CholeskyPlan &pl, int n, const std::vector<int> &
   for (size_t j = 0; j < first_pose.size(); ++j) pl.bw = std::max(pl.bw, 6 * ((int)j - first_pose[j]) + 5);
   pl.bw = std::min(pl.bw, std::max(0, n - 1));
   pl.banded = cholesky_banded_supported(n, pl.bw) && n > kBandMaxW;
+  pl.nd = NdPlan();
+  if (pl.banded && n % 6 == 0) {
+    // BA_B200_ND_DEPTH / BA_B200_ND_CHUNK: force the tree depth / the chunk size in poses (tests)
+    const int fd = getenv("BA_B200_ND_DEPTH") ? atoi(getenv("BA_B200_ND_DEPTH")) : -1;
+    const int fc = getenv("BA_B200_ND_CHUNK") ? atoi(getenv("BA_B200_ND_CHUNK")) : -1;
+    nd_make_plan(pl.nd, n / 6, (pl.bw - 5) / 6, 128, fd, fc);
+  }
   pl.T = (n + 1 + kNB - 1) / kNB;
   pl.first_tile.assign(pl.T, pl.T);
   for (size_t j = 0; j < first_pose.size(); ++j) {
@@ -478,6 +488,14 @@ inline void cholesky_solve_enqueue(const CholeskyPlan &pl, double *Saug, double 
   static const bool verbose = getenv("BA_B200_VERBOSE") != nullptr;
   if (verbose) fprintf(stderr, "[ba_b200] cholesky n=%d T=%d max_rows=%d cluster_size=%d dense_fraction=%.3f bw=%d banded=%d parts=%d\n", n, pl.T, pl.max_rows, pl.cluster_size, pl.dense_fraction, pl.bw, (int)pl.banded, parts);
   if (pl.banded && parts == 15) {
+    // BA_B200_BAND_MODE: 6 (default) partitioned, one persistent launch; 5 partitioned, one launch per level;
+    // <= 4 the serial window kernels
+    const int mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 6;
+    if (mode >= 5 && pl.nd.valid && pl.nd_dev.tpw > 0) {
+      if (nd_enqueue(pl.nd, pl.nd_dev, Saug, x, mode, verbose ? 1 : 0, st, stream, launches)) return;
+      const cudaError_t ce = cudaGetLastError();
+      if (verbose) fprintf(stderr, "[ba_b200] partitioned banded launch failed: %s\n", cudaGetErrorString(ce));
+    }
     if (cholesky_banded_enqueue(Saug, n, pl.bw, x, linv, st, stream)) {
       if (launches) *launches += 1;
       return;

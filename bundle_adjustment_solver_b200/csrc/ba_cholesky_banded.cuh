@@ -984,7 +984,8 @@ inline bool cholesky_banded_supported(int n, int bw) { return n > 0 && bw + 8 <=
 inline bool cholesky_banded_enqueue(double *Saug, int n, int bw, double *x, double *linv, const LmState *st,
                                     cudaStream_t stream) {
   static const int timing = getenv("BA_B200_VERBOSE") != nullptr;
-  static const int mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 4;
+  int mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 4;
+  if (mode > 4) mode = 4;
   if (mode == 4 && bw + 16 <= 120) {   // DMMA block steps, window in shared memory (needs W >= bw + 16)
     if (bw + 16 <= 56) return launch_band4<56>(Saug, n, bw, x, linv, timing, st, stream);
     if (bw + 16 <= 88) return launch_band4<88>(Saug, n, bw, x, linv, timing, st, stream);

@@ -1103,6 +1103,9 @@ struct ba_solver {
   int schur_mode = 1;  // 1 = register-tiled windows + fallback, 0 = direct reds only
   CholeskyPlan chol;
   DevBuf<int> d_chol_rows, d_chol_first, d_chol_rows_ptr;
+  DevBuf<NdNode> d_nd_nodes;                       // partitioned banded solve (ba_cholesky_nd.cuh)
+  DevBuf<int> d_nd_level_nodes, d_nd_cta_nodes, d_nd_cta_ptr, d_nd_flags;
+  DevBuf<double> d_nd_L, d_nd_U;
   DevBuf<double> d_band;   // multi-GPU, banded S: band rows + rhs packed for the all-reduce
   int chol_mode = -1;  // -1 auto, 0 multi-kernel, 1 cluster
   bool S_clean_outside_band = false;   // Saug was fully cleared since it was allocated / the plan changed
@@ -1181,6 +1184,8 @@ static void free_device(ba_solver *s) {
   s->d_tpt_point.release(); s->d_tpt_inc_start.release(); s->d_fallback_pairs.release(); s->d_fb_groups.release();
   s->d_inc_a.release(); s->d_inc_b.release(); s->d_tile_batches.release(); s->d_cta_batch_ptr.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
   s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release(); s->d_band.release();
+  s->d_nd_nodes.release(); s->d_nd_level_nodes.release(); s->d_nd_cta_nodes.release(); s->d_nd_cta_ptr.release();
+  s->d_nd_flags.release(); s->d_nd_L.release(); s->d_nd_U.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
@@ -1336,6 +1341,34 @@ static int upload_cholesky_plan(ba_solver *s) {
   // BA_B200_CHOL_MODE: -1 auto (banded > cluster > multi-kernel), 0 multi-kernel, 1 cluster, 2 banded
   if (s->chol_mode == 0) { s->chol.cluster_size = 0; s->chol.banded = false; }
   if (s->chol_mode == 1) s->chol.banded = false;
+  // partitioned banded solve: node table, level / CTA lists, factor and contribution-block workspaces
+  NdPlan &nd = s->chol.nd;
+  s->chol.nd_dev = NdDevice();
+  if (s->chol.banded && nd.valid) {
+    NdDevice &dv = s->chol.nd_dev;
+    dv.smem = nd_smem_bytes(nd);
+    dv.tpw = nd_tpw_for(nd.max_BT);
+    if (dv.smem > kNdSmemLimit || dv.tpw < 0) {
+      nd.valid = false;
+    } else {
+      CUDA_TRY(s->d_nd_nodes.upload(nd.nodes, st));
+      CUDA_TRY(s->d_nd_level_nodes.upload(nd.level_nodes, st));
+      CUDA_TRY(s->d_nd_cta_nodes.upload(nd.cta_nodes, st));
+      CUDA_TRY(s->d_nd_cta_ptr.upload(nd.cta_ptr, st));
+      CUDA_TRY(s->d_nd_flags.alloc(2 * nd.nodes.size() + 2));
+      CUDA_TRY(s->d_nd_L.alloc((size_t)nd.L_doubles));
+      CUDA_TRY(s->d_nd_U.alloc((size_t)nd.U_doubles));
+      CUDA_TRY(cudaMemsetAsync(s->d_nd_flags.p, 0, s->d_nd_flags.n * sizeof(int), st));
+      NdArgs a{};
+      a.nodes = s->d_nd_nodes.p;
+      a.n = nd.n; a.ld = nd.n + 1; a.bw = nd.bw;      // S and x are patched in at enqueue time
+      a.Lws = s->d_nd_L.p; a.Uws = s->d_nd_U.p;
+      a.flags = s->d_nd_flags.p; a.n_nodes = (int)nd.nodes.size();
+      a.max_R8 = nd.max_R8; a.max_tiles = nd.max_tiles;
+      dv.level_args = a; dv.level_args.list = s->d_nd_level_nodes.p; dv.level_args.list_ptr = nullptr;
+      dv.cta_args = a; dv.cta_args.list = s->d_nd_cta_nodes.p; dv.cta_args.list_ptr = s->d_nd_cta_ptr.p;
+    }
+  }
   return BA_OK;
 }
 
@@ -2112,6 +2145,16 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
   return BA_OK;
 }
 
+// the persistent partitioned solve hands over between CTAs through flags with a bounded spin; a lost hand-over
+// (CTAs not co-resident) is reported instead of hanging the device
+static int check_nd_error(ba_solver *s) {
+  if (!s->chol.nd.valid || !s->d_nd_flags.p) return BA_OK;
+  int err = 0;
+  CUDA_TRY(cudaMemcpy(&err, s->d_nd_flags.p + 2 * s->chol.nd.nodes.size() + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) { s->err = "partitioned reduced solve: hand-over between CTAs timed out"; return BA_ERR_CUDA; }
+  return BA_OK;
+}
+
 static int enqueue_iteration(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   if (int rc = enqueue_build(s, opt, ev)) return rc;
   if (int rc = enqueue_allreduce_S(s)) return rc;
@@ -2229,6 +2272,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { s->err = std::string("kernel failure: ") + cudaGetErrorString(e); return BA_ERR_CUDA; }
   }
+  if (int rc = check_nd_error(s)) return rc;
   if (max_it > 0) {
     n_done = s->h_state->iteration;
     converged = s->h_state->converged;
@@ -2302,7 +2346,7 @@ int ba_build_only(ba_solver *s, const ba_options *opt_in, double lambda, int do_
   CUDA_TRY(cudaStreamSynchronize(st));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { s->err = std::string("kernel failure: ") + cudaGetErrorString(e); return BA_ERR_CUDA; }
-  return BA_OK;
+  return check_nd_error(s);
 }
 
 static int current_buffer(ba_solver *s, int *cur) {
@@ -2439,7 +2483,17 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
   if (getenv("BA_B200_VERBOSE")) {
     unsigned long long dbg[8];
     cudaMemcpyFromSymbol(dbg, g_cl_dbg, sizeof(dbg));
-    if (s->chol.banded) {
+    if (s->chol.banded && s->chol.nd.valid) {
+      unsigned long long d3[16];
+      cudaMemcpyFromSymbol(d3, g_nd_dbg, 16 * sizeof(unsigned long long));
+      const double r = 1.0 / (3.0 + reps);   // accumulated over warm-up + timed replays
+      fprintf(stderr, "[ba_b200] partitioned banded (n=%d bw=%d depth=%d leaves=%d nodes=%zu): CTA 0 forward %llu ns, forward+backward %llu ns | per-level front ns (sum over nodes / replays):",
+              s->chol.n, s->chol.bw, s->chol.nd.depth, s->chol.nd.n_leaves, s->chol.nd.nodes.size(), d3[0], d3[1]);
+      for (int l = 0; l < 7; ++l) fprintf(stderr, " L%d %.0f", l, (double)d3[2 + l] * r);
+      fprintf(stderr, "\n");
+      unsigned long long z[16] = {0};
+      cudaMemcpyToSymbol(g_nd_dbg, z, sizeof(z));
+    } else if (s->chol.banded) {
       unsigned long long d2[16];
       cudaMemcpyFromSymbol(d2, g_band_dbg, 16 * sizeof(unsigned long long));
       fprintf(stderr, "[ba_b200] banded ns: factor %llu backward %llu (n=%d bw=%d) | cycles: producer wait %llu work %llu | consumer0 loads %llu waitL %llu priority %llu bulk %llu endbar %llu\n",
@@ -2450,6 +2504,27 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
   return BA_OK;
+}
+
+// Host-only: the partition plan of the banded reduced solve for N free poses and track span b (no device needed).
+// nodes_out: [cap][20] = own0 k k8 rb0 wr lb0 wl b8 child0 child1 parent rb_off lb_off rhs_off level cta seq L_off U_off 0
+// meta: [8] = valid depth n_leaves n_levels n_ctas max_tiles max_R8 smem_bytes.  Returns the number of nodes.
+int ba_debug_nd_plan(int N, int b, int max_ctas, int force_depth, int force_chunk, long long *meta,
+                     long long *nodes_out, int cap) {
+  NdPlan pl;
+  nd_make_plan(pl, N, b, max_ctas, force_depth, force_chunk);
+  if (meta) {
+    meta[0] = pl.valid; meta[1] = pl.depth; meta[2] = pl.n_leaves; meta[3] = pl.n_levels; meta[4] = pl.n_ctas;
+    meta[5] = pl.max_tiles; meta[6] = pl.max_R8; meta[7] = (long long)nd_smem_bytes(pl);
+  }
+  const int nn = (int)pl.nodes.size();
+  for (int i = 0; i < std::min(nn, cap) && nodes_out; ++i) {
+    const NdNode &d = pl.nodes[i];
+    const long long v[20] = {d.own0, d.k, d.k8, d.rb0, d.wr, d.lb0, d.wl, d.b8, d.child[0], d.child[1], d.parent,
+                             d.rb_off, d.lb_off, d.rhs_off, d.level, d.cta, d.seq, d.L_off, d.U_off, 0};
+    std::copy(v, v + 20, nodes_out + (size_t)i * 20);
+  }
+  return nn;
 }
 
 int ba_debug_pairs(ba_solver *s, int *pair_pose_id, int *pair_point_id) {

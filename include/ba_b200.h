@@ -145,6 +145,11 @@ long long ba_debug_dump(ba_solver *s, int which, double *buf);
 int ba_debug_pairs(ba_solver *s, int *pair_pose_id, int *pair_point_id); /* original ids per pair */
 /* In-situ timing of parts of the reduced solve (bit 0 diag, 1 trsm, 2 syrk, 3 backward); timing only. */
 int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep);
+/* Host-only (no device): partition plan of the banded reduced solve (csrc/ba_nd_plan.h) for N free poses and track
+ * span b.  nodes_out [cap][20]; meta [8]; returns the number of tree nodes.  Used by the CPU test that emulates the
+ * fronts in numpy. */
+int ba_debug_nd_plan(int N, int b, int max_ctas, int force_depth, int force_chunk, long long *meta,
+                     long long *nodes_out, int cap);
 
 /* ---- multi-GPU (one process per GPU; landmarks sharded, S all-reduced) -- */
 /* 128-byte NCCL unique id; rank 0 creates it, the host distributes it (torch.distributed, MPI...). */

@@ -203,10 +203,12 @@ def test_c3_scaled_blocks_and_iterations(oracle_mod, engine_lib):
         assert a.iteration_status == b.iteration_status
 
 
-def _solve_vs_numpy(sc, monkeypatch=None, chol_mode=None, band_mode=None):
+def _solve_vs_numpy(sc, monkeypatch=None, chol_mode=None, band_mode=None, nd_depth=None, nd_chunk=None):
     """Build S, rhs on the device, solve with the engine's reduced solver, compare with numpy."""
     import os
-    for k, v in (("BA_B200_CHOL_MODE", chol_mode), ("BA_B200_BAND_MODE", band_mode)):
+    env = (("BA_B200_CHOL_MODE", chol_mode), ("BA_B200_BAND_MODE", band_mode), ("BA_B200_ND_DEPTH", nd_depth),
+           ("BA_B200_ND_CHUNK", nd_chunk))
+    for k, v in env:
         if v is None:
             os.environ.pop(k, None)
         else:
@@ -221,10 +223,25 @@ def _solve_vs_numpy(sc, monkeypatch=None, chol_mode=None, band_mode=None):
         rhs = e.dump("rhs")
         x = e.dump("x")
     finally:
-        os.environ.pop("BA_B200_CHOL_MODE", None)
-        os.environ.pop("BA_B200_BAND_MODE", None)
+        for k, _ in env:
+            os.environ.pop(k, None)
     xr = np.linalg.solve(Sm, rhs)
     return float(np.abs(x - xr).max() / np.abs(xr).max()), n
+
+
+@pytest.mark.parametrize("n_poses,track,band_mode,depth,chunk", [
+    (120, 10, 5, None, None), (120, 10, 6, None, None),      # C3-like band, level launches / persistent launch
+    (100, 6, 6, None, None), (150, 13, 6, None, None),       # narrow and wide boundaries (TPW 8 / 24)
+    (200, 4, 6, 3, 5), (200, 4, 5, 3, 5),                    # leaves cut into chains of chunks
+    (400, 4, 6, None, None),                                 # C4-like: deep tree
+    (61, 5, 6, 1, None),                                     # a single separator
+])
+def test_partitioned_banded_solve_matches_numpy(n_poses, track, band_mode, depth, chunk, engine_lib):
+    """K5 partitioned (nested-dissection) banded solve, csrc/ba_cholesky_nd.cuh: x against numpy.linalg.solve of the
+    device-built S, rhs (replaces ldlt().solve, full...cpp:890-908).  Tolerance 1e-9 relative (north_star)."""
+    sc = scenes.scene_trajectory(n_poses, 40 * n_poses, track, stereo=True, seed=4, n_fixed=2)
+    err, n = _solve_vs_numpy(sc, band_mode=band_mode, nd_depth=depth, nd_chunk=chunk)
+    assert err < 1e-9, (err, n)
 
 
 @pytest.mark.parametrize("n_poses,track,band_mode", [(100, 6, 4), (120, 10, 4), (150, 14, 4), (120, 10, 3), (120, 10, 1),
