@@ -9,7 +9,9 @@ LIB = os.environ.get("BA_B200_LIB") or os.path.join(HERE, "libba_b200.so")
 SOURCES = ["ba_engine.cu", "ba_poseonly.cu"]
 HEADERS = [os.path.join("..", "..", "include", "ba_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared"]
+# BA_B200_NVCC_EXTRA: extra compiler flags for A/B builds (e.g. -DBA_ND_CONS=11), together with BA_B200_LIB
+NVCC_FLAGS += os.environ.get("BA_B200_NVCC_EXTRA", "").split()
 
 
 def _stale():
@@ -27,6 +29,6 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl", "-lgomp"]
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
     return LIB

@@ -1,6 +1,7 @@
 // ba_cholesky_nd.cuh -- K5 for banded reduced camera systems, PARTITIONED: nested dissection of the pose chain
-// into independent dense fronts (plan: ba_nd_plan.h), one CTA per front, FP64 tensor-core (DMMA) trailing updates.
-// Replaces `Am_BCinvBt_mat.ldlt().solve(am_BCinv_b_mat)` (core/full_bundle_adjustment_solver.cpp:890-908).
+// into independent dense fronts (plan: ba_nd_plan.h), one CTA per front, FP64 tensor-core (DMMA) panel solves and
+// trailing updates.  Replaces `Am_BCinvBt_mat.ldlt().solve(am_BCinv_b_mat)`
+// (core/full_bundle_adjustment_solver.cpp:890-908).
 //
 // The serial banded kernel (ba_cholesky_banded.cuh) walks n/8 dependent panel steps on ONE SM.  Here the pose
 // chain is cut by separators into 2^L leaves that are eliminated concurrently on 2^L SMs; the separators are
@@ -8,22 +9,26 @@
 //
 // One front = [own | Rb | Lb | rhs] (ba_nd_plan.h).  Per front, one CTA of 12 warps:
 //   * assembly: the own columns (own x own lower trapezoid and boundary x own) are gathered into shared memory as
-//     8 x 8 tiles: entries of S (global, column-major lower + rhs row) plus the contribution blocks U of the
-//     children (extend-add through per-child index maps); the boundary x boundary part never enters shared
-//     memory: it lives in the DMMA accumulator registers of the consumer warps for the whole front.
-//   * factor: panel steps of 8 columns.  Warp 3 (alone on its SM sub-partition) factors the 8 x 8 diagonal block
-//     redundantly in every lane and applies the triangular solve to the rows below (its lanes own rows); the nine
-//     consumer warps apply the rank-8 update with two DMMAs per tile: the tiles of the next panel first (then the
-//     panel warp may go on), then the rest of the trapezoid, then their boundary x boundary tiles in registers.
-//     Tiles have static owners, so no CTA-wide barrier is needed between steps.
-//   * the panel (L11, L21 and the forward-substituted rhs row z) goes to global memory for the backward pass, the
-//     accumulators are written out as the contribution block U.
-// Backward (root first): x_own = -L11^-T (L21^T x_boundary - z): boundary part in parallel over all warps,
-// then an 8-column block chain inside one warp with explicit inverses of the diagonal blocks.
+//     8 x 8 tiles (swizzled so that DMMA fragment reads are conflict-free): entries of S (global, column-major
+//     lower + rhs row) plus the contribution blocks U of the children (extend-add through per-child index maps),
+//     a batch of tiles per warp with every load of the batch in flight at once; the boundary x boundary part
+//     never enters shared memory: it lives in the DMMA accumulator registers of the consumer warps.
+//   * factor: panel steps of 8 columns.  The diagonal warp (warp 3, alone on its SM sub-partition) only factors
+//     the 8 x 8 diagonal block and inverts the factor (W = L_ss^-1, redundantly in every lane: no shuffles on the
+//     chain).  The nine consumer warps turn the panel solve into tensor-core work, L_Is = A_Is W^T (two DMMAs per
+//     tile, in place), and after one consumer-wide barrier apply the rank-8 update to the tiles they own (two
+//     DMMAs per tile) and to their boundary x boundary accumulators.  LOOK-AHEAD: the owner of the next diagonal
+//     tile solves row tile s+1 itself and updates tile (s+1, s+1) before that barrier, so the dependent chain per
+//     step is  diagonal factor -> 4 DMMAs -> diagonal factor.
+//   * L (tiles, as they stand in shared memory) and W go to global memory for backward passes that run after the
+//     front has left shared memory; the accumulators are written out as the contribution block U.
+// Backward (root first): x_own = -L11^-T (L21^T x_boundary - z): boundary part in parallel over the warps from the
+// tiles in shared memory, then an 8-column block chain inside one warp with the W blocks.
 //
 // Two drivers over the same per-front code: one launch per tree level (`k_nd_forward_level` / `k_nd_backward_level`)
-// and a single persistent launch (`k_nd_persistent`) in which CTA p owns leaf p, climbs the tree while it arrives as
-// a left child, and hands over through acquire / release flags in global memory.
+// and a single persistent launch (`k_nd_persistent`): every CTA walks its list of fronts, hand-overs between CTAs go
+// through acquire / release flags in global memory; the last front of a list is still resident in shared memory
+// when its backward pass starts.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -36,8 +41,14 @@
 namespace ba {
 
 constexpr int kNdThreads = 384;
-constexpr int kNdCons = 9;                           // consumer warps 0,1,2,4,5,6,8,9,10
-constexpr int kNdActive = 32 * (kNdCons + 1);        // consumers + panel warp (named barrier population)
+constexpr int kNdWarps = kNdThreads / 32;
+// NC consumer warps (template parameter): 9 = warps 0,1,2,4,5,6,8,9,10, the diagonal warp alone on its SM
+// sub-partition (small fronts: the chain of diagonal blocks bounds the step); 11 = every warp but the diagonal warp
+// (large fronts: the DMMA updates bound the step)
+constexpr int kNdBarA = 3;                           // diagonal warp -> consumers: W(s) published
+constexpr int kNdBarB = 4;                           // consumers: panel s solved
+constexpr int kNdBarC = 5;                           // look-ahead warp -> diagonal warp: tile (s+1, s+1) final
+constexpr int kNdCntC = 64;
 constexpr int kNdSpinLimit = 1 << 22;
 
 struct NdArgs {
@@ -49,18 +60,24 @@ struct NdArgs {
   double *Lws, *Uws, *x;
   int *flags;             // persistent driver: [n_nodes] forward done, [n_nodes] backward done, abort, sticky error
   int n_nodes;
-  int max_R8, max_tiles;  // shared-memory carve-up
+  int max_R8, max_tiles, max_KT;  // shared-memory carve-up
 };
 
 __device__ unsigned long long g_nd_dbg[16];
 
 __device__ __forceinline__ int nd_tidx(int I, int J) { return I * (I + 1) / 2 + J; }   // lower-triangular tile index
+// element (r, c) of a swizzled 8 x 8 tile: the two column halves of rows 2, 3, 6, 7 are exchanged, which makes the
+// DMMA operand fragment (row lane / 4, column lane % 4 [+ 4]) hit 16 distinct bank pairs per half-warp
+__device__ __forceinline__ int nd_sw(int r, int c) { return r * 8 + (c ^ ((r & 2) << 1)); }
 
 struct NdSmem {
-  double *win;    // own trapezoid tiles [max_tiles][64]
-  double *Lp;     // published panels [2][max_R8][12]
+  double *win;    // own trapezoid tiles [max_tiles][64], column by column
+  double *winv;   // inverses of the diagonal blocks [max_KT][64]
   double *xs;     // backward: x by front-local index [max_R8]
+  double *tb;     // backward: right-hand side of the block chain [max_R8]
   int *pm;        // child index maps [2][max_R8]
+  int *grow;      // global index of a front-local row / column in S (n: rhs row, -1: padding) [max_R8]
+  int *tt;        // tile table: (I << 16) | J by storage position
   NdNode *node;   // current node
   NdNode *cn;     // its two children [2]
 };
@@ -68,73 +85,120 @@ struct NdSmem {
 __device__ __forceinline__ NdSmem nd_carve(unsigned char *raw, const NdArgs &g) {
   NdSmem sm;
   sm.win = reinterpret_cast<double *>(raw);
-  sm.Lp = sm.win + (size_t)g.max_tiles * 64;
-  sm.xs = sm.Lp + (size_t)2 * g.max_R8 * kNdLpStride;
-  sm.pm = reinterpret_cast<int *>(sm.xs + g.max_R8);
-  sm.node = reinterpret_cast<NdNode *>(sm.pm + 2 * g.max_R8);
+  sm.winv = sm.win + (size_t)g.max_tiles * 64;
+  sm.xs = sm.winv + (size_t)g.max_KT * 64;
+  sm.tb = sm.xs + g.max_R8;
+  sm.pm = reinterpret_cast<int *>(sm.tb + g.max_R8);
+  sm.grow = sm.pm + 2 * g.max_R8;
+  sm.tt = sm.grow + g.max_R8;
+  sm.node = reinterpret_cast<NdNode *>(sm.tt + ((g.max_tiles + 1) & ~1));
   sm.cn = sm.node + 1;
   return sm;
 }
 inline size_t nd_smem_bytes(const NdPlan &pl) {
-  return (size_t)pl.max_tiles * 64 * sizeof(double) + (size_t)2 * pl.max_R8 * kNdLpStride * sizeof(double) +
-         (size_t)pl.max_R8 * sizeof(double) + (size_t)2 * pl.max_R8 * sizeof(int) + 3 * sizeof(NdNode) + 64;
+  return ((size_t)pl.max_tiles + pl.max_KT) * 64 * sizeof(double) + (size_t)2 * pl.max_R8 * sizeof(double) +
+         (size_t)3 * pl.max_R8 * sizeof(int) + (size_t)((pl.max_tiles + 1) & ~1) * sizeof(int) + 3 * sizeof(NdNode) + 64;
 }
 
-// element (a, b), a >= b, of a node's contribution block
-__device__ __forceinline__ double nd_load_U(const double *U, int a, int b) {
-  return __ldcg(U + (size_t)nd_tidx(a >> 3, b >> 3) * 64 + (a & 7) * 8 + (b & 7));
-}
-
-// initial value of front entry (i, j), i >= j (front-local indices): S part (own columns only) + children
-__device__ __forceinline__ double nd_front_value(const NdArgs &g, const NdSmem &sm, int i, int j) {
-  const NdNode &nd = *sm.node;
-  double v = 0.0;
-  if (j < nd.k8) {
-    if (j >= nd.k) return (i == j) ? 1.0 : 0.0;       // identity padding of the own block
-    if (i >= nd.k && i < nd.k8) return 0.0;
-    const int gj = nd.own0 + j;
-    const int bi = i - nd.k8;
-    int gi = -1;
-    if (i < nd.k) gi = nd.own0 + i;
-    else if (bi < nd.wr) gi = nd.rb0 + bi;
-    else if (bi < nd.wr + nd.wl) gi = nd.lb0 + (bi - nd.wr);
-    else if (bi == nd.wr + nd.wl) gi = g.n;
-    if (gi < 0) return 0.0;
-    if (gi == g.n) {
-      v = __ldcg(g.S + (size_t)gj * g.ld + g.n);
-    } else {
+// Sources of the initial value of front entry (i, j), i >= j (front-local indices): an entry of S (own columns only),
+// one entry of each child's contribution block, or a constant (identity padding).  Addresses first, loads later, so
+// that a batch of entries has all its loads in flight together.
+struct NdSrc {
+  unsigned os, o0, o1;   // element offsets into S / the children's contribution blocks; kNdNone: no source
+};
+constexpr unsigned kNdNone = 0xffffffffu, kNdOne = 0xfffffffeu;   // kNdOne (in os): the constant 1 (identity padding)
+// per-front constants of the gather, kept in registers
+struct NdGather {
+  const double *S, *U0, *U1;     // U0 / U1: contribution blocks of the children (nullptr: no child)
+  int ld, n, bw, off1;           // off1: offset of the second child's index map
+};
+template <bool OWN>
+__device__ __forceinline__ NdSrc nd_front_src(const NdGather &q, const NdSmem &sm, int i, int j, bool on) {
+  NdSrc r{kNdNone, kNdNone, kNdNone};
+  if (!on) return r;
+  if (OWN) {   // j is an own column
+    const int gi = sm.grow[i], gj = sm.grow[j];
+    if (gj < 0) {
+      if (i == j) r.os = kNdOne;    // identity padding of the own block
+      return r;
+    }
+    if (gi >= 0) {
       const int lo = min(gi, gj), hi = max(gi, gj);
-      if (hi - lo <= g.bw) v = __ldcg(g.S + (size_t)lo * g.ld + hi);
+      if (hi == q.n || hi - lo <= q.bw) r.os = (unsigned)lo * (unsigned)q.ld + (unsigned)hi;
     }
   }
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    if (nd.child[c] < 0) continue;
-    const int pi = sm.pm[c * g.max_R8 + i], pj = sm.pm[c * g.max_R8 + j];
-    if (pi >= 0 && pj >= 0) v += nd_load_U(g.Uws + sm.cn[c].U_off, max(pi, pj), min(pi, pj));
+  if (q.U0) {
+    const int pi = sm.pm[i], pj = sm.pm[j];
+    if ((pi | pj) >= 0) {
+      const int a = max(pi, pj), b = min(pi, pj);
+      r.o0 = (unsigned)(nd_tidx(a >> 3, b >> 3) * 64 + (a & 7) * 8 + (b & 7));
+    }
   }
-  return v;
+  if (q.U1) {
+    const int pi = sm.pm[q.off1 + i], pj = sm.pm[q.off1 + j];
+    if ((pi | pj) >= 0) {
+      const int a = max(pi, pj), b = min(pi, pj);
+      r.o1 = (unsigned)(nd_tidx(a >> 3, b >> 3) * 64 + (a & 7) * 8 + (b & 7));
+    }
+  }
+  return r;
+}
+__device__ __forceinline__ double nd_src_value(const NdGather &q, const NdSrc &s) {
+  const double a = s.os < kNdOne ? __ldcg(q.S + s.os) : (s.os == kNdOne ? 1.0 : 0.0);
+  const double b = s.o0 != kNdNone ? __ldcg(q.U0 + s.o0) : 0.0;
+  const double c = s.o1 != kNdNone ? __ldcg(q.U1 + s.o1) : 0.0;
+  return a + (b + c);
+}
+
+// stage the node record (and its children's) in shared memory; ends with a CTA barrier
+__device__ __forceinline__ void nd_stage_node(const NdArgs &g, const NdSmem &sm, int node_id, bool children) {
+  const int t = threadIdx.x;
+  constexpr int NW = (int)(sizeof(NdNode) / sizeof(int));
+  if (t < NW) reinterpret_cast<int *>(sm.node)[t] = reinterpret_cast<const int *>(g.nodes + node_id)[t];
+  __syncthreads();
+  if (children) {
+    const NdNode &nd = *sm.node;
+    for (int c = 0; c < 2; ++c)
+      if (nd.child[c] >= 0 && t >= 32 * (1 + c) && t < 32 * (1 + c) + NW)
+        reinterpret_cast<int *>(sm.cn + c)[t - 32 * (1 + c)] = reinterpret_cast<const int *>(g.nodes + nd.child[c])[t - 32 * (1 + c)];
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // forward elimination of one front.  TPW: boundary x boundary tiles per consumer warp (register accumulators)
 // ------------------------------------------------------------------------------------------------------------
-template <int TPW>
+template <int TPW, int NC>
 __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, int timing) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool is_producer = warp == 3;
-  const bool is_idle = (warp & 3) == 3 && !is_producer;
-  const int cwi = warp - (warp >> 2);            // consumer index 0..8
-  const int ct = cwi * 32 + lane;                // consumer thread 0..287
-  if (t < (int)(sizeof(NdNode) / sizeof(int))) reinterpret_cast<int *>(sm.node)[t] = reinterpret_cast<const int *>(g.nodes + node_id)[t];
-  __syncthreads();
+  const bool is_diag = warp == 3;
+  static_assert(NC == 9 || NC == 11, "consumer warps");
+  constexpr int kNdCons = NC, kNdCntA = 32 * (NC + 1), kNdCntB = 32 * NC;
+  const bool is_idle = NC == 9 && (warp & 3) == 3 && !is_diag;
+  const int cwi = NC == 9 ? warp - (warp >> 2) : warp - (warp > 3 ? 1 : 0);   // consumer index
+  unsigned long long t_in = 0;
+  if (timing && t == 0) t_in = gtime();
+  nd_stage_node(g, sm, node_id, true);
   const NdNode &nd = *sm.node;
-  for (int c = 0; c < 2; ++c) {
-    if (nd.child[c] >= 0 && t < (int)(sizeof(NdNode) / sizeof(int)))
-      reinterpret_cast<int *>(sm.cn + c)[t] = reinterpret_cast<const int *>(g.nodes + nd.child[c])[t];
-  }
-  const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, NT = KT + BT, R8 = 8 * NT;
+  const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, NT = KT + BT;
+  auto colbase = [&](int J) { return J * NT - (J * (J - 1)) / 2; };   // tile (I, J), I >= J, at colbase(J) + I - J
+  const int n_tiles = colbase(KT);
+  const int LbT0 = (nd.k8 + nd.wr) >> 3;        // first row tile of [Lb | rhs]
   for (int i = t; i < 2 * g.max_R8; i += kNdThreads) sm.pm[i] = -1;
+  for (int i = t; i < 64 * KT; i += kNdThreads) sm.winv[i] = 0.0;
+  for (int i = t; i < 8 * NT; i += kNdThreads) {
+    const int bi = i - nd.k8;
+    int gi = -1;
+    if (i < nd.k) gi = nd.own0 + i;
+    else if (bi >= 0 && bi < nd.wr) gi = nd.rb0 + bi;
+    else if (bi >= 0 && bi < nd.wr + nd.wl) gi = nd.lb0 + (bi - nd.wr);
+    else if (bi == nd.wr + nd.wl) gi = g.n;
+    sm.grow[i] = gi;
+  }
+  for (int J = warp; J < KT; J += kNdWarps) {
+    const int base = colbase(J) - J;
+    for (int I = J + lane; I < NT; I += 32) sm.tt[base + I] = (I << 16) | J;
+  }
   __syncthreads();
   for (int c = 0; c < 2; ++c) {
     if (nd.child[c] < 0) continue;
@@ -145,250 +209,307 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
     if (t == 0) pm[cn.rhs_off] = cn.wr + cn.wl;
   }
   __syncthreads();
-  auto colbase = [&](int J) { return J * NT - (J * (J - 1)) / 2; };   // tile (I, J), I >= J, at colbase(J) + I - J
-  // ---- assembly of the own columns (coalesced along the rows of a column of S)
-  for (int J = 0; J < KT; ++J) {
-    const int nrows = R8 - 8 * J;
-    double *colt = sm.win + (size_t)colbase(J) * 64;
-    for (int e = t; e < 8 * nrows; e += kNdThreads) {
-      const int jj = e / nrows, ri = e - jj * nrows;
-      const int i = 8 * J + ri, j = 8 * J + jj;
-      const double v = (i >= j) ? nd_front_value(g, sm, i, j) : 0.0;
-      colt[(size_t)(ri >> 3) * 64 + (ri & 7) * 8 + jj] = v;
+  if (timing && t == 0 && blockIdx.x == 0) g_nd_dbg[13] += gtime() - t_in;   // staging, index maps
+  const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
+  const int swz = (fr & 2) << 1;
+  const int offC = fr * 8 + (fc ^ swz);                          // accumulator fragment (double2) inside a tile
+  const int offA0 = fr * 8 + (kq ^ swz), offA1 = offA0 ^ 4;      // operand fragments: columns kq and kq + 4
+  NdGather gq;
+  gq.S = g.S; gq.ld = g.ld; gq.n = g.n; gq.bw = g.bw; gq.off1 = g.max_R8;
+  gq.U0 = nd.child[0] >= 0 ? g.Uws + sm.cn[0].U_off : nullptr;
+  gq.U1 = nd.child[1] >= 0 ? g.Uws + sm.cn[1].U_off : nullptr;
+  const bool has_children = gq.U0 || gq.U1;
+  // ---- assembly of the own columns: a warp takes UN tiles per round, lane (fr, fc) two adjacent entries of each
+  {
+    constexpr int UN = 8;
+    for (int tb0 = warp; tb0 < n_tiles; tb0 += kNdWarps * UN) {
+      NdSrc src[UN][2];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int tile = tb0 + kNdWarps * u;
+        const bool live = tile < n_tiles;
+        const int ij = sm.tt[live ? tile : tb0];
+        const int I = ij >> 16, J = ij & 0xffff;
+        const int i = 8 * I + fr, j = 8 * J + fc;
+        // a front without children holds nothing but the band of S: tiles entirely outside it are zero
+        bool in_band = true;
+        if (!has_children && I > J) {
+          const int gr = sm.grow[8 * I], gr7 = sm.grow[8 * I + 7], gc = sm.grow[8 * J], gc7 = sm.grow[8 * J + 7];
+          const bool rows_ok = gr >= 0 && gr7 - gr == 7 && gr7 != g.n;     // eight consecutive rows of S
+          in_band = !(rows_ok && ((gc7 >= 0 && gr - gc7 > g.bw) || gc - gr7 > g.bw));
+        }
+        src[u][0] = nd_front_src<true>(gq, sm, i, j, live && in_band && i >= j);
+        src[u][1] = nd_front_src<true>(gq, sm, i, j + 1, live && in_band && i >= j + 1);
+      }
+      double2 v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) v[u] = make_double2(nd_src_value(gq, src[u][0]), nd_src_value(gq, src[u][1]));
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int tile = tb0 + kNdWarps * u;
+        if (tile < n_tiles) *reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC) = v[u];
+      }
     }
   }
+  if (timing && t == 0 && blockIdx.x == 0) g_nd_dbg[14] += gtime() - t_in;   // + own columns (warp 0's share)
   // ---- boundary x boundary accumulators (consumers): children's contributions passed through
-  const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
   const int n_utiles = BT * (BT + 1) / 2;
   double2 acc[TPW];
-  int ubi[TPW], ubj[TPW];
+  int ub[TPW];                                   // (row tile << 8) | column tile of the boundary block, -1: none
 #pragma unroll
   for (int q = 0; q < TPW; ++q) {
     acc[q] = make_double2(0.0, 0.0);
-    ubi[q] = 0; ubj[q] = 0;
+    ub[q] = -1;
   }
-  if (!is_producer && !is_idle) {
+  if (!is_diag && !is_idle) {
 #pragma unroll
     for (int q = 0; q < TPW; ++q) {
-      int e = cwi + kNdCons * q;
+      const int e = cwi + kNdCons * q;
       if (e < n_utiles) {
-        int I = 0;
-        while (e > I) { e -= I + 1; ++I; }     // row I holds I + 1 tiles
-        ubi[q] = I; ubj[q] = e;
-        if (nd.child[0] >= 0 || nd.child[1] >= 0) {
-          const int i = nd.k8 + 8 * I + fr, j = nd.k8 + 8 * e + fc;
-          if (i >= j) acc[q].x = nd_front_value(g, sm, i, j);
-          if (i >= j + 1) acc[q].y = nd_front_value(g, sm, i, j + 1);
+        int I = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while (I * (I + 1) / 2 > e) --I;
+        while ((I + 1) * (I + 2) / 2 <= e) ++I;
+        ub[q] = (I << 8) | (e - I * (I + 1) / 2);
+      }
+    }
+    if (has_children) {
+      constexpr int UQ = 8;
+#pragma unroll
+      for (int q0 = 0; q0 < TPW; q0 += UQ) {
+        NdSrc src[UQ][2];
+#pragma unroll
+        for (int u = 0; u < UQ; ++u) {
+          if (q0 + u < TPW) {
+            const int q = q0 + u;
+            const bool live = ub[q] >= 0;
+            const int i = nd.k8 + 8 * (ub[q] >> 8) + fr, j = nd.k8 + 8 * (ub[q] & 0xff) + fc;
+            src[u][0] = nd_front_src<false>(gq, sm, i, j, live && i >= j);
+            src[u][1] = nd_front_src<false>(gq, sm, i, j + 1, live && i >= j + 1);
+          }
         }
-      } else {
-        ubi[q] = -1;
+#pragma unroll
+        for (int u = 0; u < UQ; ++u)
+          if (q0 + u < TPW) acc[q0 + u] = make_double2(nd_src_value(gq, src[u][0]), nd_src_value(gq, src[u][1]));
       }
     }
   }
   __syncthreads();
   unsigned long long t0 = 0;
-  if (timing && t == 0) t0 = gtime();
+  if (timing && t == 0) {
+    t0 = gtime();
+    if (blockIdx.x == 0) g_nd_dbg[10] += t0 - t_in;     // staging + assembly (CTA 0 / first front of a level)
+  }
 
   // ---- factorisation of the own columns
   double *Lg = g.Lws + nd.L_off;
-  const int LpBuf = g.max_R8 * kNdLpStride;
+  double *Wg = Lg + (size_t)n_tiles * 64;
   if (is_idle) {
     // nothing
-  } else if (is_producer) {
+  } else if (is_diag) {
 #pragma unroll 1
     for (int s = 0; s < KT; ++s) {
-      const int par = s & 1;
-      if (s > 0) asm volatile("bar.sync %0, %1;" ::"r"(5 + par), "n"(kNdActive) : "memory");
-      const int nb = R8 - 8 * (s + 1);                    // rows below the diagonal block
-      const double *col = sm.win + (size_t)colbase(s) * 64;   // tile (s + q, s) at col + 64 q
-      double *LpS = sm.Lp + par * LpBuf;
-      double a[4][8];
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl) {
-        const int pos = lane + 32 * sl;
-        if (pos < nb) {
-          const double4 *src = reinterpret_cast<const double4 *>(col + (size_t)(1 + (pos >> 3)) * 64 + (pos & 7) * 8);
-          const double4 v0 = src[0], v1 = src[1];
-          a[sl][0] = v0.x; a[sl][1] = v0.y; a[sl][2] = v0.z; a[sl][3] = v0.w;
-          a[sl][4] = v1.x; a[sl][5] = v1.y; a[sl][6] = v1.z; a[sl][7] = v1.w;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) a[sl][k] = 0.0;
-        }
-      }
-      double D[8][8], rc[8], rs[8];
+      long long c0 = 0;
+      if (timing) c0 = clock64();
+      if (s > 0) asm volatile("bar.sync %0, %1;" ::"n"(kNdBarC), "n"(kNdCntC) : "memory");
+      long long c1 = 0;
+      if (timing) c1 = clock64();
+      double *dt = sm.win + (size_t)colbase(s) * 64;          // tile (s, s)
+      double D[8][8], rs[8];
       {
-        const double4 *dsrc = reinterpret_cast<const double4 *>(col);
+        const double4 *dsrc = reinterpret_cast<const double4 *>(dt);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const double4 v0 = dsrc[2 * i], v1 = dsrc[2 * i + 1];
-          D[i][0] = v0.x; D[i][1] = v0.y; D[i][2] = v0.z; D[i][3] = v0.w;
-          D[i][4] = v1.x; D[i][5] = v1.y; D[i][6] = v1.z; D[i][7] = v1.w;
+          const double4 lo = dsrc[2 * i + ((i & 2) ? 1 : 0)], hi = dsrc[2 * i + ((i & 2) ? 0 : 1)];
+          D[i][0] = lo.x; D[i][1] = lo.y; D[i][2] = lo.z; D[i][3] = lo.w;
+          D[i][4] = hi.x; D[i][5] = hi.y; D[i][6] = hi.z; D[i][7] = hi.w;
         }
       }
+      // Cholesky with the reciprocal square root on the chain: the columns come out scaled (D becomes L), which
+      // measured shorter than a reciprocal chain plus square roots off it (profiles/micro/diag8_bench.cu)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double d = D[k][k];
-        const bool pos_def = d > 0.0;
-        rc[k] = pos_def ? fast_rcp(d) : 0.0;          // non-positive pivot: LDLT's D^+ = 0
-        rs[k] = pos_def ? fast_rsqrt(d) : 0.0;
+        rs[k] = (d > 0.0) ? fast_rsqrt(d) : 0.0;       // non-positive pivot: zero column, like LDLT's D^+ = 0
+#pragma unroll
+        for (int i = k; i < 8; ++i) D[i][k] *= rs[k];
 #pragma unroll
         for (int i = k + 1; i < 8; ++i) {
-          const double ti = D[i][k] * rc[k];
 #pragma unroll
-          for (int j = k + 1; j <= i; ++j) D[i][j] -= ti * D[j][k];
-        }
-#pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          const double u = a[sl][k] * rc[k];
-#pragma unroll
-          for (int m = k + 1; m < 8; ++m) a[sl][m] -= u * D[m][k];
+          for (int j = k + 1; j <= i; ++j) D[i][j] -= D[i][k] * D[j][k];
         }
       }
+      // W = L^-1 by forward substitution on the identity, column by column
+      double W[8][8];
 #pragma unroll
-      for (int sl = 0; sl < 4; ++sl) {
-        const int pos = lane + 32 * sl;
-        if (pos < nb) {
-          double4 *dst = reinterpret_cast<double4 *>(LpS + (size_t)(8 * (s + 1) + pos) * kNdLpStride);
-          dst[0] = make_double4(a[sl][0] * rs[0], a[sl][1] * rs[1], a[sl][2] * rs[2], a[sl][3] * rs[3]);
-          dst[1] = make_double4(a[sl][4] * rs[4], a[sl][5] * rs[5], a[sl][6] * rs[6], a[sl][7] * rs[7]);
+      for (int j = 0; j < 8; ++j) {
+        W[j][j] = rs[j];
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int m = j; m < i; ++m) sacc += D[i][m] * W[m][j];
+          W[i][j] = -sacc * rs[i];
         }
       }
-      // the diagonal block's own rows: L_ss (lower), for the global copy
+      // publish W (lower part; the upper part was cleared during assembly): every lane holds every entry, so the
+      // stores are warp-uniform with compile-time addresses (a lane-dependent selection of registers costs 1,400 cycles)
+      double *wt = sm.winv + (size_t)s * 64;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (lane == i) {
-          double l[8];
+      for (int r = 0; r < 8; ++r) {
 #pragma unroll
-          for (int m = 0; m < 8; ++m) l[m] = (m < i) ? D[i][m] * rs[m] : (m == i ? D[i][i] * rs[i] : 0.0);
-          double4 *dst = reinterpret_cast<double4 *>(LpS + (size_t)(8 * s + i) * kNdLpStride);
-          dst[0] = make_double4(l[0], l[1], l[2], l[3]);
-          dst[1] = make_double4(l[4], l[5], l[6], l[7]);
-        }
+        for (int c = 0; c <= r; c += 2)
+          *reinterpret_cast<double2 *>(wt + r * 8 + (c ^ ((r & 2) << 1))) = make_double2(W[r][c], (c + 1 <= r) ? W[r][c + 1] : 0.0);
       }
-      // rows beyond the first 128: same multipliers, two slices at a time
-#pragma unroll 1
-      for (int p0 = 128; p0 < nb; p0 += 64) {
-        double b[2][8];
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int pos = p0 + lane + 32 * sl;
-          if (pos < nb) {
-            const double4 *src = reinterpret_cast<const double4 *>(col + (size_t)(1 + (pos >> 3)) * 64 + (pos & 7) * 8);
-            const double4 v0 = src[0], v1 = src[1];
-            b[sl][0] = v0.x; b[sl][1] = v0.y; b[sl][2] = v0.z; b[sl][3] = v0.w;
-            b[sl][4] = v1.x; b[sl][5] = v1.y; b[sl][6] = v1.z; b[sl][7] = v1.w;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) b[sl][k] = 0.0;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            const double u = b[sl][k] * rc[k];
-#pragma unroll
-            for (int m = k + 1; m < 8; ++m) b[sl][m] -= u * D[m][k];
-          }
-        }
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const int pos = p0 + lane + 32 * sl;
-          if (pos < nb) {
-            double4 *dst = reinterpret_cast<double4 *>(LpS + (size_t)(8 * (s + 1) + pos) * kNdLpStride);
-            dst[0] = make_double4(b[sl][0] * rs[0], b[sl][1] * rs[1], b[sl][2] * rs[2], b[sl][3] * rs[3]);
-            dst[1] = make_double4(b[sl][4] * rs[4], b[sl][5] * rs[5], b[sl][6] * rs[6], b[sl][7] * rs[7]);
-          }
-        }
+      asm volatile("bar.arrive %0, %1;" ::"n"(kNdBarA), "n"(kNdCntA) : "memory");
+      if (timing && lane == 0 && nd.parent < 0) {    // root front: cycles waiting for the look-ahead warp / working
+        g_nd_dbg[8] += (unsigned long long)(c1 - c0);
+        g_nd_dbg[15] += (unsigned long long)(clock64() - c1);
       }
-      asm volatile("bar.arrive %0, %1;" ::"r"(3 + par), "n"(kNdActive) : "memory");
     }
   } else {
     // ---------------------------------------------- consumers ----------------------------------------------
-    const int laneL = fr * kNdLpStride + kq, laneC = fr * 8 + fc;
-    auto column_update = [&](const double *LpS, int J) {
-      // tiles (I, J) owned by this warp: (I + 4 J) mod 9 == cwi
-      int I = J + ((cwi - 5 * J) % kNdCons + kNdCons) % kNdCons;
-      const double bf0 = LpS[(size_t)J * 8 * kNdLpStride + laneL], bf1 = LpS[(size_t)J * 8 * kNdLpStride + laneL + 4];
-      double *colt = sm.win + (size_t)(colbase(J) - J) * 64 + laneC;   // tile (I, J) at colt + 64 I
-      for (; I < NT; I += 4 * kNdCons) {
-        double2 cv[4];
-        double af[4][2];
-        bool live[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int Iq = I + kNdCons * q;
-          live[q] = Iq < NT;
-          const int Ic = live[q] ? Iq : I;
-          cv[q] = *reinterpret_cast<const double2 *>(colt + (size_t)Ic * 64);
-          af[q][0] = -LpS[(size_t)Ic * 8 * kNdLpStride + laneL];
-          af[q][1] = -LpS[(size_t)Ic * 8 * kNdLpStride + laneL + 4];
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dmma_884b(cv[q].x, cv[q].y, af[q][0], bf0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dmma_884b(cv[q].x, cv[q].y, af[q][1], bf1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (live[q]) *reinterpret_cast<double2 *>(colt + (size_t)(I + kNdCons * q) * 64) = cv[q];
-      }
+    // L_Is = A_Is W^T in place (tile (I, s) at `tile`), also to global memory
+    auto solve_tile = [&](double *tile, const double *wt, size_t goff) {
+      const double a0 = tile[offA0], a1 = tile[offA1];
+      const double b0 = wt[offA0], b1 = wt[offA1];
+      double2 c = make_double2(0.0, 0.0);
+      dmma_884b(c.x, c.y, a0, b0);
+      dmma_884b(c.x, c.y, a1, b1);
+      __syncwarp();
+      *reinterpret_cast<double2 *>(tile + offC) = c;
+      *reinterpret_cast<double2 *>(Lg + goff + offC) = c;
     };
+    // Row tile I of the trapezoid (tiles (I, J), J <= min(I, KT - 1)) belongs to consumer I mod 9: the panel solve of
+    // tile (I, s) and every update of the row stay inside one warp, the operand of the row is loaded once per step
 #pragma unroll 1
     for (int s = 0; s < KT; ++s) {
-      const int par = s & 1;
-      const double *LpS = sm.Lp + par * LpBuf;
-      asm volatile("bar.sync %0, %1;" ::"r"(3 + par), "n"(kNdActive) : "memory");
-      if (s + 1 < KT) {
-        column_update(LpS, s + 1);                       // the next panel first
-        asm volatile("bar.arrive %0, %1;" ::"r"(5 + (par ^ 1)), "n"(kNdActive) : "memory");
+      const double *wt = sm.winv + (size_t)s * 64;
+      double *ps = sm.win + (size_t)(colbase(s) - s) * 64;           // tile (I, s) at ps + 64 I
+      const size_t gs = (size_t)(colbase(s) - s) * 64;
+      asm volatile("bar.sync %0, %1;" ::"n"(kNdBarA), "n"(kNdCntA) : "memory");
+      if ((s + 5) % kNdCons == cwi)      // W(s) to global memory (backward passes after the front left shared memory)
+        *reinterpret_cast<double2 *>(Wg + (size_t)s * 64 + 2 * lane) = *reinterpret_cast<const double2 *>(wt + 2 * lane);
+      // look-ahead: the owner of row s + 1 solves tile (s + 1, s) and finishes the next diagonal tile
+      const bool la = (s + 1 < KT) && ((s + 1) % kNdCons == cwi);
+      int I0 = s + 1 + ((cwi - (s + 1)) % kNdCons + kNdCons) % kNdCons;   // my first row below the diagonal tile
+      if (la) {
+        solve_tile(ps + (size_t)(s + 1) * 64, wt, gs + (size_t)(s + 1) * 64);
+        __syncwarp();
+        double *dn = sm.win + (size_t)colbase(s + 1) * 64 + offC;
+        double2 cv = *reinterpret_cast<const double2 *>(dn);
+        const double a0 = ps[(size_t)(s + 1) * 64 + offA0], a1 = ps[(size_t)(s + 1) * 64 + offA1];
+        dmma_884b(cv.x, cv.y, -a0, a0);
+        dmma_884b(cv.x, cv.y, -a1, a1);
+        *reinterpret_cast<double2 *>(dn) = cv;
+        __syncwarp();
+        asm volatile("bar.arrive %0, %1;" ::"n"(kNdBarC), "n"(kNdCntC) : "memory");
+        I0 += kNdCons;                                               // row s + 1 is complete
       }
-      for (int J = s + 2; J < KT; ++J) column_update(LpS, J);
+      // rows of [own | Rb] beyond the band of column s hold zeros (no fill reaches them): skipped, zero in global L
+      const int rmax = min(NT - 1, s + nd.bandT);
+      auto row_live = [&](int I) { return I <= rmax || I >= LbT0; };
+      for (int I = I0; I < NT; I += kNdCons) {
+        if (row_live(I)) solve_tile(ps + (size_t)I * 64, wt, gs + (size_t)I * 64);
+        else *reinterpret_cast<double2 *>(Lg + gs + (size_t)I * 64 + offC) = make_double2(0.0, 0.0);
+      }
+      asm volatile("bar.sync %0, %1;" ::"n"(kNdBarB), "n"(kNdCntB) : "memory");
+      // trailing update, two rows at a time (they share the column operands), two columns per round
+      const int Jlim = min(KT - 1, rmax);                            // live column tiles of the trailing block
+      for (int I1 = I0; I1 < NT; I1 += 2 * kNdCons) {
+        const int I2 = I1 + kNdCons;
+        const bool two = I2 < NT && row_live(I2);
+        const int I2c = two ? I2 : I1;
+        const int Jm1 = row_live(I1) ? min(I1, Jlim) : -1, Jm2 = two ? min(I2, Jlim) : -1;
+        const double a10 = -ps[(size_t)I1 * 64 + offA0], a11 = -ps[(size_t)I1 * 64 + offA1];
+        const double a20 = -ps[(size_t)I2c * 64 + offA0], a21 = -ps[(size_t)I2c * 64 + offA1];
+        const int Jend = max(Jm1, Jm2);
+        for (int J = s + 1; J <= Jend; J += 2) {
+          double2 c1[2], c2[2];
+          double b0[2], b1[2];
+          bool v1[2], v2[2];
+          double *p1[2], *p2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int Ju = min(J + u, KT - 1);
+            v1[u] = J + u <= Jm1;
+            v2[u] = J + u <= Jm2;
+            double *cb = sm.win + (size_t)(colbase(Ju) - Ju) * 64 + offC;
+            p1[u] = cb + (size_t)(v1[u] ? I1 : Ju) * 64;
+            p2[u] = cb + (size_t)(v2[u] ? I2c : Ju) * 64;
+            b0[u] = ps[(size_t)Ju * 64 + offA0];
+            b1[u] = ps[(size_t)Ju * 64 + offA1];
+            c1[u] = *reinterpret_cast<const double2 *>(p1[u]);
+            c2[u] = *reinterpret_cast<const double2 *>(p2[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            dmma_884b(c1[u].x, c1[u].y, a10, b0[u]);
+            dmma_884b(c2[u].x, c2[u].y, a20, b0[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            dmma_884b(c1[u].x, c1[u].y, a11, b1[u]);
+            dmma_884b(c2[u].x, c2[u].y, a21, b1[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (v1[u]) *reinterpret_cast<double2 *>(p1[u]) = c1[u];
+            if (v2[u]) *reinterpret_cast<double2 *>(p2[u]) = c2[u];
+          }
+        }
+      }
       // boundary x boundary tiles (registers)
-      const double *LpB = LpS + (size_t)KT * 8 * kNdLpStride + laneL;
+      const double *pB = ps + (size_t)KT * 64;
 #pragma unroll
       for (int q = 0; q < TPW; ++q) {
-        if (ubi[q] >= 0) {
-          const double *pa = LpB + (size_t)ubi[q] * 8 * kNdLpStride, *pb = LpB + (size_t)ubj[q] * 8 * kNdLpStride;
-          const double a0 = -pa[0], a1 = -pa[4], b0 = pb[0], b1 = pb[4];
+        if (ub[q] >= 0 && row_live(KT + (ub[q] >> 8)) && row_live(KT + (ub[q] & 0xff))) {
+          const double *pa = pB + (size_t)(ub[q] >> 8) * 64, *pb = pB + (size_t)(ub[q] & 0xff) * 64;
+          const double a0 = -pa[offA0], a1 = -pa[offA1], b0 = pb[offA0], b1 = pb[offA1];
           dmma_884b(acc[q].x, acc[q].y, a0, b0);
           dmma_884b(acc[q].x, acc[q].y, a1, b1);
         }
       }
-      // finished panel (rows 8 s .. R8 - 1) to global memory
-      for (int r = 8 * s + ct; r < R8; r += 32 * kNdCons) {
-        const double4 *src = reinterpret_cast<const double4 *>(LpS + (size_t)r * kNdLpStride);
-        double4 *dst = reinterpret_cast<double4 *>(Lg + ((size_t)s * R8 + r) * 8);
-        dst[0] = src[0];
-        dst[1] = src[1];
-      }
     }
     // ---- contribution block
     double *Ug = g.Uws + nd.U_off;
+    const int offU = fr * 8 + fc;
 #pragma unroll
     for (int q = 0; q < TPW; ++q)
-      if (ubi[q] >= 0) *reinterpret_cast<double2 *>(Ug + (size_t)nd_tidx(ubi[q], ubj[q]) * 64 + laneC) = acc[q];
+      if (ub[q] >= 0) *reinterpret_cast<double2 *>(Ug + (size_t)nd_tidx(ub[q] >> 8, ub[q] & 0xff) * 64 + offU) = acc[q];
   }
   __syncthreads();
   if (timing && t == 0) {
-    atomicAdd(&g_nd_dbg[2 + min(nd.level, 6)], gtime() - t0);
+    const unsigned long long t1 = gtime();
+    atomicAdd(&g_nd_dbg[2 + min(nd.level, 6)], t1 - t0);
+    if (blockIdx.x == 0) g_nd_dbg[11] += t1 - t0;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // backward substitution of one front: x_own from x_boundary
 // ------------------------------------------------------------------------------------------------------------
-__device__ void nd_backward_node(const NdArgs &g, const NdSmem &sm, int node_id) {
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  if (t < (int)(sizeof(NdNode) / sizeof(int))) reinterpret_cast<int *>(sm.node)[t] = reinterpret_cast<const int *>(g.nodes + node_id)[t];
+// factor of a front that has left shared memory: node record, tiles and W blocks from global memory
+__device__ void nd_backward_load(const NdArgs &g, const NdSmem &sm, int node_id) {
+  const int t = threadIdx.x;
   __syncthreads();
+  nd_stage_node(g, sm, node_id, false);
   const NdNode &nd = *sm.node;
-  const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, R8 = 8 * (KT + BT), k8 = nd.k8;
-  const double *Lg = g.Lws + nd.L_off;
-  double *Ls = sm.win;                       // own x own part of L: panel s rows [8 s, k8) at ls_off(s)
-  double *Li = sm.Lp;                        // inverses of the diagonal blocks [KT][8][8]
-  double *tb = sm.Lp + (size_t)KT * 64;      // right-hand side of the block chain [k8]
-  auto ls_off = [&](int s) { return 8 * (s * k8 - 4 * s * (s - 1)); };
+  const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, NT = KT + BT;
+  const int n_tiles = KT * NT - (KT * (KT - 1)) / 2;
+  const double2 *src = reinterpret_cast<const double2 *>(g.Lws + nd.L_off);
+  double2 *dw = reinterpret_cast<double2 *>(sm.win), *di = reinterpret_cast<double2 *>(sm.winv);
+  const int nw = n_tiles * 32, ni = KT * 32;
+  for (int e = t; e < nw; e += kNdThreads) dw[e] = __ldcg(src + e);
+  for (int e = t; e < ni; e += kNdThreads) di[e] = __ldcg(src + nw + e);
+  __syncthreads();
+}
+
+// sm.node, sm.win and sm.winv hold the front
+__device__ void nd_backward_solve(const NdArgs &g, const NdSmem &sm) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const NdNode &nd = *sm.node;
+  const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, NT = KT + BT, R8 = 8 * NT, k8 = nd.k8;
+  auto colbase = [&](int J) { return J * NT - (J * (J - 1)) / 2; };
   for (int i = t; i < R8; i += kNdThreads) {
     double v = 0.0;
     const int bi = i - k8;
@@ -399,63 +520,35 @@ __device__ void nd_backward_node(const NdArgs &g, const NdSmem &sm, int node_id)
     }
     sm.xs[i] = v;
   }
-  for (int s = 0; s < KT; ++s) {
-    const int cnt = (k8 - 8 * s) * 8;
-    const double *src = Lg + ((size_t)s * R8 + 8 * s) * 8;
-    double *dst = Ls + ls_off(s);
-    for (int e = t; e < cnt; e += kNdThreads) dst[e] = __ldcg(src + e);
+  __syncthreads();
+  // boundary part: tb[c] = sum_{r >= k8} L[r][c] xs[r]   (warp per column tile; lane = column + 8 (row mod 4))
+  {
+    const int cc = lane & 7, rg = lane >> 3;
+    const int o0 = nd_sw(rg, cc), o1 = nd_sw(rg + 4, cc);
+    for (int J = warp; J < KT; J += kNdWarps) {
+      const double *col = sm.win + (size_t)(colbase(J) - J) * 64;   // tile (I, J) at col + 64 I
+      double p0 = 0.0, p1 = 0.0;
+      for (int I = KT; I < NT; ++I) {
+        p0 += col[(size_t)I * 64 + o0] * sm.xs[8 * I + rg];
+        p1 += col[(size_t)I * 64 + o1] * sm.xs[8 * I + rg + 4];
+      }
+      double p = p0 + p1;
+      p += __shfl_xor_sync(0xffffffffu, p, 8);
+      p += __shfl_xor_sync(0xffffffffu, p, 16);
+      if (rg == 0) sm.tb[8 * J + cc] = p;
+    }
   }
   __syncthreads();
-  // boundary part: tb[c] = sum_{r >= k8} L[r][c] xs[r]   (warp per panel, lanes over rows)
-  for (int s = warp; s < KT; s += kNdThreads / 32) {
-    double p[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) p[c] = 0.0;
-    for (int r = k8 + lane; r < R8; r += 32) {
-      const double xv = sm.xs[r];
-      const double2 *src = reinterpret_cast<const double2 *>(Lg + ((size_t)s * R8 + r) * 8);
-      const double2 w0 = __ldcg(src), w1 = __ldcg(src + 1), w2 = __ldcg(src + 2), w3 = __ldcg(src + 3);
-      const double4 v0 = make_double4(w0.x, w0.y, w1.x, w1.y), v1 = make_double4(w2.x, w2.y, w3.x, w3.y);
-      p[0] += v0.x * xv; p[1] += v0.y * xv; p[2] += v0.z * xv; p[3] += v0.w * xv;
-      p[4] += v1.x * xv; p[5] += v1.y * xv; p[6] += v1.z * xv; p[7] += v1.w * xv;
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) p[c] += __shfl_xor_sync(0xffffffffu, p[c], d);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) tb[8 * s + c] = p[c];
-    }
-  }
-  // inverses of the diagonal blocks: thread (s, c) solves L_ss y = e_c
-  if (t < 8 * KT) {
-    const int s = t >> 3, c = t & 7;
-    const double *Ld = Ls + ls_off(s);       // rows 8 s .. 8 s + 7 of panel s: L_ss[r][m] at Ld[r * 8 + m]
-    double y[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) y[r] = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const double l = Ld[r * 8 + r];
-      y[r] *= (l > 0.0) ? 1.0 / l : 0.0;     // non-positive pivot: zero component, like LDLT's D^+
-#pragma unroll
-      for (int q = r + 1; q < 8; ++q) y[q] -= Ld[q * 8 + r] * y[r];
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) Li[s * 64 + r * 8 + c] = y[r];
-  }
-  __syncthreads();
-  // block chain inside warp 0: x_s = -L_ss^-T tb_s, then tb[c] += L[8 s + q][c] x_q for the columns left of it
+  // block chain inside warp 0: x_s = -W_s^T tb_s, then tb[c] += L[8 s + q][c] x_q for the columns left of it
   if (warp == 0) {
     for (int s = KT - 1; s >= 0; --s) {
+      const double *wt = sm.winv + (size_t)s * 64;
       if (lane < 8) {
         double xa = 0.0, xb = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-          xa += (i >= lane) ? Li[s * 64 + i * 8 + lane] * tb[8 * s + i] : 0.0;
-          xb += (i + 1 >= lane) ? Li[s * 64 + (i + 1) * 8 + lane] * tb[8 * s + i + 1] : 0.0;
+          xa += (i >= lane) ? wt[nd_sw(i, lane)] * sm.tb[8 * s + i] : 0.0;
+          xb += (i + 1 >= lane) ? wt[nd_sw(i + 1, lane)] * sm.tb[8 * s + i + 1] : 0.0;
         }
         sm.xs[8 * s + lane] = -(xa + xb);
       }
@@ -464,30 +557,30 @@ __device__ void nd_backward_node(const NdArgs &g, const NdSmem &sm, int node_id)
 #pragma unroll
       for (int q = 0; q < 8; ++q) xq[q] = sm.xs[8 * s + q];
       for (int c = lane; c < 8 * s; c += 32) {
-        const double *Lc = Ls + ls_off(c >> 3) + (size_t)(8 * s - 8 * (c >> 3)) * 8 + (c & 7);   // L[8 s + q][c] at Lc[8 q]
+        const int J = c >> 3, cj = c & 7;
+        const double *Lt = sm.win + (size_t)(colbase(J) + s - J) * 64;   // tile (s, J)
         double u = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) u += Lc[8 * q] * xq[q];
-        tb[c] += u;
+        for (int q = 0; q < 8; ++q) u += Lt[nd_sw(q, cj)] * xq[q];
+        sm.tb[c] += u;
       }
       __syncwarp();
     }
   }
   __syncthreads();
   for (int j = t; j < nd.k; j += kNdThreads) g.x[nd.own0 + j] = sm.xs[j];
-  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // drivers
 // ------------------------------------------------------------------------------------------------------------
-template <int TPW>
+template <int TPW, int NC>
 __global__ void __launch_bounds__(kNdThreads, 1)
 k_nd_forward_level(NdArgs g, int list_begin, int timing, const LmState *st) {
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char nd_raw[];
   const NdSmem sm = nd_carve(nd_raw, g);
-  nd_forward_node<TPW>(g, sm, g.list[list_begin + blockIdx.x], timing);
+  nd_forward_node<TPW, NC>(g, sm, g.list[list_begin + blockIdx.x], timing);
 }
 
 __global__ void __launch_bounds__(kNdThreads, 1)
@@ -495,7 +588,8 @@ k_nd_backward_level(NdArgs g, int list_begin, const LmState *st) {
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char nd_raw[];
   const NdSmem sm = nd_carve(nd_raw, g);
-  nd_backward_node(g, sm, g.list[list_begin + blockIdx.x]);
+  nd_backward_load(g, sm, g.list[list_begin + blockIdx.x]);
+  nd_backward_solve(g, sm);
 }
 
 __device__ __forceinline__ int nd_ld_acquire(const int *p) {
@@ -516,7 +610,7 @@ __device__ __forceinline__ void nd_wait_flag(const NdArgs &g, int idx) {
         atomicExch(g.flags + 2 * g.n_nodes + 1, 1);   // sticky: reported by the host (never cleared by the launch)
         break;
       }
-      __nanosleep(40);
+      __nanosleep(20);
     }
   }
   __syncthreads();
@@ -529,31 +623,40 @@ __device__ __forceinline__ void nd_set_flag(const NdArgs &g, int idx) {
   }
 }
 
-// One launch: CTA p eliminates leaf p and climbs while it arrives as child[0]; flags hand the contribution blocks
-// (forward) and the solved boundary values (backward) over between CTAs.  The flags are cleared by a memset node
-// that precedes the launch.  Requires all CTAs to be co-resident (grid <= SM count, one CTA per SM).
-template <int TPW>
+// One launch: every CTA walks its list of fronts forward (children first) and then backward; a front whose child
+// (forward) or parent (backward) belongs to another CTA waits for that CTA's flag.  The flags are cleared by a
+// memset node that precedes the launch.  Requires all CTAs to be co-resident (grid <= SM count, one CTA per SM).
+template <int TPW, int NC>
 __global__ void __launch_bounds__(kNdThreads, 1)
 k_nd_persistent(NdArgs g, int timing, const LmState *st) {
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char nd_raw[];
   const NdSmem sm = nd_carve(nd_raw, g);
   const int lb = g.list_ptr[blockIdx.x], le = g.list_ptr[blockIdx.x + 1];
+  const int me = blockIdx.x;
   unsigned long long t0 = 0;
   if (timing && threadIdx.x == 0) t0 = gtime();
   for (int q = lb; q < le; ++q) {
     const int id = g.list[q];
-    const int other = g.nodes[id].child[1];
-    if (other >= 0) nd_wait_flag(g, other);
-    nd_forward_node<TPW>(g, sm, id, timing);
+    unsigned long long tw = 0;
+    if (timing && threadIdx.x == 0) tw = gtime();
+    for (int c = 0; c < 2; ++c) {
+      const int ch = g.nodes[id].child[c];
+      if (ch >= 0 && g.nodes[ch].cta != me) nd_wait_flag(g, ch);
+    }
+    if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[9] += gtime() - tw;
+    nd_forward_node<TPW, NC>(g, sm, id, timing);
+    if (timing && threadIdx.x == 0) tw = gtime();
     nd_set_flag(g, id);
+    if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[12] += gtime() - tw;
   }
   if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[0] = gtime() - t0;
   for (int q = le - 1; q >= lb; --q) {
     const int id = g.list[q];
+    if (q != le - 1) nd_backward_load(g, sm, id);     // the last front of the list is still resident
     const int parent = g.nodes[id].parent;
-    if (q == le - 1 && parent >= 0) nd_wait_flag(g, g.n_nodes + parent);   // further down the list the parent is mine
-    nd_backward_node(g, sm, id);
+    if (parent >= 0 && g.nodes[parent].cta != me) nd_wait_flag(g, g.n_nodes + parent);
+    nd_backward_solve(g, sm);
     nd_set_flag(g, g.n_nodes + id);
   }
   if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[1] = gtime() - t0;
@@ -568,23 +671,31 @@ struct NdDevice {
   int tpw = 0;
 };
 
+// consumer warps and accumulator tiles per consumer warp for fronts with up to BT boundary row tiles
+inline int nd_cons_for(int BT) { return BT >= 12 ? 11 : 9; }
 inline int nd_tpw_for(int BT) {
-  const int need = (BT * (BT + 1) / 2 + kNdCons - 1) / kNdCons;
-  const int opts[] = {4, 8, 12, 17, 24, 29};
-  for (int o : opts)
-    if (need <= o) return o;
+  const int nc = nd_cons_for(BT);
+  const int need = (BT * (BT + 1) / 2 + nc - 1) / nc;
+  const int opts9[] = {4, 8}, opts11[] = {8, 12, 14, 19, 24};
+  if (nc == 9) {
+    for (int o : opts9)
+      if (need <= o) return o;
+  } else {
+    for (int o : opts11)
+      if (need <= o) return o;
+  }
   return -1;
 }
 
-template <int TPW>
+template <int TPW, int NC>
 inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Saug, double *x, int mode, int timing,
                          const LmState *st, cudaStream_t stream, long long *launches) {
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    cudaFuncSetAttribute(k_nd_forward_level<TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
-    cudaFuncSetAttribute(k_nd_persistent<TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
+    cudaFuncSetAttribute(k_nd_forward_level<TPW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
+    cudaFuncSetAttribute(k_nd_persistent<TPW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
     cudaFuncSetAttribute(k_nd_backward_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
     attr_done[dev] = true;
   }
@@ -603,10 +714,10 @@ inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Sau
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)k_nd_persistent<TPW>, args);
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)k_nd_persistent<TPW, NC>, args);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      k_nd_persistent<TPW><<<pl.n_ctas, kNdThreads, dv.smem, stream>>>(a, timing, st);
+      k_nd_persistent<TPW, NC><<<pl.n_ctas, kNdThreads, dv.smem, stream>>>(a, timing, st);
       e = cudaGetLastError();
     }
     if (launches) *launches += 1;
@@ -616,7 +727,7 @@ inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Sau
   la.S = Saug; la.x = x;
   for (int l = 0; l < pl.n_levels; ++l) {
     const int cnt = pl.level_ptr[l + 1] - pl.level_ptr[l];
-    k_nd_forward_level<TPW><<<cnt, kNdThreads, dv.smem, stream>>>(la, pl.level_ptr[l], timing, st);
+    k_nd_forward_level<TPW, NC><<<cnt, kNdThreads, dv.smem, stream>>>(la, pl.level_ptr[l], timing, st);
   }
   for (int l = pl.n_levels - 1; l >= 0; --l) {
     const int cnt = pl.level_ptr[l + 1] - pl.level_ptr[l];
@@ -629,13 +740,19 @@ inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Sau
 // mode 5: one launch per level; mode 6: one persistent launch
 inline bool nd_enqueue(const NdPlan &pl, const NdDevice &dv, const double *Saug, double *x, int mode, int timing,
                        const LmState *st, cudaStream_t stream, long long *launches) {
+  if (nd_cons_for(pl.max_BT) == 9) {
+    switch (dv.tpw) {
+      case 4: return nd_enqueue_t<4, 9>(pl, dv, Saug, x, mode, timing, st, stream, launches);
+      case 8: return nd_enqueue_t<8, 9>(pl, dv, Saug, x, mode, timing, st, stream, launches);
+      default: return false;
+    }
+  }
   switch (dv.tpw) {
-    case 4: return nd_enqueue_t<4>(pl, dv, Saug, x, mode, timing, st, stream, launches);
-    case 8: return nd_enqueue_t<8>(pl, dv, Saug, x, mode, timing, st, stream, launches);
-    case 12: return nd_enqueue_t<12>(pl, dv, Saug, x, mode, timing, st, stream, launches);
-    case 17: return nd_enqueue_t<17>(pl, dv, Saug, x, mode, timing, st, stream, launches);
-    case 24: return nd_enqueue_t<24>(pl, dv, Saug, x, mode, timing, st, stream, launches);
-    case 29: return nd_enqueue_t<29>(pl, dv, Saug, x, mode, timing, st, stream, launches);
+    case 8: return nd_enqueue_t<8, 11>(pl, dv, Saug, x, mode, timing, st, stream, launches);
+    case 12: return nd_enqueue_t<12, 11>(pl, dv, Saug, x, mode, timing, st, stream, launches);
+    case 14: return nd_enqueue_t<14, 11>(pl, dv, Saug, x, mode, timing, st, stream, launches);
+    case 19: return nd_enqueue_t<19, 11>(pl, dv, Saug, x, mode, timing, st, stream, launches);
+    case 24: return nd_enqueue_t<24, 11>(pl, dv, Saug, x, mode, timing, st, stream, launches);
     default: return false;
   }
 }

@@ -1364,7 +1364,7 @@ static int upload_cholesky_plan(ba_solver *s) {
       a.n = nd.n; a.ld = nd.n + 1; a.bw = nd.bw;      // S and x are patched in at enqueue time
       a.Lws = s->d_nd_L.p; a.Uws = s->d_nd_U.p;
       a.flags = s->d_nd_flags.p; a.n_nodes = (int)nd.nodes.size();
-      a.max_R8 = nd.max_R8; a.max_tiles = nd.max_tiles;
+      a.max_R8 = nd.max_R8; a.max_tiles = nd.max_tiles; a.max_KT = nd.max_KT;
       dv.level_args = a; dv.level_args.list = s->d_nd_level_nodes.p; dv.level_args.list_ptr = nullptr;
       dv.cta_args = a; dv.cta_args.list = s->d_nd_cta_nodes.p; dv.cta_args.list_ptr = s->d_nd_cta_ptr.p;
     }
@@ -2490,7 +2490,8 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
       fprintf(stderr, "[ba_b200] partitioned banded (n=%d bw=%d depth=%d leaves=%d nodes=%zu): CTA 0 forward %llu ns, forward+backward %llu ns | per-level front ns (sum over nodes / replays):",
               s->chol.n, s->chol.bw, s->chol.nd.depth, s->chol.nd.n_leaves, s->chol.nd.nodes.size(), d3[0], d3[1]);
       for (int l = 0; l < 7; ++l) fprintf(stderr, " L%d %.0f", l, (double)d3[2 + l] * r);
-      fprintf(stderr, "\n");
+      fprintf(stderr, " | CTA 0 per replay: wait %.0f assemble %.0f (staged at %.0f, own columns at %.0f) factor %.0f flag %.0f | root diagonal warp cycles: waiting %.0f working %.0f\n", (double)d3[9] * r, (double)d3[10] * r,
+              (double)d3[13] * r, (double)d3[14] * r, (double)d3[11] * r, (double)d3[12] * r, (double)d3[8] * r, (double)d3[15] * r);
       unsigned long long z[16] = {0};
       cudaMemcpyToSymbol(g_nd_dbg, z, sizeof(z));
     } else if (s->chol.banded) {
@@ -2507,7 +2508,7 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
 }
 
 // Host-only: the partition plan of the banded reduced solve for N free poses and track span b (no device needed).
-// nodes_out: [cap][20] = own0 k k8 rb0 wr lb0 wl b8 child0 child1 parent rb_off lb_off rhs_off level cta seq L_off U_off 0
+// nodes_out: [cap][20] = own0 k k8 rb0 wr lb0 wl b8 child0 child1 parent rb_off lb_off rhs_off level cta seq L_off U_off bandT
 // meta: [8] = valid depth n_leaves n_levels n_ctas max_tiles max_R8 smem_bytes.  Returns the number of nodes.
 int ba_debug_nd_plan(int N, int b, int max_ctas, int force_depth, int force_chunk, long long *meta,
                      long long *nodes_out, int cap) {
@@ -2521,7 +2522,7 @@ int ba_debug_nd_plan(int N, int b, int max_ctas, int force_depth, int force_chun
   for (int i = 0; i < std::min(nn, cap) && nodes_out; ++i) {
     const NdNode &d = pl.nodes[i];
     const long long v[20] = {d.own0, d.k, d.k8, d.rb0, d.wr, d.lb0, d.wl, d.b8, d.child[0], d.child[1], d.parent,
-                             d.rb_off, d.lb_off, d.rhs_off, d.level, d.cta, d.seq, d.L_off, d.U_off, 0};
+                             d.rb_off, d.lb_off, d.rhs_off, d.level, d.cta, d.seq, d.L_off, d.U_off, d.bandT};
     std::copy(v, v + 20, nodes_out + (size_t)i * 20);
   }
   return nn;

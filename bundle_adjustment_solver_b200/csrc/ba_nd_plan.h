@@ -34,7 +34,10 @@ struct NdNode {
   int rb_off, lb_off, rhs_off;   // this node's U rows in the PARENT's front-local index space
   int level;            // forward level (children have smaller levels); backward runs the levels in reverse
   int cta, seq;         // persistent kernel: CTA that owns the node and position in that CTA's list
-  long long L_off;      // doubles: factor panels [KT][R8][8]
+  int bandT;            // row tiles below the diagonal tile of a column that can be nonzero in [own | Rb] (chain fronts:
+                        // band of S; separators: all).  Rows outside (except Lb / rhs) are skipped by the factorisation
+  long long L_off;      // doubles: factor tiles of the own columns [n_tiles][64] (swizzled 8 x 8 tiles, column by
+                        // column), then the inverses of the diagonal blocks [KT][64]
   long long U_off;      // doubles: contribution block, lower-triangular 8x8 tiles [BT (BT+1) / 2][64]
 };
 
@@ -52,24 +55,25 @@ struct NdPlan {
 
 inline int nd_pad8(int v) { return (v + 7) / 8 * 8; }
 constexpr int kNdMaxBT = 22;            // boundary tile rows a consumer warp can hold in registers (9 warps x 30 tiles)
-constexpr int kNdLpStride = 12;         // doubles per row of the published panel (8 + 4: conflict-free fragment reads)
 constexpr size_t kNdSmemLimit = 227 * 1024;
 
-// shared memory of one front: own trapezoid tiles + double-buffered panel + index maps
+// shared memory of one front: own trapezoid tiles + inverses of the diagonal blocks + x / rhs vectors of the backward
+// pass + child index maps + tile table (+ node records)
 inline size_t nd_front_smem(int KT, int BT) {
   const size_t tiles = (size_t)KT * (KT + 1) / 2 + (size_t)BT * KT;
   const size_t R8 = 8 * (size_t)(KT + BT);
-  return tiles * 64 * sizeof(double) + 2 * R8 * kNdLpStride * sizeof(double) + 2 * R8 * sizeof(int) +
-         R8 * sizeof(double) + 1024;
+  return (tiles + KT) * 64 * sizeof(double) + 2 * R8 * sizeof(double) + 2 * R8 * sizeof(int) + tiles * sizeof(int) +
+         1024;
 }
 
 // N free poses (n = 6N), b = largest pose distance inside a track (scalar half-bandwidth 6b + 5).
 // max_ctas: CTAs that can be co-resident (one per SM).  Returns pl.valid = false when the band is too wide or the
 // chain too short for a partition to pay.
+constexpr int kNdTotalCtas = 144;       // persistent launch: CTAs that must be co-resident (one per SM, B200 has 148)
 inline void nd_make_plan_depth(NdPlan &pl, int N, int b, int max_ctas, int force_depth, int force_chunk) {
   pl = NdPlan();
   pl.n = 6 * N; pl.b = b; pl.bw = 6 * b + 5;
-  if (N <= 0 || b <= 0) return;
+  if (N <= 0 || b <= 0 || 6 * N >= 65000) return;   // the kernels address S with 32-bit element offsets
   const int w = 6 * b;
   const int BT = nd_pad8(2 * w + 1) / 8;
   if (BT > kNdMaxBT) return;
@@ -173,7 +177,7 @@ inline void nd_make_plan_depth(NdPlan &pl, int N, int b, int max_ctas, int force
     NdNode &nd = nodes[i];
     const int KT = nd.k8 / 8, BTn = nd.b8 / 8, R8 = nd.k8 + nd.b8;
     nd.L_off = pl.L_doubles;
-    pl.L_doubles += (long long)KT * R8 * 8;
+    pl.L_doubles += ((long long)KT * (KT + 1) / 2 + (long long)BTn * KT + KT) * 64;
     nd.U_off = pl.U_doubles;
     pl.U_doubles += (long long)BTn * (BTn + 1) / 2 * 64;
     pl.max_KT = std::max(pl.max_KT, KT);
@@ -182,20 +186,37 @@ inline void nd_make_plan_depth(NdPlan &pl, int N, int b, int max_ctas, int force
     pl.max_tiles = std::max(pl.max_tiles, KT * (KT + 1) / 2 + BTn * KT);
     pl.smem_bytes = std::max(pl.smem_bytes, nd_front_smem(KT, BTn));
   }
-  // CTA lists: a CTA starts at the first chunk of a leaf and climbs while it arrives through child[0]
+  for (int i = 0; i < nn; ++i) {
+    NdNode &nd = nodes[i];
+    nd.bandT = (nd.child[1] >= 0) ? (1 << 20) : (7 + pl.bw + (nd.k8 - nd.k) + 7) / 8;
+  }
+  // CTA lists.  A CTA starts at the first chunk of a leaf and climbs while it arrives through child[0]; fronts near
+  // the root get CTAs of their own while the launch stays co-resident (all of them when the tree is small): their
+  // factor is then still in shared memory when the backward pass comes down the tree.
   {
+    std::vector<char> own(nn, 0);
+    int n_first = 0;
+    for (int i = 0; i < nn; ++i)
+      if (nodes[i].child[0] < 0 && nodes[i].child[1] < 0) ++n_first;
+    int budget = std::max(0, std::max(kNdTotalCtas, max_ctas) - n_first);
+    for (int l = pl.n_levels - 1; l >= 1 && budget > 0; --l)
+      for (int q = pl.level_ptr[l]; q < pl.level_ptr[l + 1] && budget > 0; ++q) {
+        own[pl.level_nodes[q]] = 1;
+        --budget;
+      }
     int n_cta = 0;
     for (int i = 0; i < nn; ++i) nodes[i].cta = -1;
     pl.cta_ptr.assign(1, 0);
     for (int i = 0; i < nn; ++i) {
-      if (nodes[i].child[0] >= 0 || nodes[i].child[1] >= 0) continue;   // not a first chunk
+      const bool first = nodes[i].child[0] < 0 && nodes[i].child[1] < 0;
+      if (!first && !own[i]) continue;
       int t = i, seq = 0;
       for (;;) {
         nodes[t].cta = n_cta;
         nodes[t].seq = seq++;
         pl.cta_nodes.push_back(t);
         const int p = nodes[t].parent;
-        if (p < 0 || nodes[p].child[0] != t) break;
+        if (p < 0 || nodes[p].child[0] != t || own[p]) break;
         t = p;
       }
       pl.cta_ptr.push_back((int)pl.cta_nodes.size());
