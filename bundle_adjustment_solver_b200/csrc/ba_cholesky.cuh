@@ -509,11 +509,8 @@ inline void cholesky_solve_enqueue(const CholeskyPlan &pl, double *Saug, double 
     const cudaError_t ce = cudaGetLastError();  // cluster launch unavailable: fall through to the multi-kernel path
     if (verbose) fprintf(stderr, "[ba_b200] cluster launch failed: %s\n", cudaGetErrorString(ce));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem);
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCholDiagSmem);
   for (int k0 = 0, kb = 0; k0 < n; k0 += kNB, ++kb) {
     const int nb = (n - k0 < kNB) ? (n - k0) : kNB;
     double *Li = linv + (size_t)kb * kNB * kNB;

@@ -970,11 +970,9 @@ k_chol_banded_smem(double *A, int n, int bw, double *x_out, double *linv, int ti
 template <int W>
 inline bool launch_band4(double *Saug, int n, int bw, double *x, double *linv, int timing, const LmState *st,
                          cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first())
     cudaFuncSetAttribute(k_chol_banded_smem<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band4Smem<W>));
-    attr_set = true;
-  }
   k_chol_banded_smem<W><<<1, kBand4Threads, sizeof(Band4Smem<W>), stream>>>(Saug, n, bw, x, linv, timing, st);
   return cudaGetLastError() == cudaSuccess;
 }

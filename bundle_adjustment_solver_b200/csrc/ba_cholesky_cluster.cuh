@@ -8,6 +8,8 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include <cstdlib>
 
 #include "ba_device.cuh"
@@ -26,6 +28,21 @@ constexpr int kClusterMaxN = kCB * kCLD;  // x is staged in the second operand b
 // reciprocal off the slow division path (it sits on the per-column critical path of the sweep): hardware
 // approximation (~20 bits) refined by two Newton steps (-> ~1e-24 relative, i.e. limited by rounding); no
 // branches, no conversions.
+// cudaFuncSetAttribute applies to the current device only: one opt-in per (kernel set, device), thread-safe
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) return true;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 __device__ __forceinline__ double fast_rcp(double d) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
@@ -448,11 +465,10 @@ inline bool cholesky_cluster_enqueue(double *Saug, int n, const int *d_rows_ptr,
                                      const int *d_first_tile, double *x, const LmState *st, cudaStream_t stream,
                                      int cluster_size) {
   static const int timing = getenv("BA_B200_VERBOSE") != nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(k_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmem);
     cudaFuncSetAttribute(k_chol_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster_size);

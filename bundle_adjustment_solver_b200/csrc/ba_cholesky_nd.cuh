@@ -690,14 +690,11 @@ inline int nd_tpw_for(int BT) {
 template <int TPW, int NC>
 inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Saug, double *x, int mode, int timing,
                          const LmState *st, cudaStream_t stream, long long *launches) {
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(k_nd_forward_level<TPW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
     cudaFuncSetAttribute(k_nd_persistent<TPW, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
     cudaFuncSetAttribute(k_nd_backward_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
-    attr_done[dev] = true;
   }
   if (mode == 6) {
     cudaMemsetAsync(dv.cta_args.flags, 0, (size_t)(2 * dv.cta_args.n_nodes + 1) * sizeof(int), stream);

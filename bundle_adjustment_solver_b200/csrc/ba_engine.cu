@@ -1907,7 +1907,18 @@ int ba_finalize(ba_solver *s) {
 int ba_update_parameters(ba_solver *s, const double *T_jw, const double *X) {
   if (!s || !s->finalized) return BA_ERR_STATE;
   CUDA_TRY(cudaSetDevice(s->device));
-  // the accepted parameters live in buffer `cur`; reset to buffer 0
+  // the accepted parameters live in buffer `cur`; reset to buffer 0.  A set that is not supplied keeps its accepted
+  // values: they are copied from buffer `cur` into the other buffer before `cur` is reset
+  if (!T_jw || !X) {
+    LmState hs;
+    CUDA_TRY(cudaMemcpyAsync(&hs, s->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const int cur = hs.cur & 1;
+    if (!T_jw)
+      CUDA_TRY(cudaMemcpyAsync(s->d_poses[cur ^ 1].p, s->d_poses[cur].p, (size_t)s->N_total * 12 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if (!X)
+      CUDA_TRY(cudaMemcpyAsync(s->d_points[cur ^ 1].p, s->d_points[cur].p, (size_t)s->M_total * 3 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  }
   if (T_jw) {
     s->h_poses.assign(T_jw, T_jw + (size_t)s->N_total * 12);
     CUDA_TRY(cudaMemcpyAsync(s->d_poses[0].p, T_jw, (size_t)s->N_total * 12 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -2024,11 +2035,10 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   if (ev) cudaEventRecord(ev[Phase::Schur], st);
   // tile landmarks: linearisation + C^-1 + Schur products fused (DMMA)
   if (s->n_schur_chunks > 0) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.first()) {
       cudaFuncSetAttribute(k_build_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
       cudaFuncSetAttribute(k_build_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemBytes);
-      attr_set = true;
     }
     const TileLaunch &tl = s->tile_launch;
     const size_t smem = (size_t)tl.G * tl.bufD * sizeof(double);
@@ -2214,9 +2224,13 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
     s->launches += 3;
     CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->d_scal.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
-  cudaEvent_t ev_begin, ev_end;
-  CUDA_TRY(cudaEventCreate(&ev_begin));
-  CUDA_TRY(cudaEventCreate(&ev_end));
+  struct EventPair {   // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev_pair;
+  CUDA_TRY(cudaEventCreate(&ev_pair.a));
+  CUDA_TRY(cudaEventCreate(&ev_pair.b));
+  cudaEvent_t ev_begin = ev_pair.a, ev_end = ev_pair.b;
   CUDA_TRY(cudaEventRecord(ev_begin, st));
   double phase_ms[Phase::Count] = {0};
   int it_launched = 0;
@@ -2279,8 +2293,6 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   }
   float dev_ms = 0.f;
   cudaEventElapsedTime(&dev_ms, ev_begin, ev_end);
-  cudaEventDestroy(ev_begin);
-  cudaEventDestroy(ev_end);
   if (use_graph) s->launches += s->graph_nodes * it_launched;
   if (s->profile && !use_graph) {
     for (int it = 0; it < std::min(n_done, it_launched); ++it) {
@@ -2555,6 +2567,7 @@ int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long lon
   if (int rc = ensure_stream(s)) return rc;
   ncclUniqueId id;
   std::memcpy(&id, id128, 128);
+  if (s->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(s->comm); s->comm = nullptr; }   // re-initialisation
   ncclResult_t r = g_nccl.CommInitRank(&s->comm, nranks, id, rank);
   if (r != ncclSuccess) { s->err = "ncclCommInitRank failed"; s->comm = nullptr; return BA_ERR_NCCL; }
   s->rank = rank; s->n_ranks = nranks; s->global_M = global_M; s->global_n_obs = global_n_obs;

@@ -239,6 +239,34 @@ def scene_c5(seed=0, pixel_sigma=0.0, scale=1.0):
                             name="C5_venice_shaped")
 
 
+def restrict_poses(sc, lo, hi):
+    """Sub-scene of a FullScene: poses [lo, hi) re-indexed from 0, the observations made from them in their original
+    relative (insertion) order, and the landmarks those observations see (re-indexed in id order).  A window of a
+    trajectory scene keeps the structure of the whole (track lengths, band of the reduced system) at a size the CPU
+    oracle solves in seconds."""
+    import copy
+    keep = (sc.obs_pose >= lo) & (sc.obs_pose < hi)
+    pts = np.unique(sc.obs_point[keep])
+    remap = np.full(len(sc.points_init), -1, dtype=np.int64)
+    remap[pts] = np.arange(len(pts))
+    out = copy.copy(sc)
+    out.poses_true = sc.poses_true[lo:hi]
+    out.poses_init = sc.poses_init[lo:hi]
+    fp = np.asarray(sc.fixed_poses, dtype=np.int64)
+    out.fixed_poses = fp[(fp >= lo) & (fp < hi)] - lo
+    out.points_true = sc.points_true[pts]
+    out.points_init = sc.points_init[pts]
+    fx = np.asarray(sc.fixed_points, dtype=np.int64)
+    out.fixed_points = remap[fx[remap[fx] >= 0]] if len(fx) else fx
+    out.obs_cam = sc.obs_cam[keep]
+    out.obs_pose = (sc.obs_pose[keep] - lo).astype(np.int32)
+    out.obs_point = remap[sc.obs_point[keep]].astype(np.int32)
+    out.obs_uv = sc.obs_uv[keep]
+    out.name = f"{sc.name}[poses {lo}:{hi}]"
+    out.meta = dict(sc.meta, pose_window=(lo, hi))
+    return out
+
+
 @dataclass
 class PoseOnlyBatch:
     kind: int                   # 0 mono-6dof, 1 stereo-6dof, 2 mono-planar3dof, 3 stereo-planar3dof

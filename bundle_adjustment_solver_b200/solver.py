@@ -298,6 +298,16 @@ class FullBundleAdjustmentSolver:
     def get_points(self):
         return np.asarray(self.points).reshape(-1, 3)
 
+    def get_internal(self):
+        """Accepted parameters in the engine's internal units (T_jw as 12 doubles, X), as ba_get_poses / ba_get_points
+        return them; same layout as the oracle's get_internal()."""
+        n_p, n_x = len(np.asarray(self.poses).reshape(-1, 16)), len(np.asarray(self.points).reshape(-1, 3))
+        T = np.zeros((n_p, 12))
+        X = np.zeros((n_x, 3))
+        _check(self.L.ba_get_poses(self.h, ptr(T)), self.L, self.h, "ba_get_poses")
+        _check(self.L.ba_get_points(self.h, ptr(X)), self.L, self.h, "ba_get_points")
+        return T, X
+
     def sizes(self):
         out = np.zeros(6, dtype=np.int64)
         _check(self.L.ba_get_sizes(self.h, ptr(out)), self.L, self.h, "ba_get_sizes")

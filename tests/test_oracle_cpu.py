@@ -238,20 +238,51 @@ def test_lm_loop_quirks_and_convergence():
     assert len(infos) == 1 and not conv    # ...unless it is the last allowed iteration
 
 
+REJECT_KW = dict(max_num_iterations=25, threshold_cost_change=1e-9, threshold_step_size=1e-9, initial_lambda=1e-10)
+
+
 def test_rejected_step_reporting():
-    """A SKIPPED iteration reverts the parameters, reports previous cost / 0 change (:995-1000) and raises
-    lambda x3 (clamped at 100).  Forced with a huge Huber threshold inversion: start at the optimum with
-    lambda tiny so the first step cannot improve."""
-    sc = _small_scene(seed=5)
-    sc.poses_init = sc.poses_true.copy(); sc.points_init = sc.points_true.copy()
+    """The reject branch of the LM loop (full_bundle_adjustment_solver.cpp:939-953, 995-1005, 457-482), forced by
+    starting the test_ba.cpp scene undamped (initial_lambda 1e-10): Gauss-Newton steps from the noisy start
+    overshoot, rho <= 0.25, the step is SKIPPED.  Every assertion is unconditional."""
+    sc = scenes.scene_test_ba(seed=0)
     o = load_oracle(sc)
-    infos, _ = o.solve(oracle.default_full_options(max_num_iterations=3, threshold_cost_change=0.0,
-                                                   threshold_step_size=0.0, initial_lambda=1.0))
+    infos, conv = o.solve(oracle.default_full_options(**REJECT_KW))
     st = [i.iteration_status for i in infos]
-    if 2 in st:
-        k = st.index(2)
-        assert infos[k].cost_change == 0.0
-        assert infos[k].damping_term <= 100.0
+    n_obs = o.sizes()["n_obs"]
+    assert len(infos) == 25 and not conv
+    assert st.count(2) >= 8 and st.count(0) >= 2 and st.count(1) >= 8     # SKIPPED, UPDATE, UPDATE_TRUST_MORE all occur
+    assert st[:5] == [1, 1, 1, 1, 2] and 2 in st[12:]
+    lam = [1e-10] + [i.damping_term for i in infos]
+    inc, dec = float(np.float32(3.0)), float(np.float32(0.33))
+    for k, i in enumerate(infos):
+        if st[k] == 2:
+            # SKIPPED row: cost replaced by the previous cost, change 0, avg = sqrt(prev / n_obs) (:995-1000); lambda x3
+            assert i.cost_change == 0.0
+            assert i.average_reprojection_error == pytest.approx(np.sqrt(i.cost / n_obs), rel=1e-14)
+            assert i.damping_term == pytest.approx(min(100.0, lam[k] * inc), rel=1e-15)
+        elif st[k] == 1:
+            assert i.damping_term == pytest.approx(max(1e-10, lam[k] * dec), rel=1e-15)
+            assert i.average_reprojection_error == pytest.approx(i.cost / n_obs, rel=1e-14)
+        else:
+            assert i.damping_term == lam[k]                                # 0.25 < rho <= 0.5: lambda kept
+    # `previous_cost = current_cost` is unconditional (:1005): the row after a SKIPPED row reports the REJECTED trial
+    # cost as its previous cost, not the cost of the parameters that were kept
+    k = st.index(2)
+    assert st[k + 1] == 2
+    assert infos[k].cost == infos[k - 1].cost                  # first SKIPPED row: the accepted cost
+    assert infos[k + 1].cost > infos[k].cost * (1 + 1e-4)      # next row: the rejected trial's (higher) cost
+    # the rejected trial cost of iteration k is what a run stopped there saw (debug dump: last trial cost)
+    o2 = load_oracle(sc)
+    kw = dict(REJECT_KW); kw["max_num_iterations"] = k + 1
+    infos2, _ = o2.solve(oracle.default_full_options(**kw))
+    assert [i.iteration_status for i in infos2] == st[:k + 1]
+    assert o2.dump("scalars")[1] == infos[k + 1].cost
+    # Revert (:468-482): after the SKIPPED iteration the parameters are the reserved ones -> their cost is the accepted one
+    assert o2.cost() == pytest.approx(infos[k - 1].cost, rel=1e-13)
+    # a later accepted step can even raise the cost of the kept parameters: rho is measured against the rejected cost
+    kept = [(j, infos[j].cost) for j in range(len(st)) if st[j] != 2]
+    assert any(c1 > c0 for (_, c0), (_, c1) in zip(kept, kept[1:]))
 
 
 def test_corrected_mode_reaches_scipy_minimum():

@@ -29,14 +29,20 @@ def _both(pb, opt=OPT, hist=False):
     return out, ref
 
 
-def _check(out, ref, pb, pose_tol=2e-4):
+def _check(out, ref, pb, pose_tol=2e-4, late_frames=0):
+    """late_frames: frames allowed to differ by TWO iterations (a float-level difference of the error next to the
+    cost-change threshold delays the stop by one more step; seen on 1 of 4096 noisy frames)."""
     nf = pb.n_frames
     assert np.abs(out["poses"] - ref["poses"]).max() < pose_tol
+    late = 0
     for f in range(nf):
         a, b = out["results"][f], ref["results"][f]
         assert a.success == b.success == 1
         assert a.converged == b.converged
-        assert abs(a.n_iterations - b.n_iterations) <= 1, (f, a.n_iterations, b.n_iterations)
+        d = abs(a.n_iterations - b.n_iterations)
+        assert d <= 2, (f, a.n_iterations, b.n_iterations)
+        late += d == 2
+    assert late <= late_frames, late
     for k in ("mask_left", "mask_right"):
         diff = np.count_nonzero(out[k] != ref[k])
         assert diff <= max(2, 1e-4 * out[k].size), (k, diff)
@@ -94,3 +100,14 @@ def test_full_size_c2_properties():
     assert all(r.success and r.converged for r in out["results"])
     assert np.abs(out["poses"] - pb.poses_true).max() < 2e-3
     assert max(r.n_iterations for r in out["results"]) <= 15
+
+
+@pytest.mark.parametrize("sigma", [0.0, 0.5])
+def test_full_size_c2_matches_oracle(sigma):
+    """Config C2 at full size (4096 frames x 300 stereo points, 2.4 M observations) against the float oracle on EVERY
+    frame (the oracle needs about a second for the batch): poses, verdicts, iteration counts, inlier masks."""
+    pb = scenes.scene_poseonly_batch(n_frames=4096, n_points=300, seed=0, pixel_sigma=sigma, stereo=True)
+    out, ref = _both(pb)
+    _check(out, ref, pb, late_frames=4)        # 4 of 4096
+    if sigma == 0.0:
+        assert np.abs(out["poses"] - pb.poses_true).max() < 2e-3
