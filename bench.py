@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 bundle-adjustment engine.
 
-Metric (BASELINE.json): LM iters/s & Schur-build obs/s.  One "step" = one full Levenberg-Marquardt
-iteration (linearise, Schur complement, reduced solve, back-substitution, trial cost, accept/lambda)
-over the workload's observations.  `value` = observations x LM iterations per second (whole job, all
-ranks), device-resident; `lm_iters_per_s` and `schur_build_obs_per_s` are reported beside it.
-Workload at N=1: config C3 "stereo full BA, 200 poses / 50k landmarks / ~1M observations on 1 B200".
-N>1 (weak scaling): every rank holds all 200 poses and its own 50k landmarks (+~1M observations);
-[S | rhs] and the LM scalars are all-reduced over NCCL every iteration.
+Metric (BASELINE.json): LM iters/s & Schur-build obs/s at 1/2/4/8 B200; time-to-converge vs CPU.  One "step" = one
+full Levenberg-Marquardt iteration (linearise, Schur complement, reduced solve, back-substitution, trial cost,
+accept / lambda) over the workload's observations.  `value` = observations x LM iterations per second (whole job,
+all ranks), device-resident; `lm_iters_per_s` and `schur_build_obs_per_s` are reported beside it.
+
+Workload
+  N = 1 : config C3 "stereo full BA, 200 poses / 50k landmarks / ~1M observations on 1 B200" (the configuration the
+          metric is quoted on).
+  N > 1 : config C4 "2000 poses / 1M landmarks / ~8M observations landmark-sharded over the GPUs with S all-reduce":
+          ONE problem, every rank keeps a contiguous landmark range (strong scaling).  The same line carries
+          `strong_scaling` (the same problem on rank 0 alone), `mgpu_parity` (the first sharded LM iterations
+          against that single-GPU solve), `weak_c3` (every rank its own 50k landmarks on the same 200 poses) and the
+          frame-sharded pose-only batch C2.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference ...                     # the reference's algorithm on host cores (oracle)
 """
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -38,6 +46,7 @@ def emit(line):
 
 METRIC = "LM-iteration observation throughput (observations x LM iters/s; full iteration: linearise, Schur, solve, back-substitute, cost/accept)"
 UNIT = "obs/s"
+FP64_TENSOR_PEAK = 37.1   # TFLOP/s, measured on this pool's B200 (profiles/micro/dmma_peak.cu -> profiles/micro/dmma_peak.txt)
 
 
 def peaks():
@@ -69,33 +78,91 @@ WORKLOAD_NAMES = {
 }
 
 
-def algorithmic_bytes(sz, n_obs_free_pose):
-    """Algorithmic bytes / flops per LM iteration of the implemented design (DESIGN.md 'Kernels').
-    pose side  (k_linearize_by_pose + k_finish_poses): 28 B/obs in pose order, A/a and the S diagonal
+def algorithmic_bytes(sz, n_obs_free_pose, solve_info):
+    """Algorithmic bytes per LM iteration of the implemented design (DESIGN.md 'Kernels').
+    pose side  (k_linearize_by_pose + k_finish_poses): 28 B/obs in pose order, A / a and the S diagonal; clearing S costs
+               8 (6N+1)^2 bytes when the whole buffer is cleared and 8 (6N)(bw+2) when only the band is
     point side (k_build_tiles, fused K1+K3+K4): 20 B/obs (pixel, camera) + 24 B per (pose, landmark) incidence,
-               pose/point gathers, B written once (144 B/pair), per-landmark blocks (144 B), S tile flush
+               pose / point gathers, B written once (144 B/pair), per-landmark blocks (144 B), S tile flush
     back-substitution: B read once (144 B/pair) + per-landmark blocks;   cost: 28 B/obs."""
     O, Nt, Mt, N, M, P = sz["n_obs"], sz["N_total"], sz["M_total"], sz["N"], sz["M"], sz["P"]
     n = 6 * N
+    clear = 8 * n * (int(solve_info["bw"]) + 2) if solve_info["band_clear"] else 8 * (n + 1) * (n + 1)
     b = {}
-    b["linearize"] = 28 * n_obs_free_pose + 96 * Nt + 24 * Mt + 2 * 336 * N + 8 * (n + 1) * (n + 1)  # pose side + S memset
-    b["schur"] = 20 * O + 24 * P + 96 * Nt + 24 * Mt + 144 * P + 144 * M + 8 * n * (n + 1) // 2 + 8 * n
+    b["linearize"] = 28 * n_obs_free_pose + 96 * Nt + 24 * Mt + 2 * 336 * N + clear
+    b["schur"] = 20 * O + 24 * P + 96 * Nt + 24 * Mt + 144 * P + 144 * M + int(solve_info["alg_bytes"])
     b["backsub"] = 144 * P + 8 * P + 48 * N + 24 * M + (144 + 24 + 24 + 24 + 24) * Mt
     b["update_cost"] = 28 * O + 96 * Nt * 2 + 24 * Mt
-    b["solve_flops"] = n ** 3 / 3.0 + 2.0 * n * n
-    # build flops: ~330 per observation (projection, weight, Jacobians, C/b/B) + Schur 216 per block pair
     b["schur_flops"] = 330.0 * O
     return b
 
 
-def poseonly_c2(device, stream, frames=4096, points=300, reps=5):
-    """Config C2: batched 6-DoF stereo pose-only BA, `frames` independent frames x `points` observations,
-    device-resident (ba_poseonly_upload / ba_poseonly_run), timed with CUDA events on the launching stream."""
+def solve_info(L, s):
+    import ctypes as C
+    name = C.create_string_buffer(512)
+    vals = np.zeros(8)
+    rc = L.ba_debug_solve_info(s.h, name, 512, vals.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise SystemExit("ba_debug_solve_info failed")
+    return {"kernel": name.value.decode(), "alg_flops": float(vals[0]), "exec_flops": float(vals[1]),
+            "dense_flops": float(vals[2]), "bw": int(vals[3]), "ctas": int(vals[4]), "chain_steps": float(vals[5]),
+            "band_clear": bool(vals[6]), "alg_bytes": float(vals[7])}
+
+
+def ncu_traffic_table():
+    """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, MB) of each kernel from the newest
+    committed `ncu --set full` summary of the default C3 workload (profiles/rNN_ncu_full_c3_summary.md)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_c3_summary.md")))
+    if not files:
+        return None, None
+    tab = {}
+    hdr = None
+    for ln in open(files[-1]):
+        cells = [c.strip() for c in ln.strip().strip("|").split("|")]
+        if ln.startswith("| kernel"):
+            hdr = [re.sub(r"\s*\[.*\]", "", c) for c in cells]
+            continue
+        if hdr is None or not ln.startswith("|") or ln.startswith("|---"):
+            continue
+        try:
+            row = dict(zip(hdr, cells))
+            tab[row["kernel"]] = (float(row["dram_rd"]) + float(row["dram_wr"])) * 1e6
+        except (KeyError, ValueError):
+            continue
+    return tab, os.path.relpath(files[-1], ROOT)
+
+
+PHASE_KERNELS = {   # kernel-name prefixes of the ncu summary per phase
+    "linearize": ("k_linearize_by_pose", "k_finish_poses"),
+    "schur": ("k_build_tiles", "k_linearize_by_point", "k_pair_blocks", "k_finish_points", "k_schur"),
+    "solve": ("k_nd_", "k_chol_"),
+    "backsub": ("k_backsub_pairs", "k_backsub_points"),
+    "update_cost": ("k_cost", "k_update_poses", "k_reduce_decide"),
+}
+
+
+def phase_traffic(tab, phase):
+    if not tab:
+        return None
+    v = [b for k, b in tab.items() if k.startswith(PHASE_KERNELS[phase])]
+    return float(sum(v)) if v else None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# config C2: batched pose-only BA
+# ------------------------------------------------------------------------------------------------------------
+def poseonly_c2(device, stream, rank, world, dist, dev, frames=4096, points=300, reps=5, cpu_legs=True):
+    """Config C2: batched 6-DoF stereo pose-only BA, `frames` independent frames x `points` observations, frames split
+    evenly over the ranks with no communication.  Device-resident timing (ba_poseonly_upload / ba_poseonly_run, CUDA
+    events on the launching stream), end to end through ba_poseonly_solve_batched from host buffers, and the float
+    oracle on 1 and on all host cores (rank 0, N = 1)."""
     import ctypes as C
     import torch
-    from bundle_adjustment_solver_b200 import capi, scenes
+    from bundle_adjustment_solver_b200 import capi, scenes, sharding
+    from bundle_adjustment_solver_b200 import solver as S
     L = capi.lib()
-    pb = scenes.scene_poseonly_batch(n_frames=frames, n_points=points, seed=1)
+    full = scenes.scene_poseonly_batch(n_frames=frames, n_points=points, seed=1)
+    pb = sharding.shard_poseonly_batch(full, rank, world) if world > 1 else full
     f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
     off = np.ascontiguousarray(pb.offsets, dtype=np.int32)
     arrs = [f32(pb.points), f32(pb.px_left), f32(pb.px_right), f32(pb.intr_left), f32(pb.intr_right),
@@ -107,6 +174,9 @@ def poseonly_c2(device, stream, frames=4096, points=300, reps=5):
     opt = capi.PoseOnlyOptions(1e-6, 1e-6, 1.5, 2.5, 100)
     for _ in range(3):
         L.ba_poseonly_run(h, C.byref(opt), C.c_void_p(stream.cuda_stream))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(reps):
@@ -114,17 +184,74 @@ def poseonly_c2(device, stream, frames=4096, points=300, reps=5):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    res = (capi.PoseOnlyResult * pb.n_frames)()
+    res = (capi.PoseOnlyResult * max(1, pb.n_frames))()
     poses = np.zeros((pb.n_frames, 12), dtype=np.float32)
     L.ba_poseonly_download(h, capi.ptr(poses), None, None, res)
     L.ba_poseonly_free(h)
-    iters = float(np.mean([res[k].n_iterations for k in range(pb.n_frames)]))
+    iters_sum = float(np.sum([res[k].n_iterations for k in range(pb.n_frames)]))
     n_pts = int(off[-1])
-    return {"workload": f"C2 batched 6-DoF stereo pose-only BA, {frames} frames x {points} points (FP32)",
-            "ms_per_batch": ms, "frames_per_s": pb.n_frames / (ms * 1e-3),
-            "point_iterations_per_s": n_pts * iters / (ms * 1e-3), "mean_gn_iterations": iters,
-            "max_pose_err_vs_truth": float(np.abs(poses - pb.poses_true).max()),
-            "bytes_per_solve": int(28 * n_pts), "note": "one warp per frame, persistent over the GN iterations; working set is L2-resident"}
+    # end to end from host buffers through the reference-facing batched entry point (H2D + solve + D2H inside)
+    po = S.PoseOnlyBundleAdjustmentSolver(device=device)
+    run = lambda: po.solve_batched(pb.kind, pb.offsets, pb.points, pb.px_left, pb.px_right, pb.intr_left, pb.intr_right,
+                                   pb.poses_init, opt, left_to_right=pb.left_to_right)
+    run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = run()
+    e2e_s = time.perf_counter() - t0
+    agg = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    tot = torch.tensor([iters_sum, float(n_pts), float(np.abs(poses - pb.poses_true).max()) if pb.n_frames else 0.0],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        err = tot[2:].clone()
+        dist.all_reduce(tot)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        tot[2] = err[0]
+    ms, e2e_s = float(agg[0]), float(agg[1])
+    iters = float(tot[0]) / frames
+    all_pts = float(tot[1])
+    # 240 FP32 flop per stereo point per GN iteration; FP32 ALU peak = SMs x 128 lanes x 2 x clock
+    prop = torch.cuda.get_device_properties(device)
+    fp32_peak = prop.multi_processor_count * 128 * 2 * 1.965e9 / 1e12 * world
+    fp32_tf = 240.0 * all_pts * iters / (ms * 1e-3) / 1e12
+    r = {"workload": f"C2 batched 6-DoF stereo pose-only BA, {frames} frames x {points} points (FP32)",
+         "n_gpus": world, "frames_per_gpu": pb.n_frames, "sharding": "frames split evenly over the ranks, no communication",
+         "ms_per_batch": ms, "frames_per_s": frames / (ms * 1e-3),
+         "point_iterations_per_s": all_pts * iters / (ms * 1e-3), "mean_gn_iterations": iters,
+         "max_pose_err_vs_truth": float(tot[2]),
+         "roofline": {"bound": "fp32 alu / latency (34 MB working set is L2-resident; not HBM)", "achieved_tflops": fp32_tf,
+                      "peak_tflops": fp32_peak, "frac": fp32_tf / fp32_peak,
+                      "peak_source": "SMs x 128 FMA lanes x 2 x 1.965 GHz (nominal FP32 ALU rate, no measured figure in MEASURED_PEAKS.json)",
+                      "hbm_frac_if_streamed_once": 28.0 * all_pts / (ms * 1e-3) / 1e9 / (peaks()[0] * world)},
+         "e2e": {"frames_per_s": frames / e2e_s, "wall_ms": 1e3 * e2e_s,
+                 "h2d_bytes": int(28 * n_pts + 48 * pb.n_frames + 4 * len(off)), "d2h_bytes": int(48 * pb.n_frames + 2 * n_pts + 24 * pb.n_frames),
+                 "through": "ba_poseonly_solve_batched (host buffers in, poses / masks / results out)"},
+         "note": "one warp per frame, persistent over the GN iterations"}
+    del out
+    if cpu_legs and rank == 0 and world == 1:
+        import oracle
+        from concurrent.futures import ThreadPoolExecutor
+        oopt = oracle.PoseOnlyOptions(1e-6, 1e-6, 1.5, 2.5, 100)
+        solve = lambda b, native=True: oracle.poseonly_solve_batched(b.kind, b.offsets, b.points, b.px_left, b.px_right, b.intr_left,
+                                                                    b.intr_right, b.poses_init, oopt, left_to_right=b.left_to_right,
+                                                                    native=native)
+        solve(sharding.shard_poseonly_batch(full, 0, 64))          # builds / loads the native library
+        t0 = time.perf_counter()
+        solve(full)
+        t1 = time.perf_counter() - t0
+        cores = os.cpu_count() or 1
+        parts = [sharding.shard_poseonly_batch(full, q, cores) for q in range(cores)]
+        with ThreadPoolExecutor(cores) as ex:                      # ctypes releases the GIL during the call
+            t0 = time.perf_counter()
+            list(ex.map(solve, parts))
+            tn = time.perf_counter() - t0
+        r["cpu_baseline"] = {"kind": "port", "unit": "frames/s", "one_core": {"value": frames / t1, "cores": 1, "wall_s": t1},
+                             "all_cores": {"value": frames / tn, "cores": cores, "wall_s": tn},
+                             "sample": f"all {frames} frames, float oracle built -O2 -march=native (the reference's flags)"}
+    return r
 
 
 class ClockSampler:
@@ -179,37 +306,78 @@ class ClockSampler:
                 "samples": len(sm), "samples_under_load": int(sum(loaded))}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own algorithm on the host cores.  The reference cannot be
-    compiled here (no Eigen/Ceres/OpenCV), so this is the oracle port (kind 'port'), single thread like
-    the reference (it has no threads), on a bounded number of LM iterations of the same workload."""
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker / the reported baseline, never the product path)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_iterations(sc, iters, native):
     import oracle
     from bundle_adjustment_solver_b200 import solver as S
-    sc = make_scene(args.workload, 0, args.scale)
-    o = S.load_scene(oracle.FullBAOracle(), sc)
+    o = S.load_scene(oracle.FullBAOracle(native=native), sc)
     o.sizes()
+    oo = oracle.default_full_options(max_num_iterations=iters, threshold_cost_change=0.0, threshold_step_size=0.0)
+    t0 = time.perf_counter()
+    infos, _ = o.solve(oo)
+    return time.perf_counter() - t0, len(infos)
+
+
+def cpu_to_convergence(sc, native=True, max_iters=300):
+    import oracle
+    from bundle_adjustment_solver_b200 import solver as S
+    t0 = time.perf_counter()
+    o = S.load_scene(oracle.FullBAOracle(native=native), sc)
+    oo = oracle.default_full_options(max_num_iterations=max_iters, threshold_cost_change=1e-6, threshold_step_size=1e-6)
+    infos, conv = o.solve(oo)
+    return {"wall_s": time.perf_counter() - t0, "lm_iterations": len(infos), "converged": bool(conv),
+            "final_cost": infos[-1].cost if infos else None}
+
+
+def gpu_to_convergence(sc, device, stream, max_iters=300):
+    """Registration, FinalizeParameters (sorts, H2D), LM loop to convergence, D2H write-back: wall time from host buffers."""
+    import torch
+    from bundle_adjustment_solver_b200 import capi
+    from bundle_adjustment_solver_b200 import solver as S
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s = S.FullBundleAdjustmentSolver(device=device, stream=stream)
+    S.load_scene(s, sc)
+    summ = S.Summary()
+    s.solve(capi.default_options(max_num_iterations=max_iters, threshold_cost_change=1e-6, threshold_step_size=1e-6), summ)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    it = len(summ.optimization_info_list)
+    return {"wall_s": dt, "lm_iterations": it, "converged": bool(summ.convergence_status),
+            "final_cost": summ.optimization_info_list[-1].cost if it else None}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own algorithm on the host cores.  The reference cannot be compiled here (no
+    Eigen / Ceres / OpenCV), so this is the oracle port (kind 'port') built with the reference's flags
+    (CMakeLists.txt:6: -O2 -march=native), single thread like the reference (it has no threads), on a bounded number
+    of LM iterations of the same workload."""
+    if rank != 0:
+        return
+    workload = args.workload or ("c3" if world == 1 else "c4")
+    sc = make_scene(workload, 0, args.scale)
     iters = max(1, min(args.steps, args.cpu_iters))
     warm = 1 if args.warmup > 0 else 0
-    opt = oracle.default_full_options(max_num_iterations=max(1, warm), threshold_cost_change=0.0,
-                                      threshold_step_size=0.0)
     if warm:
-        o.solve(opt)
-    opt.max_num_iterations = iters
-    t0 = time.perf_counter()
-    infos, _ = o.solve(opt)
-    dt = time.perf_counter() - t0
-    value = sc.n_obs * len(infos) / dt
+        cpu_iterations(sc, 1, True)
+    dt, n = cpu_iterations(sc, iters, True)
+    dt_p, n_p = cpu_iterations(sc, iters, False)
+    value = sc.n_obs * n / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(infos),
-        "warmup": warm, "ms_per_step": 1e3 * dt / len(infos), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": warm, "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "n_obs": sc.n_obs, "scale": args.scale},
-        "lm_iters_per_s": len(infos) / dt,
+        "config": {"workload": WORKLOAD_NAMES[workload], "n_obs": sc.n_obs, "scale": args.scale},
+        "lm_iters_per_s": n / dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{len(infos)} LM iterations of the same workload, oracle/ba_oracle.cpp -O2, "
-                                   f"host has {os.cpu_count()} cores; the reference is single-threaded"},
+                         "sample": f"{n} LM iterations of the same workload, oracle/ba_oracle.cpp built -O2 -march=native "
+                                   f"(the reference's CMake flags), host has {os.cpu_count()} cores; the reference is single-threaded",
+                         "portable_build_value": sc.n_obs * n_p / dt_p,
+                         "caveat": "a port of the reference's algorithm with sparse B storage and a scalar unblocked LDLT; the "
+                                   "reference itself (Eigen) cannot be built in this image, so a GPU / CPU ratio taken from "
+                                   "this line is an upper bound on what the Eigen build would give"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -222,12 +390,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=list(WORKLOAD_NAMES))
+    ap.add_argument("--workload", default=None, choices=list(WORKLOAD_NAMES),
+                    help="default: c3 on one GPU, c4 (one problem sharded over the GPUs) on several")
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--weak", action="store_true", help="N > 1: every rank its own scene of the workload (weak scaling) as the headline")
     ap.add_argument("--cpu-iters", type=int, default=4, help="LM iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-poseonly", action="store_true", help="skip the C2 pose-only sub-benchmark")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip strong_scaling / mgpu_parity / weak_c3")
+    ap.add_argument("--no-converge", action="store_true", help="skip the time-to-converge legs (C1 and C3, GPU and CPU)")
     ap.add_argument("--e2e-max-iters", type=int, default=300,
                     help="iteration cap of the end-to-end solve (SURVEY 8d: thresholds 1e-6f, max 300 iterations)")
     ap.add_argument("--quick", action="store_true", help="profiling run: no clock-settling loop, phases, e2e or CPU baseline")
@@ -240,13 +412,14 @@ def main():
         return
     args.steps = max(1, args.steps)
     args.warmup = max(3, args.warmup)
+    workload = args.workload or ("c3" if world == 1 else "c4")
 
     import ctypes as C
 
     import torch
     import torch.distributed as dist
 
-    from bundle_adjustment_solver_b200 import capi
+    from bundle_adjustment_solver_b200 import capi, sharding
     from bundle_adjustment_solver_b200 import solver as S
 
     if not torch.cuda.is_available():
@@ -256,89 +429,100 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
-
-    # N > 1: C3 (the default) is weak scaling -- every rank brings its own 50k landmarks seen from the SAME 200 poses
-    # (pose_noise_seed fixed).  C4 / C5 are quoted in BASELINE.json as ONE problem sharded over the GPUs: every rank
-    # generates the same scene and keeps its contiguous landmark range (strong scaling).
-    strong = world > 1 and args.workload in ("c4", "c5")
-    if strong:
-        from bundle_adjustment_solver_b200 import sharding
-        sc = sharding.shard_scene(make_scene(args.workload, 0, args.scale), rank, world)
-    else:
-        sc = make_scene(args.workload, rank, args.scale)
     L = capi.lib()
 
-    def new_solver():
-        s = S.FullBundleAdjustmentSolver(device=local_rank, stream=stream.cuda_stream)
-        S.load_scene(s, sc)
-        return s
+    # N > 1: ONE problem, every rank generates the same scene and keeps its contiguous landmark range (strong scaling);
+    # --weak: every rank brings its own landmarks seen from the SAME poses (pose_noise_seed fixed)
+    strong = world > 1 and not args.weak
+    full_sc = make_scene(workload, 0, args.scale) if strong else None
+    sc = sharding.shard_scene(full_sc, rank, world) if strong else make_scene(workload, rank, args.scale)
+
+    comm_ready = [False]
 
     def join_comm(s, sz):
+        """First call: create the process's communicator (NCCL set-up, ~0.4 s); later solvers attach to it."""
         if world == 1:
             return
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            raw = (C.c_ubyte * 128)()
-            assert L.ba_comm_get_unique_id(raw) == 0
-            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
-        idbuf = idbuf.to(dev)
-        dist.broadcast(idbuf, 0)
         tot = torch.tensor([sz["M"], sz["n_obs"]], dtype=torch.int64, device=dev)
         dist.all_reduce(tot)
-        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
-        rc = L.ba_comm_init(s.h, raw, rank, world, int(tot[0]), int(tot[1]))
+        if comm_ready[0]:
+            rc = L.ba_comm_attach(s.h, int(tot[0]), int(tot[1]))
+        else:
+            idbuf = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                raw = (C.c_ubyte * 128)()
+                assert L.ba_comm_get_unique_id(raw) == 0
+                idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+            idbuf = idbuf.to(dev)
+            dist.broadcast(idbuf, 0)
+            raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+            rc = L.ba_comm_init(s.h, raw, rank, world, int(tot[0]), int(tot[1]))
+            comm_ready[0] = True
         if rc != 0:
-            raise SystemExit(f"ba_comm_init failed: {L.ba_last_error(s.h)}")
+            raise SystemExit(f"ba_comm_init / attach failed: {L.ba_last_error(s.h)}")
 
-    with torch.cuda.stream(stream):
-        s = new_solver()
+    def new_solver(scene, comm=True):
+        s = S.FullBundleAdjustmentSolver(device=local_rank, stream=stream.cuda_stream)
+        S.load_scene(s, scene)
         s._upload()
-        sz = s.sizes()
-        join_comm(s, sz)
-        T12_0, X_0 = s.internal_parameters()
-        n_obs_free_pose = int(np.count_nonzero(~np.isin(sc.obs_pose, sc.fixed_poses)))
+        if comm:
+            join_comm(s, s.sizes())
+        return s
 
-        def solve_n(n_it, check_every=None, profile=False):
-            s.set_profile(profile)
-            opt = capi.default_options(max_num_iterations=n_it, threshold_cost_change=0.0, threshold_step_size=0.0,
-                                       check_every=check_every or n_it)
-            res = capi.Result()
-            rc = L.ba_solve(s.h, C.byref(opt), None, 0, C.byref(res))
-            if rc != 0:
-                raise SystemExit(f"ba_solve failed: {L.ba_last_error(s.h)}")
-            assert res.n_iterations == n_it, (res.n_iterations, n_it)
-            return res
+    def solve_n(s, n_it, check_every=None, profile=False):
+        s.set_profile(profile)
+        opt = capi.default_options(max_num_iterations=n_it, threshold_cost_change=0.0, threshold_step_size=0.0,
+                                   check_every=check_every or n_it)
+        res = capi.Result()
+        rc = L.ba_solve(s.h, C.byref(opt), None, 0, C.byref(res))
+        if rc != 0:
+            raise SystemExit(f"ba_solve failed: {L.ba_last_error(s.h)}")
+        assert res.n_iterations == n_it, (res.n_iterations, n_it)
+        return res
 
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        # ---- warm-up (untimed): W steps, then keep the GPU busy ~1 s so the clock samples see load
-        solve_n(args.warmup)
+    def timed_steps(s, steps, warmup, settle=True, collective=True):
+        """W warm-up steps, then exactly `steps` LM iterations from the initial guess between CUDA events on the
+        launching stream; max over ranks."""
+        T0, X0 = s.internal_parameters()
+        solve_n(s, warmup)
         t_w = time.perf_counter()
-        while not args.quick and time.perf_counter() - t_w < 1.0:
-            solve_n(args.steps)
-        # ---- timed: exactly K steps from the initial guess
-        s.update_parameters_internal(T12_0, X_0)
+        while settle and time.perf_counter() - t_w < 1.0:
+            solve_n(s, steps)
+        s.update_parameters_internal(T0, X0)
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 and collective:
             dist.barrier()
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        res = solve_n(args.steps)
+        res = solve_n(s, steps)
         ev1.record(stream)
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 and collective:
             dist.barrier()
         ms = ev0.elapsed_time(ev1)
+        if world > 1 and collective:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, res
+
+    with torch.cuda.stream(stream):
+        s = new_solver(sc)
+        sz = s.sizes()
+        sinfo = solve_info(L, s)
+        T12_0, X_0 = s.internal_parameters()
+        n_obs_free_pose = int(np.count_nonzero(~np.isin(sc.obs_pose, sc.fixed_poses)))
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ms, res = timed_steps(s, args.steps, args.warmup, settle=not args.quick)
         launches = int(res.kernel_launches)
         clocks = sampler.stop() if rank == 0 else None
-        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
         nobs_all = torch.tensor([sz["n_obs"]], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(nobs_all)
-        ms = float(tmax[0])
         total_obs = float(nobs_all[0])
         value = total_obs * args.steps / (ms * 1e-3)
 
@@ -350,25 +534,54 @@ def main():
             return
         # ---- per-phase device times (CUDA events on the launching stream, plain launches)
         s.update_parameters_internal(T12_0, X_0)
-        solve_n(args.warmup, profile=True)
+        solve_n(s, args.warmup, profile=True)
         s.update_parameters_internal(T12_0, X_0)
-        resp = solve_n(args.steps, profile=True)
+        resp = solve_n(s, args.steps, profile=True)
         s.set_profile(False)
         ph = {"linearize": resp.t_linearize_ms / args.steps, "schur": resp.t_schur_ms / args.steps,
               "solve": resp.t_solve_ms / args.steps, "backsub": resp.t_backsub_ms / args.steps,
               "update_cost": resp.t_update_cost_ms / args.steps}
 
-        # ---- end to end through the C-ABI from host buffers: register + finalize (H2D pack) +
-        #      solve to convergence + read back.  Per-step bytes = totals / LM iterations.
+        # ---- N > 1: the first sharded LM iterations against the same problem solved on rank 0 alone, and the time of
+        #      that single-GPU solve (strong-scaling reference measured in the same job)
+        extras = {}
+        if strong and not args.no_extras:
+            K = 3
+            s.update_parameters_internal(T12_0, X_0)
+            summ = S.Summary()
+            s.solve(capi.default_options(max_num_iterations=K, threshold_cost_change=0.0, threshold_step_size=0.0), summ)
+            rows = [(i.cost, i.damping_term, i.iteration_status) for i in summ.optimization_info_list]
+            if rank == 0:
+                s1 = new_solver(full_sc, comm=False)
+                summ1 = S.Summary()
+                s1.solve(capi.default_options(max_num_iterations=K, threshold_cost_change=0.0, threshold_step_size=0.0), summ1)
+                rows1 = [(i.cost, i.damping_term, i.iteration_status) for i in summ1.optimization_info_list]
+                ok = len(rows) == len(rows1) == K and all(
+                    abs(a[0] - b[0]) <= 1e-9 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-12 * b[1] and a[2] == b[2]
+                    for a, b in zip(rows, rows1))
+                extras["mgpu_parity"] = bool(ok)
+                extras["mgpu_parity_detail"] = {
+                    "iterations": K, "tolerance": "cost 1e-9 relative, lambda 1e-12, identical status",
+                    "max_rel_cost_diff": float(max(abs(a[0] - b[0]) / abs(b[0]) for a, b in zip(rows, rows1))) if rows1 else None}
+                s1.update_parameters_internal(*s1.internal_parameters())
+                ms1, _ = timed_steps(s1, args.steps, args.warmup, settle=False, collective=False)
+                extras["strong_scaling"] = {"single_gpu_ms_per_step": ms1 / args.steps, "ms_per_step": ms / args.steps,
+                                            "speedup": ms1 / ms, "efficiency": ms1 / ms / world,
+                                            "single_gpu_solve_kernel": solve_info(L, s1)["kernel"]}
+                del s1
+            dist.barrier()
+
+        # ---- end to end through the C-ABI from host buffers: register + finalize (H2D pack) + solve to convergence
+        #      + read back.  Per-step bytes = totals / LM iterations.  N > 1: the communicator of this process is
+        #      already up (a process joins once and then solves problem after problem); the solver attaches to it.
         e2e = None
         if not args.no_e2e:
             # the timed solver above is done: release it, so that the end-to-end solve runs in the steady state of a
             # process that solves one problem after another (device buffers come back from the stream-ordered pool
-            # instead of growing it next to a live 300 MB problem -- that growth alone varied between 10 and 150 ms)
+            # instead of growing it next to a live problem -- that growth alone varied between 10 and 150 ms)
             del s
             torch.cuda.synchronize()
             s2 = S.FullBundleAdjustmentSolver(device=local_rank, stream=stream.cuda_stream)
-            join_comm_needed = world > 1
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -376,8 +589,7 @@ def main():
             S.load_scene(s2, sc)
             t_reg = time.perf_counter()
             s2._upload()
-            if join_comm_needed:
-                join_comm(s2, sz)   # N > 1: communicator creation (NCCL set-up, ~0.5 s) is inside the timed region
+            join_comm(s2, sz)
             t_fin = time.perf_counter()
             opt = capi.default_options(max_num_iterations=args.e2e_max_iters, threshold_cost_change=1e-6,
                                        threshold_step_size=1e-6)
@@ -397,13 +609,47 @@ def main():
             e2e = {"value": total_obs * it / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(it, 1)),
                    "d2h_bytes_per_step": int(d2h / max(it, 1)), "lm_iterations": it, "converged": bool(summ.convergence_status),
                    "wall_s": dt, "stages_ms": stages, "final_cost": summ.optimization_info_list[-1].cost if it else None,
-                   "includes": "host registration, FinalizeParameters (sorts, H2D pack), LM loop to convergence, D2H write-back"}
+                   "includes": "host registration, FinalizeParameters (sorts, H2D pack), LM loop to convergence, D2H write-back"
+                               + ("; the process's NCCL communicator already exists (ba_comm_attach)" if world > 1 else "")}
             del s2
 
-    po2 = None
-    if world == 1 and not args.no_poseonly:
-        with torch.cuda.stream(stream):
-            po2 = poseonly_c2(local_rank, stream)
+        # ---- N > 1: weak scaling of C3 (every rank its own 50k landmarks on the same 200 poses) beside the headline
+        if strong and not args.no_extras:
+            w_sc = make_scene("c3", rank, 1.0)
+            sw = new_solver(w_sc)
+            ms_w, _ = timed_steps(sw, args.steps, args.warmup, settle=False)
+            nw = torch.tensor([float(w_sc.n_obs)], dtype=torch.float64, device=dev)
+            dist.all_reduce(nw)
+            del sw
+            weak = {"workload": WORKLOAD_NAMES["c3"] + " per GPU (own landmarks, same poses)", "ms_per_step": ms_w / args.steps,
+                    "value": float(nw[0]) * args.steps / (ms_w * 1e-3), "unit": UNIT, "scaling": "weak"}
+            if rank == 0:
+                s1 = new_solver(w_sc, comm=False)
+                ms1, _ = timed_steps(s1, args.steps, args.warmup, settle=False, collective=False)
+                weak["single_gpu_ms_per_step"] = ms1 / args.steps
+                weak["efficiency"] = ms1 / ms_w
+                del s1
+            dist.barrier()
+            extras["weak_c3"] = weak
+
+        po2 = None
+        if not args.no_poseonly:
+            po2 = poseonly_c2(local_rank, stream, rank, world, dist, dev, cpu_legs=not args.no_cpu_baseline)
+
+        # ---- time to converge (third BASELINE metric): GPU from host buffers (N = 1) vs the CPU port, C1 and C3
+        converge = None
+        if world == 1 and not args.no_converge and not args.no_cpu_baseline:
+            converge = {}
+            for wl in ("c1", "c3"):
+                wsc = make_scene(wl, 0, 1.0)
+                gpu_to_convergence(wsc, local_rank, stream.cuda_stream)             # warm pool / code
+                g = gpu_to_convergence(wsc, local_rank, stream.cuda_stream)
+                c = cpu_to_convergence(wsc, native=True)
+                converge[wl] = {"workload": WORKLOAD_NAMES[wl], "gpu": g, "cpu": dict(c, cores=1, kind="port", build="-O2 -march=native"),
+                                "speedup": c["wall_s"] / g["wall_s"],
+                                "same_verdict": g["converged"] == c["converged"],
+                                "iterations_within_1": abs(g["lm_iterations"] - c["lm_iterations"]) <= 1,
+                                "final_cost_rel_diff": abs(g["final_cost"] - c["final_cost"]) / abs(c["final_cost"])}
 
     if rank != 0:
         if world > 1:
@@ -411,73 +657,83 @@ def main():
         return
 
     hbm_peak, peak_src = peaks()
-    ab = algorithmic_bytes(sz, n_obs_free_pose)
+    ab = algorithmic_bytes(sz, n_obs_free_pose, sinfo)
+    tab, tab_src = ncu_traffic_table() if (workload == "c3" and args.scale == 1.0 and world == 1) else (None, None)
     phases = {}
     for k in ("linearize", "schur", "backsub", "update_cost"):
         gbs = ab[k] / (ph[k] * 1e-3) / 1e9 if ph[k] > 0 else 0.0
-        phases[k] = {"ms": ph[k], "algorithmic_bytes": ab[k], "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak}
-    phases["solve"] = {"ms": ph["solve"], "algorithmic_flops": ab["solve_flops"],
-                       "achieved_tflops": ab["solve_flops"] / (ph["solve"] * 1e-3) / 1e12 if ph["solve"] > 0 else 0.0}
+        phases[k] = {"ms": ph[k], "algorithmic_bytes": ab[k], "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak,
+                     "traffic": phase_traffic(tab, k)}
+    t_solve = ph["solve"] * 1e-3
+    tf = lambda fl: fl / t_solve / 1e12 if t_solve > 0 else 0.0
+    phases["solve"] = {"ms": ph["solve"], "kernel": sinfo["kernel"], "algorithmic_flops": sinfo["alg_flops"],
+                       "achieved_tflops": tf(sinfo["alg_flops"]), "executed_flops": sinfo["exec_flops"],
+                       "executed_tflops": tf(sinfo["exec_flops"]), "dense_equivalent_flops": sinfo["dense_flops"],
+                       "dense_equivalent_tflops": tf(sinfo["dense_flops"]), "half_bandwidth": sinfo["bw"],
+                       "ctas": sinfo["ctas"], "dependent_panel_steps": sinfo["chain_steps"], "traffic": phase_traffic(tab, "solve")}
     t_build = ph["linearize"] + ph["schur"]
     kernels = {"linearize": "k_linearize_by_pose+k_finish_poses", "schur": "k_build_tiles (linearise + C^-1 + Schur DMMA GEMM)",
-               "backsub": "k_backsub_pairs+k_backsub_points", "update_cost": "k_cost+k_update_poses",
-               "solve": "k_chol_banded_smem (DMMA window update; cluster / multi-kernel DMMA variants for other structures)"}
-    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the default C3 workload from the
-    # committed `ncu --set full` capture profiles/r01_ncu_full_c3_summary.md; None for any other workload
-    ncu_traffic = {"solve": 0.99e6, "schur": 34.66e6 + 27.96e6, "linearize": 25.38e6 + 0.25e6,
-                   "backsub": 76.02e6 + 2.67e6 + 9.86e6, "update_cost": 29.24e6 + 0.11e6}
-    traffic = (lambda k: ncu_traffic[k]) if (args.workload == "c3" and args.scale == 1.0 and world == 1) else (lambda k: None)
+               "backsub": "k_backsub_pairs+k_backsub_points", "update_cost": "k_cost+k_update_poses+k_reduce_decide",
+               "solve": sinfo["kernel"]}
     # the dominant kernel of the step by device time
     dom = max(ph, key=lambda k: ph[k])
-    fp64_tensor_peak = 37.1   # TFLOP/s, measured on this pool's B200 with profiles/micro/dmma_peak.cu (m8n8k4 DMMA)
     if dom == "solve":
         roofline = {"bound": "tensor", "kernel": kernels[dom], "achieved": phases["solve"]["achieved_tflops"],
-                    "peak": fp64_tensor_peak, "unit": "TFLOP/s", "frac": phases["solve"]["achieved_tflops"] / fp64_tensor_peak,
-                    "traffic": traffic("solve"),
+                    "peak": FP64_TENSOR_PEAK, "unit": "TFLOP/s", "frac": phases["solve"]["achieved_tflops"] / FP64_TENSOR_PEAK,
+                    "traffic": phases["solve"]["traffic"],
+                    "executed_frac": phases["solve"]["executed_tflops"] / FP64_TENSOR_PEAK,
                     "peak_source": "measured FP64 DMMA throughput (profiles/micro/dmma_peak.cu; MEASURED_PEAKS.json has no FP64 figure)",
-                    "note": "achieved = dense-equivalent n^3/3 + 2n^2 flops / solve time; the banded factorisation is bound by "
-                            "its chain of n/8 dependent panel steps (latency), not by FP64 throughput - see DESIGN.md 4 (K5)"}
+                    "note": "achieved = ALGORITHMIC flops of the reduced solve (Cholesky inside the envelope of S + the two triangular "
+                            "solves) / solve time; executed_frac counts the flops the partitioned kernel really issues (fill of the "
+                            "fronts, padding).  The solve is bound by its chain of dependent 8-column panel steps "
+                            f"({sinfo['chain_steps']:.0f} on the critical path) on {sinfo['ctas']} of 148 SMs, not by FP64 throughput; "
+                            "the dense-equivalent n^3/3 figure is kept under phases.solve only"}
     else:
         roofline = {"bound": "hbm", "kernel": kernels[dom], "achieved": phases[dom]["achieved_gbs"], "peak": hbm_peak,
-                    "unit": "GB/s", "frac": phases[dom]["frac_hbm"], "traffic": traffic(dom), "peak_source": peak_src}
+                    "unit": "GB/s", "frac": phases[dom]["frac_hbm"], "traffic": phases[dom]["traffic"], "peak_source": peak_src}
     # the Jacobian / Schur build (BASELINE metric "Schur-build obs/s"): both build phases together
     build_bytes = ab["linearize"] + ab["schur"]
     build_gbs = build_bytes / (t_build * 1e-3) / 1e9 if t_build > 0 else 0.0
+    tl, ts = phase_traffic(tab, "linearize"), phase_traffic(tab, "schur")
     roofline_build = {"bound": "hbm", "kernel": kernels["linearize"] + " ; " + kernels["schur"], "achieved": build_gbs,
                       "peak": hbm_peak, "unit": "GB/s", "frac": build_gbs / hbm_peak, "algorithmic_bytes": build_bytes,
-                      "traffic": (traffic("linearize") + traffic("schur")) if traffic("schur") is not None else None,
+                      "traffic": (tl + ts) if (tl is not None and ts is not None) else None, "traffic_source": tab_src,
                       "peak_source": peak_src,
                       "fp64_tflops": (ab["schur_flops"] / (t_build * 1e-3) / 1e12) if t_build > 0 else 0.0}
+    for name, fr in [("roofline", roofline["frac"]), ("roofline_build", roofline_build["frac"])] + [
+            (k, v["frac_hbm"]) for k, v in phases.items() if "frac_hbm" in v]:
+        assert fr <= 1.2, f"{name}: fraction {fr:.2f} of peak is not a roofline point -- the accounting is wrong"
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        import oracle
-        o = S.load_scene(oracle.FullBAOracle(), sc)
-        o.sizes()
         it_cpu = max(1, args.cpu_iters)
-        oo = oracle.default_full_options(max_num_iterations=it_cpu, threshold_cost_change=0.0, threshold_step_size=0.0)
-        t0 = time.perf_counter()
-        infos, _ = o.solve(oo)
-        dtc = time.perf_counter() - t0
-        cpu = {"value": sc.n_obs * len(infos) / dtc, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{len(infos)} LM iterations of the same workload on 1 of {os.cpu_count()} host cores "
-                         f"(oracle/ba_oracle.cpp; the reference is single-threaded), {dtc:.1f} s",
-               "ms_per_step": 1e3 * dtc / len(infos)}
+        dtc, n_c = cpu_iterations(sc, it_cpu, True)
+        dtp, n_p = cpu_iterations(sc, it_cpu, False)
+        cpu = {"value": sc.n_obs * n_c / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{n_c} LM iterations of the same workload on 1 of {os.cpu_count()} host cores "
+                         f"(oracle/ba_oracle.cpp built -O2 -march=native like the reference's CMakeLists.txt:6; the reference is "
+                         f"single-threaded), {dtc:.1f} s",
+               "ms_per_step": 1e3 * dtc / n_c,
+               "portable_build": {"value": sc.n_obs * n_p / dtp, "ms_per_step": 1e3 * dtp / n_p, "flags": "-O2 -ffp-contract=off (the parity checker)"},
+               "caveat": "port with sparse B storage and a scalar unblocked LDLT; the Eigen reference cannot be built in this image"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "per_gpu": {k: sz[k] for k in ("N", "M", "P", "n_obs")},
-                   "scale": args.scale, "parallelism": f"landmark-sharded x{world}, S all-reduce" if world > 1 else "single GPU",
+        "config": {"workload": WORKLOAD_NAMES[workload], "per_gpu": {k: sz[k] for k in ("N", "M", "P", "n_obs")},
+                   "scale": args.scale,
+                   "parallelism": (f"one problem, landmarks sharded x{world}, band of S all-reduced (NCCL), LM scalars exchanged through "
+                                   f"peer memory" if strong else f"landmark-sharded x{world}, S all-reduce") if world > 1 else "single GPU",
                    "l2": "no flush: per-iteration working set %.0f MB exceeds the 126 MB L2" % (
                        (ab["linearize"] + ab["schur"] + ab["backsub"] + ab["update_cost"]) / 1e6),
-                   "cuda_graph": world == 1},
+                   "cuda_graph": True},
         "lm_iters_per_s": args.steps / (ms * 1e-3),
         "schur_build_obs_per_s": total_obs / (t_build * 1e-3) if t_build > 0 else None,
-        "phases": phases, "roofline": roofline, "roofline_build": roofline_build, "poseonly_c2": po2, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-        "clocks": clocks,
+        "phases": phases, "roofline": roofline, "roofline_build": roofline_build, "poseonly_c2": po2, "cpu_baseline": cpu,
+        "time_to_converge": converge, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+    line.update(extras)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -79,8 +79,8 @@ SYMBOLS = [
     "ba_create", "ba_destroy", "ba_reset", "ba_last_error", "ba_set_stream", "ba_set_profile", "ba_set_debug",
     "ba_set_cameras", "ba_set_poses", "ba_set_points", "ba_set_observations", "ba_finalize",
     "ba_update_parameters", "ba_solve", "ba_build_only", "ba_cost", "ba_get_poses", "ba_get_points",
-    "ba_get_sizes", "ba_debug_dump", "ba_debug_pairs", "ba_debug_time_solve", "ba_debug_nd_plan", "ba_comm_get_unique_id", "ba_comm_init",
-    "ba_comm_destroy", "ba_poseonly_solve_batched", "ba_poseonly_upload", "ba_poseonly_run",
+    "ba_get_sizes", "ba_debug_dump", "ba_debug_pairs", "ba_debug_time_solve", "ba_debug_nd_plan", "ba_debug_solve_info", "ba_comm_get_unique_id", "ba_comm_init",
+    "ba_comm_destroy", "ba_comm_attach", "ba_comm_shutdown", "ba_poseonly_solve_batched", "ba_poseonly_upload", "ba_poseonly_run",
     "ba_poseonly_download", "ba_poseonly_free", "ba_version",
 ]
 
@@ -124,9 +124,12 @@ def lib():
         L.ba_debug_pairs.argtypes = [vp, vp, vp]
         L.ba_debug_time_solve.argtypes = [vp, i, i, C.POINTER(C.c_float)]
         L.ba_debug_nd_plan.argtypes = [i, i, i, i, i, vp, vp, i]
+        L.ba_debug_solve_info.argtypes = [vp, C.c_char_p, i, vp]
         L.ba_comm_get_unique_id.argtypes = [vp]
         L.ba_comm_init.argtypes = [vp, vp, i, i, ll, ll]
         L.ba_comm_destroy.argtypes = [vp]
+        L.ba_comm_attach.argtypes = [vp, ll, ll]
+        L.ba_comm_shutdown.argtypes = [i]
         L.ba_poseonly_solve_batched.argtypes = [i, i, i] + [vp] * 12 + [C.POINTER(PoseOnlyOptions)] + [vp] * 4
         L.ba_poseonly_upload.argtypes = [C.POINTER(vp), i, i, i] + [vp] * 10
         L.ba_poseonly_run.argtypes = [vp, C.POINTER(PoseOnlyOptions), vp]

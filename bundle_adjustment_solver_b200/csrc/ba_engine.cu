@@ -32,6 +32,9 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -747,6 +750,18 @@ k_schur_dense_gemm(const int2 *__restrict__ groups /*pair range [x, y) of one la
       }
 }
 
+// peer exchange of the LM scalars (see SharedComm below)
+constexpr int kMaxRanks = 16;
+struct PeerExch {                       // one per rank, written by the peers
+  double vals[2][kMaxRanks][8];         // [epoch parity][source rank][scalar]
+  unsigned flag[2][kMaxRanks];          // epoch of the values
+};
+struct PeerTable {                      // device-side view
+  PeerExch *peer[kMaxRanks];
+  unsigned *epoch;                      // exchanges done so far (device counter, identical on all ranks)
+  int *error;                           // sticky: a peer did not answer
+  int rank, n_ranks;
+};
 struct DecideArgs {
   const double *cost_partials; int n_cost;
   const double *point_partials; int n_point;   // {model, step} per block
@@ -888,6 +903,80 @@ __global__ void __launch_bounds__(kThreads) k_reduce_decide(DecideArgs g, LmStat
   }
 }
 
+// Multi-GPU: ordered sums of the partials, one-shot exchange of the five scalars through the peers' mapped buffers
+// (one remote store per peer + a flag; the sum runs in rank order on every rank, so all ranks take bit-identical
+// decisions) and the trust-region decision, in ONE launch.  Replaces k_reduce_scalars + ncclAllReduce + k_decide.
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__global__ void __launch_bounds__(kThreads) k_exchange_decide(DecideArgs g, PeerTable pt, LmState *st, ba_iter_info *infos,
+                                                             int cap) {
+  if (st->done) return;
+  __shared__ double sm[kWarps][5];
+  __shared__ double mine[5], all[kMaxRanks][5];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < g.n_cost; i += kThreads) acc[0] += g.cost_partials[i];
+  for (int i = threadIdx.x; i < g.n_point; i += kThreads) {
+    acc[1] += g.point_partials[2 * i];
+    acc[2] += g.point_partials[2 * i + 1];
+  }
+  for (int i = threadIdx.x; i < g.n_pose; i += kThreads) {
+    acc[3] += g.pose_partials[2 * i];
+    acc[4] += g.pose_partials[2 * i + 1];
+  }
+  block_sum<5, kWarps>(acc, sm);
+  if (threadIdx.x == 0) {
+    mine[0] = acc[0]; mine[1] = acc[1]; mine[2] = acc[2]; mine[3] = acc[3];
+    mine[4] = acc[4] / (double)g.n_ranks;   // the pose step is computed redundantly on every rank (see k_reduce_scalars)
+  }
+  __syncthreads();
+  const unsigned epoch = *pt.epoch + 1;
+  const int par = epoch & 1;
+  if (threadIdx.x < pt.n_ranks) {
+    const int p = threadIdx.x;
+    PeerExch *dst = pt.peer[p];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst->vals[par][pt.rank][i] = mine[i];
+    __threadfence_system();
+    st_release_sys(&dst->flag[par][pt.rank], epoch);
+    // the values of rank p arrive in MY buffer
+    const PeerExch *own = pt.peer[pt.rank];
+    long long spins = 0;
+    bool ok = true;
+    while (ld_acquire_sys(&own->flag[par][p]) != epoch) {
+      if (++spins > (1ll << 28) || *((volatile int *)pt.error)) { ok = false; break; }
+    }
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) all[p][i] = *((volatile const double *)&own->vals[par][p][i]);
+    } else {
+      *pt.error = 1;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) all[p][i] = 0.0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *pt.epoch = epoch;
+    if (*((volatile int *)pt.error)) {   // a peer is gone: stop the loop, the host reports it
+      st->done = 1;
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double v = 0.0;
+      for (int r = 0; r < pt.n_ranks; ++r) v += all[r][i];
+      g.scal[i] = v;
+    }
+    decide(g, st, infos, cap);
+  }
+}
+
 // Multi-GPU, banded reduced system: only the band of S (row r: columns r .. r + bw of the upper triangle, what the
 // build writes and the banded factorisation reads) and the rhs column take part in the all-reduce.
 __global__ void k_band_pack(const double *__restrict__ S, int n, int ld, int bw, double *__restrict__ packed,
@@ -936,6 +1025,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
@@ -947,12 +1037,44 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
     return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
   }
 };
 NcclApi g_nccl;
+
+// One communicator per process and device, shared by the solvers that attach to it (creating an NCCL communicator
+// costs ~0.4 s per rank: a process that solves problem after problem joins once).  Besides the NCCL handle it owns
+// the PEER EXCHANGE buffers of the LM scalars: every rank maps every other rank's buffer (CUDA IPC over NVLink), so
+// the five scalars of an iteration travel as one remote store per peer plus a flag instead of an NCCL all-reduce.
+struct SharedComm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1, device = 0;
+  PeerExch *local = nullptr;
+  PeerExch *peer[kMaxRanks] = {};
+  unsigned *d_epoch = nullptr;
+  int *d_error = nullptr;
+  bool peer_ok = false;
+  PeerTable table() const {
+    PeerTable t{};
+    for (int r = 0; r < kMaxRanks; ++r) t.peer[r] = peer[r];
+    t.epoch = d_epoch; t.error = d_error; t.rank = rank; t.n_ranks = n_ranks;
+    return t;
+  }
+  ~SharedComm() {
+    cudaSetDevice(device);
+    for (int r = 0; r < n_ranks && r < kMaxRanks; ++r)
+      if (peer[r] && r != rank) cudaIpcCloseMemHandle(peer[r]);
+    if (local) cudaFree(local);
+    if (d_epoch) cudaFree(d_epoch);
+    if (d_error) cudaFree(d_error);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+  }
+};
+std::mutex g_comm_mu;
+std::map<int, std::shared_ptr<SharedComm>> g_comm_registry;   // by device
 
 // Device buffers come from the device's default stream-ordered memory pool (cudaMallocAsync) with the release
 // threshold lifted, so the ~40 buffers of a problem cost a handful of driver allocations and a re-finalised or
@@ -1125,6 +1247,7 @@ struct ba_solver {
   long long graph_nodes = 0;    // kernel nodes per replay
 
   // comm
+  std::shared_ptr<SharedComm> shared;   // keeps the communicator alive; `comm` mirrors shared->comm
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
   long long global_M = -1, global_n_obs = -1;
@@ -1203,7 +1326,8 @@ void ba_destroy(ba_solver *s) {
   for (auto e : s->ev) cudaEventDestroy(e);
   pinned_put(s->h_state);
   pinned_put(s->h_scal);
-  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  s->comm = nullptr;
+  s->shared.reset();
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -2145,6 +2269,9 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
   if (!s->comm) {
     k_reduce_decide<<<1, kThreads, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
     s->launches++;
+  } else if (s->shared && s->shared->peer_ok) {
+    k_exchange_decide<<<1, kThreads, 0, st>>>(g, s->shared->table(), dst, s->d_infos.p, (int)s->d_infos.n);
+    s->launches++;
   } else {
     k_reduce_scalars<<<1, kThreads, 0, st>>>(g, 0, dst);
     if (int rc = enqueue_allreduce_scal(s)) return rc;
@@ -2158,6 +2285,11 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
 // the persistent partitioned solve hands over between CTAs through flags with a bounded spin; a lost hand-over
 // (CTAs not co-resident) is reported instead of hanging the device
 static int check_nd_error(ba_solver *s) {
+  if (s->shared && s->shared->peer_ok) {
+    int perr = 0;
+    CUDA_TRY(cudaMemcpy(&perr, s->shared->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) { s->err = "multi-GPU scalar exchange: a peer rank did not answer"; return BA_ERR_NCCL; }
+  }
   if (!s->chol.nd.valid || !s->d_nd_flags.p) return BA_OK;
   int err = 0;
   CUDA_TRY(cudaMemcpy(&err, s->d_nd_flags.p + 2 * s->chol.nd.nodes.size() + 1, sizeof(int), cudaMemcpyDeviceToHost));
@@ -2235,7 +2367,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   double phase_ms[Phase::Count] = {0};
   int it_launched = 0;
   int n_done = 0, converged = 0;
-  const bool use_graph = opt.use_graph != 0 && !s->profile && !s->comm;
+  const bool use_graph = opt.use_graph != 0 && !s->profile;   // NCCL collectives are captured with the kernels
   if (s->debug_keep) {
     const size_t ld = (size_t)6 * s->N + 1;
     CUDA_TRY(s->d_Scopy.alloc(ld * ld));
@@ -2519,6 +2651,63 @@ int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep) {
   return BA_OK;
 }
 
+// Which reduced-solve path the plan selected and what it costs (bench.py's roofline accounting).
+//   vals[0] algorithmic flops: Cholesky of S inside its row envelope (sum over rows of width^2) + the two
+//           triangular solves -- the work the PROBLEM needs, independent of the kernel
+//   vals[1] executed flops of the selected path (partitioned: partial factorisations of all fronts incl. fill and
+//           padding; serial banded: n (W^2); cluster / dense: envelope tiles)
+//   vals[2] dense equivalent n^3 / 3 + 2 n^2     vals[3] half-bandwidth bw      vals[4] CTAs of the launch
+//   vals[5] dependent 8-column panel steps on the critical path     vals[6] 1 if S is cleared band-only
+//   vals[7] algorithmic bytes of the solve: the envelope of S read once + rhs + x
+int ba_debug_solve_info(ba_solver *s, char *name, int cap, double *vals) {
+  if (!s || !s->finalized || !vals) return BA_ERR_STATE;
+  const CholeskyPlan &pl = s->chol;
+  const int n = pl.n;
+  double alg = 0.0, env_entries = 0.0;
+  for (int j = 0; j < s->N; ++j) {
+    const double w = 6.0 * (j - s->h_first_pose[j]);
+    for (int r = 0; r < 6; ++r) { alg += (w + r + 1) * (w + r + 1); env_entries += w + r + 1; }
+  }
+  alg += 4.0 * env_entries;
+  std::string nm;
+  double exec = 0.0, ctas = 1.0, chain = 0.0;
+  static const int band_mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 6;
+  if (pl.banded && pl.nd.valid && pl.nd_dev.tpw > 0 && band_mode >= 5) {
+    for (const NdNode &nd : pl.nd.nodes) {
+      const double R = nd.k8 + nd.b8;
+      for (int c = 0; c < nd.k8; ++c) exec += (R - c) * (R - c);
+    }
+    chain = nd_plan_cost(pl.nd);
+    ctas = band_mode == 6 ? pl.nd.n_ctas : pl.nd.n_leaves;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s<%d,%d> (partitioned banded Cholesky: nested dissection depth %d, %d fronts, DMMA panel solves and updates)",
+             band_mode == 6 ? "k_nd_persistent" : "k_nd_forward_level+k_nd_backward_level", pl.nd_dev.tpw, nd_cons_for(pl.nd.max_BT),
+             pl.nd.depth, (int)pl.nd.nodes.size());
+    nm = buf;
+  } else if (pl.banded) {
+    const double W = pl.bw + 16.0;
+    exec = (double)n * W * W;
+    chain = n / 8.0;
+    nm = "k_chol_banded_smem (serial banded Cholesky, one CTA, DMMA window update)";
+  } else {
+    for (int k = 0; k < pl.T; ++k) {
+      const double m = pl.rows_ptr[k + 1] - pl.rows_ptr[k];
+      exec += (double)kNB * kNB * kNB * (1.0 / 3.0 + m + m * (m + 1) / 2.0);
+    }
+    chain = n / 8.0;
+    ctas = pl.cluster_size > 0 ? pl.cluster_size : 148;
+    nm = pl.cluster_size > 0 ? "k_chol_cluster (blocked Cholesky in one thread-block-cluster launch)"
+                             : "k_chol_diag+k_chol_trsm+k_syrk_update (blocked dense Cholesky, DMMA TRSM and trailing update)";
+  }
+  const size_t ld = (size_t)n + 1;
+  static const size_t band_clear_min = (size_t)(getenv("BA_B200_BAND_CLEAR_MIN_MB") ? atoi(getenv("BA_B200_BAND_CLEAR_MIN_MB")) : 64) << 20;
+  const bool band_clear = pl.banded && ld * ld * sizeof(double) > band_clear_min;   // steady state of the LM loop
+  vals[0] = alg; vals[1] = exec; vals[2] = (double)n * n * n / 3.0 + 2.0 * n * n; vals[3] = pl.bw; vals[4] = ctas;
+  vals[5] = chain; vals[6] = band_clear ? 1.0 : 0.0; vals[7] = 8.0 * (env_entries + 2.0 * n);
+  if (name && cap > 0) { strncpy(name, nm.c_str(), cap - 1); name[cap - 1] = 0; }
+  return BA_OK;
+}
+
 // Host-only: the partition plan of the banded reduced solve for N free poses and track span b (no device needed).
 // nodes_out: [cap][20] = own0 k k8 rb0 wr lb0 wl b8 child0 child1 parent rb_off lb_off rhs_off level cta seq L_off U_off bandT
 // meta: [8] = valid depth n_leaves n_levels n_ctas max_tiles max_R8 smem_bytes.  Returns the number of nodes.
@@ -2559,6 +2748,74 @@ int ba_comm_get_unique_id(void *id128) {
   return BA_OK;
 }
 
+// peer exchange set-up: every rank allocates its PeerExch, the IPC handles travel by ncclAllGather, every rank maps
+// the others.  All-or-nothing: the ranks agree (min-reduce) and fall back to the NCCL all-reduce of the scalars.
+static void setup_peer_exchange(SharedComm &sc, cudaStream_t st) {
+  sc.peer_ok = false;
+  if (getenv("BA_B200_NO_PEER_EXCHANGE") || sc.n_ranks > kMaxRanks || !g_nccl.AllGather) return;
+  int ok = 1;
+  if (cudaMalloc(&sc.local, sizeof(PeerExch)) != cudaSuccess) { sc.local = nullptr; ok = 0; }
+  if (cudaMalloc(&sc.d_epoch, sizeof(unsigned)) != cudaSuccess) { sc.d_epoch = nullptr; ok = 0; }
+  if (cudaMalloc(&sc.d_error, sizeof(int)) != cudaSuccess) { sc.d_error = nullptr; ok = 0; }
+  cudaIpcMemHandle_t mine{};
+  if (ok) {
+    cudaMemset(sc.local, 0, sizeof(PeerExch));
+    cudaMemset(sc.d_epoch, 0, sizeof(unsigned));
+    cudaMemset(sc.d_error, 0, sizeof(int));
+    if (cudaIpcGetMemHandle(&mine, sc.local) != cudaSuccess) ok = 0;
+  }
+  cudaGetLastError();
+  // handles (and the per-rank ok flag in the byte after them) to every rank
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  unsigned char *d_send = nullptr, *d_recv = nullptr;
+  if (cudaMalloc(&d_send, rec) != cudaSuccess || cudaMalloc(&d_recv, rec * sc.n_ranks) != cudaSuccess) {
+    cudaGetLastError();
+    if (d_send) cudaFree(d_send);
+    return;   // cannot even talk: every rank fails the same way only by luck, so never use the peers
+  }
+  std::vector<unsigned char> h_send(rec, 0), h_recv(rec * sc.n_ranks, 0);
+  std::memcpy(h_send.data(), &mine, sizeof(mine));
+  h_send[sizeof(mine)] = (unsigned char)ok;
+  cudaMemcpyAsync(d_send, h_send.data(), rec, cudaMemcpyHostToDevice, st);
+  bool talked = g_nccl.AllGather(d_send, d_recv, rec, ncclChar, sc.comm, st) == ncclSuccess;
+  cudaMemcpyAsync(h_recv.data(), d_recv, rec * sc.n_ranks, cudaMemcpyDeviceToHost, st);
+  talked = talked && cudaStreamSynchronize(st) == cudaSuccess;
+  int all_ok = talked ? 1 : 0;
+  for (int r = 0; r < sc.n_ranks && all_ok; ++r) all_ok = h_recv[r * rec + sizeof(mine)] ? 1 : 0;
+  if (all_ok) {
+    for (int r = 0; r < sc.n_ranks; ++r) {
+      if (r == sc.rank) { sc.peer[r] = sc.local; continue; }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, h_recv.data() + r * rec, sizeof(h));
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = 0; break; }
+      sc.peer[r] = static_cast<PeerExch *>(ptr);
+    }
+  }
+  // second round: did every rank map every peer?
+  if (talked) {
+    int *d_flag = reinterpret_cast<int *>(d_send);
+    cudaMemcpyAsync(d_flag, &all_ok, sizeof(int), cudaMemcpyHostToDevice, st);
+    if (g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, sc.comm, st) != ncclSuccess) all_ok = 0;
+    int agreed = 0;
+    cudaMemcpyAsync(&agreed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) agreed = 0;
+    sc.peer_ok = all_ok && agreed;
+  }
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  if (getenv("BA_B200_VERBOSE")) fprintf(stderr, "[ba_b200] rank %d/%d: scalar exchange over %s\n", sc.rank, sc.n_ranks, sc.peer_ok ? "peer memory (CUDA IPC)" : "ncclAllReduce");
+}
+
+static int adopt_comm(ba_solver *s, const std::shared_ptr<SharedComm> &sc, long long global_M, long long global_n_obs) {
+  s->shared = sc;
+  s->comm = sc->comm;
+  s->rank = sc->rank; s->n_ranks = sc->n_ranks; s->global_M = global_M; s->global_n_obs = global_n_obs;
+  destroy_graph(s);
+  if (s->finalized) return agree_on_envelope(s);
+  return BA_OK;
+}
+
 int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long long global_M,
                  long long global_n_obs) {
   if (!s || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return BA_ERR_INVALID;
@@ -2567,20 +2824,53 @@ int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long lon
   if (int rc = ensure_stream(s)) return rc;
   ncclUniqueId id;
   std::memcpy(&id, id128, 128);
-  if (s->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(s->comm); s->comm = nullptr; }   // re-initialisation
-  ncclResult_t r = g_nccl.CommInitRank(&s->comm, nranks, id, rank);
-  if (r != ncclSuccess) { s->err = "ncclCommInitRank failed"; s->comm = nullptr; return BA_ERR_NCCL; }
-  s->rank = rank; s->n_ranks = nranks; s->global_M = global_M; s->global_n_obs = global_n_obs;
-  destroy_graph(s);
-  if (s->finalized) return agree_on_envelope(s);
-  return BA_OK;
+  s->comm = nullptr;
+  s->shared.reset();                       // re-initialisation: the old communicator goes when its last user does
+  auto sc = std::make_shared<SharedComm>();
+  sc->device = s->device; sc->rank = rank; sc->n_ranks = nranks;
+  ncclResult_t r = g_nccl.CommInitRank(&sc->comm, nranks, id, rank);
+  if (r != ncclSuccess) { s->err = "ncclCommInitRank failed"; sc->comm = nullptr; return BA_ERR_NCCL; }
+  setup_peer_exchange(*sc, s->stream);
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    g_comm_registry[s->device] = sc;       // the device's communicator for later ba_comm_attach calls
+  }
+  return adopt_comm(s, sc, global_M, global_n_obs);
+}
+
+int ba_comm_attach(ba_solver *s, long long global_M, long long global_n_obs) {
+  if (!s) return BA_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (int rc = ensure_stream(s)) return rc;
+  std::shared_ptr<SharedComm> sc;
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    auto it = g_comm_registry.find(s->device);
+    if (it != g_comm_registry.end()) sc = it->second;
+  }
+  if (!sc) { s->err = "ba_comm_attach: no communicator on this device (call ba_comm_init once first)"; return BA_ERR_STATE; }
+  return adopt_comm(s, sc, global_M, global_n_obs);
 }
 
 int ba_comm_destroy(ba_solver *s) {
   if (!s) return BA_ERR_INVALID;
-  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
-  s->comm = nullptr; s->rank = 0; s->n_ranks = 1; s->global_M = s->global_n_obs = -1;
+  s->comm = nullptr;
+  s->shared.reset();
+  s->rank = 0; s->n_ranks = 1; s->global_M = s->global_n_obs = -1;
+  destroy_graph(s);
   return BA_OK;
+}
+
+int ba_comm_shutdown(int device) {
+  std::shared_ptr<SharedComm> sc;
+  {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    auto it = g_comm_registry.find(device);
+    if (it == g_comm_registry.end()) return BA_OK;
+    sc = it->second;
+    g_comm_registry.erase(it);
+  }
+  return BA_OK;   // destroyed here unless a solver still holds it
 }
 
 }  // extern "C"

@@ -41,3 +41,31 @@ def shard_scene(sc, rank, world):
     out.name = f"{sc.name}[shard {rank}/{world}]"
     out.meta = dict(sc.meta, landmark_range=(lo, hi))
     return out
+
+
+def frame_ranges(n_frames, world):
+    """Batches of independent pose-only problems (config C2) split evenly over the GPUs, no communication
+    (SURVEY.md 8e row 2): frame range [lo, hi) per rank, sizes differ by at most one."""
+    base, extra = divmod(int(n_frames), int(world))
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < extra else 0))
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def shard_poseonly_batch(pb, rank, world):
+    """The rank's frames of a scenes.PoseOnlyBatch (offsets rebased, per-point arrays sliced; the rig is shared)."""
+    lo, hi = frame_ranges(pb.n_frames, world)[rank]
+    p0, p1 = int(pb.offsets[lo]), int(pb.offsets[hi])
+    out = copy.copy(pb)
+    out.offsets = (np.asarray(pb.offsets[lo:hi + 1]) - p0).astype(np.int32)
+    out.points = pb.points[p0:p1]
+    out.px_left = pb.px_left[p0:p1]
+    out.px_right = None if pb.px_right is None else pb.px_right[p0:p1]
+    out.poses_true = pb.poses_true[lo:hi]
+    out.poses_init = pb.poses_init[lo:hi]
+    for name in ("base_to_camera", "world_to_last"):      # per-frame (n_frames, 12) or shared (12,)
+        a = getattr(pb, name)
+        if a is not None and np.ndim(a) == 2 and len(a) == pb.n_frames:
+            setattr(out, name, a[lo:hi])
+    return out

@@ -145,6 +145,10 @@ long long ba_debug_dump(ba_solver *s, int which, double *buf);
 int ba_debug_pairs(ba_solver *s, int *pair_pose_id, int *pair_point_id); /* original ids per pair */
 /* In-situ timing of parts of the reduced solve (bit 0 diag, 1 trsm, 2 syrk, 3 backward); timing only. */
 int ba_debug_time_solve(ba_solver *s, int parts, int reps, float *ms_per_rep);
+/* Reduced-solve path selected by the plan and its flop / byte counts (measurement only, bench.py):
+ * vals[8] = algorithmic flops (envelope Cholesky + solves), executed flops, dense equivalent, half-bandwidth,
+ * CTAs, dependent panel steps, band-only clearing (0/1), algorithmic bytes. */
+int ba_debug_solve_info(ba_solver *s, char *name, int cap, double *vals);
 /* Host-only (no device): partition plan of the banded reduced solve (csrc/ba_nd_plan.h) for N free poses and track
  * span b.  nodes_out [cap][20]; meta [8]; returns the number of tree nodes.  Used by the CPU test that emulates the
  * fronts in numpy. */
@@ -161,7 +165,12 @@ int ba_comm_get_unique_id(void *id128);
  * ranks, so that every rank factors the summed reduced system with the same (global) plan. */
 int ba_comm_init(ba_solver *s, const void *id128, int rank, int nranks, long long global_num_opt_points,
                  long long global_num_observations);
+/* Attaches the solver to the communicator this process already created on the solver's device with ba_comm_init
+ * (communicator creation costs ~0.4 s per rank; a process that solves problem after problem joins once). */
+int ba_comm_attach(ba_solver *s, long long global_num_opt_points, long long global_num_observations);
+/* Detaches the solver.  The communicator lives until ba_comm_shutdown(device) and its last attached solver is gone. */
 int ba_comm_destroy(ba_solver *s);
+int ba_comm_shutdown(int device);
 
 /* ---- batched pose-only solvers (pose_only_bundle_adjustment_solver.cpp:8-900) ---------- */
 typedef struct ba_poseonly_options {

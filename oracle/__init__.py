@@ -83,46 +83,78 @@ class PoseOnlyResult(C.Structure):
 _lib = None
 
 
-def lib():
-    global _lib
+def build_native():
+    """The TIMING build of the oracle: the reference's own flags (CMakeLists.txt:6, -O2 -march=native, FMA contraction
+    on).  -march=native binds the library to the CPU it was compiled on, so it is built where it runs (a temporary
+    directory keyed by the CPU's flags), never shipped.  Only bench.py's CPU legs use it; parity tests use the
+    portable build, whose arithmetic is the plain IEEE sequence."""
+    import hashlib
+    import tempfile
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except Exception:
+        flags = "unknown"
+    src = os.path.join(_HERE, "ba_oracle.cpp")
+    key = hashlib.sha1((flags + str(os.path.getmtime(src))).encode()).hexdigest()[:12]
+    out = os.path.join(tempfile.gettempdir(), f"libba_oracle_native_{key}.so")
+    if not os.path.exists(out):
+        tmp = out + f".{os.getpid()}"
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-march=native", "-fPIC", "-shared",
+                               "-o", tmp, src])
+        os.replace(tmp, out)
+    return out
+
+
+_native = None
+
+
+def lib(native=False):
+    global _lib, _native
+    if native:
+        if _native is None:
+            _native = _declare(C.CDLL(build_native()))
+        return _native
     if _lib is None:
         build()
-        L = C.CDLL(_LIB_PATH)
-        L.orc_full_create.restype = C.c_void_p
-        L.orc_full_destroy.argtypes = [C.c_void_p]
-        L.orc_full_add_camera.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4 + [C.c_void_p]
-        L.orc_full_add_poses.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.orc_full_add_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.orc_full_make_pose_fixed.argtypes = [C.c_void_p, C.c_int]
-        L.orc_full_make_point_fixed.argtypes = [C.c_void_p, C.c_int]
-        L.orc_full_add_observation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
-        L.orc_full_add_observations.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
-        L.orc_full_add_observations.restype = C.c_longlong
-        L.orc_full_solve.argtypes = [C.c_void_p, C.POINTER(FullOptions), C.c_void_p, C.c_int]
-        L.orc_full_converged.argtypes = [C.c_void_p]
-        L.orc_full_initial_cost.argtypes = [C.c_void_p]
-        L.orc_full_initial_cost.restype = C.c_double
-        L.orc_full_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.orc_full_get_point.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.orc_full_get_internal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.orc_full_sizes.argtypes = [C.c_void_p, C.c_void_p]
-        L.orc_full_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.orc_full_dump.restype = C.c_longlong
-        L.orc_full_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.orc_full_opt_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.orc_full_build_only.argtypes = [C.c_void_p, C.c_float, C.c_double, C.c_int, C.c_int]
-        L.orc_full_build_only.restype = C.c_double
-        L.orc_full_cost.argtypes = [C.c_void_p]
-        L.orc_full_cost.restype = C.c_double
-        L.orc_ldlt_solve_f64.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-        L.orc_ldlt_solve_f32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-        L.orc_se3_exp_f64.argtypes = [C.c_void_p, C.c_void_p]
-        L.orc_poseonly_solve.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 11 + [
-            C.POINTER(PoseOnlyOptions), C.POINTER(PoseOnlyResult)] + [C.c_void_p] * 3
-        L.orc_poseonly_solve_batched.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 12 + [
-            C.POINTER(PoseOnlyOptions), C.c_void_p]
-        _lib = L
+        _lib = _declare(C.CDLL(_LIB_PATH))
     return _lib
+
+
+def _declare(L):
+    L.orc_full_create.restype = C.c_void_p
+    L.orc_full_destroy.argtypes = [C.c_void_p]
+    L.orc_full_add_camera.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 4 + [C.c_void_p]
+    L.orc_full_add_poses.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_full_add_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_full_make_pose_fixed.argtypes = [C.c_void_p, C.c_int]
+    L.orc_full_make_point_fixed.argtypes = [C.c_void_p, C.c_int]
+    L.orc_full_add_observation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.orc_full_add_observations.argtypes = [C.c_void_p, C.c_longlong] + [C.c_void_p] * 4
+    L.orc_full_add_observations.restype = C.c_longlong
+    L.orc_full_solve.argtypes = [C.c_void_p, C.POINTER(FullOptions), C.c_void_p, C.c_int]
+    L.orc_full_converged.argtypes = [C.c_void_p]
+    L.orc_full_initial_cost.argtypes = [C.c_void_p]
+    L.orc_full_initial_cost.restype = C.c_double
+    L.orc_full_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_full_get_point.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_full_get_internal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_full_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_full_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_full_dump.restype = C.c_longlong
+    L.orc_full_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_full_opt_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_full_build_only.argtypes = [C.c_void_p, C.c_float, C.c_double, C.c_int, C.c_int]
+    L.orc_full_build_only.restype = C.c_double
+    L.orc_full_cost.argtypes = [C.c_void_p]
+    L.orc_full_cost.restype = C.c_double
+    L.orc_ldlt_solve_f64.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_ldlt_solve_f32.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_se3_exp_f64.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_poseonly_solve.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 11 + [
+        C.POINTER(PoseOnlyOptions), C.POINTER(PoseOnlyResult)] + [C.c_void_p] * 3
+    L.orc_poseonly_solve_batched.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 12 + [
+        C.POINTER(PoseOnlyOptions), C.c_void_p]
+    return L
 
 
 def _p(a):
@@ -147,8 +179,8 @@ class FullBAOracle:
     exactly what the reference's AddPose/AddPoint receive; ids are insertion indices.
     """
 
-    def __init__(self):
-        self.L = lib()
+    def __init__(self, native=False):
+        self.L = lib(native)
         self.h = C.c_void_p(self.L.orc_full_create())
         self.n_poses = 0
         self.n_points = 0
@@ -250,9 +282,9 @@ def pose12(R, t):
 
 
 def poseonly_solve(kind, Xw, pxl, pxr, intr_l, intr_r, pose_io, options, left_to_right=None,
-                   base_to_camera=None, world_to_last=None, want_history=False):
+                   base_to_camera=None, world_to_last=None, want_history=False, native=False):
     """kind: 0 mono-6dof, 1 stereo-6dof, 2 mono-planar3dof, 3 stereo-planar3dof.  Poses: 12 float32."""
-    L = lib()
+    L = lib(native)
     Xw = np.ascontiguousarray(Xw, dtype=np.float32)
     pxl = np.ascontiguousarray(pxl, dtype=np.float32)
     pxr = None if pxr is None else np.ascontiguousarray(pxr, dtype=np.float32)
@@ -280,8 +312,8 @@ def poseonly_solve(kind, Xw, pxl, pxr, intr_l, intr_r, pose_io, options, left_to
 
 
 def poseonly_solve_batched(kind, offsets, Xw, pxl, pxr, intr_l, intr_r, poses_io, options,
-                           left_to_right=None, base_to_camera=None, world_to_last=None):
-    L = lib()
+                           left_to_right=None, base_to_camera=None, world_to_last=None, native=False):
+    L = lib(native)
     offsets = np.ascontiguousarray(offsets, dtype=np.int32)
     nf = len(offsets) - 1
     Xw = np.ascontiguousarray(Xw, dtype=np.float32)

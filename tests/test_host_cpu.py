@@ -163,3 +163,49 @@ def test_shard_scene_preserves_relative_insertion_order():
     k = (sc.obs_point >= lo) & (sc.obs_point < hi)
     assert np.array_equal(parts[1].obs_uv, sc.obs_uv[k])       # same relative order => same last-writer pairs
     assert parts[1].obs_point.min() == 0
+
+
+_GLOO_POSEONLY_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["BA_ROOT"])
+import oracle
+from bundle_adjustment_solver_b200 import scenes, sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+pb = scenes.scene_poseonly_batch(n_frames=37, n_points=60, seed=11, pixel_sigma=0.3, stereo=True, ragged=True)
+sh = sharding.shard_poseonly_batch(pb, rank, world)
+opt = oracle.PoseOnlyOptions(1e-6, 1e-6, 1.5, 2.5, 100)
+mine = oracle.poseonly_solve_batched(sh.kind, sh.offsets, sh.points, sh.px_left, sh.px_right, sh.intr_left, sh.intr_right,
+                                     sh.poses_init, opt, left_to_right=sh.left_to_right)
+# frames are independent: no collective on the data path; the gather below only serves the check
+lo, hi = sharding.frame_ranges(pb.n_frames, world)[rank]
+buf = torch.zeros(pb.n_frames, 12, dtype=torch.float32)
+buf[lo:hi] = torch.from_numpy(mine["poses"])
+dist.all_reduce(buf)
+if rank == 0:
+    full = oracle.poseonly_solve_batched(pb.kind, pb.offsets, pb.points, pb.px_left, pb.px_right, pb.intr_left, pb.intr_right,
+                                         pb.poses_init, opt, left_to_right=pb.left_to_right)
+    assert np.array_equal(buf.numpy(), full["poses"])          # bit-identical: same frames, same arithmetic
+    print("GLOO_POSEONLY_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_poseonly_frame_sharding_gloo(tmp_path):
+    """Config C2 over several GPUs = frames split evenly, no communication (SURVEY 8e row 2): world_size-2 gloo run
+    of the split on the CPU oracle; the shards' poses put together are bit-identical to the unsharded batch."""
+    assert sharding.frame_ranges(4096, 8) == [(512 * r, 512 * (r + 1)) for r in range(8)]
+    assert sharding.frame_ranges(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert sharding.frame_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]          # more ranks than frames: empty shards
+    script = tmp_path / "worker_po.py"
+    script.write_text(_GLOO_POSEONLY_WORKER)
+    env = dict(os.environ, BA_ROOT=ROOT, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    port = 30500 + (os.getpid() % 1000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "GLOO_POSEONLY_OK" in out.stdout

@@ -111,3 +111,19 @@ def test_full_size_c2_matches_oracle(sigma):
     _check(out, ref, pb, late_frames=4)        # 4 of 4096
     if sigma == 0.0:
         assert np.abs(out["poses"] - pb.poses_true).max() < 2e-3
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_frame_sharding_is_exact(world):
+    """Frames split over `world` ranks (sharding.shard_poseonly_batch; each rank would run on its own GPU, no
+    communication): the shards' outputs put together are bit-identical to the unsharded launch."""
+    from bundle_adjustment_solver_b200 import sharding
+    pb = scenes.scene_poseonly_batch(n_frames=203, n_points=120, seed=8, pixel_sigma=0.4, stereo=True, ragged=True)
+    po = S.PoseOnlyBundleAdjustmentSolver(device=0)
+    run = lambda b: po.solve_batched(b.kind, b.offsets, b.points, b.px_left, b.px_right, b.intr_left, b.intr_right,
+                                     b.poses_init, capi.PoseOnlyOptions(*OPT), left_to_right=b.left_to_right)
+    full = run(pb)
+    parts = [run(sharding.shard_poseonly_batch(pb, r, world)) for r in range(world)]
+    assert np.array_equal(np.concatenate([p["poses"] for p in parts]), full["poses"])
+    assert np.array_equal(np.concatenate([p["mask_left"] for p in parts]), full["mask_left"])
+    assert [r.n_iterations for p in parts for r in p["results"]] == [r.n_iterations for r in full["results"]]
