@@ -6,8 +6,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # BA_B200_LIB: alternative build of the same sources (A/B kernel experiments); product default is in-tree
 LIB = os.environ.get("BA_B200_LIB") or os.path.join(HERE, "libba_b200.so")
-SOURCES = ["ba_engine.cu", "ba_poseonly.cu"]
-HEADERS = [os.path.join("..", "..", "include", "ba_b200.h")]
+SOURCES = ["ba_engine.cu", "ba_poseonly.cu", "ba_geometry.cu"]
+HEADERS = [os.path.join("..", "..", "include", "ba_b200.h"),
+           os.path.join("..", "..", "include", "ba_b200", "utility", "geometry_math.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 # BA_B200_NVCC_EXTRA: extra compiler flags for A/B builds (e.g. -DBA_ND_CONS=11), together with BA_B200_LIB

@@ -80,7 +80,7 @@ SYMBOLS = [
     "ba_set_cameras", "ba_set_poses", "ba_set_points", "ba_set_observations", "ba_finalize",
     "ba_update_parameters", "ba_solve", "ba_build_only", "ba_cost", "ba_get_poses", "ba_get_points",
     "ba_get_sizes", "ba_debug_dump", "ba_debug_pairs", "ba_debug_time_solve", "ba_debug_nd_plan", "ba_debug_solve_info", "ba_comm_get_unique_id", "ba_comm_init",
-    "ba_comm_destroy", "ba_comm_attach", "ba_comm_shutdown", "ba_poseonly_solve_batched", "ba_poseonly_upload", "ba_poseonly_run",
+    "ba_comm_destroy", "ba_comm_attach", "ba_comm_shutdown", "ba_geometry_batched", "ba_geometry_batched_f", "ba_poseonly_solve_batched", "ba_poseonly_upload", "ba_poseonly_run",
     "ba_poseonly_download", "ba_poseonly_free", "ba_version",
 ]
 
@@ -130,6 +130,8 @@ def lib():
         L.ba_comm_destroy.argtypes = [vp]
         L.ba_comm_attach.argtypes = [vp, ll, ll]
         L.ba_comm_shutdown.argtypes = [i]
+        L.ba_geometry_batched.argtypes = [i, i, ll, vp, vp, vp]
+        L.ba_geometry_batched_f.argtypes = [i, i, ll, vp, vp, vp]
         L.ba_poseonly_solve_batched.argtypes = [i, i, i] + [vp] * 12 + [C.POINTER(PoseOnlyOptions)] + [vp] * 4
         L.ba_poseonly_upload.argtypes = [C.POINTER(vp), i, i, i] + [vp] * 10
         L.ba_poseonly_run.argtypes = [vp, C.POINTER(PoseOnlyOptions), vp]

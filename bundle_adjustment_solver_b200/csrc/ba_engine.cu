@@ -2205,7 +2205,7 @@ static int enqueue_allreduce_S(ba_solver *s) {
     // every rank holds the same plan (ba_comm_init agreed on the global envelope): band + rhs only
     const int bw = s->chol.bw;
     const size_t count = (size_t)n * (bw + 2);
-    if (s->d_band.n < count) CUDA_TRY(s->d_band.alloc(count));
+    if (s->d_band.n < count) { s->err = "band exchange buffer not allocated"; return BA_ERR_STATE; }
     k_band_pack<<<n, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, bw, s->d_band.p, s->d_state.p);
     r = g_nccl.AllReduce(s->d_band.p, s->d_band.p, count, ncclDouble, ncclSum, s->comm, s->stream);
     k_band_unpack<<<n, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, bw, s->d_band.p, s->d_state.p);
@@ -2371,6 +2371,12 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   if (s->debug_keep) {
     const size_t ld = (size_t)6 * s->N + 1;
     CUDA_TRY(s->d_Scopy.alloc(ld * ld));
+  }
+  if (s->comm && s->chol.banded && s->N > 0) {
+    // exchange buffer of the band: allocated HERE, outside the capture (an allocation inside would become a graph
+    // node that allocates again at every replay)
+    const size_t count = (size_t)6 * s->N * (s->chol.bw + 2);
+    if (s->d_band.n < count) CUDA_TRY(s->d_band.alloc(count));
   }
   if (use_graph && max_it > 0) {
     ba_options key = opt;

@@ -226,6 +226,26 @@ void ba_poseonly_free(ba_poseonly_batch *b);
 
 const char *ba_version(void);
 
+/* ---- batched geometry helpers (utility/geometry_library.cpp:93-736 on the device) ---------------------------
+ * One element per thread; host buffers in and out.  Rotation matrices row-major (9), rigid transforms as R (9) | t (3),
+ * quaternions (w, x, y, z), twists [v; w].  in2 is only read by the two-operand ops. */
+enum {
+  BA_GEOM_SE3_EXP = 0,       /* se3Exp   :370   6 -> 12 */
+  BA_GEOM_SE3_LOG = 1,       /* SE3Log   :488  12 -> 6  */
+  BA_GEOM_SO3_EXP = 2,       /* so3Exp   :590   3 -> 9  */
+  BA_GEOM_SO3_LOG = 3,       /* SO3Log   :659   9 -> 3  */
+  BA_GEOM_Q2R = 4,           /* q2r      :93    4 -> 9  */
+  BA_GEOM_R2Q = 5,           /* r2q      :206   9 -> 4  */
+  BA_GEOM_ROTVEC2Q = 6,      /* rotvec2q :146   3 -> 4  */
+  BA_GEOM_R2EULER = 7,       /* r2euler  :322   9 -> 3  */
+  BA_GEOM_A2R = 8,           /* a2r      :181   3 (roll, pitch, yaw) -> 9 */
+  BA_GEOM_INVERSE_SE3 = 9,   /* inverseSE3 :729 12 -> 12 */
+  BA_GEOM_ADD_FRONT_SE3 = 10,/* addFrontse3 :712  xi (6), dxi (6) -> 6 */
+  BA_GEOM_Q_MULT = 11        /* q1_mult_q2 :74   4, 4 -> 4 */
+};
+int ba_geometry_batched(int device, int op, long long n, const double *in, const double *in2, double *out);
+int ba_geometry_batched_f(int device, int op, long long n, const float *in, const float *in2, float *out);
+
 #ifdef __cplusplus
 }
 #endif

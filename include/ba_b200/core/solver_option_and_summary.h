@@ -94,7 +94,55 @@ class Summary {
     ss << std::setprecision(default_precision);
     return ss.str();
   }
-  std::string FullReport() { return BriefReport(); }  // declared but never defined in the reference (:83)
+  // Declared at solver_option_and_summary.h:83 of the reference and never defined there.  Here: the brief report
+  // plus what the brief one leaves out -- the settings the solve ran with, how the trust region behaved (accepted /
+  // trusted-more / skipped steps, range of the damping term), where the time went and which test ended the loop.
+  std::string FullReport() {
+    std::stringstream ss;
+    ss << BriefReport();
+    const size_t n = optimization_info_list_.size();
+    int n_update = 0, n_trust = 0, n_skip = 0;
+    double t_sum = 0.0, t_max = 0.0, lam_min = 0.0, lam_max = 0.0;
+    for (size_t k = 0; k < n; ++k) {
+      const OptimizationInfo &info = optimization_info_list_[k];
+      n_update += info.iteration_status == IterationStatus::UPDATE;
+      n_trust += info.iteration_status == IterationStatus::UPDATE_TRUST_MORE;
+      n_skip += info.iteration_status == IterationStatus::SKIPPED;
+      t_sum += info.iter_time;
+      t_max = info.iter_time > t_max ? info.iter_time : t_max;
+      lam_min = (k == 0 || info.damping_term < lam_min) ? info.damping_term : lam_min;
+      lam_max = (k == 0 || info.damping_term > lam_max) ? info.damping_term : lam_max;
+    }
+    ss << std::setprecision(6);
+    ss << "Analytic Solver Full Report:\n";
+    ss << "  Settings\n";
+    ss << "    max iterations        : " << max_iteration_ << "\n";
+    ss << "    threshold step size   : " << threshold_step_size_ << "\n";
+    ss << "    threshold cost change : " << threshold_cost_change_ << "\n";
+    ss << "  Trust region\n";
+    ss << "    steps accepted        : " << (n_update + n_trust) << " (" << n_trust << " with the damping term lowered)\n";
+    ss << "    steps skipped         : " << n_skip << "\n";
+    ss << "    damping term range    : [" << lam_min << ", " << lam_max << "]\n";
+    if (n > 0) {
+      const OptimizationInfo &first = optimization_info_list_.front(), &last = optimization_info_list_.back();
+      ss << "  Cost\n";
+      ss << "    initial -> final      : " << first.cost << " -> " << last.cost;
+      if (first.cost != 0.0) ss << "  (x" << last.cost / first.cost << ")";
+      ss << "\n";
+      ss << "    last cost change      : " << last.cost_change << "\n";
+      ss << "    last average step     : " << last.abs_step << "\n";
+      ss << "  Time\n";
+      ss << "    total                 : " << total_time_in_millisecond_ << " [ms]\n";
+      ss << "    iterations (sum, max) : " << t_sum << ", " << t_max << " [ms]\n";
+      ss << "    outside the iterations: " << (total_time_in_millisecond_ - t_sum) << " [ms] (finalisation, transfers)\n";
+      ss << "  Stopped because         : ";
+      if (!convergence_status_) ss << "the iteration limit was reached\n";
+      else if (last.abs_step < threshold_step_size_) ss << "the average step size fell below its threshold\n";
+      else if (last.cost_change < threshold_cost_change_) ss << "the cost change fell below its threshold\n";
+      else ss << "convergence was reported\n";
+    }
+    return ss.str();
+  }
   const double GetTotalTimeInSecond() const { return total_time_in_millisecond_ * 0.001; }
   // read access for tests / callers (the reference exposes these only to its friend solvers)
   const std::vector<OptimizationInfo> &optimization_info_list() const { return optimization_info_list_; }

@@ -73,6 +73,7 @@ typedef Matrix<double, 2, 1> Vector2d; typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<double, 3, 1> Vector3d; typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<double, 3, 3> Matrix3d; typedef Matrix<float, 3, 3> Matrix3f;
 typedef Matrix<double, 4, 4> Matrix4d; typedef Matrix<float, 4, 4> Matrix4f;
+typedef Matrix<double, 4, 1> Vector4d; typedef Matrix<float, 4, 1> Vector4f;
 
 template <typename T>
 class AngleAxis {
@@ -131,6 +132,7 @@ class Transform {
   };
   Transform() { for (int i = 0; i < 16; ++i) m_[i] = T(0); m_[15] = T(1); }
   static Transform Identity() { Transform t; t.m_[0] = t.m_[5] = t.m_[10] = T(1); return t; }
+  void setIdentity() { *this = Identity(); }
   LinearRef linear() { return LinearRef(m_); }
   LinearMatrix linear() const { return LinearMatrix(LinearRef(const_cast<T *>(m_))); }
   LinearMatrix rotation() const { return linear(); }

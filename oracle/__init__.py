@@ -332,3 +332,19 @@ def poseonly_solve_batched(kind, offsets, Xw, pxl, pxr, intr_l, intr_r, poses_io
                                  _p(l2r), _p(b2c), _p(w2l), _p(poses), _p(ml), _p(mr), C.byref(options),
                                  results)
     return dict(poses=poses, mask_left=ml.astype(bool), mask_right=mr.astype(bool), results=results)
+
+
+GEOM_OPS = dict(se3_exp=(0, 6, 0, 12), se3_log=(1, 12, 0, 6), so3_exp=(2, 3, 0, 9), so3_log=(3, 9, 0, 3), q2r=(4, 4, 0, 9),
+                r2q=(5, 9, 0, 4), rotvec2q=(6, 3, 0, 4), r2euler=(7, 9, 0, 3), a2r=(8, 3, 0, 9), inverse_se3=(9, 12, 0, 12),
+                add_front_se3=(10, 6, 6, 6), q_mult=(11, 4, 4, 4))
+
+
+def geometry(name, a, b=None, dtype=np.float64):
+    """utility/geometry_library.cpp restated (geom_ref in ba_oracle.cpp): rows of `a` (and `b`) -> rows of the result."""
+    op, si, s2, so = GEOM_OPS[name]
+    a = np.ascontiguousarray(a, dtype=dtype).reshape(-1, si)
+    b = None if not s2 else np.ascontiguousarray(b, dtype=dtype).reshape(-1, s2)
+    out = np.zeros((len(a), so), dtype=dtype)
+    f = lib().orc_geometry if dtype == np.float64 else lib().orc_geometry_f
+    assert f(op, len(a), _p(a), _p(b), _p(out)) == 0
+    return out

@@ -1133,3 +1133,181 @@ void orc_poseonly_solve_batched(int kind, int n_frames, const int *offsets, cons
 }
 
 }  // extern "C"
+
+// ===========================================================================
+// utility/geometry_library.cpp restated (the checker of ba_geometry_batched and of the drop-in header
+// ba_b200/utility/geometry_library.h).  Written the way the reference writes it: explicit 3 x 3 matrices, the
+// skew matrix and its square formed and multiplied out.  Rotation matrices row-major, transforms R | t.
+// ===========================================================================
+namespace geom_ref {
+template <typename T> struct M3 { T m[3][3]; };
+template <typename T> M3<T> eye3() { M3<T> I{}; for (int i = 0; i < 3; ++i) I.m[i][i] = T(1); return I; }
+template <typename T> M3<T> skew(T a, T b, T c) {       // :6-12  [w]x
+  M3<T> S{};
+  S.m[0][1] = -c; S.m[0][2] = b; S.m[1][0] = c; S.m[1][2] = -a; S.m[2][0] = -b; S.m[2][1] = a;
+  return S;
+}
+template <typename T> M3<T> mul(const M3<T> &A, const M3<T> &B) {
+  M3<T> C{};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) for (int k = 0; k < 3; ++k) C.m[i][j] += A.m[i][k] * B.m[k][j];
+  return C;
+}
+template <typename T> M3<T> lin(T a, const M3<T> &A, T b, const M3<T> &B, T c, const M3<T> &C) {
+  M3<T> R{};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R.m[i][j] = a * A.m[i][j] + b * B.m[i][j] + c * C.m[i][j];
+  return R;
+}
+template <typename T> void put(const M3<T> &A, T *o) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[3 * i + j] = A.m[i][j]; }
+template <typename T> M3<T> get(const T *o) { M3<T> A; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A.m[i][j] = o[3 * i + j]; return A; }
+
+template <typename T> void se3Exp(const T *xi, T *R9, T *t3) {   // :370-427
+  const T v[3] = {xi[0], xi[1], xi[2]}, w[3] = {xi[3], xi[4], xi[5]};
+  const T theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const M3<T> wx = skew(w[0], w[1], w[2]), wxwx = mul(wx, wx), I = eye3<T>();
+  M3<T> R, V;
+  if (theta < T(1e-9)) {
+    R = lin(T(1), I, T(1), wx, T(0.5), wxwx);
+    V = lin(T(1), I, T(0.5), wx, T(0.33333333333333333333333333), wxwx);
+  } else {
+    const T invtheta2 = T(1) / (theta * theta);
+    R = lin(T(1), I, std::sin(theta) / theta, wx, (T(1) - std::cos(theta)) * invtheta2, wxwx);
+    V = lin(T(1), I, (T(1) - std::cos(theta)) * invtheta2, wx, (theta - std::sin(theta)) / (theta * theta * theta), wxwx);
+  }
+  put(R, R9);
+  for (int i = 0; i < 3; ++i) t3[i] = V.m[i][0] * v[0] + V.m[i][1] * v[1] + V.m[i][2] * v[2];
+}
+template <typename T> void so3Exp(const T *w, T *R9) {            // :590-611
+  const T theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const M3<T> wx = skew(w[0], w[1], w[2]), wxwx = mul(wx, wx), I = eye3<T>();
+  M3<T> R;
+  if (theta < T(1e-9)) R = lin(T(1), I, T(1), wx, T(0.5), wxwx);
+  else R = lin(T(1), I, std::sin(theta) / theta, wx, (T(1) - std::cos(theta)) * (T(1) / (theta * theta)), wxwx);
+  put(R, R9);
+}
+template <typename T> bool so3LogCore(const M3<T> &R, T *w, T &theta) {   // :659-679 ; false: the small-angle branch
+  const T inCos = (R.m[0][0] + R.m[1][1] + R.m[2][2] - T(1)) * T(0.5);
+  theta = T(0);
+  if (inCos >= T(0.999999999)) { w[0] = w[1] = w[2] = T(0); return false; }
+  theta = std::acos(inCos);
+  const T k = theta / (T(2) * std::sin(theta));
+  M3<T> lnR;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) lnR.m[i][j] = k * (R.m[i][j] - R.m[j][i]);
+  w[0] = -lnR.m[1][2]; w[1] = lnR.m[0][2]; w[2] = -lnR.m[0][1];
+  return true;
+}
+template <typename T> void SE3Log(const T *R9, const T *t3, T *xi) {       // :488-546
+  const M3<T> R = get(R9), I = eye3<T>();
+  T w[3], theta;
+  M3<T> Vin = I;
+  if (so3LogCore(R, w, theta)) {
+    const T invTheta = T(1) / theta, invTheta2 = invTheta * invTheta;
+    const M3<T> wx = skew(w[0], w[1], w[2]);
+    const T A = std::sin(theta) * invTheta, B = (T(1) - std::cos(theta)) * invTheta2;
+    Vin = lin(T(1), I, T(-0.5), wx, invTheta2 * (T(1) - A / (T(2) * B)), mul(wx, wx));
+  }
+  for (int i = 0; i < 3; ++i) xi[i] = Vin.m[i][0] * t3[0] + Vin.m[i][1] * t3[1] + Vin.m[i][2] * t3[2];
+  xi[3] = w[0]; xi[4] = w[1]; xi[5] = w[2];
+}
+template <typename T> void q2r(const T *q, T *R9) {                        // :93-117
+  const T qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+  const T qw2 = qw * qw, qx2 = qx * qx, qy2 = qy * qy, qz2 = qz * qz;
+  const T qxqy = qx * qy, qwqz = qw * qz, qxqz = qx * qz, qwqy = qw * qy, qwqx = qw * qx, qyqz = qy * qz;
+  const T R[9] = {qw2 + qx2 - qy2 - qz2, T(2) * (qxqy - qwqz), T(2) * (qxqz + qwqy),
+                  T(2) * (qxqy + qwqz), qw2 - qx2 + qy2 - qz2, T(2) * (qyqz - qwqx),
+                  T(2) * (qxqz - qwqy), T(2) * (qyqz + qwqx), qw2 - qx2 - qy2 + qz2};
+  for (int i = 0; i < 9; ++i) R9[i] = R[i];
+}
+template <typename T> void r2q(const T *R9, T *q) {                        // :206-262
+  const M3<T> R = get(R9);
+  const T m00 = R.m[0][0], m11 = R.m[1][1], m22 = R.m[2][2], m21 = R.m[2][1], m12 = R.m[1][2], m02 = R.m[0][2],
+          m20 = R.m[2][0], m10 = R.m[1][0], m01 = R.m[0][1];
+  const T tr = m00 + m11 + m22;
+  T qw, qx, qy, qz;
+  if (tr > 0) {
+    const T S = std::sqrt(tr + T(1)) * 2; qw = T(0.25) * S; qx = (m21 - m12) / S; qy = (m02 - m20) / S; qz = (m10 - m01) / S;
+  } else if ((m00 > m11) & (m00 > m22)) {
+    const T S = std::sqrt(T(1) + m00 - m11 - m22) * 2; qw = (m21 - m12) / S; qx = T(0.25) * S; qy = (m01 + m10) / S; qz = (m02 + m20) / S;
+  } else if (m11 > m22) {
+    const T S = std::sqrt(T(1) + m11 - m00 - m22) * 2; qw = (m02 - m20) / S; qx = (m01 + m10) / S; qy = T(0.25) * S; qz = (m12 + m21) / S;
+  } else {
+    const T S = std::sqrt(T(1) + m22 - m00 - m11) * 2; qw = (m10 - m01) / S; qx = (m02 + m20) / S; qy = (m12 + m21) / S; qz = T(0.25) * S;
+  }
+  q[0] = qw; q[1] = qx; q[2] = qy; q[3] = qz;
+}
+template <typename T> void rotvec2q(const T *w, T *q) {                    // :146-161
+  T th = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  if (th < T(1e-7)) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  const T invthsinth05 = std::sin(th * T(0.5)) / th;
+  q[0] = std::cos(th * T(0.5)); q[1] = w[0] * invthsinth05; q[2] = w[1] * invthsinth05; q[3] = w[2] * invthsinth05;
+  const T n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+}
+template <typename T> void r2euler(const T *R9, T *e) {                    // :322-344
+  const M3<T> R = get(R9);
+  const T sy = std::sqrt(R.m[0][0] * R.m[0][0] + R.m[1][0] * R.m[1][0]);
+  if (sy < T(1e-6)) { e[0] = std::atan2(-R.m[1][2], R.m[1][1]); e[1] = std::atan2(-R.m[2][0], sy); e[2] = 0; }
+  else { e[0] = std::atan2(R.m[2][1], R.m[2][2]); e[1] = std::atan2(-R.m[2][0], sy); e[2] = std::atan2(R.m[1][0], R.m[0][0]); }
+}
+template <typename T> void a2r(const T *rpy, T *R9) {                      // :181-191  Rz Ry Rx
+  const T r = rpy[0], p = rpy[1], y = rpy[2];
+  M3<T> Rx = eye3<T>(), Ry = eye3<T>(), Rz = eye3<T>();
+  Rx.m[1][1] = std::cos(r); Rx.m[1][2] = -std::sin(r); Rx.m[2][1] = std::sin(r); Rx.m[2][2] = std::cos(r);
+  Ry.m[0][0] = std::cos(p); Ry.m[0][2] = std::sin(p); Ry.m[2][0] = -std::sin(p); Ry.m[2][2] = std::cos(p);
+  Rz.m[0][0] = std::cos(y); Rz.m[0][1] = -std::sin(y); Rz.m[1][0] = std::sin(y); Rz.m[1][1] = std::cos(y);
+  put(mul(mul(Rz, Ry), Rx), R9);
+}
+template <typename T> void inverseSE3(const T *R9, const T *t3, T *Ri9, T *ti3) {   // :721-736
+  const M3<T> R = get(R9);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) Ri9[3 * i + j] = R.m[j][i];
+    ti3[i] = -(R.m[0][i] * t3[0] + R.m[1][i] * t3[1] + R.m[2][i] * t3[2]);
+  }
+}
+template <typename T> void addFrontse3(const T *xi, const T *dxi, T *out) {  // :703-719
+  T R[9], t[3], dR[9], dt[3];
+  se3Exp(xi, R, t);
+  se3Exp(dxi, dR, dt);
+  const M3<T> Rn = mul(get(dR), get(R));
+  const M3<T> D = get(dR);
+  T Rn9[9], tn[3];
+  put(Rn, Rn9);
+  for (int i = 0; i < 3; ++i) tn[i] = D.m[i][0] * t[0] + D.m[i][1] * t[1] + D.m[i][2] * t[2] + dt[i];
+  SE3Log(Rn9, tn, out);
+}
+template <typename T> void q1_mult_q2(const T *q1, const T *q2, T *q) {     // :74-81
+  q[0] = q1[0] * q2[0] - q1[1] * q2[1] - q1[2] * q2[2] - q1[3] * q2[3];
+  q[1] = q1[0] * q2[1] + q1[1] * q2[0] + q1[2] * q2[3] - q1[3] * q2[2];
+  q[2] = q1[0] * q2[2] - q1[1] * q2[3] + q1[2] * q2[0] + q1[3] * q2[1];
+  q[3] = q1[0] * q2[3] + q1[1] * q2[2] - q1[2] * q2[1] + q1[3] * q2[0];
+}
+template <typename T> int run(int op, long long n, const T *in, const T *in2, T *out) {
+  static const int shape[12][3] = {{6, 0, 12}, {12, 0, 6}, {3, 0, 9}, {9, 0, 3}, {4, 0, 9}, {9, 0, 4}, {3, 0, 4},
+                                   {9, 0, 3}, {3, 0, 9}, {12, 0, 12}, {6, 6, 6}, {4, 4, 4}};
+  if (op < 0 || op > 11) return -1;
+  const int si = shape[op][0], s2 = shape[op][1], so = shape[op][2];
+  for (long long i = 0; i < n; ++i) {
+    const T *a = in + i * si, *b = in2 ? in2 + i * s2 : nullptr;
+    T *o = out + i * so;
+    switch (op) {
+      case 0: se3Exp(a, o, o + 9); break;
+      case 1: SE3Log(a, a + 9, o); break;
+      case 2: so3Exp(a, o); break;
+      case 3: { T th; so3LogCore(get(a), o, th); break; }
+      case 4: q2r(a, o); break;
+      case 5: r2q(a, o); break;
+      case 6: rotvec2q(a, o); break;
+      case 7: r2euler(a, o); break;
+      case 8: a2r(a, o); break;
+      case 9: inverseSE3(a, a + 9, o, o + 9); break;
+      case 10: addFrontse3(a, b, o); break;
+      case 11: q1_mult_q2(a, b, o); break;
+    }
+  }
+  return 0;
+}
+}  // namespace geom_ref
+
+extern "C" {
+int orc_geometry(int op, long long n, const double *in, const double *in2, double *out) { return geom_ref::run<double>(op, n, in, in2, out); }
+int orc_geometry_f(int op, long long n, const float *in, const float *in2, float *out) { return geom_ref::run<float>(op, n, in, in2, out); }
+}

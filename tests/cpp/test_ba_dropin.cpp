@@ -66,6 +66,13 @@ int main(int argc, char **argv) {
   Summary summary;
   ba_solver.Solve(options, &summary);
   std::cout << summary.BriefReport() << std::endl;
+  const std::string full = summary.FullReport();   // declared by the reference (:83), defined only here
+  if (full.find("Analytic Solver Full Report") == std::string::npos || full.find("Stopped because") == std::string::npos ||
+      full.size() <= summary.BriefReport().size()) {
+    std::cout << "FULL_REPORT_BAD" << std::endl;
+    return 3;
+  }
+  std::cout << full.substr(summary.BriefReport().size()) << std::endl;
 
   FILE *o = std::fopen(argv[2], "wb");
   const auto &infos = summary.optimization_info_list();

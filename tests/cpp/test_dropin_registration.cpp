@@ -67,6 +67,7 @@ int main() {
   EXPECT(threw);
   Summary s;
   s.BriefReport();  // empty summary must not crash
+  s.FullReport();
   std::printf("REGISTRATION_OK\n");
   return 0;
 }

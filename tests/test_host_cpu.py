@@ -209,3 +209,86 @@ def test_poseonly_frame_sharding_gloo(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "GLOO_POSEONLY_OK" in out.stdout
+
+
+def load_oracle(sc):
+    import oracle
+    from bundle_adjustment_solver_b200 import solver as S
+    return S.load_scene(oracle.FullBAOracle(), sc)
+
+
+def test_bal_format_round_trip_and_camera_model(tmp_path):
+    """bal.py: a mono scene written in the 'Bundle Adjustment in the Large' layout and read back is
+    the same problem (same oracle cost); a file with radial distortion and per-image focal lengths projects, after
+    the loader's undistortion / focal normalisation, exactly where the format's camera model says."""
+    from bundle_adjustment_solver_b200 import bal
+    sc = scenes.scene_trajectory(9, 60, 4, stereo=False, seed=2, n_fixed=2)
+    sc.cam_intr[0, 2:] = 0.0                                 # the format has no principal point
+    # regenerate the pixels for cx = cy = 0 through the oracle-independent projection of the scene generator
+    T_cw = scenes.inv_T(sc.poses_true)
+    Xc = np.einsum("nij,nj->ni", T_cw[sc.obs_pose, :3, :3], sc.points_true[sc.obs_point]) + T_cw[sc.obs_pose, :3, 3]
+    f0 = sc.cam_intr[0, 0]
+    sc.obs_uv = np.stack([f0 * Xc[:, 0] / Xc[:, 2], f0 * Xc[:, 1] / Xc[:, 2]], axis=1)
+    p = tmp_path / "problem.txt"
+    bal.save_bal(sc, p)
+    back = bal.load_bal(p, n_fixed=2)
+    assert back.n_obs == sc.n_obs and len(back.points_init) == len(sc.points_init)
+    assert np.abs(back.poses_init - sc.poses_init).max() < 1e-12
+    assert np.abs(back.obs_uv - sc.obs_uv).max() < 1e-9
+    c0 = load_oracle(sc); c0.sizes()
+    c1 = load_oracle(back); c1.sizes()
+    assert abs(c0.cost() - c1.cost()) <= 1e-9 * c0.cost()
+    # distortion + per-image focal: write the file by hand with the format's own model
+    rng = np.random.default_rng(5)
+    nc, npt = 3, 40
+    w = rng.normal(size=(nc, 3)) * 0.1
+    t = rng.normal(size=(nc, 3)) * 0.2 + [0, 0, -6.0]        # points end up in front of the -z looking cameras
+    fk = np.stack([rng.uniform(900, 1400, nc), rng.uniform(-0.05, 0.0, nc), rng.uniform(0.0, 0.01, nc)], axis=1)
+    X = rng.uniform(-1, 1, size=(npt, 3))
+    from scipy.spatial.transform import Rotation
+    rows = []
+    for c in range(nc):
+        P = Rotation.from_rotvec(w[c]).apply(X) + t[c]
+        q = -P[:, :2] / P[:, 2:3]
+        r2 = (q * q).sum(axis=1)
+        px = fk[c, 0] * (1 + fk[c, 1] * r2 + fk[c, 2] * r2 * r2)[:, None] * q
+        rows += [(c, i, px[i, 0], px[i, 1]) for i in range(npt)]
+    with open(tmp_path / "dist.txt", "w") as fh:
+        fh.write(f"{nc} {npt} {len(rows)}\n")
+        fh.writelines(f"{a} {b} {x:.17g} {y:.17g}\n" for a, b, x, y in rows)
+        fh.writelines(f"{v:.17g}\n" for c in range(nc) for v in (*w[c], *t[c], *fk[c]))
+        fh.writelines(f"{v:.17g}\n" for v in X.reshape(-1))
+    sd = bal.load_bal(tmp_path / "dist.txt")
+    od = load_oracle(sd); od.sizes()
+    assert od.cost() < 1e-9                                   # exact data: zero reprojection error after loading
+
+
+def test_cpp_bal_loader_matches_python_loader(tmp_path):
+    """include/ba_b200/utility/bal_loader.h against bal.py on a file with distortion and per-image focal lengths."""
+    from bundle_adjustment_solver_b200 import bal
+    rng = np.random.default_rng(8)
+    nc, npt = 4, 25
+    rows = [(c, i, *rng.uniform(-400, 400, 2)) for c in range(nc) for i in range(npt) if (c + i) % 3]
+    cams = np.column_stack([rng.normal(size=(nc, 3)) * 0.3, rng.normal(size=(nc, 3)), rng.uniform(800, 1500, nc),
+                            rng.uniform(-0.04, 0.0, nc), rng.uniform(0, 0.005, nc)])
+    X = rng.normal(size=(npt, 3))
+    path = tmp_path / "p.txt"
+    with open(path, "w") as fh:
+        fh.write(f"{nc} {npt} {len(rows)}\n")
+        fh.writelines(f"{a} {b} {x:.17g} {y:.17g}\n" for a, b, x, y in rows)
+        fh.writelines(f"{v:.17g}\n" for v in cams.reshape(-1))
+        fh.writelines(f"{v:.17g}\n" for v in X.reshape(-1))
+    exe = tmp_path / "bal"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-DBA_B200_FORCE_EIGEN_SHIM", "-o", str(exe),
+                        os.path.join(ROOT, "tests", "cpp", "test_bal_loader.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = subprocess.run([str(exe), str(path)], capture_output=True, text=True, check=True).stdout.splitlines()
+    sc = bal.load_bal(path)
+    assert out[0].split()[1:] == [str(nc), str(npt), str(len(rows))]
+    assert abs(float(out[1].split()[1]) - sc.meta["f0"]) < 1e-12
+    poses = np.array([[float(v) for v in ln.split()[1:]] for ln in out if ln.startswith("POSE")]).reshape(nc, 4, 4).transpose(0, 2, 1)
+    assert np.abs(poses - sc.poses_init).max() < 1e-12
+    obs = np.array([[float(v) for v in ln.split()[1:]] for ln in out if ln.startswith("OBS")])
+    assert np.array_equal(obs[:, 0], sc.obs_pose) and np.array_equal(obs[:, 1], sc.obs_point)
+    assert np.abs(obs[:, 2:] - sc.obs_uv).max() < 1e-9
+    assert subprocess.run([str(exe), str(tmp_path / "missing.txt")], capture_output=True, text=True).returncode == 2
