@@ -903,6 +903,20 @@ __global__ void __launch_bounds__(kThreads) k_reduce_decide(DecideArgs g, LmStat
   }
 }
 
+// finalize: the pose-ordered copies of the observations, gathered from the point-ordered arrays
+__global__ void k_gather_pose_order(long long nA, const int *__restrict__ perm, const double2 *__restrict__ uv,
+                                    const int *__restrict__ obs_point, const int *__restrict__ camflags,
+                                    const int *__restrict__ obs_pose, double2 *__restrict__ uvA, int *__restrict__ pointA,
+                                    int *__restrict__ camA, int *__restrict__ poseidA) {
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < nA; w += (long long)gridDim.x * blockDim.x) {
+    const int q = perm[w];
+    uvA[w] = uv[q];
+    pointA[w] = obs_point[q];
+    camA[w] = camflags[q] & kCamMask;
+    poseidA[w] = obs_pose[q];
+  }
+}
+
 // Multi-GPU: ordered sums of the partials, one-shot exchange of the five scalars through the peers' mapped buffers
 // (one remote store per peer + a flag; the sum runs in rank order on every rank, so all ranks take bit-identical
 // decisions) and the trust-region decision, in ONE launch.  Replaces k_reduce_scalars + ncclAllReduce + k_decide.
@@ -1092,10 +1106,10 @@ inline void pool_setup(int device) {
 }
 
 // Host-side data-parallel loops of set_observations / finalize: plain threads that are joined at the end of the
-// loop (at most 8).  An OpenMP team would keep spinning on every core after each of the dozen short regions, which
+// loop (at most 16).  An OpenMP team would keep spinning on every core after each of the dozen short regions, which
 // starves the caller's own thread (and the driver's staging copies that follow) on hosts with a CPU quota.
 static int host_threads() {
-  static const int n = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  static const int n = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   return n;
 }
 template <typename F>
@@ -1543,12 +1557,13 @@ int ba_finalize(ba_solver *s) {
   // --- stable counting sort by pose, then by point  => order (point, pose, insertion)
   std::vector<int> by_pose(n), by_point(n);
   std::vector<long long> pose_begin(Nt + 1, 0);   // observation range of every pose in by_pose order
+  std::vector<int> pose_to_point_order;
   {
     // both sorts: per-thread histograms over contiguous ranges of the input, bucket offsets per thread, parallel
     // scatter -- stable because every thread's range is contiguous and the ranges are ordered
     std::vector<long long> starts;
     auto counting_sort = [&](long long count, int n_buckets, auto &&key_of /*(q) -> bucket*/, auto &&item_of /*(q) -> value*/,
-                             std::vector<int> &out) {
+                             std::vector<int> &out, std::vector<int> *dest /*position every input went to*/) {
       const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, count / 65536));
       std::vector<std::vector<int>> hist(nth, std::vector<int>((size_t)n_buckets, 0));
       parallel_ranges(nth, [&](long long t0, long long t1, int) {
@@ -1566,13 +1581,19 @@ int ba_finalize(ba_solver *s) {
       parallel_ranges(nth, [&](long long t0, long long t1, int) {
         for (long long t = t0; t < t1; ++t) {
           std::vector<int> &h = hist[t];
-          for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) out[h[key_of(q)]++] = item_of(q);
+          if (dest) {
+            for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) { const int pos = h[key_of(q)]++; out[pos] = item_of(q); (*dest)[q] = pos; }
+          } else {
+            for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) out[h[key_of(q)]++] = item_of(q);
+          }
         }
       }, 1);
     };
-    counting_sort(n, Nt, [&](long long k) { return s->h_obs_pose[k]; }, [&](long long k) { return (int)k; }, by_pose);
+    counting_sort(n, Nt, [&](long long k) { return s->h_obs_pose[k]; }, [&](long long k) { return (int)k; }, by_pose, nullptr);
     pose_begin = starts;
-    counting_sort(n, Mt, [&](long long q) { return s->h_obs_point[by_pose[q]]; }, [&](long long q) { return by_pose[q]; }, by_point);
+    pose_to_point_order.resize(n);   // position in POINT order of the q-th observation of the POSE order
+    counting_sort(n, Mt, [&](long long q) { return s->h_obs_point[by_pose[q]]; }, [&](long long q) { return by_pose[q]; }, by_point,
+                  &pose_to_point_order);
   }
   lap("counting sorts");
   // --- point-ordered observation arrays, pairs, last-writer flags
@@ -1639,6 +1660,25 @@ int ba_finalize(ba_solver *s) {
       for (int p = grp_start[g]; p < grp_start[g + 1]; ++p) pair_end[p] = grp_start[g + 1];
   });
   lap("point order, pairs");
+  // The point-ordered observation arrays (36 of the ~60 MB this function uploads) are final: a helper thread sends
+  // them while this thread builds the tile / chunk structures.  +1 sentinels so that obs_point[k+1] / obs_pair[k+1]
+  // reads of the kernels stay in bounds (the host code below never reads past n).
+  cudaStream_t st = s->stream;
+  o_point.push_back(-1);
+  o_pair.push_back(-2);
+  cudaError_t early_err = cudaSuccess;
+  std::thread early_upload([&]() {
+    cudaSetDevice(s->device);
+    g_alloc_stream = st;
+    cudaError_t e = s->d_obs_uv.upload(uv, st);
+    if (e == cudaSuccess) e = s->d_obs_pose.upload(o_pose, st);
+    if (e == cudaSuccess) e = s->d_obs_point.upload(o_point, st);
+    if (e == cudaSuccess) e = s->d_obs_pair.upload(o_pair, st);
+    if (e == cudaSuccess) e = s->d_pair_obs.upload(pair_obs, st);
+    if (e == cudaSuccess) e = s->d_pair_end.upload(pair_end, st);
+    early_err = e;
+  });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } early_joiner{early_upload};
   // --- observation range of every landmark in point order
   std::vector<long long> pt_q0(Mt + 1, 0);
   for (long long q = 0; q < n; ++q) pt_q0[o_point[q] + 1]++;
@@ -1862,7 +1902,9 @@ int ba_finalize(ba_solver *s) {
   s->n_split_pairs = (int)split_pairs.size();
   lap("point chunks");
   // --- pose-ordered arrays (free poses only) and their chunks
-  std::vector<double2> uvA; std::vector<int> pointA, camA, poseidA;
+  // the pose-ordered copies of the observations (uvA, pointA, camA, poseidA) are gathered ON THE DEVICE from the
+  // point-ordered arrays through permA (position in point order of every pose-ordered slot): 4 B/obs instead of 28
+  std::vector<int> permA;
   std::vector<ChunkA> chunksA; std::vector<int> pose_chunk_ptr(s->N + 1, 0);
   {
     // A-order = the by_pose order restricted to free poses: offsets per pose, chunks per pose (serial over poses),
@@ -1871,7 +1913,7 @@ int ba_finalize(ba_solver *s) {
     for (int ps = 0; ps < Nt; ++ps)
       a_begin[ps + 1] = a_begin[ps] + (s->h_pose_opt[ps] >= 0 ? pose_begin[ps + 1] - pose_begin[ps] : 0);
     const long long nA = a_begin[Nt];
-    uvA.resize(nA); pointA.resize(nA); camA.resize(nA); poseidA.resize(nA);
+    permA.resize(nA);
     // Chunk size: enough observations per thread to amortise the 27-value block reduction at the end of a chunk
     // (it costs as much as two observations), while the grid still fills the GPU (two 256-thread CTAs per SM);
     // a pose's observations are split evenly over its chunks.
@@ -1896,12 +1938,7 @@ int ba_finalize(ba_solver *s) {
         if (s->h_pose_opt[ps] < 0) continue;
         const long long len = pose_begin[ps + 1] - pose_begin[ps];
         for (long long r = 0; r < len; ++r) {
-          const int k = by_pose[pose_begin[ps] + r];
-          const long long w = a_begin[ps] + r;
-          uvA[w] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
-          pointA[w] = s->h_obs_point[k];
-          camA[w] = s->h_obs_cam[k];
-          poseidA[w] = ps;
+          permA[a_begin[ps] + r] = pose_to_point_order[pose_begin[ps] + r];
         }
       }
     }, 1);
@@ -1914,7 +1951,8 @@ int ba_finalize(ba_solver *s) {
   s->n_chunksA = (int)chunksA.size();
   lap("pose order");
   // --- upload
-  cudaStream_t st = s->stream;
+  early_upload.join();
+  if (early_err != cudaSuccess) { s->err = std::string("upload of the observation arrays: ") + cudaGetErrorString(early_err); return BA_ERR_CUDA; }
   std::vector<uint8_t> point_free(Mt);
   for (int i = 0; i < Mt; ++i) point_free[i] = s->h_point_fixed[i] ? 0 : 1;
   CUDA_TRY(s->d_cams.upload(s->h_cams, st));
@@ -1922,21 +1960,21 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_poses[1].upload(s->h_poses, st));
   CUDA_TRY(s->d_points[0].upload(s->h_points, st));
   CUDA_TRY(s->d_points[1].upload(s->h_points, st));
-  CUDA_TRY(s->d_obs_uv.upload(uv, st));
-  CUDA_TRY(s->d_obs_pose.upload(o_pose, st));
-  // +1 sentinel so that obs_point[k+1] / pair_point[p+1] reads stay in bounds
-  o_point.push_back(-1);
-  CUDA_TRY(s->d_obs_point.upload(o_point, st));
   CUDA_TRY(s->d_obs_camflags.upload(o_cf, st));
-  o_pair.push_back(-2);
-  CUDA_TRY(s->d_obs_pair.upload(o_pair, st));
-  CUDA_TRY(s->d_uvA.upload(uvA, st));
-  CUDA_TRY(s->d_pointA.upload(pointA, st));
-  CUDA_TRY(s->d_camA.upload(camA, st));
-  CUDA_TRY(s->d_poseidA.upload(poseidA, st));
+  {
+    const size_t nA = permA.size();
+    DevBuf<int> d_perm;
+    CUDA_TRY(d_perm.upload(permA, st));
+    CUDA_TRY(s->d_uvA.alloc(nA)); CUDA_TRY(s->d_pointA.alloc(nA)); CUDA_TRY(s->d_camA.alloc(nA)); CUDA_TRY(s->d_poseidA.alloc(nA));
+    if (nA > 0)
+      k_gather_pose_order<<<(unsigned)std::min<size_t>((nA + 255) / 256, 148 * 16), 256, 0, st>>>(
+          (long long)nA, d_perm.p, s->d_obs_uv.p, s->d_obs_point.p, s->d_obs_camflags.p, s->d_obs_pose.p, s->d_uvA.p,
+          s->d_pointA.p, s->d_camA.p, s->d_poseidA.p);
+    CUDA_TRY(cudaGetLastError());
+    d_perm.release();   // stream-ordered: freed after the gather
+  }
   CUDA_TRY(s->d_chunks.upload(chunks, st));
   CUDA_TRY(s->d_chunk_pts.upload(chunk_pts, st));
-  CUDA_TRY(s->d_pair_obs.upload(pair_obs, st));
   CUDA_TRY(s->d_cpts.upload(cpts, st));
   CUDA_TRY(s->d_chunk_pair_count.upload(chunk_pair_count, st));
   CUDA_TRY(s->d_chunksA.upload(chunksA, st));
@@ -1948,7 +1986,6 @@ int ba_finalize(ba_solver *s) {
     pp.push_back(-1);
     CUDA_TRY(s->d_pair_point.upload(pp, st));
   }
-  CUDA_TRY(s->d_pair_end.upload(pair_end, st));
   CUDA_TRY(s->d_point_has_pairs.upload(point_has_pairs, st));
   CUDA_TRY(s->d_point_free.upload(point_free, st));
   if (int rc = upload_cholesky_plan(s)) return rc;
