@@ -77,7 +77,7 @@ class PoseOnlyResult(C.Structure):
 # every symbol include/ba_b200.h declares
 SYMBOLS = [
     "ba_create", "ba_destroy", "ba_reset", "ba_last_error", "ba_set_stream", "ba_set_profile", "ba_set_debug",
-    "ba_set_cameras", "ba_set_poses", "ba_set_points", "ba_set_observations", "ba_finalize",
+    "ba_set_cameras", "ba_set_poses", "ba_set_points", "ba_set_observations", "ba_set_observations_scaled", "ba_finalize",
     "ba_update_parameters", "ba_solve", "ba_build_only", "ba_cost", "ba_get_poses", "ba_get_points",
     "ba_get_sizes", "ba_debug_dump", "ba_debug_pairs", "ba_debug_time_solve", "ba_debug_nd_plan", "ba_debug_solve_info", "ba_comm_get_unique_id", "ba_comm_init",
     "ba_comm_destroy", "ba_comm_attach", "ba_comm_shutdown", "ba_geometry_batched", "ba_geometry_batched_f", "ba_poseonly_solve_batched", "ba_poseonly_upload", "ba_poseonly_run",
@@ -111,6 +111,7 @@ def lib():
         L.ba_set_poses.argtypes = [vp, i, vp, vp]
         L.ba_set_points.argtypes = [vp, i, vp, vp]
         L.ba_set_observations.argtypes = [vp, ll, vp, vp, vp, vp, C.POINTER(ll)]
+        L.ba_set_observations_scaled.argtypes = [vp, ll, vp, vp, vp, vp, C.c_double, C.POINTER(ll)]
         L.ba_finalize.argtypes = [vp]
         L.ba_update_parameters.argtypes = [vp, vp, vp]
         L.ba_solve.argtypes = [vp, C.POINTER(Options), vp, i, C.POINTER(Result)]

@@ -63,7 +63,8 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
                const double2 *__restrict__ obs_uv, const int *__restrict__ obs_camflags, Params prm,
                const double *__restrict__ cams, double thres_huber, double *__restrict__ Bsoa, size_t Pp,
                double *__restrict__ ptblk, size_t Mp, double *__restrict__ Saug, int ld,
-               const LmState *__restrict__ st) {
+               const int *__restrict__ cta_seg_ptr /*first staging segment of every CTA; nullptr: flush with FP64 reds into S*/,
+               const long long *__restrict__ seg_off, double *__restrict__ stage, const LmState *__restrict__ st) {
   if (st->done) return;
   extern __shared__ double tsm[];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -313,8 +314,40 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
     int aofs[kT2SPW], bofs[kT2SPW];  // 16 I, 16 J
     double acc[kT2SPW][4][2];
     int mycnt = 0, cur_chunk = -1, nrows = 0, row0 = 0, nt = 0;
-    // flush: upper triangle of S (row-major) and the rhs column
+    // flush: upper triangle of the chunk's window (row-major) and its rhs column.  Deterministic mode: every
+    // (CTA, chunk) SEGMENT of the batch list owns a private staging window, written with plain stores (every entry,
+    // zeros included, so nothing has to be cleared); k_tile_reduce then adds the windows into S in segment order and S
+    // is bit-reproducible.  Otherwise: one FP64 red per live entry straight into S.
+    int seg = cta_seg_ptr ? __ldg(cta_seg_ptr + blockIdx.x) - 1 : 0;
+    double *stg = stage;
     auto flush = [&]() {
+      if (cta_seg_ptr) {
+        const int ldc = nrows + 1;
+#pragma unroll
+        for (int i = 0; i < kT2SPW; ++i) {
+          if (i >= mycnt) continue;
+          const int I = sdesc[i] & 0xff, J = (sdesc[i] >> 8) & 0xff;
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int tj = 2 * J + q;
+              const int lr = 8 * (2 * I + p) + fr;
+              if (lr >= nrows || tj > nt) continue;
+              double *srow = stg + (size_t)lr * ldc;
+              if (tj == nt) {
+                if (fc == 0) __stcg(srow + nrows, acc[i][2 * p + q][0]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int lc = 8 * tj + fc + e;
+                  if (lc < nrows && lc >= lr) __stcg(srow + lc, acc[i][2 * p + q][e]);
+                }
+              }
+            }
+        }
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < kT2SPW; ++i) {
         if (i >= mycnt) continue;
@@ -348,6 +381,7 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
       if (rec.z != cur_chunk) {
         if (cur_chunk >= 0) flush();
         cur_chunk = rec.z;
+        if (cta_seg_ptr) stg = stage + __ldg(seg_off + (++seg));
         const SchurChunk ch = chunks[cur_chunk];
         nrows = 6 * ch.width;
         row0 = 6 * ch.jmin;
@@ -396,4 +430,31 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
     }
     if (cur_chunk >= 0) flush();
   }
+}// Second stage of the deterministic flush: S(r, c) += sum over the staging segments whose window holds (r, c), in
+// segment order.  One CTA per scalar row; segments are sorted by their first pose, so the candidates of a row are a
+// contiguous range (pose_seg).
+__global__ void __launch_bounds__(96) k_tile_reduce(int n, int ld, int span /*largest column distance written*/,
+                                                     const int4 *__restrict__ seg_win /*6 jmin, rows, offset lo, offset hi*/,
+                                                     const int2 *__restrict__ pose_seg,
+                                                     const double *__restrict__ stage, double *__restrict__ Saug,
+                                                     const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int r = blockIdx.x;
+  const int2 range = __ldg(pose_seg + r / 6);
+  for (int t = threadIdx.x; t <= span + 1; t += blockDim.x) {
+    const bool rhs = t == span + 1;
+    const int c = rhs ? n : r + t;
+    if (!rhs && c >= n) continue;
+    double sum = 0.0;
+    for (int sg = range.x; sg < range.y; ++sg) {
+      const int4 w = __ldg(seg_win + sg);
+      const int lr = r - w.x;
+      if (lr < 0 || lr >= w.y || (!rhs && c - w.x >= w.y)) continue;
+      const long long off = ((long long)w.w << 32) | (unsigned)w.z;
+      sum += __ldcg(stage + off + (size_t)lr * (w.y + 1) + (rhs ? w.y : c - w.x));
+    }
+    if (sum != 0.0) Saug[(size_t)r * ld + (rhs ? ld - 1 : c)] += sum;
+  }
 }
+
+

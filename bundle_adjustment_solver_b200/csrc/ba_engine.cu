@@ -1229,6 +1229,13 @@ struct ba_solver {
   DevBuf<int4> d_inc_a, d_tile_batches;
   DevBuf<int2> d_inc_b;
   DevBuf<int> d_cta_batch_ptr;
+  // deterministic tile flush: one staging window per (CTA, chunk) segment of the batch list
+  DevBuf<int> d_cta_seg_ptr;     // first segment of every CTA
+  DevBuf<long long> d_seg_off;   // window offset in d_stage (doubles)
+  DevBuf<int4> d_seg_win;        // 6 jmin, rows, offset (lo, hi)
+  DevBuf<int2> d_pose_seg;       // per free pose: range of segments whose window may hold it
+  DevBuf<double> d_stage;
+  int stage_span = 0;
   TileLaunch tile_launch{};
   DevBuf<Chunk> d_chunks_fb;
   DevBuf<int2> d_chunk_pts_fb;
@@ -1319,7 +1326,7 @@ static void free_device(ba_solver *s) {
   s->d_pair_end.release(); s->d_point_has_pairs.release(); s->d_point_free.release();
   s->d_split_points.release(); s->d_split_pairs.release(); s->d_schur_chunks.release();
   s->d_tpt_point.release(); s->d_tpt_inc_start.release(); s->d_fallback_pairs.release(); s->d_fb_groups.release();
-  s->d_inc_a.release(); s->d_inc_b.release(); s->d_tile_batches.release(); s->d_cta_batch_ptr.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
+  s->d_inc_a.release(); s->d_inc_b.release(); s->d_tile_batches.release(); s->d_cta_batch_ptr.release(); s->d_cta_seg_ptr.release(); s->d_seg_off.release(); s->d_seg_win.release(); s->d_pose_seg.release(); s->d_stage.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
   s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release(); s->d_band.release();
   s->d_nd_nodes.release(); s->d_nd_level_nodes.release(); s->d_nd_cta_nodes.release(); s->d_nd_cta_ptr.release();
   s->d_nd_flags.release(); s->d_nd_L.release(); s->d_nd_U.release();
@@ -1407,6 +1414,12 @@ int ba_set_points(ba_solver *s, int m, const double *X, const uint8_t *fixed) {
 
 int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const int *pose, const int *point,
                         const double *uv, long long *n_kept) {
+  return ba_set_observations_scaled(s, n_obs, cam_id, pose, point, uv, 1.0, n_kept);
+}
+
+// pixels in the caller's units: multiplied by uv_scale (the reference's scaler_, full...cpp:176) during the copy
+int ba_set_observations_scaled(ba_solver *s, long long n_obs, const int *cam_id, const int *pose, const int *point,
+                               const double *uv, double uv_scale, long long *n_kept) {
   if (!s || n_obs < 0 || (n_obs > 0 && (!cam_id || !pose || !point || !uv))) return BA_ERR_INVALID;
   if (n_obs > 2000000000LL) { s->err = "too many observations for 32-bit indexing"; return BA_ERR_INVALID; }
   s->h_obs_cam.clear(); s->h_obs_pose.clear(); s->h_obs_point.clear(); s->h_obs_uv.clear();
@@ -1434,9 +1447,13 @@ int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const 
         parallel_ranges(n_obs, [&](long long lo_, long long hi_, int) {
           for (long long k = (long long)lo_; k < (long long)hi_; ++k) s->h_obs_cam[k] = table[cam_id[k]];
         });
-        s->h_obs_pose.assign(pose, pose + n_obs);
-        s->h_obs_point.assign(point, point + n_obs);
-        s->h_obs_uv.assign(uv, uv + 2 * n_obs);
+        s->h_obs_pose.resize(n_obs); s->h_obs_point.resize(n_obs); s->h_obs_uv.resize(2 * n_obs);
+        parallel_ranges(n_obs, [&](long long lo_, long long hi_, int) {
+          std::memcpy(s->h_obs_pose.data() + lo_, pose + lo_, (size_t)(hi_ - lo_) * sizeof(int));
+          std::memcpy(s->h_obs_point.data() + lo_, point + lo_, (size_t)(hi_ - lo_) * sizeof(int));
+          if (uv_scale == 1.0) std::memcpy(s->h_obs_uv.data() + 2 * lo_, uv + 2 * lo_, (size_t)(hi_ - lo_) * 2 * sizeof(double));
+          else for (long long k = 2 * lo_; k < 2 * hi_; ++k) s->h_obs_uv[k] = uv[k] * uv_scale;
+        });
         s->n_obs = n_obs;
         if (n_kept) *n_kept = s->n_obs;
         s->finalized = false;
@@ -1454,8 +1471,8 @@ int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const 
     s->h_obs_cam.push_back(it->second);
     s->h_obs_pose.push_back(pose[k]);
     s->h_obs_point.push_back(point[k]);
-    s->h_obs_uv.push_back(uv[2 * k]);
-    s->h_obs_uv.push_back(uv[2 * k + 1]);
+    s->h_obs_uv.push_back(uv[2 * k] * uv_scale);
+    s->h_obs_uv.push_back(uv[2 * k + 1] * uv_scale);
   }
   s->n_obs = (long long)s->h_obs_cam.size();
   if (n_kept) *n_kept = s->n_obs;
@@ -1785,6 +1802,11 @@ int ba_finalize(ba_solver *s) {
   // --- flat list of 8-landmark batches over the tile chunks, split evenly over one persistent CTA per SM
   std::vector<int4> tile_batches;
   std::vector<int> cta_batch_ptr;
+  std::vector<int> cta_seg_ptr;
+  std::vector<long long> seg_off;
+  std::vector<int4> seg_win;
+  std::vector<int2> pose_seg;
+  long long stage_doubles = 0;
   {
     int nt_max = 1;
     for (size_t c = 0; c < schur_chunks.size(); ++c) {
@@ -1805,6 +1827,33 @@ int ba_finalize(ba_solver *s) {
     tl.n_cta = (int)std::min<long long>(sms, std::max<long long>(1, (nbt + tl.G - 1) / tl.G));
     cta_batch_ptr.resize(tl.n_cta + 1);
     for (int k = 0; k <= tl.n_cta; ++k) cta_batch_ptr[k] = (int)(nbt * k / tl.n_cta);
+    // deterministic flush: every (CTA, chunk) run of the batch list owns a staging window
+    cta_seg_ptr.assign(tl.n_cta + 1, 0);
+    pose_seg.assign(std::max(1, s->N), make_int2(0, 0));
+    long long off = 0;
+    int span = 0;
+    for (int c = 0; c < tl.n_cta; ++c) {
+      cta_seg_ptr[c] = (int)seg_off.size();
+      int prev = -1;
+      for (int fb = cta_batch_ptr[c]; fb < cta_batch_ptr[c + 1]; ++fb) {
+        const int chunk = tile_batches[fb].z;
+        if (chunk == prev) continue;
+        prev = chunk;
+        const SchurChunk &ch = schur_chunks[chunk];
+        const int sg = (int)seg_off.size(), nr = 6 * ch.width;
+        seg_off.push_back(off);
+        seg_win.push_back(make_int4(6 * ch.jmin, nr, (int)(unsigned)(off & 0xffffffffLL), (int)(off >> 32)));
+        off += (long long)nr * (nr + 1);
+        span = std::max(span, nr - 1);
+        for (int j = ch.jmin; j < ch.jmin + ch.width && j < s->N; ++j) {
+          if (pose_seg[j].y == 0) pose_seg[j].x = sg;
+          pose_seg[j].y = sg + 1;
+        }
+      }
+    }
+    cta_seg_ptr[tl.n_cta] = (int)seg_off.size();
+    stage_doubles = off;
+    s->stage_span = span;
   }
   lap("tile chunks, incidences");
   // --- Cholesky envelope plan from the co-visibility structure (first co-visible pose of every free pose)
@@ -1996,6 +2045,13 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_inc_b.upload(inc_b, st));
   CUDA_TRY(s->d_tile_batches.upload(tile_batches, st));
   CUDA_TRY(s->d_cta_batch_ptr.upload(cta_batch_ptr, st));
+  // BA_B200_TILE_FLUSH=atomic: the earlier flush (one FP64 red per entry straight into S), for A/B runs
+  if (getenv("BA_B200_TILE_FLUSH") && std::string(getenv("BA_B200_TILE_FLUSH")) == "atomic") { cta_seg_ptr.clear(); stage_doubles = 0; }
+  CUDA_TRY(s->d_cta_seg_ptr.upload(cta_seg_ptr, st));
+  CUDA_TRY(s->d_seg_off.upload(seg_off, st));
+  CUDA_TRY(s->d_seg_win.upload(seg_win, st));
+  CUDA_TRY(s->d_pose_seg.upload(pose_seg, st));
+  CUDA_TRY(s->d_stage.alloc((size_t)std::max<long long>(1, stage_doubles)));
   CUDA_TRY(s->d_chunks_fb.upload(pc_fb.chunks, st));
   CUDA_TRY(s->d_chunk_pts_fb.upload(pc_fb.chunk_pts, st));
   CUDA_TRY(s->d_cpts_fb.upload(pc_fb.cpts, st));
@@ -2203,17 +2259,22 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
     }
     const TileLaunch &tl = s->tile_launch;
     const size_t smem = (size_t)tl.G * tl.bufD * sizeof(double);
+    const int *stage_tab = s->d_cta_seg_ptr.n > 0 ? s->d_cta_seg_ptr.p : nullptr;
     if (opt->b_accumulate)
       k_build_tiles<true><<<tl.n_cta, kT2Threads, smem, st>>>(
           s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
           s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
-          s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+          s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, stage_tab, s->d_seg_off.p, s->d_stage.p, dst);
     else
       k_build_tiles<false><<<tl.n_cta, kT2Threads, smem, st>>>(
           s->d_schur_chunks.p, s->d_tile_batches.p, s->d_cta_batch_ptr.p, tl, s->d_tpt_point.p, s->d_tpt_inc_start.p,
           s->d_inc_a.p, s->d_inc_b.p, s->d_obs_uv.p, s->d_obs_camflags.p, prm, s->d_cams.p, thres, s->d_Bsoa.p,
-          s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, dst);
+          s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, stage_tab, s->d_seg_off.p, s->d_stage.p, dst);
     s->launches++;
+    if (stage_tab && s->N > 0) {
+      k_tile_reduce<<<6 * s->N, 96, 0, st>>>(6 * s->N, ld, s->stage_span, s->d_seg_win.p, s->d_pose_seg.p, s->d_stage.p, s->d_Saug.p, dst);
+      s->launches++;
+    }
   }
   static const int dense_max = getenv("BA_B200_DENSE_SCHUR_MAX") ? atoi(getenv("BA_B200_DENSE_SCHUR_MAX")) : 6 * kDenseMaxPoses + 1;
   if (s->n_fallback_pairs > 0 && ld <= dense_max) {

@@ -243,17 +243,16 @@ class FullBundleAdjustmentSolver:
         _check(L.ba_set_poses(h, len(pf), ptr(T12), ptr(pf)), L, h, "ba_set_poses")
         _check(L.ba_set_points(h, len(qf), ptr(X), ptr(qf)), L, h, "ba_set_points")
         self._flush_scalar_obs()
-        if self._obs_chunks:
-            cam = np.ascontiguousarray(np.concatenate([c[0] for c in self._obs_chunks]))
-            pose = np.ascontiguousarray(np.concatenate([c[1] for c in self._obs_chunks]))
-            point = np.ascontiguousarray(np.concatenate([c[2] for c in self._obs_chunks]))
-            uv = np.ascontiguousarray(np.concatenate([c[3] for c in self._obs_chunks]) * self.scaler)
+        if len(self._obs_chunks) == 1:       # one bulk AddObservation call: no host copy, the engine scales while it copies
+            cam, pose, point, uv = (np.ascontiguousarray(a) for a in self._obs_chunks[0])
+        elif self._obs_chunks:
+            cam, pose, point, uv = (np.ascontiguousarray(np.concatenate([c[k] for c in self._obs_chunks])) for k in range(4))
         else:
             cam = pose = point = np.zeros(0, dtype=np.int32)
             uv = np.zeros((0, 2))
         kept = C.c_longlong(0)
-        _check(L.ba_set_observations(h, len(cam), ptr(cam), ptr(pose), ptr(point), ptr(uv), C.byref(kept)),
-               L, h, "ba_set_observations")
+        _check(L.ba_set_observations_scaled(h, len(cam), ptr(cam), ptr(pose), ptr(point), ptr(uv), self.scaler, C.byref(kept)),
+               L, h, "ba_set_observations_scaled")
         self.num_total_observations = kept.value
         _check(L.ba_finalize(h), L, h, "ba_finalize")
         self._uploaded = True

@@ -115,6 +115,10 @@ int ba_set_points(ba_solver *s, int m, const double *X, const uint8_t *fixed);
  * drops them; the number kept is returned through n_kept (may be NULL). */
 int ba_set_observations(ba_solver *s, long long n_obs, const int *cam_id, const int *pose, const int *point,
                         const double *uv, long long *n_kept);
+/* The same with the pixels in the caller's units: every coordinate is multiplied by uv_scale (the reference's
+ * scaler_ = 0.01, core/full_bundle_adjustment_solver.cpp:38, :176) while it is copied. */
+int ba_set_observations_scaled(ba_solver *s, long long n_obs, const int *cam_id, const int *pose, const int *point,
+                               const double *uv, double uv_scale, long long *n_kept);
 /* FinalizeParameters + SetProblemSize + connectivity (:182-206,243-308,669-700): index assignment,
  * the two sort orders, last-writer flags, chunking, and the H2D pack into SoA device buffers.
  * Idempotent. */
