@@ -75,11 +75,12 @@ struct NdSmem {
   double *winv;   // inverses of the diagonal blocks [max_KT][64]
   double *xs;     // backward: x by front-local index [max_R8]
   double *tb;     // backward: right-hand side of the block chain [max_R8]
-  int *pm;        // child index maps [2][max_R8]
+  int *pm;        // my boundary index -> front-local index of my parent [max_R8] (second half unused)
   int *grow;      // global index of a front-local row / column in S (n: rhs row, -1: padding) [max_R8]
   int *tt;        // tile table: (I << 16) | J by storage position
   NdNode *node;   // current node
   NdNode *cn;     // its two children [2]
+  NdNode *par;    // its parent
 };
 
 __device__ __forceinline__ NdSmem nd_carve(unsigned char *raw, const NdArgs &g) {
@@ -93,61 +94,35 @@ __device__ __forceinline__ NdSmem nd_carve(unsigned char *raw, const NdArgs &g) 
   sm.tt = sm.grow + g.max_R8;
   sm.node = reinterpret_cast<NdNode *>(sm.tt + ((g.max_tiles + 1) & ~1));
   sm.cn = sm.node + 1;
+  sm.par = sm.node + 3;
   return sm;
 }
 inline size_t nd_smem_bytes(const NdPlan &pl) {
   return ((size_t)pl.max_tiles + pl.max_KT) * 64 * sizeof(double) + (size_t)2 * pl.max_R8 * sizeof(double) +
-         (size_t)3 * pl.max_R8 * sizeof(int) + (size_t)((pl.max_tiles + 1) & ~1) * sizeof(int) + 3 * sizeof(NdNode) + 64;
+         (size_t)3 * pl.max_R8 * sizeof(int) + (size_t)((pl.max_tiles + 1) & ~1) * sizeof(int) + 4 * sizeof(NdNode) + 64;
 }
 
 // Sources of the initial value of front entry (i, j), i >= j (front-local indices): an entry of S (own columns only),
 // one entry of each child's contribution block, or a constant (identity padding).  Addresses first, loads later, so
 // that a batch of entries has all its loads in flight together.
-struct NdSrc {
-  unsigned os, o0, o1;   // element offsets into S / the children's contribution blocks; kNdNone: no source
-};
-constexpr unsigned kNdNone = 0xffffffffu, kNdOne = 0xfffffffeu;   // kNdOne (in os): the constant 1 (identity padding)
-// per-front constants of the gather, kept in registers
+// Initial value of front entry (i, j), i >= j, j an own column, as far as S is concerned: the offset of the entry in
+// S, kNdNone (nothing), or kNdOne (identity padding).  The children's contributions arrive as whole tiles.
+constexpr unsigned kNdNone = 0xffffffffu, kNdOne = 0xfffffffeu;
 struct NdGather {
-  const double *S, *U0, *U1;     // U0 / U1: contribution blocks of the children (nullptr: no child)
-  int ld, n, bw, off1;           // off1: offset of the second child's index map
+  const double *S, *U0, *U1;     // U0 / U1: the children's contribution blocks in THIS front's layout (nullptr: no child)
+  int ld, n, bw;
 };
-template <bool OWN>
-__device__ __forceinline__ NdSrc nd_front_src(const NdGather &q, const NdSmem &sm, int i, int j, bool on) {
-  NdSrc r{kNdNone, kNdNone, kNdNone};
-  if (!on) return r;
-  if (OWN) {   // j is an own column
-    const int gi = sm.grow[i], gj = sm.grow[j];
-    if (gj < 0) {
-      if (i == j) r.os = kNdOne;    // identity padding of the own block
-      return r;
-    }
-    if (gi >= 0) {
-      const int lo = min(gi, gj), hi = max(gi, gj);
-      if (hi == q.n || hi - lo <= q.bw) r.os = (unsigned)lo * (unsigned)q.ld + (unsigned)hi;
-    }
-  }
-  if (q.U0) {
-    const int pi = sm.pm[i], pj = sm.pm[j];
-    if ((pi | pj) >= 0) {
-      const int a = max(pi, pj), b = min(pi, pj);
-      r.o0 = (unsigned)(nd_tidx(a >> 3, b >> 3) * 64 + (a & 7) * 8 + (b & 7));
-    }
-  }
-  if (q.U1) {
-    const int pi = sm.pm[q.off1 + i], pj = sm.pm[q.off1 + j];
-    if ((pi | pj) >= 0) {
-      const int a = max(pi, pj), b = min(pi, pj);
-      r.o1 = (unsigned)(nd_tidx(a >> 3, b >> 3) * 64 + (a & 7) * 8 + (b & 7));
-    }
-  }
-  return r;
+__device__ __forceinline__ unsigned nd_front_src(const NdGather &q, const NdSmem &sm, int i, int j, bool on) {
+  if (!on) return kNdNone;
+  const int gi = sm.grow[i], gj = sm.grow[j];
+  if (gj < 0) return (i == j) ? kNdOne : kNdNone;    // identity padding of the own block
+  if (gi < 0) return kNdNone;
+  const int lo = min(gi, gj), hi = max(gi, gj);
+  if (hi == q.n || hi - lo <= q.bw) return (unsigned)lo * (unsigned)q.ld + (unsigned)hi;
+  return kNdNone;
 }
-__device__ __forceinline__ double nd_src_value(const NdGather &q, const NdSrc &s) {
-  const double a = s.os < kNdOne ? __ldcg(q.S + s.os) : (s.os == kNdOne ? 1.0 : 0.0);
-  const double b = s.o0 != kNdNone ? __ldcg(q.U0 + s.o0) : 0.0;
-  const double c = s.o1 != kNdNone ? __ldcg(q.U1 + s.o1) : 0.0;
-  return a + (b + c);
+__device__ __forceinline__ double nd_src_value(const NdGather &q, unsigned os) {
+  return os < kNdOne ? __ldcg(q.S + os) : (os == kNdOne ? 1.0 : 0.0);
 }
 
 // stage the node record (and its children's) in shared memory; ends with a CTA barrier
@@ -161,6 +136,8 @@ __device__ __forceinline__ void nd_stage_node(const NdArgs &g, const NdSmem &sm,
     for (int c = 0; c < 2; ++c)
       if (nd.child[c] >= 0 && t >= 32 * (1 + c) && t < 32 * (1 + c) + NW)
         reinterpret_cast<int *>(sm.cn + c)[t - 32 * (1 + c)] = reinterpret_cast<const int *>(g.nodes + nd.child[c])[t - 32 * (1 + c)];
+    if (nd.parent >= 0 && t >= 96 && t < 96 + NW)
+      reinterpret_cast<int *>(sm.par)[t - 96] = reinterpret_cast<const int *>(g.nodes + nd.parent)[t - 96];
     __syncthreads();
   }
 }
@@ -184,7 +161,16 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
   auto colbase = [&](int J) { return J * NT - (J * (J - 1)) / 2; };   // tile (I, J), I >= J, at colbase(J) + I - J
   const int n_tiles = colbase(KT);
   const int LbT0 = (nd.k8 + nd.wr) >> 3;        // first row tile of [Lb | rhs]
-  for (int i = t; i < 2 * g.max_R8; i += kNdThreads) sm.pm[i] = -1;
+  // pm: my boundary index -> front-local index of my PARENT (where my Schur complement goes); -1: padding
+  for (int i = t; i < nd.b8; i += kNdThreads) {
+    int m = -1;
+    if (nd.parent >= 0) {
+      if (i < nd.wr) m = nd.rb_off + i;
+      else if (i < nd.wr + nd.wl) m = nd.lb_off + (i - nd.wr);
+      else if (i == nd.wr + nd.wl) m = nd.rhs_off;
+    }
+    sm.pm[i] = m;
+  }
   for (int i = t; i < 64 * KT; i += kNdThreads) sm.winv[i] = 0.0;
   for (int i = t; i < 8 * NT; i += kNdThreads) {
     const int bi = i - nd.k8;
@@ -200,30 +186,23 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
     for (int I = J + lane; I < NT; I += 32) sm.tt[base + I] = (I << 16) | J;
   }
   __syncthreads();
-  for (int c = 0; c < 2; ++c) {
-    if (nd.child[c] < 0) continue;
-    const NdNode &cn = sm.cn[c];
-    int *pm = sm.pm + c * g.max_R8;
-    for (int i = t; i < cn.wr; i += kNdThreads) pm[cn.rb_off + i] = i;
-    for (int i = t; i < cn.wl; i += kNdThreads) pm[cn.lb_off + i] = cn.wr + i;
-    if (t == 0) pm[cn.rhs_off] = cn.wr + cn.wl;
-  }
-  __syncthreads();
   if (timing && t == 0 && blockIdx.x == 0) g_nd_dbg[13] += gtime() - t_in;   // staging, index maps
   const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
   const int swz = (fr & 2) << 1;
   const int offC = fr * 8 + (fc ^ swz);                          // accumulator fragment (double2) inside a tile
   const int offA0 = fr * 8 + (kq ^ swz), offA1 = offA0 ^ 4;      // operand fragments: columns kq and kq + 4
   NdGather gq;
-  gq.S = g.S; gq.ld = g.ld; gq.n = g.n; gq.bw = g.bw; gq.off1 = g.max_R8;
+  gq.S = g.S; gq.ld = g.ld; gq.n = g.n; gq.bw = g.bw;
   gq.U0 = nd.child[0] >= 0 ? g.Uws + sm.cn[0].U_off : nullptr;
   gq.U1 = nd.child[1] >= 0 ? g.Uws + sm.cn[1].U_off : nullptr;
   const bool has_children = gq.U0 || gq.U1;
-  // ---- assembly of the own columns: a warp takes UN tiles per round, lane (fr, fc) two adjacent entries of each
+  // ---- assembly of the own columns: a warp takes UN tiles per round, lane (fr, fc) two adjacent entries of each:
+  //      the band of S (gathered) plus the children's contribution tiles (already in this front's layout: coalesced)
   {
     constexpr int UN = 8;
     for (int tb0 = warp; tb0 < n_tiles; tb0 += kNdWarps * UN) {
-      NdSrc src[UN][2];
+      unsigned src[UN][2];
+      double2 c0[UN], c1[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int tile = tb0 + kNdWarps * u;
@@ -233,21 +212,22 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
         const int i = 8 * I + fr, j = 8 * J + fc;
         // a front without children holds nothing but the band of S: tiles entirely outside it are zero
         bool in_band = true;
-        if (!has_children && I > J) {
+        if (I > J) {
           const int gr = sm.grow[8 * I], gr7 = sm.grow[8 * I + 7], gc = sm.grow[8 * J], gc7 = sm.grow[8 * J + 7];
           const bool rows_ok = gr >= 0 && gr7 - gr == 7 && gr7 != g.n;     // eight consecutive rows of S
           in_band = !(rows_ok && ((gc7 >= 0 && gr - gc7 > g.bw) || gc - gr7 > g.bw));
         }
-        src[u][0] = nd_front_src<true>(gq, sm, i, j, live && in_band && i >= j);
-        src[u][1] = nd_front_src<true>(gq, sm, i, j + 1, live && in_band && i >= j + 1);
+        src[u][0] = nd_front_src(gq, sm, i, j, live && in_band && i >= j);
+        src[u][1] = nd_front_src(gq, sm, i, j + 1, live && in_band && i >= j + 1);
+        c0[u] = (live && gq.U0) ? __ldcg(reinterpret_cast<const double2 *>(gq.U0 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
+        c1[u] = (live && gq.U1) ? __ldcg(reinterpret_cast<const double2 *>(gq.U1 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
       }
-      double2 v[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) v[u] = make_double2(nd_src_value(gq, src[u][0]), nd_src_value(gq, src[u][1]));
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int tile = tb0 + kNdWarps * u;
-        if (tile < n_tiles) *reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC) = v[u];
+        if (tile < n_tiles)
+          *reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC) =
+              make_double2(nd_src_value(gq, src[u][0]) + (c0[u].x + c1[u].x), nd_src_value(gq, src[u][1]) + (c0[u].y + c1[u].y));
       }
     }
   }
@@ -273,23 +253,15 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
       }
     }
     if (has_children) {
-      constexpr int UQ = 8;
+      const int offU = fr * 8 + fc;
 #pragma unroll
-      for (int q0 = 0; q0 < TPW; q0 += UQ) {
-        NdSrc src[UQ][2];
-#pragma unroll
-        for (int u = 0; u < UQ; ++u) {
-          if (q0 + u < TPW) {
-            const int q = q0 + u;
-            const bool live = ub[q] >= 0;
-            const int i = nd.k8 + 8 * (ub[q] >> 8) + fr, j = nd.k8 + 8 * (ub[q] & 0xff) + fc;
-            src[u][0] = nd_front_src<false>(gq, sm, i, j, live && i >= j);
-            src[u][1] = nd_front_src<false>(gq, sm, i, j + 1, live && i >= j + 1);
-          }
+      for (int q = 0; q < TPW; ++q) {
+        if (ub[q] >= 0) {
+          const size_t off = ((size_t)n_tiles + nd_tidx(ub[q] >> 8, ub[q] & 0xff)) * 64 + offU;
+          const double2 a = gq.U0 ? __ldcg(reinterpret_cast<const double2 *>(gq.U0 + off)) : make_double2(0.0, 0.0);
+          const double2 b = gq.U1 ? __ldcg(reinterpret_cast<const double2 *>(gq.U1 + off)) : make_double2(0.0, 0.0);
+          acc[q] = make_double2(a.x + b.x, a.y + b.y);
         }
-#pragma unroll
-        for (int u = 0; u < UQ; ++u)
-          if (q0 + u < TPW) acc[q0 + u] = make_double2(nd_src_value(gq, src[u][0]), nd_src_value(gq, src[u][1]));
       }
     }
   }
@@ -470,12 +442,34 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
         }
       }
     }
-    // ---- contribution block
-    double *Ug = g.Uws + nd.U_off;
-    const int offU = fr * 8 + fc;
+    // ---- contribution block: my Schur complement, scattered into the layout of my parent's front (own-column tiles
+    //      swizzled like its shared-memory window, then its boundary x boundary tiles)
+    if (nd.parent >= 0) {
+      double *Ug = g.Uws + nd.U_off;
+      const int KTp = sm.par->k8 >> 3, NTp = (sm.par->k8 + sm.par->b8) >> 3, k8p = sm.par->k8;
+      const int ntp = KTp * NTp - (KTp * (KTp - 1)) / 2;
 #pragma unroll
-    for (int q = 0; q < TPW; ++q)
-      if (ub[q] >= 0) *reinterpret_cast<double2 *>(Ug + (size_t)nd_tidx(ub[q] >> 8, ub[q] & 0xff) * 64 + offU) = acc[q];
+      for (int q = 0; q < TPW; ++q) {
+        if (ub[q] < 0) continue;
+        const int bi = 8 * (ub[q] >> 8) + fr, bj0 = 8 * (ub[q] & 0xff) + fc;
+        const int pi = sm.pm[bi];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int bj = bj0 + e;
+          if (bj > bi || pi < 0) continue;                  // upper half of a diagonal tile / padding rows
+          const int pj = sm.pm[bj];
+          if (pj < 0) continue;
+          const int a = max(pi, pj), b = min(pi, pj);
+          const double v = e ? acc[q].y : acc[q].x;
+          if (b < k8p) {
+            const int I = a >> 3, J = b >> 3;
+            Ug[(size_t)(J * NTp - (J * (J - 1)) / 2 + I - J) * 64 + nd_sw(a & 7, b & 7)] = v;
+          } else {
+            Ug[((size_t)ntp + nd_tidx((a - k8p) >> 3, (b - k8p) >> 3)) * 64 + ((a - k8p) & 7) * 8 + ((b - k8p) & 7)] = v;
+          }
+        }
+      }
+    }
   }
   __syncthreads();
   if (timing && t == 0) {

@@ -38,7 +38,10 @@ struct NdNode {
                         // band of S; separators: all).  Rows outside (except Lb / rhs) are skipped by the factorisation
   long long L_off;      // doubles: factor tiles of the own columns [n_tiles][64] (swizzled 8 x 8 tiles, column by
                         // column), then the inverses of the diagonal blocks [KT][64]
-  long long U_off;      // doubles: contribution block, lower-triangular 8x8 tiles [BT (BT+1) / 2][64]
+  long long U_off;      // doubles: contribution block IN THE PARENT'S FRONT LAYOUT: the parent's own-column tiles
+                        // [n_tiles_parent][64] (swizzled like the shared-memory window) followed by the parent's
+                        // boundary x boundary tiles [BT_p (BT_p + 1) / 2][64] (plain).  The child scatters its
+                        // Schur complement there, the parent's assembly is then a streaming add of whole tiles
 };
 
 struct NdPlan {
@@ -179,7 +182,11 @@ inline void nd_make_plan_depth(NdPlan &pl, int N, int b, int max_ctas, int force
     nd.L_off = pl.L_doubles;
     pl.L_doubles += ((long long)KT * (KT + 1) / 2 + (long long)BTn * KT + KT) * 64;
     nd.U_off = pl.U_doubles;
-    pl.U_doubles += (long long)BTn * (BTn + 1) / 2 * 64;
+    if (nd.parent >= 0) {
+      const NdNode &pn = nodes[nd.parent];
+      const long long KTp = pn.k8 / 8, BTp = pn.b8 / 8;
+      pl.U_doubles += (KTp * (KTp + 1) / 2 + BTp * KTp + BTp * (BTp + 1) / 2) * 64;
+    }
     pl.max_KT = std::max(pl.max_KT, KT);
     pl.max_BT = std::max(pl.max_BT, BTn);
     pl.max_R8 = std::max(pl.max_R8, R8);
