@@ -441,19 +441,57 @@ __global__ void __launch_bounds__(96) k_tile_reduce(int n, int ld, int span /*la
   if (st->done) return;
   const int r = blockIdx.x;
   const int2 range = __ldg(pose_seg + r / 6);
-  for (int t = threadIdx.x; t <= span + 1; t += blockDim.x) {
+  // the segment records that hold this row, once per CTA and in segment order (read per entry they would be the bulk
+  // of the traffic), kKeep at a time
+  constexpr int kKeep = 128;
+  __shared__ int4 rec[kKeep];
+  __shared__ int n_rec;
+  double sum[2] = {0.0, 0.0};                 // up to two columns per thread (span + 2 <= 2 x 96)
+  for (int s0 = range.x; s0 < range.y; s0 += kKeep) {
+    __syncthreads();
+    if (threadIdx.x < 32) {       // ordered compaction of the segments that hold row r (warp 0, ballots)
+      const int lane = threadIdx.x, end = min(range.y, s0 + kKeep);
+      int cnt = 0;
+      for (int base = s0; base < end; base += 32) {
+        const int sg = base + lane;
+        int4 w = make_int4(0, 0, 0, 0);
+        if (sg < end) w = __ldg(seg_win + sg);
+        const bool hit = sg < end && r - w.x >= 0 && r - w.x < w.y;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) rec[cnt + __popc(m & ((1u << lane) - 1u))] = w;
+        cnt += __popc(m);
+      }
+      if (lane == 0) n_rec = cnt;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = threadIdx.x + u * blockDim.x;
+      if (t > span + 1) continue;
+      const bool rhs = t == span + 1;
+      const int c = rhs ? n : r + t;
+      if (!rhs && c >= n) continue;
+      for (int k0 = 0; k0 < n_rec; k0 += 8) {        // eight loads in flight, summed in segment order
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int4 w = rec[min(k0 + q, n_rec - 1)];
+          const bool ok = k0 + q < n_rec && (rhs || c - w.x < w.y);
+          const long long off = ((long long)w.w << 32) | (unsigned)w.z;
+          v[q] = ok ? __ldcg(stage + off + (size_t)(r - w.x) * (w.y + 1) + (rhs ? w.y : c - w.x)) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum[u] += v[q];
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = threadIdx.x + u * blockDim.x;
+    if (t > span + 1) continue;
     const bool rhs = t == span + 1;
     const int c = rhs ? n : r + t;
-    if (!rhs && c >= n) continue;
-    double sum = 0.0;
-    for (int sg = range.x; sg < range.y; ++sg) {
-      const int4 w = __ldg(seg_win + sg);
-      const int lr = r - w.x;
-      if (lr < 0 || lr >= w.y || (!rhs && c - w.x >= w.y)) continue;
-      const long long off = ((long long)w.w << 32) | (unsigned)w.z;
-      sum += __ldcg(stage + off + (size_t)lr * (w.y + 1) + (rhs ? w.y : c - w.x));
-    }
-    if (sum != 0.0) Saug[(size_t)r * ld + (rhs ? ld - 1 : c)] += sum;
+    if ((rhs || c < n) && sum[u] != 0.0) Saug[(size_t)r * ld + (rhs ? ld - 1 : c)] += sum[u];
   }
 }
 

@@ -1190,9 +1190,6 @@ struct ba_solver {
   std::string err;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaStream_t side_stream = nullptr;            // forked branch of the iteration (pose update beside the back-substitution)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool forked = false;                           // the branch of the iteration being enqueued is open
   bool profile = false, debug_keep = false;
 
   // host problem
@@ -1286,12 +1283,6 @@ static int ensure_stream(ba_solver *s) {
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
   }
-  if (!s->side_stream) {
-    CUDA_TRY(cudaSetDevice(s->device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
-  }
   pool_setup(s->device);
   g_alloc_stream = s->stream;
   return BA_OK;
@@ -1358,9 +1349,6 @@ void ba_destroy(ba_solver *s) {
   pinned_put(s->h_scal);
   s->comm = nullptr;
   s->shared.reset();
-  if (s->side_stream) { cudaStreamDestroy(s->side_stream); s->side_stream = nullptr; }
-  if (s->ev_fork) { cudaEventDestroy(s->ev_fork); s->ev_fork = nullptr; }
-  if (s->ev_join) { cudaEventDestroy(s->ev_join); s->ev_join = nullptr; }
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -2352,19 +2340,6 @@ static int enqueue_solve_backsub(ba_solver *s, const ba_options *opt, cudaEvent_
     cholesky_solve_enqueue(s->chol, s->d_Saug.p, s->d_x.p, s->d_z.p, s->d_linv.p, dst, st, &s->launches);
   }
   if (ev) cudaEventRecord(ev[Phase::Backsub], st);
-  // The pose update (se3Exp, pose part of the model change) needs x only: outside the per-phase profiling mode it
-  // runs on a forked branch beside the back-substitution of the landmarks and joins before the trial cost
-  s->forked = false;
-  if (!ev && s->side_stream) {
-    const ParamsW prw2{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
-    cudaEventRecord(s->ev_fork, st);
-    cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
-    k_update_poses<<<s->pose_grid, kThreads, 0, s->side_stream>>>(s->N_total, s->d_pose_opt.p, s->d_x.p, s->d_A.p, s->d_a.p,
-                                                                 prm, prw2, s->d_pose_partials.p, dst);
-    cudaEventRecord(s->ev_join, s->side_stream);
-    s->launches++;
-    s->forked = true;
-  }
   if (!gd && s->n_split_pairs > 0) cudaMemsetAsync(s->d_Btx.p, 0, 3 * s->Mp * sizeof(double), st);
   if (!gd && s->n_chunks > 0 && s->P > 0) {
     k_backsub_pairs<<<s->n_chunks, kThreads, 0, st>>>(s->d_chunks.p, s->d_chunk_pair_count.p, s->d_pair_pose.p,
@@ -2385,14 +2360,10 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
   const ParamsW prw{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
   LmState *dst = s->d_state.p;
   if (ev) cudaEventRecord(ev[Phase::Update], st);
-  if (s->forked) {
-    cudaStreamWaitEvent(st, s->ev_join, 0);
-    s->forked = false;
-    s->launches--;   // counted at the fork
-  } else {
-    k_update_poses<<<s->pose_grid, kThreads, 0, st>>>(s->N_total, s->d_pose_opt.p, s->d_x.p, s->d_A.p, s->d_a.p,
-                                                      prm, prw, s->d_pose_partials.p, dst);
-  }
+  // (tried: the pose update on a forked graph branch beside the back-substitution -- the cross-stream edges cost more
+  //  than the 9 us they hide: C3 0.419 -> 0.431 ms per iteration)
+  k_update_poses<<<s->pose_grid, kThreads, 0, st>>>(s->N_total, s->d_pose_opt.p, s->d_x.p, s->d_A.p, s->d_a.p,
+                                                    prm, prw, s->d_pose_partials.p, dst);
   k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
                                             s->d_obs_camflags.p, prm, 1, s->d_cams.p, s->d_cost_partials.p, 0, dst);
   DecideArgs g = make_decide_args(s, opt);
