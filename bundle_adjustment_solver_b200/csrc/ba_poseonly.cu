@@ -453,6 +453,7 @@ struct ba_poseonly_batch {
   ba_poseonly_result *results = nullptr;
   float *hist_cost = nullptr, *hist_step = nullptr, *debug_poses = nullptr;
   int hist_iters = 0;
+  void *arena = nullptr;       // one pool allocation behind offsets .. results
   float intr_l[4], intr_r[4], l2r[12], b2c[12];
   int group = 32;
 };
@@ -471,9 +472,9 @@ extern "C" {
 void ba_poseonly_free(ba_poseonly_batch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  cudaFree(b->offsets); cudaFree(b->points); cudaFree(b->pxl); cudaFree(b->pxr); cudaFree(b->w2l);
-  cudaFree(b->poses_in); cudaFree(b->poses_out); cudaFree(b->mask_l); cudaFree(b->mask_r); cudaFree(b->results);
-  cudaFree(b->hist_cost); cudaFree(b->hist_step); cudaFree(b->debug_poses);
+  // one arena from the device's stream-ordered pool (a dozen cudaMalloc / cudaFree pairs per call cost 5 - 50 ms)
+  if (b->arena) cudaFreeAsync(b->arena, 0);
+  if (b->hist_cost) cudaFreeAsync(b->hist_cost, 0);
   delete b;
 }
 
@@ -502,16 +503,34 @@ int ba_poseonly_upload(ba_poseonly_batch **out, int device, int kind, int n_fram
   std::memcpy(b->l2r, left_to_right ? left_to_right : ident, 48);
   std::memcpy(b->b2c, base_to_camera ? base_to_camera : ident, 48);
   const size_t nz = (size_t)std::max<long long>(n, 1), fz = (size_t)std::max(n_frames, 1);
-  PO_TRY(cudaMalloc(&b->offsets, (fz + 1) * sizeof(int)));
-  PO_TRY(cudaMalloc(&b->points, nz * 12));
-  PO_TRY(cudaMalloc(&b->pxl, nz * 8));
-  PO_TRY(cudaMalloc(&b->pxr, nz * 8));
-  PO_TRY(cudaMalloc(&b->w2l, fz * 48));
-  PO_TRY(cudaMalloc(&b->poses_in, fz * 48));
-  PO_TRY(cudaMalloc(&b->poses_out, fz * 48));
-  PO_TRY(cudaMalloc(&b->mask_l, nz));
-  PO_TRY(cudaMalloc(&b->mask_r, nz));
-  PO_TRY(cudaMalloc(&b->results, fz * sizeof(ba_poseonly_result)));
+  {
+    static bool pool_ready[64] = {};
+    if (device >= 0 && device < 64 && !pool_ready[device]) {   // keep freed blocks in the pool between calls
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready[device] = true;
+    }
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t sz[10] = {al((fz + 1) * sizeof(int)), al(nz * 12), al(nz * 8), al(nz * 8), al(fz * 48), al(fz * 48), al(fz * 48),
+                           al(nz), al(nz), al(fz * sizeof(ba_poseonly_result))};
+    size_t total = 0;
+    for (size_t v : sz) total += v;
+    PO_TRY(cudaMallocAsync(&b->arena, total, 0));
+    char *p = static_cast<char *>(b->arena);
+    b->offsets = reinterpret_cast<decltype(b->offsets)>(p); p += sz[0];
+    b->points = reinterpret_cast<decltype(b->points)>(p); p += sz[1];
+    b->pxl = reinterpret_cast<decltype(b->pxl)>(p); p += sz[2];
+    b->pxr = reinterpret_cast<decltype(b->pxr)>(p); p += sz[3];
+    b->w2l = reinterpret_cast<decltype(b->w2l)>(p); p += sz[4];
+    b->poses_in = reinterpret_cast<decltype(b->poses_in)>(p); p += sz[5];
+    b->poses_out = reinterpret_cast<decltype(b->poses_out)>(p); p += sz[6];
+    b->mask_l = reinterpret_cast<decltype(b->mask_l)>(p); p += sz[7];
+    b->mask_r = reinterpret_cast<decltype(b->mask_r)>(p); p += sz[8];
+    b->results = reinterpret_cast<decltype(b->results)>(p);
+  }
   PO_TRY(cudaMemcpy(b->offsets, offsets, ((size_t)n_frames + 1) * sizeof(int), cudaMemcpyHostToDevice));
   PO_TRY(cudaMemcpy(b->points, points, (size_t)n * 12, cudaMemcpyHostToDevice));
   PO_TRY(cudaMemcpy(b->pxl, px_left, (size_t)n * 8, cudaMemcpyHostToDevice));
@@ -527,11 +546,14 @@ int ba_poseonly_upload(ba_poseonly_batch **out, int device, int kind, int n_fram
 
 static int po_alloc_hist(ba_poseonly_batch *b, int max_iter) {
   if (b->hist_iters >= max_iter && b->hist_cost) return BA_OK;
-  cudaFree(b->hist_cost); cudaFree(b->hist_step); cudaFree(b->debug_poses);
+  if (b->hist_cost) cudaFreeAsync(b->hist_cost, 0);
   const size_t fz = (size_t)std::max(b->n_frames, 1) * std::max(max_iter, 1);
-  PO_TRY(cudaMalloc(&b->hist_cost, fz * 4));
-  PO_TRY(cudaMalloc(&b->hist_step, fz * 4));
-  PO_TRY(cudaMalloc(&b->debug_poses, fz * 48));
+  const size_t a4 = (fz * 4 + 255) / 256 * 256;
+  void *blk = nullptr;
+  PO_TRY(cudaMallocAsync(&blk, 2 * a4 + fz * 48, 0));       // hist_cost | hist_step | debug_poses
+  b->hist_cost = reinterpret_cast<decltype(b->hist_cost)>(blk);
+  b->hist_step = reinterpret_cast<decltype(b->hist_step)>(static_cast<char *>(blk) + a4);
+  b->debug_poses = reinterpret_cast<decltype(b->debug_poses)>(static_cast<char *>(blk) + 2 * a4);
   b->hist_iters = max_iter;
   return BA_OK;
 }
