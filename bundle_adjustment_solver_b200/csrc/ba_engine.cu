@@ -991,6 +991,79 @@ __global__ void __launch_bounds__(kThreads) k_exchange_decide(DecideArgs g, Peer
   }
 }
 
+// Multi-GPU, banded reduced system, ranks with mapped peer memory: the band exchange as ONE-SHOT pushes over NVLink.
+// k_band_push packs row r (columns r .. r + bw of the upper triangle + the rhs entry) and stores it into EVERY rank's
+// receive buffer (slot = my rank); the last CTA to finish publishes the epoch flag to every peer.  k_band_pull waits
+// for the flags of all ranks and writes S(band) = sum of the slots in rank order -- bit-identical on every rank, no
+// NCCL call, no intermediate buffer.  Buffers are double-buffered by epoch parity (a rank can only be one exchange
+// ahead of the slowest: its next push waits on nothing, but its next pull needs the slow rank's flag).
+struct BandPeers {
+  double *buf[kMaxRanks];       // every rank's receive buffer: [2][n_ranks][cap]
+  unsigned *flag[kMaxRanks];    // every rank's flags: [2][kMaxRanks]
+  unsigned *epoch;              // local: exchanges completed
+  unsigned *counters;           // local: [0] CTAs of the push that finished, [1] of the pull
+  int *error;
+  long long cap;                // doubles per slot
+  int rank, n_ranks;
+};
+__global__ void __launch_bounds__(128) k_band_push(const double *__restrict__ S, int n, int ld, int bw, BandPeers bp,
+                                                   const LmState *__restrict__ st) {
+  if (st->done) return;
+  const unsigned epoch = *bp.epoch + 1;
+  const int par = epoch & 1, w = bw + 2;
+  const size_t slot = ((size_t)par * bp.n_ranks + bp.rank) * (size_t)bp.cap;
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    for (int t = threadIdx.x; t < w; t += blockDim.x) {
+      double v = 0.0;
+      if (t <= bw) { if (r + t < n) v = S[(size_t)r * ld + r + t]; }
+      else v = S[(size_t)r * ld + (ld - 1)];
+      const size_t o = slot + (size_t)r * w + t;
+      for (int p = 0; p < bp.n_ranks; ++p) bp.buf[p][o] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(bp.counters, 1u);
+    if (done == gridDim.x - 1) {           // every CTA's stores are fenced: publish
+      bp.counters[0] = 0;
+      __threadfence_system();
+      for (int p = 0; p < bp.n_ranks; ++p) st_release_sys(bp.flag[p] + par * kMaxRanks + bp.rank, epoch);
+    }
+  }
+}
+__global__ void __launch_bounds__(128) k_band_pull(double *__restrict__ S, int n, int ld, int bw, BandPeers bp,
+                                                   const LmState *__restrict__ st) {
+  if (st->done) return;
+  const unsigned epoch = *bp.epoch + 1;
+  const int par = epoch & 1, w = bw + 2;
+  if (threadIdx.x < bp.n_ranks) {
+    const unsigned *f = bp.flag[bp.rank] + par * kMaxRanks + threadIdx.x;
+    long long spins = 0;
+    while (ld_acquire_sys(f) != epoch) {
+      if (++spins > (1ll << 26) || *((volatile int *)bp.error)) { *bp.error = 1; break; }
+    }
+  }
+  __syncthreads();
+  const double *mine = bp.buf[bp.rank] + (size_t)par * bp.n_ranks * (size_t)bp.cap;
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    for (int t = threadIdx.x; t < w; t += blockDim.x) {
+      double v = 0.0;
+      for (int p = 0; p < bp.n_ranks; ++p) v += __ldcg(mine + (size_t)p * bp.cap + (size_t)r * w + t);
+      if (t <= bw) { if (r + t < n) S[(size_t)r * ld + r + t] = v; }
+      else S[(size_t)r * ld + (ld - 1)] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(bp.counters + 1, 1u);
+    if (done == gridDim.x - 1) {
+      bp.counters[1] = 0;
+      *bp.epoch = epoch;
+    }
+  }
+}
+
 // Multi-GPU, banded reduced system: only the band of S (row r: columns r .. r + bw of the upper triangle, what the
 // build writes and the banded factorisation reads) and the rhs column take part in the all-reduce.
 __global__ void k_band_pack(const double *__restrict__ S, int n, int ld, int bw, double *__restrict__ packed,
@@ -1071,6 +1144,45 @@ struct SharedComm {
   unsigned *d_epoch = nullptr;
   int *d_error = nullptr;
   bool peer_ok = false;
+  // band exchange through peer memory (k_band_push / k_band_pull): receive buffer [2][n_ranks][band_cap], flags
+  double *band_local = nullptr, *band_peer[kMaxRanks] = {};
+  unsigned *bflag_local = nullptr, *bflag_peer[kMaxRanks] = {};
+  unsigned *d_band_epoch = nullptr, *d_band_counters = nullptr;
+  long long band_cap = 0;
+  bool band_ok = false;
+  struct RetiredBand { double *local; unsigned *flags, *epoch, *counters; double *peer[kMaxRanks]; unsigned *fpeer[kMaxRanks]; };
+  std::vector<RetiredBand> retired;   // replaced by a larger set; kept alive for the graphs that captured it
+  void retire_band() {
+    RetiredBand rb{band_local, bflag_local, d_band_epoch, d_band_counters, {}, {}};
+    for (int r = 0; r < kMaxRanks; ++r) { rb.peer[r] = band_peer[r]; rb.fpeer[r] = bflag_peer[r]; band_peer[r] = nullptr; bflag_peer[r] = nullptr; }
+    retired.push_back(rb);
+    band_local = nullptr; bflag_local = nullptr; d_band_epoch = nullptr; d_band_counters = nullptr;
+    band_cap = 0; band_ok = false;
+  }
+  void close_band() {
+    for (RetiredBand &rb : retired) {
+      for (int r = 0; r < n_ranks && r < kMaxRanks; ++r) {
+        if (rb.peer[r] && r != rank) cudaIpcCloseMemHandle(rb.peer[r]);
+        if (rb.fpeer[r] && r != rank) cudaIpcCloseMemHandle(rb.fpeer[r]);
+      }
+      if (rb.local) cudaFree(rb.local);
+      if (rb.flags) cudaFree(rb.flags);
+      if (rb.epoch) cudaFree(rb.epoch);
+      if (rb.counters) cudaFree(rb.counters);
+    }
+    retired.clear();
+    for (int r = 0; r < n_ranks && r < kMaxRanks; ++r) {
+      if (band_peer[r] && r != rank) cudaIpcCloseMemHandle(band_peer[r]);
+      if (bflag_peer[r] && r != rank) cudaIpcCloseMemHandle(bflag_peer[r]);
+      band_peer[r] = nullptr; bflag_peer[r] = nullptr;
+    }
+    if (band_local) cudaFree(band_local);
+    if (bflag_local) cudaFree(bflag_local);
+    if (d_band_epoch) cudaFree(d_band_epoch);
+    if (d_band_counters) cudaFree(d_band_counters);
+    band_local = nullptr; bflag_local = nullptr; d_band_epoch = nullptr; d_band_counters = nullptr;
+    band_cap = 0; band_ok = false;
+  }
   PeerTable table() const {
     PeerTable t{};
     for (int r = 0; r < kMaxRanks; ++r) t.peer[r] = peer[r];
@@ -1081,6 +1193,7 @@ struct SharedComm {
     cudaSetDevice(device);
     for (int r = 0; r < n_ranks && r < kMaxRanks; ++r)
       if (peer[r] && r != rank) cudaIpcCloseMemHandle(peer[r]);
+    close_band();
     if (local) cudaFree(local);
     if (d_epoch) cudaFree(d_epoch);
     if (d_error) cudaFree(d_error);
@@ -1269,6 +1382,7 @@ struct ba_solver {
 
   // comm
   std::shared_ptr<SharedComm> shared;   // keeps the communicator alive; `comm` mirrors shared->comm
+  BandPeers band_peers{};               // snapshot taken when the plan was agreed (cap == 0: NCCL all-reduce of the band)
   ncclComm_t comm = nullptr;
   int rank = 0, n_ranks = 1;
   long long global_M = -1, global_n_obs = -1;
@@ -1532,6 +1646,7 @@ static int upload_cholesky_plan(ba_solver *s) {
 // Multi-GPU: the reduced solve is replicated, so every rank must factor the all-reduced S with the SAME plan, built
 // from the co-visibility of ALL landmarks, not of its shard: min over ranks of the first co-visible pose.  Called by
 // whichever comes second, ba_comm_init or ba_finalize.
+static void ensure_band_exchange(SharedComm &sc, cudaStream_t st, long long count);
 static int agree_on_envelope(ba_solver *s) {
   if (!s->comm || s->N <= 0) return BA_OK;
   cudaStream_t st = s->stream;
@@ -1546,6 +1661,20 @@ static int agree_on_envelope(ba_solver *s) {
   cholesky_make_plan(s->chol, 6 * s->N, s->h_first_pose);
   if (int rc = upload_cholesky_plan(s)) return rc;
   CUDA_TRY(cudaStreamSynchronize(st));
+  // band exchange through peer memory (same count on every rank: the plan is global now)
+  s->band_peers = BandPeers{};
+  if (s->shared && s->chol.banded) {
+    SharedComm &sc = *s->shared;
+    const long long count = (long long)6 * s->N * (s->chol.bw + 2);
+    ensure_band_exchange(sc, st, count);
+    if (sc.band_ok && count <= sc.band_cap) {
+      BandPeers bp{};
+      for (int r = 0; r < kMaxRanks; ++r) { bp.buf[r] = sc.band_peer[r]; bp.flag[r] = sc.bflag_peer[r]; }
+      bp.epoch = sc.d_band_epoch; bp.counters = sc.d_band_counters; bp.error = sc.d_error;
+      bp.cap = sc.band_cap; bp.rank = sc.rank; bp.n_ranks = sc.n_ranks;
+      s->band_peers = bp;
+    }
+  }
   return BA_OK;
 }
 
@@ -2301,6 +2430,13 @@ static int enqueue_allreduce_S(ba_solver *s) {
   const int n = 6 * s->N;
   const size_t ld = (size_t)n + 1;
   ncclResult_t r;
+  if (s->chol.banded && n > 0 && s->band_peers.cap > 0) {
+    const int grid = std::min(n, 148 * 8);
+    k_band_push<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
+    k_band_pull<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
+    s->launches += 2;
+    return BA_OK;
+  }
   if (s->chol.banded && n > 0) {
     // every rank holds the same plan (ba_comm_init agreed on the global envelope): band + rhs only
     const int bw = s->chol.bw;
@@ -2858,28 +2994,22 @@ int ba_comm_get_unique_id(void *id128) {
 
 // peer exchange set-up: every rank allocates its PeerExch, the IPC handles travel by ncclAllGather, every rank maps
 // the others.  All-or-nothing: the ranks agree (min-reduce) and fall back to the NCCL all-reduce of the scalars.
-static void setup_peer_exchange(SharedComm &sc, cudaStream_t st) {
-  sc.peer_ok = false;
-  if (getenv("BA_B200_NO_PEER_EXCHANGE") || sc.n_ranks > kMaxRanks || !g_nccl.AllGather) return;
-  int ok = 1;
-  if (cudaMalloc(&sc.local, sizeof(PeerExch)) != cudaSuccess) { sc.local = nullptr; ok = 0; }
-  if (cudaMalloc(&sc.d_epoch, sizeof(unsigned)) != cudaSuccess) { sc.d_epoch = nullptr; ok = 0; }
-  if (cudaMalloc(&sc.d_error, sizeof(int)) != cudaSuccess) { sc.d_error = nullptr; ok = 0; }
+// Collective over the communicator: every rank contributes one device allocation (`local`, nullptr = this rank failed
+// to allocate), receives the IPC handles of all ranks and maps them.  All-or-nothing: returns true on every rank or
+// on none (min-reduce of the per-rank outcome).
+static bool ipc_map_all(SharedComm &sc, cudaStream_t st, void *local, void **mapped /*[n_ranks]*/) {
+  for (int r = 0; r < sc.n_ranks; ++r) mapped[r] = nullptr;
+  if (!g_nccl.AllGather) return false;
   cudaIpcMemHandle_t mine{};
-  if (ok) {
-    cudaMemset(sc.local, 0, sizeof(PeerExch));
-    cudaMemset(sc.d_epoch, 0, sizeof(unsigned));
-    cudaMemset(sc.d_error, 0, sizeof(int));
-    if (cudaIpcGetMemHandle(&mine, sc.local) != cudaSuccess) ok = 0;
-  }
+  int ok = local != nullptr;
+  if (ok && cudaIpcGetMemHandle(&mine, local) != cudaSuccess) ok = 0;
   cudaGetLastError();
-  // handles (and the per-rank ok flag in the byte after them) to every rank
   const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
   unsigned char *d_send = nullptr, *d_recv = nullptr;
   if (cudaMalloc(&d_send, rec) != cudaSuccess || cudaMalloc(&d_recv, rec * sc.n_ranks) != cudaSuccess) {
     cudaGetLastError();
     if (d_send) cudaFree(d_send);
-    return;   // cannot even talk: every rank fails the same way only by luck, so never use the peers
+    return false;   // cannot even talk: every rank fails the same way only by luck, so never use the peers
   }
   std::vector<unsigned char> h_send(rec, 0), h_recv(rec * sc.n_ranks, 0);
   std::memcpy(h_send.data(), &mine, sizeof(mine));
@@ -2892,27 +3022,87 @@ static void setup_peer_exchange(SharedComm &sc, cudaStream_t st) {
   for (int r = 0; r < sc.n_ranks && all_ok; ++r) all_ok = h_recv[r * rec + sizeof(mine)] ? 1 : 0;
   if (all_ok) {
     for (int r = 0; r < sc.n_ranks; ++r) {
-      if (r == sc.rank) { sc.peer[r] = sc.local; continue; }
+      if (r == sc.rank) { mapped[r] = local; continue; }
       cudaIpcMemHandle_t h;
       std::memcpy(&h, h_recv.data() + r * rec, sizeof(h));
       void *ptr = nullptr;
       if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = 0; break; }
-      sc.peer[r] = static_cast<PeerExch *>(ptr);
+      mapped[r] = ptr;
     }
   }
-  // second round: did every rank map every peer?
-  if (talked) {
+  bool agreed_ok = false;
+  if (talked) {   // second round: did every rank map every peer?
     int *d_flag = reinterpret_cast<int *>(d_send);
     cudaMemcpyAsync(d_flag, &all_ok, sizeof(int), cudaMemcpyHostToDevice, st);
     if (g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, sc.comm, st) != ncclSuccess) all_ok = 0;
     int agreed = 0;
     cudaMemcpyAsync(&agreed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) agreed = 0;
-    sc.peer_ok = all_ok && agreed;
+    agreed_ok = all_ok && agreed;
   }
   cudaFree(d_send);
   cudaFree(d_recv);
+  if (!agreed_ok)
+    for (int r = 0; r < sc.n_ranks; ++r) {
+      if (mapped[r] && r != sc.rank) cudaIpcCloseMemHandle(mapped[r]);
+      mapped[r] = nullptr;
+    }
+  return agreed_ok;
+}
+
+// peer exchange of the LM scalars: every rank allocates its PeerExch and maps the others'; falls back to the NCCL
+// all-reduce of the scalars when that fails anywhere
+static void setup_peer_exchange(SharedComm &sc, cudaStream_t st) {
+  sc.peer_ok = false;
+  if (getenv("BA_B200_NO_PEER_EXCHANGE") || sc.n_ranks > kMaxRanks) return;
+  bool ok = true;
+  if (cudaMalloc(&sc.local, sizeof(PeerExch)) != cudaSuccess) { sc.local = nullptr; ok = false; }
+  if (cudaMalloc(&sc.d_epoch, sizeof(unsigned)) != cudaSuccess) { sc.d_epoch = nullptr; ok = false; }
+  if (cudaMalloc(&sc.d_error, sizeof(int)) != cudaSuccess) { sc.d_error = nullptr; ok = false; }
+  if (ok) {
+    cudaMemset(sc.local, 0, sizeof(PeerExch));
+    cudaMemset(sc.d_epoch, 0, sizeof(unsigned));
+    cudaMemset(sc.d_error, 0, sizeof(int));
+  }
+  cudaGetLastError();
+  void *mapped[kMaxRanks] = {};
+  sc.peer_ok = ipc_map_all(sc, st, ok ? sc.local : nullptr, mapped);
+  for (int r = 0; r < sc.n_ranks; ++r) sc.peer[r] = sc.peer_ok ? static_cast<PeerExch *>(mapped[r]) : nullptr;
   if (getenv("BA_B200_VERBOSE")) fprintf(stderr, "[ba_b200] rank %d/%d: scalar exchange over %s\n", sc.rank, sc.n_ranks, sc.peer_ok ? "peer memory (CUDA IPC)" : "ncclAllReduce");
+}
+
+// band exchange through peer memory: (re)allocated when a problem needs more than the current capacity.  Collective:
+// every rank calls it at the same point (agree_on_envelope) with the same count (same global plan).
+static void ensure_band_exchange(SharedComm &sc, cudaStream_t st, long long count) {
+  if (!sc.peer_ok || getenv("BA_B200_NO_PEER_BAND") || count <= 0) return;
+  if (sc.band_ok && count <= sc.band_cap) return;
+  if (sc.band_local) sc.retire_band();           // graphs of earlier solvers keep using the old set
+  const long long cap = (count + 511) / 512 * 512;
+  bool ok = true;
+  if (cudaMalloc(&sc.band_local, sizeof(double) * 2 * sc.n_ranks * (size_t)cap) != cudaSuccess) { sc.band_local = nullptr; ok = false; }
+  if (cudaMalloc(&sc.bflag_local, sizeof(unsigned) * 2 * kMaxRanks) != cudaSuccess) { sc.bflag_local = nullptr; ok = false; }
+  if (cudaMalloc(&sc.d_band_epoch, sizeof(unsigned)) != cudaSuccess) { sc.d_band_epoch = nullptr; ok = false; }
+  if (cudaMalloc(&sc.d_band_counters, 2 * sizeof(unsigned)) != cudaSuccess) { sc.d_band_counters = nullptr; ok = false; }
+  if (ok) {
+    cudaMemset(sc.bflag_local, 0, sizeof(unsigned) * 2 * kMaxRanks);
+    cudaMemset(sc.d_band_epoch, 0, sizeof(unsigned));
+    cudaMemset(sc.d_band_counters, 0, 2 * sizeof(unsigned));
+  }
+  cudaGetLastError();
+  void *m1[kMaxRanks] = {}, *m2[kMaxRanks] = {};
+  const bool ok1 = ipc_map_all(sc, st, ok ? (void *)sc.band_local : nullptr, m1);
+  const bool ok2 = ipc_map_all(sc, st, ok ? (void *)sc.bflag_local : nullptr, m2);
+  sc.band_ok = ok1 && ok2;
+  for (int r = 0; r < sc.n_ranks; ++r) {
+    sc.band_peer[r] = sc.band_ok ? static_cast<double *>(m1[r]) : nullptr;
+    sc.bflag_peer[r] = sc.band_ok ? static_cast<unsigned *>(m2[r]) : nullptr;
+    if (!sc.band_ok) {   // one of the two mapped: undo
+      if (m1[r] && r != sc.rank) cudaIpcCloseMemHandle(m1[r]);
+      if (m2[r] && r != sc.rank) cudaIpcCloseMemHandle(m2[r]);
+    }
+  }
+  sc.band_cap = sc.band_ok ? cap : 0;
+  if (getenv("BA_B200_VERBOSE")) fprintf(stderr, "[ba_b200] rank %d/%d: band exchange over %s (%lld doubles per slot)\n", sc.rank, sc.n_ranks, sc.band_ok ? "peer memory (CUDA IPC)" : "ncclAllReduce", cap);
 }
 
 static int adopt_comm(ba_solver *s, const std::shared_ptr<SharedComm> &sc, long long global_M, long long global_n_obs) {
