@@ -991,6 +991,19 @@ __global__ void __launch_bounds__(kThreads) k_exchange_decide(DecideArgs g, Peer
   }
 }
 
+// band-only clearing of a large banded S: row r's columns r .. r + bw and its rhs entry (two strided 2-D memsets of
+// 12 k short rows took 40 us on C4)
+__global__ void __launch_bounds__(256) k_clear_band(double *__restrict__ S, int n, int ld, int bw, const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int w = bw + 2;
+  const long long total = (long long)n * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / w), t = (int)(i - (long long)r * w);
+    if (t <= bw) { if (r + t < n) S[(size_t)r * ld + r + t] = 0.0; }
+    else S[(size_t)r * ld + (ld - 1)] = 0.0;
+  }
+}
+
 // Multi-GPU, banded reduced system, ranks with mapped peer memory: the band exchange as ONE-SHOT pushes over NVLink.
 // k_band_push packs row r (columns r .. r + bw of the upper triangle + the rhs entry) and stores it into EVERY rank's
 // receive buffer (slot = my rank); the last CTA to finish publishes the epoch flag to every peer.  k_band_pull waits
@@ -1012,14 +1025,14 @@ __global__ void __launch_bounds__(128) k_band_push(const double *__restrict__ S,
   const unsigned epoch = *bp.epoch + 1;
   const int par = epoch & 1, w = bw + 2;
   const size_t slot = ((size_t)par * bp.n_ranks + bp.rank) * (size_t)bp.cap;
-  for (int r = blockIdx.x; r < n; r += gridDim.x) {
-    for (int t = threadIdx.x; t < w; t += blockDim.x) {
-      double v = 0.0;
-      if (t <= bw) { if (r + t < n) v = S[(size_t)r * ld + r + t]; }
-      else v = S[(size_t)r * ld + (ld - 1)];
-      const size_t o = slot + (size_t)r * w + t;
-      for (int p = 0; p < bp.n_ranks; ++p) bp.buf[p][o] = v;
-    }
+  // flat index over the packed band (row r, entry t): every lane busy, the stores of a warp are contiguous per peer
+  const long long total = (long long)n * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / w), t = (int)(i - (long long)r * w);
+    double v = 0.0;
+    if (t <= bw) { if (r + t < n) v = S[(size_t)r * ld + r + t]; }
+    else v = S[(size_t)r * ld + (ld - 1)];
+    for (int p = 0; p < bp.n_ranks; ++p) bp.buf[p][slot + i] = v;
   }
   __threadfence_system();
   __syncthreads();
@@ -1046,13 +1059,17 @@ __global__ void __launch_bounds__(128) k_band_pull(double *__restrict__ S, int n
   }
   __syncthreads();
   const double *mine = bp.buf[bp.rank] + (size_t)par * bp.n_ranks * (size_t)bp.cap;
-  for (int r = blockIdx.x; r < n; r += gridDim.x) {
-    for (int t = threadIdx.x; t < w; t += blockDim.x) {
-      double v = 0.0;
-      for (int p = 0; p < bp.n_ranks; ++p) v += __ldcg(mine + (size_t)p * bp.cap + (size_t)r * w + t);
-      if (t <= bw) { if (r + t < n) S[(size_t)r * ld + r + t] = v; }
-      else S[(size_t)r * ld + (ld - 1)] = v;
-    }
+  const long long total = (long long)n * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / w), t = (int)(i - (long long)r * w);
+    double vv[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) vv[p] = p < bp.n_ranks ? __ldcg(mine + (size_t)p * bp.cap + i) : 0.0;
+    double v = 0.0;
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) v += vv[p];      // rank order; the slots beyond n_ranks add exact zeros
+    if (t <= bw) { if (r + t < n) S[(size_t)r * ld + r + t] = v; }
+    else S[(size_t)r * ld + (ld - 1)] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -2335,8 +2352,9 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
     // large banded reduced system (C4: 1.15 GB dense; a small one is cleared faster by one linear memset): everything outside the band (and the rhs column) stays zero once cleared -- the
     // build, the factorisation and the exchange only touch row r's columns r .. r + bw and the last column
     const int n = 6 * s->N;
-    cudaMemset2DAsync(s->d_Saug.p, (size_t)(ld + 1) * sizeof(double), 0, (size_t)(s->chol.bw + 1) * sizeof(double), n, st);
-    cudaMemset2DAsync(s->d_Saug.p + (ld - 1), (size_t)ld * sizeof(double), 0, sizeof(double), n, st);
+    const long long total = (long long)n * (s->chol.bw + 2);
+    k_clear_band<<<(int)std::min<long long>(148 * 8, (total + 255) / 256), 256, 0, st>>>(s->d_Saug.p, n, ld, s->chol.bw, dst);
+    s->launches++;
   } else {
     cudaMemsetAsync(s->d_Saug.p, 0, (size_t)ld * ld * sizeof(double), st);
   }
@@ -2431,7 +2449,7 @@ static int enqueue_allreduce_S(ba_solver *s) {
   const size_t ld = (size_t)n + 1;
   ncclResult_t r;
   if (s->chol.banded && n > 0 && s->band_peers.cap > 0) {
-    const int grid = std::min(n, 148 * 8);
+    const int grid = (int)std::min<long long>(148 * 8, ((long long)n * (s->chol.bw + 2) + 127) / 128);
     k_band_push<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
     k_band_pull<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
     s->launches += 2;
