@@ -1290,6 +1290,63 @@ static void pinned_put(void *p) {
   g_pinned_free.push_back(p);
 }
 
+// Host scratch arrays of ba_finalize: blocks come from a process-wide cache and are NOT zero-filled -- value-initialised
+// std::vectors of 50 MB (zero fill + first-touch page faults on fresh pages) were a quarter of the finalisation time
+// of a process that solves problem after problem.
+struct HostScratchCache {
+  std::mutex mu;
+  std::vector<std::pair<void *, size_t>> free_blocks;
+  size_t cached = 0;
+  void *get(size_t bytes, size_t *got) {
+    bytes = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int best = -1;
+      for (int i = 0; i < (int)free_blocks.size(); ++i)
+        if (free_blocks[i].second >= bytes && (best < 0 || free_blocks[i].second < free_blocks[best].second)) best = i;
+      if (best >= 0 && free_blocks[best].second <= 2 * bytes + (8u << 20)) {
+        void *p = free_blocks[best].first;
+        *got = free_blocks[best].second;
+        cached -= *got;
+        free_blocks.erase(free_blocks.begin() + best);
+        return p;
+      }
+    }
+    *got = bytes;
+    void *p = std::malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+  }
+  void put(void *p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cached + bytes > ((size_t)2 << 30) || free_blocks.size() > 64) { std::free(p); return; }   // keep at most 2 GB
+    free_blocks.emplace_back(p, bytes);
+    cached += bytes;
+  }
+};
+inline HostScratchCache &host_scratch() { static HostScratchCache c; return c; }
+template <typename T>
+struct ScratchAlloc {
+  using value_type = T;
+  ScratchAlloc() = default;
+  template <typename U> ScratchAlloc(const ScratchAlloc<U> &) {}
+  T *allocate(size_t n) {
+    size_t got = 0;
+    char *raw = static_cast<char *>(host_scratch().get(n * sizeof(T) + 64, &got));
+    *reinterpret_cast<size_t *>(raw) = got;      // block size in front of the array (64 B keeps the alignment)
+    return reinterpret_cast<T *>(raw + 64);
+  }
+  void deallocate(T *p, size_t) {
+    char *raw = reinterpret_cast<char *>(p) - 64;
+    host_scratch().put(raw, *reinterpret_cast<size_t *>(raw));
+  }
+  template <typename U> void construct(U *p) { ::new ((void *)p) U; }                 // default-init: no zero fill
+  template <typename U, typename... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+  template <typename U> bool operator==(const ScratchAlloc<U> &) const { return true; }
+  template <typename U> bool operator!=(const ScratchAlloc<U> &) const { return false; }
+};
+template <typename T> using hvec = std::vector<T, ScratchAlloc<T>>;
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -1301,7 +1358,8 @@ struct DevBuf {
     if (count == 0) return cudaSuccess;
     return cudaMallocAsync((void **)&p, count * sizeof(T), g_alloc_stream);
   }
-  cudaError_t upload(const std::vector<T> &h, cudaStream_t st) {
+  template <typename V>
+  cudaError_t upload(const V &h, cudaStream_t st) {
     cudaError_t e = alloc(h.size());
     if (e != cudaSuccess || h.empty()) return e;
     return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
@@ -1720,15 +1778,16 @@ int ba_finalize(ba_solver *s) {
   s->N = (int)s->h_opt_pose.size();
   s->M = (int)s->h_opt_point.size();
   // --- stable counting sort by pose, then by point  => order (point, pose, insertion)
-  std::vector<int> by_pose(n), by_point(n);
+  hvec<int> by_pose(n), by_point(n);
   std::vector<long long> pose_begin(Nt + 1, 0);   // observation range of every pose in by_pose order
-  std::vector<int> pose_to_point_order;
+  hvec<int> pose_to_point_order;
+  std::vector<long long> pt_q0;                   // observation range of every landmark in point order
   {
     // both sorts: per-thread histograms over contiguous ranges of the input, bucket offsets per thread, parallel
     // scatter -- stable because every thread's range is contiguous and the ranges are ordered
     std::vector<long long> starts;
     auto counting_sort = [&](long long count, int n_buckets, auto &&key_of /*(q) -> bucket*/, auto &&item_of /*(q) -> value*/,
-                             std::vector<int> &out, std::vector<int> *dest /*position every input went to*/) {
+                             auto &out, hvec<int> *dest /*position every input went to*/) {
       const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, count / 65536));
       std::vector<std::vector<int>> hist(nth, std::vector<int>((size_t)n_buckets, 0));
       parallel_ranges(nth, [&](long long t0, long long t1, int) {
@@ -1759,11 +1818,12 @@ int ba_finalize(ba_solver *s) {
     pose_to_point_order.resize(n);   // position in POINT order of the q-th observation of the POSE order
     counting_sort(n, Mt, [&](long long q) { return s->h_obs_point[by_pose[q]]; }, [&](long long q) { return by_pose[q]; }, by_point,
                   &pose_to_point_order);
+    pt_q0 = starts;                  // the bucket offsets of this sort ARE the observation range of every landmark
   }
   lap("counting sorts");
   // --- point-ordered observation arrays, pairs, last-writer flags
-  std::vector<double2> uv(n);
-  std::vector<int> o_pose(n), o_point(n), o_cf(n), o_pair(n);
+  hvec<double2> uv(n);
+  hvec<int> o_pose(n), o_point(n), o_cf(n), o_pair(n);
   s->h_pair_pose.clear(); s->h_pair_point.clear();
   std::vector<int> point_has_pairs(Mt, 0);
   {
@@ -1779,7 +1839,8 @@ int ba_finalize(ba_solver *s) {
     });
     // a pair starts at every free (pose, point) observation whose predecessor in point order belongs to another
     // (point, pose): flags, exclusive scan, fill -- three parallel passes instead of one serial scan
-    std::vector<int> pair_rank(n + 1, 0);
+    hvec<int> pair_rank(n + 1);
+    pair_rank[n] = 0;
     parallel_ranges(n, [&](long long lo_, long long hi_, int) {
       for (long long q = (long long)lo_; q < (long long)hi_; ++q) {
         const bool both = (o_cf[q] & kFlagPoseFree) && (o_cf[q] & kFlagPointFree);
@@ -1845,9 +1906,7 @@ int ba_finalize(ba_solver *s) {
   });
   struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } early_joiner{early_upload};
   // --- observation range of every landmark in point order
-  std::vector<long long> pt_q0(Mt + 1, 0);
-  for (long long q = 0; q < n; ++q) pt_q0[o_point[q] + 1]++;
-  for (int i = 0; i < Mt; ++i) pt_q0[i + 1] += pt_q0[i];
+  if ((long long)pt_q0.size() != (long long)Mt + 1) pt_q0.assign((size_t)Mt + 1, 0);   // (no observations at all)
   // --- tile chunks: runs of consecutive landmarks whose free poses fit one window of kTileW poses
   std::vector<SchurChunk> schur_chunks;
   std::vector<int> tpt_point, tpt_inc_start, fallback_pairs;
@@ -2086,8 +2145,13 @@ int ba_finalize(ba_solver *s) {
     }
     return pc;
   };
-  PointChunks pc_all = build_point_chunks(false);
-  PointChunks pc_fb = build_point_chunks(true);
+  // the two lists are independent serial scans: side by side
+  PointChunks pc_all, pc_fb;
+  {
+    std::thread other([&]() { pc_fb = build_point_chunks(true); });
+    pc_all = build_point_chunks(false);
+    other.join();
+  }
   std::vector<Chunk> &chunks = pc_all.chunks;
   std::vector<int> &chunk_pair_count = pc_all.chunk_pair_count;
   std::vector<int> &split_points = pc_fb.split_points, &split_pairs = pc_all.split_pairs;
@@ -2101,7 +2165,7 @@ int ba_finalize(ba_solver *s) {
   // --- pose-ordered arrays (free poses only) and their chunks
   // the pose-ordered copies of the observations (uvA, pointA, camA, poseidA) are gathered ON THE DEVICE from the
   // point-ordered arrays through permA (position in point order of every pose-ordered slot): 4 B/obs instead of 28
-  std::vector<int> permA;
+  hvec<int> permA;
   std::vector<ChunkA> chunksA; std::vector<int> pose_chunk_ptr(s->N + 1, 0);
   {
     // A-order = the by_pose order restricted to free poses: offsets per pose, chunks per pose (serial over poses),
