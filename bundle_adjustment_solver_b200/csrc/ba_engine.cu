@@ -1315,11 +1315,18 @@ struct HostScratchCache {
     *got = bytes;
     void *p = std::malloc(bytes);
     if (!p) throw std::bad_alloc();
+    // page-locked once, reused by every later problem of the process: the uploads out of these arrays then run at
+    // the link rate and really overlap the host work (a failed registration only costs that)
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) cudaGetLastError();
     return p;
   }
   void put(void *p, size_t bytes) {
     std::lock_guard<std::mutex> lk(mu);
-    if (cached + bytes > ((size_t)2 << 30) || free_blocks.size() > 64) { std::free(p); return; }   // keep at most 2 GB
+    if (cached + bytes > ((size_t)2 << 30) || free_blocks.size() > 64) {   // keep at most 2 GB
+      if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+      std::free(p);
+      return;
+    }
     free_blocks.emplace_back(p, bytes);
     cached += bytes;
   }
@@ -1910,8 +1917,8 @@ int ba_finalize(ba_solver *s) {
   // --- tile chunks: runs of consecutive landmarks whose free poses fit one window of kTileW poses
   std::vector<SchurChunk> schur_chunks;
   std::vector<int> tpt_point, tpt_inc_start, fallback_pairs;
-  std::vector<int4> inc_a;
-  std::vector<int2> inc_b;
+  hvec<int4> inc_a;
+  hvec<int2> inc_b;
   std::vector<uint8_t> is_tile_point(Mt, 0);
   {
     struct Cand { int point, p0, p1, jmin, jmax, n_inc, ok; };
