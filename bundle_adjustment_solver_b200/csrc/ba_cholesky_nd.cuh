@@ -145,22 +145,14 @@ __device__ __forceinline__ void nd_stage_node(const NdArgs &g, const NdSmem &sm,
 // ------------------------------------------------------------------------------------------------------------
 // forward elimination of one front.  TPW: boundary x boundary tiles per consumer warp (register accumulators)
 // ------------------------------------------------------------------------------------------------------------
-template <int TPW, int NC>
-__device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, int timing) {
+// Everything of a front that does not depend on its children's results: node records and index tables in shared
+// memory.  The persistent driver runs it BEFORE it waits for the children's flags (off the critical path).
+__device__ void nd_forward_prepare(const NdArgs &g, const NdSmem &sm, int node_id) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool is_diag = warp == 3;
-  static_assert(NC == 9 || NC == 11, "consumer warps");
-  constexpr int kNdCons = NC, kNdCntA = 32 * (NC + 1), kNdCntB = 32 * NC;
-  const bool is_idle = NC == 9 && (warp & 3) == 3 && !is_diag;
-  const int cwi = NC == 9 ? warp - (warp >> 2) : warp - (warp > 3 ? 1 : 0);   // consumer index
-  unsigned long long t_in = 0;
-  if (timing && t == 0) t_in = gtime();
   nd_stage_node(g, sm, node_id, true);
   const NdNode &nd = *sm.node;
   const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, NT = KT + BT;
   auto colbase = [&](int J) { return J * NT - (J * (J - 1)) / 2; };   // tile (I, J), I >= J, at colbase(J) + I - J
-  const int n_tiles = colbase(KT);
-  const int LbT0 = (nd.k8 + nd.wr) >> 3;        // first row tile of [Lb | rhs]
   // pm: my boundary index -> front-local index of my PARENT (where my Schur complement goes); -1: padding
   for (int i = t; i < nd.b8; i += kNdThreads) {
     int m = -1;
@@ -186,7 +178,23 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
     for (int I = J + lane; I < NT; I += 32) sm.tt[base + I] = (I << 16) | J;
   }
   __syncthreads();
-  if (timing && t == 0 && blockIdx.x == 0) g_nd_dbg[13] += gtime() - t_in;   // staging, index maps
+}
+
+template <int TPW, int NC>
+__device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, int timing) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const bool is_diag = warp == 3;
+  static_assert(NC == 9 || NC == 11, "consumer warps");
+  constexpr int kNdCons = NC, kNdCntA = 32 * (NC + 1), kNdCntB = 32 * NC;
+  const bool is_idle = NC == 9 && (warp & 3) == 3 && !is_diag;
+  const int cwi = NC == 9 ? warp - (warp >> 2) : warp - (warp > 3 ? 1 : 0);   // consumer index
+  unsigned long long t_in = 0;
+  if (timing && t == 0) t_in = gtime();
+  const NdNode &nd = *sm.node;                  // staged by nd_forward_prepare
+  const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, NT = KT + BT;
+  auto colbase = [&](int J) { return J * NT - (J * (J - 1)) / 2; };   // tile (I, J), I >= J, at colbase(J) + I - J
+  const int n_tiles = colbase(KT);
+  const int LbT0 = (nd.k8 + nd.wr) >> 3;        // first row tile of [Lb | rhs]
   const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
   const int swz = (fr & 2) << 1;
   const int offC = fr * 8 + (fc ^ swz);                          // accumulator fragment (double2) inside a tile
@@ -574,6 +582,7 @@ k_nd_forward_level(NdArgs g, int list_begin, int timing, const LmState *st) {
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char nd_raw[];
   const NdSmem sm = nd_carve(nd_raw, g);
+  nd_forward_prepare(g, sm, g.list[list_begin + blockIdx.x]);
   nd_forward_node<TPW, NC>(g, sm, g.list[list_begin + blockIdx.x], timing);
 }
 
@@ -633,10 +642,11 @@ k_nd_persistent(NdArgs g, int timing, const LmState *st) {
   for (int q = lb; q < le; ++q) {
     const int id = g.list[q];
     unsigned long long tw = 0;
+    nd_forward_prepare(g, sm, id);       // records and tables while the children are still working
     if (timing && threadIdx.x == 0) tw = gtime();
     for (int c = 0; c < 2; ++c) {
-      const int ch = g.nodes[id].child[c];
-      if (ch >= 0 && g.nodes[ch].cta != me) nd_wait_flag(g, ch);
+      const int ch = sm.node->child[c];
+      if (ch >= 0 && sm.cn[c].cta != me) nd_wait_flag(g, ch);
     }
     if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[9] += gtime() - tw;
     nd_forward_node<TPW, NC>(g, sm, id, timing);
