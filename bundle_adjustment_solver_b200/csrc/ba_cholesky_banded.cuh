@@ -3,22 +3,14 @@
 // Replaces `Am_BCinvBt_mat.ldlt().solve(am_BCinv_b_mat)` (core/full_bundle_adjustment_solver.cpp:890-908).
 //
 // The dependency chain of a Cholesky factorisation is n column steps long no matter how it is blocked; for a
-// band the work per step is only bw^2/2 FMAs, so the solve is bound by the LATENCY of one column step.  This
-// kernel therefore keeps the whole active window of the factorisation in the REGISTERS of one CTA and spends
-// exactly one __syncthreads per column:
-//
-//   * window = the W x W symmetric block rows/cols j .. j+W-1 (W >= bw+1, multiple of 16), stored FULL
-//     (both triangles, so the rank-1 update needs no predicates) in a 2-D cyclic layout: thread (ty, tx) of the
-//     16 x 16 CTA owns slots (ty + 16a, tx + 16b); matrix index i lives in slot i mod W.  The slot -> register
-//     mapping is static: the W column steps of one trip around the ring are fully unrolled.
-//   * step j: the owners of column j publish it (and the pivot reciprocal) through a double-buffered shared
-//     vector, barrier, every thread applies a_rc -= a_rj a_cj / d_j to its (W/16)^2 slots.  The slots of the
-//     NEXT column are updated first and published before the bulk of the update is issued, so the bulk overlaps
-//     the shared-memory round trip (software pipelining of the column chain).
-//   * after step j, ring slot j mod W is recycled for index j + W: the new row/column (original S values, they
-//     receive their first update at step j+1 at the earliest) was prefetched one 16-step group ahead.
-//   * columns stay unscaled in registers (L = A D^-1/2 is applied when a column is written out, off the
-//     critical path, by a rotating warp).  The rhs travels as one more window row, so z = L^-1 rhs falls out.
+// band the work per step is only bw^2/2 FMAs, so the solve is bound by the LATENCY of the chain.  This file holds
+// the SERIAL banded kernel k_chol_banded_smem: one CTA, 8-column block steps, the W x W window (W >= bw + 16) in
+// shared memory as 8 x 8 tiles in ring slots, nine consumer warps apply the rank-8 update with DMMAs, one producer
+// warp factors the 8 x 8 diagonal block and applies the triangular solve.  Since round 2 it is the FALLBACK of the
+// partitioned (nested-dissection) solve in ba_cholesky_nd.cuh -- used when no partition is valid -- and its
+// yardstick (BA_B200_BAND_MODE=4).  The two earlier variants (scalar register window, DMMA register tiles) were
+// removed from the build.
+//   * the rhs travels as one more window row, so z = L^-1 rhs falls out of the factorisation;
 //   * non-positive pivots (pose without observations) emulate Eigen LDLT's D^+ = 0.
 //
 // The backward sweep L^T x = z runs in the same launch: 16-column blocks from the bottom; the block's
@@ -220,215 +212,6 @@ __device__ __forceinline__ void band_backward(double *A, int n, int bw, double *
 // ty == jm (and the b == 0 slots of tx == jm) hold index 16G + jm + W instead.  After the group the slot
 // arrays are rotated by one so that the next group is again at a == b == 0: the 16-step body is the same code
 // for every group (it stays resident in the instruction cache).
-template <int W>
-__global__ void __launch_bounds__(kBandThreads, 1)
-k_chol_banded(double *A, int n, int bw, double *x_out, double *linv, int timing, const LmState *st) {
-  if (st->done) return;
-  constexpr int NS = W / 16;
-  __shared__ BandSmem<W> sm;
-  const int t = threadIdx.x, ty = t >> 4, tx = t & 15, warp = t >> 5, lane = t & 31;
-  const int ld = n + 1;
-  unsigned long long t_begin = 0;
-  if (timing) t_begin = gtime();
-
-  double v[NS][NS];   // window slots
-  double zr[NS];      // rhs row entries of the column slots (replicated over ty)
-#pragma unroll
-  for (int a = 0; a < NS; ++a)
-#pragma unroll
-    for (int b = 0; b < NS; ++b) v[a][b] = band_load_sym(A, ld, n, bw, ty + 16 * a, tx + 16 * b);
-#pragma unroll
-  for (int b = 0; b < NS; ++b) {
-    const int c = tx + 16 * b;
-    zr[b] = (c < n) ? __ldcg(A + (size_t)c * ld + n) : 0.0;
-  }
-  // entries entering the window during group G: the row 16G + ty + W (held by threads ty, slots a == 0) and
-  // the column 16G + tx + W (threads tx, slots b == 0), in the frame of group G at the time they enter
-  double cur_row[NS], cur_col[NS], cur_z, nxt_row[NS], nxt_col[NS], nxt_z;
-  auto prefetch = [&](int G, double (&prow)[NS], double (&pcol)[NS], double &pz) {
-    const int qr = 16 * G + ty + W, qc = 16 * G + tx + W;
-#pragma unroll
-    for (int b = 0; b < NS; ++b) {
-      const int c = 16 * (G + b) + tx + ((b == 0 && tx <= ty) ? W : 0);
-      prow[b] = band_load_sym(A, ld, n, bw, qr, c);
-    }
-#pragma unroll
-    for (int a = 0; a < NS; ++a) {
-      const int r = 16 * (G + a) + ty + ((a == 0 && ty <= tx) ? W : 0);
-      pcol[a] = band_load_sym(A, ld, n, bw, r, qc);
-    }
-    pz = (qc < n) ? __ldcg(A + (size_t)qc * ld + n) : 0.0;
-  };
-  prefetch(0, cur_row, cur_col, cur_z);
-  if (t == 0) mbar_init(&sm.mbar, kBandThreads / 32);
-  __syncthreads();
-  unsigned phase = 0;
-  // column 0
-  if (tx == 0) {
-#pragma unroll
-    for (int a = 0; a < NS; ++a) sm.cb[0][0][ty + 16 * a] = v[a][0];
-    if (ty == 0) {
-      const double d = v[0][0];
-      const double r = fast_rcp(d);
-      sm.cb[0][0][W + 1] = (d > 0.0) ? r : 0.0;
-      sm.cb[0][0][W] = zr[0];
-    }
-  }
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&sm.mbar);
-  const int n_groups = (n + 15) / 16;
-#pragma unroll 1
-  for (int G = 0; G < n_groups; ++G) {
-    const int gp = G & 1;
-    // loads for the next group (consumed 16..31 steps from now)
-    prefetch(G + 1, nxt_row, nxt_col, nxt_z);
-    // one column step; GN = slot group of column j + 1 (0 inside the group, 1 for the last step, whose
-    // published column already uses the NEXT group's frame positions)
-    auto step = [&](auto gn_c, const int jm) {
-      constexpr int gn = decltype(gn_c)::value;
-      const int jm1 = (jm + 1) & 15;
-      const int np = gn ? (gp ^ 1) : gp;  // group parity of column j + 1
-      mbar_wait(&sm.mbar, phase);          // column j published by every warp
-      phase ^= 1;
-      const double *cbj = sm.cb[gp][jm];
-      const double di = cbj[W + 1];
-      double lc[NS], lr[NS];
-#pragma unroll
-      for (int b = 0; b < NS; ++b) lc[b] = cbj[tx + 16 * b];
-#pragma unroll
-      for (int a = 0; a < NS; ++a) lr[a] = cbj[ty + 16 * a] * di;
-      const double zl = cbj[W] * di;
-      // priority: the slots of column j + 1, recycle what that column needs, publish it
-#pragma unroll
-      for (int a = 0; a < NS; ++a) v[a][gn] -= lr[a] * lc[gn];
-      zr[gn] -= zl * lc[gn];
-      if (ty == jm) v[0][gn] = cur_row[gn];
-      if (tx == jm1) {
-        double *cbn = sm.cb[np][jm1];
-#pragma unroll
-        for (int a = 0; a < NS; ++a) cbn[ty + 16 * ((a + NS - gn) % NS)] = v[a][gn];
-        if (ty == jm1) {
-          const double d = v[gn][gn];
-          const double r = fast_rcp(d);
-          cbn[W + 1] = (d > 0.0) ? r : 0.0;
-        }
-        if (ty == 0) cbn[W] = zr[gn];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.mbar);  // this warp's part of column j + 1 is out
-      // bulk of the rank-1 update
-#pragma unroll
-      for (int b = 0; b < NS; ++b) {
-        if (b == gn) continue;
-#pragma unroll
-        for (int a = 0; a < NS; ++a) v[a][b] -= lr[a] * lc[b];
-        zr[b] -= zl * lc[b];
-      }
-      // recycle the slots of index j for index j + W
-      if (ty == jm) {
-#pragma unroll
-        for (int b = 0; b < NS; ++b)
-          if (b != gn) v[0][b] = cur_row[b];
-      }
-      if (tx == jm) {
-#pragma unroll
-        for (int a = 0; a < NS; ++a) v[a][0] = cur_col[a];
-        zr[0] = cur_z;
-      }
-    };
-#ifdef BA_BAND_UNROLL_ALL
-#pragma unroll
-#else
-#pragma unroll 3
-#endif
-    for (int jm = 0; jm < 15; ++jm) step(std::integral_constant<int, 0>{}, jm);
-    step(std::integral_constant<int, 1>{}, 15);
-    // the 16 finished columns of this group to global memory: L_rj = a_rj / sqrt(d_j) (and z_j); warp w
-    // writes columns w and w + 8.  cb[gp] is not written again before the next group's last step.
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int jm = warp + 8 * h, j = 16 * G + jm;
-      if (j < n) {
-        const double *cbj = sm.cb[gp][jm];
-        const double d = cbj[jm];
-        const double s = (d > 0.0) ? rsqrt(d) : 0.0;
-        double *col = A + (size_t)j * ld;
-#pragma unroll
-        for (int k = 0; k < (W + 31) / 32; ++k) {
-          const int rel = lane + 32 * k;
-          const int r = j + rel;
-          if (rel <= bw && r < n) {
-            int pos = jm + rel;
-            if (pos >= W) pos -= W;
-            double l = cbj[pos] * s;
-            if (rel == 0 && !(d > 0.0)) l = __longlong_as_double(0x7ff0000000000000LL);
-            col[r] = l;
-          }
-        }
-        if (lane == 0) col[n] = cbj[W] * s;
-      }
-    }
-    // rotate the frame by one group
-    {
-      double tmp[NS][NS], tz[NS];
-#pragma unroll
-      for (int a = 0; a < NS; ++a)
-#pragma unroll
-        for (int b = 0; b < NS; ++b) tmp[a][b] = v[(a + 1) % NS][(b + 1) % NS];
-#pragma unroll
-      for (int b = 0; b < NS; ++b) tz[b] = zr[(b + 1) % NS];
-#pragma unroll
-      for (int a = 0; a < NS; ++a)
-#pragma unroll
-        for (int b = 0; b < NS; ++b) v[a][b] = tmp[a][b];
-#pragma unroll
-      for (int b = 0; b < NS; ++b) { zr[b] = tz[b]; cur_row[b] = nxt_row[b]; cur_col[b] = nxt_col[b]; }
-      cur_z = nxt_z;
-    }
-  }
-  __syncthreads();
-  unsigned long long t_factor = 0;
-  if (timing) t_factor = gtime();
-
-  band_backward<W>(A, n, bw, x_out, linv, sm);
-  if (timing && t == 0) {
-    g_band_dbg[0] = t_factor - t_begin;
-    g_band_dbg[1] = gtime() - t_factor;
-  }
-}
-
-// =====================================================================================================
-// v3: 8-column block steps, FP64 tensor-core (DMMA) window update, dedicated panel warp.
-//
-// The chain of a blocked factorisation is one PANEL (8 columns) long per step instead of one column: a single
-// producer warp factors the 8 x 8 diagonal block redundantly in the registers of every lane (no shuffles, no
-// barriers inside the 8-pivot chain) and applies the triangular solve to the panel rows its lanes own, while
-// eight consumer warps keep the W x W window as m8n8 DMMA accumulator tiles (one of each symmetric pair, by
-// ring slot) and apply the rank-8 update with two mma.sync.m8n8k4.f64 per tile.  Hand-off through shared
-// memory and two pairs of mbarriers: consumers publish the NEXT panel (raw, after its priority update) before
-// they touch the rest of the window, so the producer's chain overlaps the bulk of the update.
-//   ring slot X holds absolute 8-row tile I with I = X (mod NT); slot s mod NT retires at step s and is
-//   recycled for tile s + NT (original S values, prefetched during the previous step).  Requires W >= bw + 8.
-// =====================================================================================================
-constexpr int kBand3Threads = 288;  // 8 consumer warps + 1 producer warp
-
-template <int W>
-struct Band3Smem {
-  union {
-    struct {
-      double raw[2][W + 1][8];    // published raw panel by ring position; row W = rhs entries z
-      double Lp[2][W + 1][12];    // factored panel (row stride 12: conflict-free 8 x 4 fragment reads)
-    } f;
-    struct {
-      double lst[8][2][16][17];
-      double linvd[8][2][16];
-    } pre;
-  };
-  double xr[W + 32];
-  double acc[2][16];
-  unsigned long long bar_raw[2], bar_L[2];
-};
-
 // reciprocal square root off the slow libm path: hardware approximation (2^-22) + two Newton steps
 __device__ __forceinline__ double fast_rsqrt(double d) {
   double y;
@@ -441,246 +224,6 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
   return y;
 }
 
-template <int W>
-__global__ void __launch_bounds__(kBand3Threads, 1)
-k_chol_banded_dmma(double *A, int n, int bw, double *x_out, double *linv, int timing, const LmState *st) {
-  if (st->done) return;
-  constexpr int NT = W / 8;
-  constexpr int NTILES = NT * (NT + 1) / 2;
-  constexpr int TPW = (NTILES + 7) / 8;        // tiles per consumer warp
-  constexpr int NSL = (W + 1 + 31) / 32;       // panel rows per producer lane
-  __shared__ Band3Smem<W> sm;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int ld = n + 1;
-  const int nsteps = (n + 7) / 8;
-  unsigned long long t_begin = 0;
-  if (timing) t_begin = gtime();
-  if (t == 0) {
-    mbar_init(&sm.bar_raw[0], 8); mbar_init(&sm.bar_raw[1], 8);
-    mbar_init(&sm.bar_L[0], 1);   mbar_init(&sm.bar_L[1], 1);
-  }
-  __syncthreads();
-
-  if (warp == 8) {
-    // ------------------------------------------------ producer: panel factorisation ----------------
-    // Unscaled right-looking elimination (a_rc -= a_rk a_ck / d_k): the pivot chain needs one reciprocal per
-    // column; the square-root scaling L = A D^-1/2 is applied at the end, off the chain.
-    int P = 0;
-#pragma unroll 1
-    for (int s = 0; s < nsteps; ++s) {
-      const int par = s & 1;
-      mbar_wait(&sm.bar_raw[par], (s >> 1) & 1);
-      double a[NSL][8];
-#pragma unroll
-      for (int sl = 0; sl < NSL; ++sl) {
-        const int pos = lane + 32 * sl;
-        const double4 *src = reinterpret_cast<const double4 *>(&sm.f.raw[par][pos <= W ? pos : W][0]);
-        const double4 v0 = src[0], v1 = src[1];
-        a[sl][0] = v0.x; a[sl][1] = v0.y; a[sl][2] = v0.z; a[sl][3] = v0.w;
-        a[sl][4] = v1.x; a[sl][5] = v1.y; a[sl][6] = v1.z; a[sl][7] = v1.w;
-      }
-      double D[8][8], rs[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) D[i][j] = sm.f.raw[par][8 * P + i][j];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const double d = D[k][k];
-        const bool pos_def = d > 0.0;
-        const double rc = pos_def ? fast_rcp(d) : 0.0;       // non-positive pivot: LDLT's D^+ = 0
-        rs[k] = pos_def ? fast_rsqrt(d) : 0.0;
-#pragma unroll
-        for (int i = k + 1; i < 8; ++i) {
-          const double ti = D[i][k] * rc;
-#pragma unroll
-          for (int j = k + 1; j <= i; ++j) D[i][j] -= ti * D[j][k];
-        }
-#pragma unroll
-        for (int sl = 0; sl < NSL; ++sl) {
-          const double u = a[sl][k] * rc;
-#pragma unroll
-          for (int m = k + 1; m < 8; ++m) a[sl][m] -= u * D[m][k];
-        }
-      }
-#pragma unroll
-      for (int sl = 0; sl < NSL; ++sl) {
-        const int pos = lane + 32 * sl;
-        if (pos <= W) {
-          double4 *dst = reinterpret_cast<double4 *>(&sm.f.Lp[par][pos][0]);
-          dst[0] = make_double4(a[sl][0] * rs[0], a[sl][1] * rs[1], a[sl][2] * rs[2], a[sl][3] * rs[3]);
-          dst[1] = make_double4(a[sl][4] * rs[4], a[sl][5] * rs[5], a[sl][6] * rs[6], a[sl][7] * rs[7]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.bar_L[par]);
-      P = (P + 1 == NT) ? 0 : P + 1;
-    }
-  } else {
-    // ------------------------------------------------ consumers: window tiles -----------------------
-    const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
-    const int laneL = fr * 12 + kq;      // fragment offset inside an 8-row tile of Lp
-    const int lanePB = fr * 8 + fc;      // publish offset when the tile's column slot is the panel
-    const int lanePA = fc * 8 + fr;      // ... when its row slot is the panel (transposed)
-    int As[TPW], Bs[TPW];
-    double acc[TPW][2], pre[TPW][2];
-#pragma unroll
-    for (int i = 0; i < TPW; ++i) {
-      const int e = warp + 8 * i;   // enumeration of slot pairs As >= Bs
-      int ia = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-      while (ia * (ia + 1) / 2 > e) --ia;
-      while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
-      const bool live = e < NTILES;
-      As[i] = live ? ia : -1;
-      Bs[i] = live ? e - ia * (ia + 1) / 2 : -1;
-      acc[i][0] = acc[i][1] = pre[i][0] = pre[i][1] = 0.0;
-      if (live) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) acc[i][q] = band_load_sym(A, ld, n, bw, 8 * As[i] + fr, 8 * Bs[i] + fc + q);
-      }
-    }
-    double zv = (t < W && t < n) ? __ldcg(A + (size_t)t * ld + n) : 0.0, zpre = 0.0;
-    // loads for the tiles that ring slot X takes over when it retires at step sr (new absolute tile sr + NT;
-    // the other slot Y of a tile then holds tile sr + 1 + ((Y - X - 1) mod NT)); zero outside band / matrix
-    auto prefetch = [&](int X, int sr) {
-      const int Inew = sr + NT;
-#pragma unroll
-      for (int i = 0; i < TPW; ++i) {
-        const bool tA = As[i] == X, tB = Bs[i] == X;
-        if (!(tA || tB)) continue;
-        const int Y = tA ? Bs[i] : As[i];
-        int d = Y - X - 1;
-        if (d < 0) d += NT;
-        const int Iy = (Y == X) ? Inew : sr + 1 + d;
-        const int r = 8 * (tA ? Inew : Iy) + fr, c0 = 8 * (tA ? Iy : Inew) + fc;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c = c0 + q;
-          const int lo = min(r, c), hi = max(r, c);
-          pre[i][q] = (hi < n && hi - lo <= bw) ? __ldcg(A + (size_t)lo * ld + hi) : 0.0;
-        }
-      }
-      if (t >= 8 * X && t < 8 * X + 8) {
-        const int zc = 8 * Inew + (t - 8 * X);
-        zpre = (zc < n) ? __ldcg(A + (size_t)zc * ld + n) : 0.0;
-      }
-    };
-    // first panel
-#pragma unroll
-    for (int i = 0; i < TPW; ++i)
-      if (Bs[i] == 0) {
-        sm.f.raw[0][0][As[i] * 64 + lanePB] = acc[i][0];
-        sm.f.raw[0][0][As[i] * 64 + lanePB + 1] = acc[i][1];
-      }
-    if (t < 8) sm.f.raw[0][W][t] = zv;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.bar_raw[0]);
-    prefetch(0, 0);
-
-    int P = 0;
-#pragma unroll 1
-    for (int s = 0; s < nsteps; ++s) {
-      const int par = s & 1;
-      const int Pn = (P + 1 == NT) ? 0 : P + 1;
-      const double *Lp = &sm.f.Lp[par][0][0];
-      double *rawn = &sm.f.raw[par ^ 1][0][0];
-      mbar_wait(&sm.bar_L[par], (s >> 1) & 1);
-      const bool z_retire = (t >= 8 * P && t < 8 * P + 8);
-      const bool z_next = (t >= 8 * Pn && t < 8 * Pn + 8);
-      auto update_z = [&]() {
-        if (t < W) {
-          if (z_retire) zv = zpre;
-          else {
-            const double4 *lz = reinterpret_cast<const double4 *>(Lp + W * 12);
-            const double4 *lt = reinterpret_cast<const double4 *>(Lp + t * 12);
-            const double4 z0 = lz[0], z1 = lz[1], l0 = lt[0], l1 = lt[1];
-            zv -= z0.x * l0.x + z0.y * l0.y + z0.z * l0.z + z0.w * l0.w + z1.x * l1.x + z1.y * l1.y + z1.z * l1.z + z1.w * l1.w;
-          }
-        }
-      };
-      // priority: everything the next panel needs, published before the bulk
-#pragma unroll
-      for (int i = 0; i < TPW; ++i) {
-        const bool nA = As[i] == Pn, nB = Bs[i] == Pn;
-        if (nA || nB) {
-          if (As[i] == P || Bs[i] == P) {
-            acc[i][0] = pre[i][0];
-            acc[i][1] = pre[i][1];
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              dmma_884b(acc[i][0], acc[i][1], -Lp[As[i] * 96 + laneL + 4 * h], Lp[Bs[i] * 96 + laneL + 4 * h]);
-          }
-          if (nB) {
-            rawn[As[i] * 64 + lanePB] = acc[i][0];
-            rawn[As[i] * 64 + lanePB + 1] = acc[i][1];
-          } else {
-            rawn[Bs[i] * 64 + lanePA] = acc[i][0];
-            rawn[Bs[i] * 64 + lanePA + 8] = acc[i][1];
-          }
-        }
-      }
-      if (z_next) {
-        update_z();
-        rawn[W * 8 + (t - 8 * Pn)] = zv;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.bar_raw[par ^ 1]);
-      // bulk
-#pragma unroll
-      for (int i = 0; i < TPW; ++i) {
-        if (As[i] < 0 || As[i] == Pn || Bs[i] == Pn) continue;
-        if (As[i] == P || Bs[i] == P) {
-          acc[i][0] = pre[i][0];
-          acc[i][1] = pre[i][1];
-        } else {
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            dmma_884b(acc[i][0], acc[i][1], -Lp[As[i] * 96 + laneL + 4 * h], Lp[Bs[i] * 96 + laneL + 4 * h]);
-        }
-      }
-      if (!z_next) update_z();
-      // finished panel to global memory: warp w writes column w (coalesced over rows)
-      {
-        const int c = 8 * s + warp;
-        if (c < n) {
-          double *col = A + (size_t)c * ld + 8 * s;
-#pragma unroll
-          for (int q = 0; q < (W + 31) / 32; ++q) {
-            const int pos = lane + 32 * q;
-            int rel = pos - 8 * P;
-            if (rel < 0) rel += W;
-            if (pos < W && rel >= warp && rel - warp <= bw && 8 * s + rel < n) {
-              double l = Lp[pos * 12 + warp];
-              if (rel == warp && !(l > 0.0)) l = __longlong_as_double(0x7ff0000000000000LL);
-              col[rel] = l;
-            }
-          }
-          if (lane == 0) A[(size_t)c * ld + n] = Lp[W * 12 + warp];
-        }
-      }
-      // loads for the slot that retires at the next step
-      prefetch(Pn, s + 1);
-      P = Pn;
-    }
-  }
-  __syncthreads();
-  unsigned long long t_factor = 0;
-  if (timing) t_factor = gtime();
-  if (warp < 8) band_backward<W>(A, n, bw, x_out, linv, sm);
-  if (timing && t == 0) {
-    g_band_dbg[0] = t_factor - t_begin;
-    g_band_dbg[1] = gtime() - t_factor;
-  }
-}
-
-// =====================================================================================================
-// v4: same block-step scheme (8-column panels, DMMA update, dedicated panel warp), but the window lives in
-// SHARED memory as 8 x 8 tiles (lower triangle, ring slots).  Work is assigned by RELATIVE tile position, the
-// same for every step: the tiles of the next panel first (one per warp), then the rest; nothing is searched,
-// recycled through registers or published - the panel warp reads its panel straight out of the window.
-// Requires W >= bw + 16: the rows that enter the window during a step then only meet zeros in the next panel.
-// =====================================================================================================
 constexpr int kBand4Cons = 9;                        // consumer warps (sub-partitions 0-2)
 constexpr int kBand4Threads = 384;                   // 12 warps: 9 consumers, 1 producer (warp 3), 2 idle
 constexpr int kBand4Active = 32 * (kBand4Cons + 1);  // threads that take part in the hand-off barriers
@@ -982,25 +525,11 @@ inline bool cholesky_banded_supported(int n, int bw) { return n > 0 && bw + 8 <=
 inline bool cholesky_banded_enqueue(double *Saug, int n, int bw, double *x, double *linv, const LmState *st,
                                     cudaStream_t stream) {
   static const int timing = getenv("BA_B200_VERBOSE") != nullptr;
-  int mode = getenv("BA_B200_BAND_MODE") ? atoi(getenv("BA_B200_BAND_MODE")) : 4;
-  if (mode > 4) mode = 4;
-  if (mode == 4 && bw + 16 <= 120) {   // DMMA block steps, window in shared memory (needs W >= bw + 16)
-    if (bw + 16 <= 56) return launch_band4<56>(Saug, n, bw, x, linv, timing, st, stream);
-    if (bw + 16 <= 88) return launch_band4<88>(Saug, n, bw, x, linv, timing, st, stream);
-    return launch_band4<120>(Saug, n, bw, x, linv, timing, st, stream);
-  }
-  if (mode >= 3) {   // DMMA block steps (needs W >= bw + 8)
-    if (bw + 8 <= 48) k_chol_banded_dmma<48><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
-    else if (bw + 8 <= 80) k_chol_banded_dmma<80><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
-    else if (bw + 8 <= 112) k_chol_banded_dmma<112><<<1, kBand3Threads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
-    else return false;
-    return cudaGetLastError() == cudaSuccess;
-  }
-  if (bw + 1 <= 48) k_chol_banded<48><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
-  else if (bw + 1 <= 80) k_chol_banded<80><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
-  else if (bw + 1 <= 112) k_chol_banded<112><<<1, kBandThreads, 0, stream>>>(Saug, n, bw, x, linv, timing, st);
-  else return false;
-  return cudaGetLastError() == cudaSuccess;
+  // DMMA block steps, window in shared memory (needs W >= bw + 16; cholesky_banded_supported guarantees bw <= 104)
+  if (bw + 16 <= 56) return launch_band4<56>(Saug, n, bw, x, linv, timing, st, stream);
+  if (bw + 16 <= 88) return launch_band4<88>(Saug, n, bw, x, linv, timing, st, stream);
+  if (bw + 16 <= 120) return launch_band4<120>(Saug, n, bw, x, linv, timing, st, stream);
+  return false;
 }
 
 }  // namespace ba
