@@ -614,12 +614,10 @@ k_update_poses(int N_total, const int *__restrict__ pose_opt, const double *__re
 }
 
 // EvaluateCurrentCost (:381-433): sum over observations of ||r||_2 ; which = 0 current, 1 trial.
-__global__ void __launch_bounds__(kThreads)
-k_cost(long long n_obs, const double2 *__restrict__ obs_uv, const int *__restrict__ obs_pose,
-       const int *__restrict__ obs_point, const int *__restrict__ obs_camflags, Params prm, int which,
-       const double *__restrict__ cams, double *__restrict__ partials, int ignore_done,
-       const LmState *__restrict__ st) {
-  if (!ignore_done && st->done) return;
+__device__ __forceinline__ double cost_block_sum(long long n_obs, const double2 *__restrict__ obs_uv,
+                                                 const int *__restrict__ obs_pose, const int *__restrict__ obs_point,
+                                                 const int *__restrict__ obs_camflags, const Params &prm, int which,
+                                                 const double *__restrict__ cams, const LmState *__restrict__ st) {
   __shared__ double sm[kWarps][1];
   const int buf = st->cur ^ which;
   const double *poses = prm.poses[buf];
@@ -650,7 +648,16 @@ k_cost(long long n_obs, const double2 *__restrict__ obs_uv, const int *__restric
     k = kn;
   }
   block_sum<1, kWarps>(acc, sm);
-  if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
+  return acc[0];     // the CTA's sum, valid in thread 0
+}
+__global__ void __launch_bounds__(kThreads)
+k_cost(long long n_obs, const double2 *__restrict__ obs_uv, const int *__restrict__ obs_pose,
+       const int *__restrict__ obs_point, const int *__restrict__ obs_camflags, Params prm, int which,
+       const double *__restrict__ cams, double *__restrict__ partials, int ignore_done,
+       const LmState *__restrict__ st) {
+  if (!ignore_done && st->done) return;
+  const double v = cost_block_sum(n_obs, obs_uv, obs_pose, obs_point, obs_camflags, prm, which, cams, st);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -897,6 +904,44 @@ __global__ void __launch_bounds__(kThreads) k_reduce_decide(DecideArgs g, LmStat
   }
   block_sum<5, kWarps>(acc, sm);
   if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) g.scal[i] = acc[i];
+    decide(g, st, infos, cap);
+  }
+}
+
+// single GPU: the trial cost AND the decision in one launch -- the last CTA to finish (ticket counter) sums all the
+// partials in their fixed order and takes the trust-region decision (saves k_reduce_decide's launch and its 6 us)
+__global__ void __launch_bounds__(kThreads)
+k_cost_decide(long long n_obs, const double2 *__restrict__ obs_uv, const int *__restrict__ obs_pose,
+              const int *__restrict__ obs_point, const int *__restrict__ obs_camflags, Params prm,
+              const double *__restrict__ cams, double *__restrict__ partials, unsigned *__restrict__ ticket, DecideArgs g,
+              LmState *st, ba_iter_info *infos, int cap) {
+  if (st->done) return;
+  const double v = cost_block_sum(n_obs, obs_uv, obs_pose, obs_point, obs_camflags, prm, 1, cams, st);
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    __stcg(partials + blockIdx.x, v);
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  __shared__ double sm2[kWarps][5];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < g.n_cost; i += kThreads) acc[0] += __ldcg(g.cost_partials + i);
+  for (int i = threadIdx.x; i < g.n_point; i += kThreads) {
+    acc[1] += __ldcg(g.point_partials + 2 * i);
+    acc[2] += __ldcg(g.point_partials + 2 * i + 1);
+  }
+  for (int i = threadIdx.x; i < g.n_pose; i += kThreads) {
+    acc[3] += __ldcg(g.pose_partials + 2 * i);
+    acc[4] += __ldcg(g.pose_partials + 2 * i + 1);
+  }
+  block_sum<5, kWarps>(acc, sm2);
+  if (threadIdx.x == 0) {
+    *ticket = 0;
 #pragma unroll
     for (int i = 0; i < 5; ++i) g.scal[i] = acc[i];
     decide(g, st, infos, cap);
@@ -1452,6 +1497,7 @@ struct ba_solver {
   DevBuf<double> d_ptblk, d_Bsoa, d_A, d_a, d_partialsA, d_Saug, d_Scopy, d_x, d_z, d_linv, d_Btx, d_y;
   DevBuf<double> d_cost_partials, d_point_partials, d_pose_partials, d_scal;
   DevBuf<LmState> d_state;
+  DevBuf<unsigned> d_ticket;     // k_cost_decide: CTAs that have finished
   DevBuf<ba_iter_info> d_infos;
   int cost_grid = 0, point_grid = 0, pose_grid = 0;
   LmState *h_state = nullptr;  // pinned
@@ -1529,7 +1575,7 @@ static void free_device(ba_solver *s) {
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
-  s->d_point_partials.release(); s->d_pose_partials.release(); s->d_scal.release(); s->d_state.release();
+  s->d_point_partials.release(); s->d_pose_partials.release(); s->d_scal.release(); s->d_state.release(); s->d_ticket.release();
   s->d_infos.release();
 }
 
@@ -2328,6 +2374,8 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_pose_partials.alloc(2 * (size_t)s->pose_grid));
   CUDA_TRY(s->d_scal.alloc(8));
   CUDA_TRY(s->d_state.alloc(1));
+  CUDA_TRY(s->d_ticket.alloc(1));
+  CUDA_TRY(cudaMemsetAsync(s->d_ticket.p, 0, sizeof(unsigned), st));
   CUDA_TRY(cudaMemsetAsync(s->d_state.p, 0, sizeof(LmState), st));
   CUDA_TRY(cudaMemsetAsync(s->d_scal.p, 0, 8 * sizeof(double), st));
   static_assert(sizeof(LmState) <= kPinnedBlock, "pinned block");
@@ -2589,9 +2637,17 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
   //  than the 9 us they hide: C3 0.419 -> 0.431 ms per iteration)
   k_update_poses<<<s->pose_grid, kThreads, 0, st>>>(s->N_total, s->d_pose_opt.p, s->d_x.p, s->d_A.p, s->d_a.p,
                                                     prm, prw, s->d_pose_partials.p, dst);
+  DecideArgs g = make_decide_args(s, opt);
+  if (!s->comm) {
+    k_cost_decide<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                                     s->d_obs_camflags.p, prm, s->d_cams.p, s->d_cost_partials.p,
+                                                     s->d_ticket.p, g, dst, s->d_infos.p, (int)s->d_infos.n);
+    s->launches += 2;
+    if (ev) cudaEventRecord(ev[Phase::End], st);
+    return BA_OK;
+  }
   k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
                                             s->d_obs_camflags.p, prm, 1, s->d_cams.p, s->d_cost_partials.p, 0, dst);
-  DecideArgs g = make_decide_args(s, opt);
   s->launches += 2;
   if (!s->comm) {
     k_reduce_decide<<<1, kThreads, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
