@@ -1831,16 +1831,18 @@ int ba_finalize(ba_solver *s) {
   s->N = (int)s->h_opt_pose.size();
   s->M = (int)s->h_opt_point.size();
   // --- stable counting sort by pose, then by point  => order (point, pose, insertion)
-  hvec<int> by_pose(n), by_point(n);
+  hvec<int> by_pose(n);
   std::vector<long long> pose_begin(Nt + 1, 0);   // observation range of every pose in by_pose order
-  hvec<int> pose_to_point_order;
+  hvec<int> pose_to_point_order(n);               // position in POINT order of the q-th observation of the POSE order
   std::vector<long long> pt_q0;                   // observation range of every landmark in point order
+  // point-ordered observation arrays: written by the scatter pass of the second sort
+  hvec<double2> uv(n);
+  hvec<int> o_pose(n), o_point(n), o_cf(n), o_pair(n);
   {
     // both sorts: per-thread histograms over contiguous ranges of the input, bucket offsets per thread, parallel
     // scatter -- stable because every thread's range is contiguous and the ranges are ordered
     std::vector<long long> starts;
-    auto counting_sort = [&](long long count, int n_buckets, auto &&key_of /*(q) -> bucket*/, auto &&item_of /*(q) -> value*/,
-                             auto &out, hvec<int> *dest /*position every input went to*/) {
+    auto counting_sort = [&](long long count, int n_buckets, auto &&key_of /*(q) -> bucket*/, auto &&place /*(q, position)*/) {
       const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, count / 65536));
       std::vector<std::vector<int>> hist(nth, std::vector<int>((size_t)n_buckets, 0));
       parallel_ranges(nth, [&](long long t0, long long t1, int) {
@@ -1858,38 +1860,29 @@ int ba_finalize(ba_solver *s) {
       parallel_ranges(nth, [&](long long t0, long long t1, int) {
         for (long long t = t0; t < t1; ++t) {
           std::vector<int> &h = hist[t];
-          if (dest) {
-            for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) { const int pos = h[key_of(q)]++; out[pos] = item_of(q); (*dest)[q] = pos; }
-          } else {
-            for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) out[h[key_of(q)]++] = item_of(q);
-          }
+          for (long long q = count * t / nth; q < count * (t + 1) / nth; ++q) place(q, h[key_of(q)]++);
         }
       }, 1);
     };
-    counting_sort(n, Nt, [&](long long k) { return s->h_obs_pose[k]; }, [&](long long k) { return (int)k; }, by_pose, nullptr);
+    counting_sort(n, Nt, [&](long long k) { return s->h_obs_pose[k]; }, [&](long long k, int pos) { by_pose[pos] = (int)k; });
     pose_begin = starts;
-    pose_to_point_order.resize(n);   // position in POINT order of the q-th observation of the POSE order
-    counting_sort(n, Mt, [&](long long q) { return s->h_obs_point[by_pose[q]]; }, [&](long long q) { return by_pose[q]; }, by_point,
-                  &pose_to_point_order);
+    // the second scatter writes the point-ordered arrays directly (one random pass instead of sort + gather)
+    counting_sort(n, Mt, [&](long long q) { return s->h_obs_point[by_pose[q]]; }, [&](long long q, int pos) {
+      const int k = by_pose[q];
+      const int ps = s->h_obs_pose[k], pt = s->h_obs_point[k];
+      const bool pf = s->h_pose_opt[ps] >= 0, qf = s->h_point_opt[pt] >= 0;
+      pose_to_point_order[q] = pos;
+      uv[pos] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
+      o_pose[pos] = ps; o_point[pos] = pt;
+      o_cf[pos] = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
+    });
     pt_q0 = starts;                  // the bucket offsets of this sort ARE the observation range of every landmark
   }
   lap("counting sorts");
-  // --- point-ordered observation arrays, pairs, last-writer flags
-  hvec<double2> uv(n);
-  hvec<int> o_pose(n), o_point(n), o_cf(n), o_pair(n);
+  // --- pairs, last-writer flags
   s->h_pair_pose.clear(); s->h_pair_point.clear();
   std::vector<int> point_has_pairs(Mt, 0);
   {
-    parallel_ranges(n, [&](long long lo_, long long hi_, int) {
-      for (long long q = (long long)lo_; q < (long long)hi_; ++q) {
-        const int k = by_point[q];
-        const int ps = s->h_obs_pose[k], pt = s->h_obs_point[k];
-        const bool pf = s->h_pose_opt[ps] >= 0, qf = s->h_point_opt[pt] >= 0;
-        uv[q] = make_double2(s->h_obs_uv[2 * (size_t)k], s->h_obs_uv[2 * (size_t)k + 1]);
-        o_pose[q] = ps; o_point[q] = pt;
-        o_cf[q] = s->h_obs_cam[k] | (pf ? kFlagPoseFree : 0) | (qf ? kFlagPointFree : 0);
-      }
-    });
     // a pair starts at every free (pose, point) observation whose predecessor in point order belongs to another
     // (point, pose): flags, exclusive scan, fill -- three parallel passes instead of one serial scan
     hvec<int> pair_rank(n + 1);
@@ -1930,9 +1923,20 @@ int ba_finalize(ba_solver *s) {
   });
   // pairs of one landmark are contiguous: group starts, then one past the last pair of the landmark for every pair
   std::vector<int> pair_end(P), grp_start;
-  for (long long p = 0; p < P; ++p)
-    if (p == 0 || s->h_pair_point[p] != s->h_pair_point[p - 1]) grp_start.push_back((int)p);
-  grp_start.push_back((int)P);
+  {
+    hvec<int> gflag(P + 1);     // flags, exclusive scan, fill (parallel) instead of one serial pass over the pairs
+    gflag[P] = 0;
+    parallel_ranges(P, [&](long long lo_, long long hi_, int) {
+      for (long long p = lo_; p < hi_; ++p) gflag[p] = (p == 0 || s->h_pair_point[p] != s->h_pair_point[p - 1]) ? 1 : 0;
+    });
+    const long long ng = exclusive_scan_inplace(gflag.data(), P);
+    grp_start.resize((size_t)ng + 1);
+    parallel_ranges(P, [&](long long lo_, long long hi_, int) {
+      for (long long p = lo_; p < hi_; ++p)
+        if ((p + 1 < P ? gflag[p + 1] : (int)ng) != gflag[p]) grp_start[gflag[p]] = (int)p;
+    });
+    grp_start[ng] = (int)P;
+  }
   const long long n_grp = (long long)grp_start.size() - 1;
   parallel_ranges(n_grp, [&](long long lo_, long long hi_, int) {
     for (long long g = (long long)lo_; g < (long long)hi_; ++g)
