@@ -32,6 +32,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -1287,15 +1289,65 @@ static int host_threads() {
   static const int n = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   return n;
 }
+// Worker pool behind parallel_ranges / exclusive_scan_inplace: ba_finalize runs ~25 short data-parallel passes, and
+// creating + joining 15 threads per pass cost more than some of the passes.  Workers sleep on a condition variable
+// between jobs (no spinning: see host_threads), the pool lives for the process (leaked singleton).
+class HostPool {
+ public:
+  static HostPool &get() { static HostPool *p = new HostPool(); return *p; }
+  // runs job(t) for t in [0, nth), t = 0 on the caller; returns when all are done.  One job at a time (mutex).
+  void run(int nth, const std::function<void(int)> &job) {
+    if (nth <= 1) { job(0); return; }
+    std::lock_guard<std::mutex> serial(run_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      grow(nth - 1);
+      job_ = &job; n_active_ = nth - 1; pending_ = nth - 1; ++epoch_;
+    }
+    cv_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void grow(int n) {   // mu_ held
+    while ((int)workers_.size() < n) {
+      const int id = (int)workers_.size();
+      workers_.emplace_back([this, id] { loop(id); });
+      workers_.back().detach();
+    }
+  }
+  void loop(int id) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void(int)> *job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (id < n_active_) job = job_;
+      }
+      if (!job) continue;
+      (*job)(id + 1);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_cv_.notify_one();
+    }
+  }
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)> *job_ = nullptr;
+  int n_active_ = 0, pending_ = 0;
+  unsigned long long epoch_ = 0;
+};
+
 template <typename F>
 static void parallel_ranges(long long n, F &&fn /*(lo, hi, tid)*/, long long grain = 4096) {
   const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, n / grain));
   if (nth <= 1) { fn(0LL, n, 0); return; }
-  std::vector<std::thread> th;
-  th.reserve(nth - 1);
-  for (int t = 1; t < nth; ++t) th.emplace_back([&fn, n, nth, t] { fn(n * t / nth, n * (t + 1) / nth, t); });
-  fn(0LL, n / nth, 0);
-  for (auto &x : th) x.join();
+  HostPool::get().run(nth, [&fn, n, nth](int t) { fn(n * t / nth, n * (t + 1) / nth, t); });
 }
 
 // exclusive prefix sum of v[0..n) in place (v has n + 1 entries; v[n] and the return value = total), two passes
@@ -1303,13 +1355,7 @@ static long long exclusive_scan_inplace(int *v, long long n) {
   const int nth = (int)std::min<long long>(host_threads(), std::max<long long>(1, n / 4096));
   std::vector<long long> part(nth + 1, 0);
   auto range = [&](int t, long long &lo, long long &hi) { lo = n * t / nth; hi = n * (t + 1) / nth; };
-  auto run = [&](auto &&body) {
-    if (nth <= 1) { body(0); return; }
-    std::vector<std::thread> th;
-    for (int t = 1; t < nth; ++t) th.emplace_back([&body, t] { body(t); });
-    body(0);
-    for (auto &x : th) x.join();
-  };
+  auto run = [&](auto &&body) { HostPool::get().run(nth, [&body](int t) { body(t); }); };
   run([&](int t) { long long lo, hi; range(t, lo, hi); long long sum = 0; for (long long q = lo; q < hi; ++q) sum += v[q]; part[t + 1] = sum; });
   for (int k = 0; k < nth; ++k) part[k + 1] += part[k];
   run([&](int t) { long long lo, hi; range(t, lo, hi); long long acc = part[t]; for (long long q = lo; q < hi; ++q) { const int x = v[q]; v[q] = (int)acc; acc += x; } });
