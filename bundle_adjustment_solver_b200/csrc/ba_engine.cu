@@ -2188,9 +2188,10 @@ int ba_finalize(ba_solver *s) {
     std::vector<int2> chunk_pts;
     std::vector<ChunkPoint> cpts;
   };
-  auto build_point_chunks = [&](bool skip_tile_points) {
+  auto build_point_chunks = [&](bool skip_tile_points, long long q_begin, long long q_end) {
     PointChunks pc;
-    long long q = 0;
+    long long q = q_begin;
+    const long long n = q_end;     // this part's observations end here (shadows the total on purpose)
     Chunk cur{0, 0, 0, 0};
     int cur_pairs_first = -1, cur_pairs_last = -1;
     long long cur_end = 0;
@@ -2248,12 +2249,37 @@ int ba_finalize(ba_solver *s) {
     }
     return pc;
   };
-  // the two lists are independent serial scans: side by side
+  // Both lists are serial scans; the landmark sequence is cut into kParts parts of about equal observation count
+  // (always kParts, whatever the number of host threads: the chunking, hence the summation order on the device, must
+  // not depend on the machine) that are scanned independently and concatenated
   PointChunks pc_all, pc_fb;
   {
-    std::thread other([&]() { pc_fb = build_point_chunks(true); });
-    pc_all = build_point_chunks(false);
-    other.join();
+    constexpr int kParts = 16;
+    long long cut[kParts + 1];
+    cut[0] = 0; cut[kParts] = n;
+    for (int p = 1; p < kParts; ++p) {
+      const long long target = n * p / kParts;
+      const int lm = (int)(std::lower_bound(pt_q0.begin(), pt_q0.end(), target) - pt_q0.begin());
+      cut[p] = std::max(cut[p - 1], pt_q0[std::min(lm, Mt)]);
+    }
+    std::vector<PointChunks> parts(2 * kParts);
+    parallel_ranges(2 * kParts, [&](long long lo_, long long hi_, int) {
+      for (long long j = lo_; j < hi_; ++j) parts[j] = build_point_chunks(j >= kParts, cut[j % kParts], cut[j % kParts + 1]);
+    }, 1);
+    auto merge = [&](PointChunks &dst, int first) {
+      for (int p = first; p < first + kParts; ++p) {
+        PointChunks &src = parts[p];
+        const int cp0 = (int)dst.cpts.size();
+        dst.chunks.insert(dst.chunks.end(), src.chunks.begin(), src.chunks.end());
+        dst.chunk_pair_count.insert(dst.chunk_pair_count.end(), src.chunk_pair_count.begin(), src.chunk_pair_count.end());
+        dst.split_points.insert(dst.split_points.end(), src.split_points.begin(), src.split_points.end());
+        dst.split_pairs.insert(dst.split_pairs.end(), src.split_pairs.begin(), src.split_pairs.end());
+        for (int2 cp : src.chunk_pts) dst.chunk_pts.push_back(make_int2(cp.x + cp0, cp.y));
+        dst.cpts.insert(dst.cpts.end(), src.cpts.begin(), src.cpts.end());
+      }
+    };
+    merge(pc_all, 0);
+    merge(pc_fb, kParts);
   }
   std::vector<Chunk> &chunks = pc_all.chunks;
   std::vector<int> &chunk_pair_count = pc_all.chunk_pair_count;
