@@ -1051,22 +1051,116 @@ __global__ void __launch_bounds__(256) k_clear_band(double *__restrict__ S, int 
   }
 }
 
-// Multi-GPU, banded reduced system, ranks with mapped peer memory: the band exchange as ONE-SHOT pushes over NVLink.
-// k_band_push packs row r (columns r .. r + bw of the upper triangle + the rhs entry) and stores it into EVERY rank's
-// receive buffer (slot = my rank); the last CTA to finish publishes the epoch flag to every peer.  k_band_pull waits
-// for the flags of all ranks and writes S(band) = sum of the slots in rank order -- bit-identical on every rank, no
-// NCCL call, no intermediate buffer.  Buffers are double-buffered by epoch parity (a rank can only be one exchange
-// ahead of the slowest: its next push waits on nothing, but its next pull needs the slow rank's flag).
+// Multi-GPU, banded reduced system, ranks with mapped peer memory: the band exchange as a TWO-SHOT all-reduce over
+// NVLink, hand-written (BA_B200_BAND_XCHG=2; the default is the one-shot form below, see enqueue_allreduce_S).  The packed band (row r: columns r .. r + bw of the upper triangle + the rhs entry) is split by
+// rows over the ranks.  k_band_push sends every row's partial to the row's OWNER (slot = my rank); k_band_reduce
+// (owner) waits for the flags of all ranks, sums the slots in rank order and stores the result into EVERY rank's
+// result buffer; k_band_pull waits for all owners and copies the result into S.  Bit-identical on every rank, no NCCL
+// call; 2 (R-1)/R of the band leaves a rank instead of R-1 times the band with one-shot pushes (measured at R = 8 on
+// C4: the one-shot exchange cost 0.10 ms).  Buffers are double-buffered by epoch parity.
 struct BandPeers {
-  double *buf[kMaxRanks];       // every rank's receive buffer: [2][n_ranks][cap]
-  unsigned *flag[kMaxRanks];    // every rank's flags: [2][kMaxRanks]
+  double *buf[kMaxRanks];       // every rank's buffer: [2][ n_ranks x pslot partial slots | cap result ]
+  unsigned *flag[kMaxRanks];    // every rank's flags: [2][2][kMaxRanks] (partials delivered, results delivered)
   unsigned *epoch;              // local: exchanges completed
-  unsigned *counters;           // local: [0] CTAs of the push that finished, [1] of the pull
+  unsigned *counters;           // local: CTAs of the push / reduce / pull that finished
   int *error;
-  long long cap;                // doubles per slot
+  long long cap, pslot;         // doubles of the result region / of one partial slot
   int rank, n_ranks;
 };
+__device__ __forceinline__ int band_row0(int n, int R, int p) { return (int)(((long long)n * p) / R); }
+__device__ __forceinline__ bool band_wait_flags(const BandPeers &bp, const unsigned *flags, unsigned epoch) {
+  if (threadIdx.x < bp.n_ranks) {
+    const unsigned *f = flags + threadIdx.x;
+    long long spins = 0;
+    while (ld_acquire_sys(f) != epoch) {
+      if (++spins > (1ll << 26) || *((volatile int *)bp.error)) { *bp.error = 1; break; }
+    }
+  }
+  __syncthreads();
+  return true;
+}
+// last CTA of a grid (ticket counter) publishes `epoch` into flags[...][my rank] of every peer
+__device__ __forceinline__ void band_publish(const BandPeers &bp, unsigned *counter, int which, int par, unsigned epoch) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int p = 0; p < bp.n_ranks; ++p) st_release_sys(bp.flag[p] + (par * 2 + which) * kMaxRanks + bp.rank, epoch);
+    }
+  }
+}
 __global__ void __launch_bounds__(128) k_band_push(const double *__restrict__ S, int n, int ld, int bw, BandPeers bp,
+                                                   const LmState *__restrict__ st) {
+  if (st->done) return;
+  const unsigned epoch = *bp.epoch + 1;
+  const int par = epoch & 1, w = bw + 2, R = bp.n_ranks;
+  const long long parstride = (long long)R * bp.pslot + bp.cap;
+  const long long total = (long long)n * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / w), t = (int)(i - (long long)r * w);
+    double v = 0.0;
+    if (t <= bw) { if (r + t < n) v = S[(size_t)r * ld + r + t]; }
+    else v = S[(size_t)r * ld + (ld - 1)];
+    int p = (int)(((long long)r * R) / n);
+    while (p > 0 && r < band_row0(n, R, p)) --p;
+    while (p + 1 < R && r >= band_row0(n, R, p + 1)) ++p;
+    bp.buf[p][par * parstride + (long long)bp.rank * bp.pslot + (long long)(r - band_row0(n, R, p)) * w + t] = v;
+  }
+  band_publish(bp, bp.counters, 0, par, epoch);
+}
+__global__ void __launch_bounds__(128) k_band_reduce(int n, int bw, BandPeers bp, const LmState *__restrict__ st) {
+  if (st->done) return;
+  const unsigned epoch = *bp.epoch + 1;
+  const int par = epoch & 1, w = bw + 2, R = bp.n_ranks;
+  const long long parstride = (long long)R * bp.pslot + bp.cap;
+  band_wait_flags(bp, bp.flag[bp.rank] + (par * 2 + 0) * kMaxRanks, epoch);
+  const int r0 = band_row0(n, R, bp.rank), r1 = band_row0(n, R, bp.rank + 1);
+  const long long total = (long long)(r1 - r0) * w;
+  const double *mine = bp.buf[bp.rank] + par * parstride;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    double vv[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) vv[p] = p < R ? __ldcg(mine + (long long)p * bp.pslot + i) : 0.0;
+    double v = 0.0;
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) v += vv[p];      // rank order; the slots beyond n_ranks add exact zeros
+    const long long o = par * parstride + (long long)R * bp.pslot + (long long)r0 * w + i;
+    for (int q = 0; q < R; ++q) bp.buf[q][o] = v;
+  }
+  band_publish(bp, bp.counters + 1, 1, par, epoch);
+}
+__global__ void __launch_bounds__(128) k_band_pull(double *__restrict__ S, int n, int ld, int bw, BandPeers bp,
+                                                   const LmState *__restrict__ st) {
+  if (st->done) return;
+  const unsigned epoch = *bp.epoch + 1;
+  const int par = epoch & 1, w = bw + 2, R = bp.n_ranks;
+  const long long parstride = (long long)R * bp.pslot + bp.cap;
+  band_wait_flags(bp, bp.flag[bp.rank] + (par * 2 + 1) * kMaxRanks, epoch);
+  const double *res = bp.buf[bp.rank] + par * parstride + (long long)R * bp.pslot;
+  const long long total = (long long)n * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / w), t = (int)(i - (long long)r * w);
+    const double v = __ldcg(res + i);
+    if (t <= bw) { if (r + t < n) S[(size_t)r * ld + r + t] = v; }
+    else S[(size_t)r * ld + (ld - 1)] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(bp.counters + 2, 1u);
+    if (done == gridDim.x - 1) {
+      bp.counters[2] = 0;
+      *bp.epoch = epoch;
+    }
+  }
+}
+
+// One-shot form of the exchange (default): every rank pushes its whole packed band into every rank's receive buffer
+// (slot = its rank) and publishes one epoch flag per peer; k_band_pull1 waits for all flags and writes S(band) = the
+// sum of the slots in rank order.  One hand-over per exchange.
+__global__ void __launch_bounds__(128) k_band_push1(const double *__restrict__ S, int n, int ld, int bw, BandPeers bp,
                                                    const LmState *__restrict__ st) {
   if (st->done) return;
   const unsigned epoch = *bp.epoch + 1;
@@ -1092,7 +1186,7 @@ __global__ void __launch_bounds__(128) k_band_push(const double *__restrict__ S,
     }
   }
 }
-__global__ void __launch_bounds__(128) k_band_pull(double *__restrict__ S, int n, int ld, int bw, BandPeers bp,
+__global__ void __launch_bounds__(128) k_band_pull1(double *__restrict__ S, int n, int ld, int bw, BandPeers bp,
                                                    const LmState *__restrict__ st) {
   if (st->done) return;
   const unsigned epoch = *bp.epoch + 1;
@@ -1120,9 +1214,9 @@ __global__ void __launch_bounds__(128) k_band_pull(double *__restrict__ S, int n
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(bp.counters + 1, 1u);
+    const unsigned done = atomicAdd(bp.counters + 2, 1u);
     if (done == gridDim.x - 1) {
-      bp.counters[1] = 0;
+      bp.counters[2] = 0;
       *bp.epoch = epoch;
     }
   }
@@ -1212,7 +1306,7 @@ struct SharedComm {
   double *band_local = nullptr, *band_peer[kMaxRanks] = {};
   unsigned *bflag_local = nullptr, *bflag_peer[kMaxRanks] = {};
   unsigned *d_band_epoch = nullptr, *d_band_counters = nullptr;
-  long long band_cap = 0;
+  long long band_cap = 0, band_pslot = 0;
   bool band_ok = false;
   struct RetiredBand { double *local; unsigned *flags, *epoch, *counters; double *peer[kMaxRanks]; unsigned *fpeer[kMaxRanks]; };
   std::vector<RetiredBand> retired;   // replaced by a larger set; kept alive for the graphs that captured it
@@ -1845,7 +1939,7 @@ static int agree_on_envelope(ba_solver *s) {
       BandPeers bp{};
       for (int r = 0; r < kMaxRanks; ++r) { bp.buf[r] = sc.band_peer[r]; bp.flag[r] = sc.bflag_peer[r]; }
       bp.epoch = sc.d_band_epoch; bp.counters = sc.d_band_counters; bp.error = sc.d_error;
-      bp.cap = sc.band_cap; bp.rank = sc.rank; bp.n_ranks = sc.n_ranks;
+      bp.cap = sc.band_cap; bp.pslot = sc.band_pslot; bp.rank = sc.rank; bp.n_ranks = sc.n_ranks;
       s->band_peers = bp;
     }
   }
@@ -2645,9 +2739,22 @@ static int enqueue_allreduce_S(ba_solver *s) {
   ncclResult_t r;
   if (s->chol.banded && n > 0 && s->band_peers.cap > 0) {
     const int grid = (int)std::min<long long>(148 * 8, ((long long)n * (s->chol.bw + 2) + 127) / 128);
+    // BA_B200_BAND_XCHG: 1 (default) one-shot pushes, 2 two-shot (reduce-scatter + all-gather).  Measured on 8 B200:
+    // C4 (3.5 MB band) 0.507 vs 0.502 ms per iteration, weak C3 (0.7 MB) 0.487 vs 0.507 ms; on 2 B200 the two-shot form
+    // is 0.1 ms slower on C4 -- the exchange is bound by its hand-overs, not by NVLink bytes, so fewer hand-overs win
+    static const int xchg_env = getenv("BA_B200_BAND_XCHG") ? atoi(getenv("BA_B200_BAND_XCHG")) : 0;
+    const int xchg = xchg_env ? xchg_env : 1;
+    if (xchg == 1) {
+      k_band_push1<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
+      k_band_pull1<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
+      s->launches += 2;
+      return BA_OK;
+    }
+    const int grid_r = (int)std::min<long long>(148 * 8, ((long long)(n / s->n_ranks + 1) * (s->chol.bw + 2) + 127) / 128);
     k_band_push<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
+    k_band_reduce<<<grid_r, 128, 0, s->stream>>>(n, s->chol.bw, s->band_peers, s->d_state.p);
     k_band_pull<<<grid, 128, 0, s->stream>>>(s->d_Saug.p, n, (int)ld, s->chol.bw, s->band_peers, s->d_state.p);
-    s->launches += 2;
+    s->launches += 3;
     return BA_OK;
   }
   if (s->chol.banded && n > 0) {
@@ -3300,14 +3407,16 @@ static void ensure_band_exchange(SharedComm &sc, cudaStream_t st, long long coun
   if (sc.band_local) sc.retire_band();           // graphs of earlier solvers keep using the old set
   const long long cap = (count + 511) / 512 * 512;
   bool ok = true;
-  if (cudaMalloc(&sc.band_local, sizeof(double) * 2 * sc.n_ranks * (size_t)cap) != cudaSuccess) { sc.band_local = nullptr; ok = false; }
-  if (cudaMalloc(&sc.bflag_local, sizeof(unsigned) * 2 * kMaxRanks) != cudaSuccess) { sc.bflag_local = nullptr; ok = false; }
+  const long long pslot = (cap + sc.n_ranks - 1) / sc.n_ranks + 1024;     // one rank's rows of the band (+ one row of slack)
+  const size_t band_doubles = (size_t)2 * ((size_t)sc.n_ranks * cap + cap + (size_t)sc.n_ranks * 1024);   // room for either layout
+  if (cudaMalloc(&sc.band_local, sizeof(double) * band_doubles) != cudaSuccess) { sc.band_local = nullptr; ok = false; }
+  if (cudaMalloc(&sc.bflag_local, sizeof(unsigned) * 4 * kMaxRanks) != cudaSuccess) { sc.bflag_local = nullptr; ok = false; }
   if (cudaMalloc(&sc.d_band_epoch, sizeof(unsigned)) != cudaSuccess) { sc.d_band_epoch = nullptr; ok = false; }
-  if (cudaMalloc(&sc.d_band_counters, 2 * sizeof(unsigned)) != cudaSuccess) { sc.d_band_counters = nullptr; ok = false; }
+  if (cudaMalloc(&sc.d_band_counters, 4 * sizeof(unsigned)) != cudaSuccess) { sc.d_band_counters = nullptr; ok = false; }
   if (ok) {
-    cudaMemset(sc.bflag_local, 0, sizeof(unsigned) * 2 * kMaxRanks);
+    cudaMemset(sc.bflag_local, 0, sizeof(unsigned) * 4 * kMaxRanks);
     cudaMemset(sc.d_band_epoch, 0, sizeof(unsigned));
-    cudaMemset(sc.d_band_counters, 0, 2 * sizeof(unsigned));
+    cudaMemset(sc.d_band_counters, 0, 4 * sizeof(unsigned));
   }
   cudaGetLastError();
   void *m1[kMaxRanks] = {}, *m2[kMaxRanks] = {};
@@ -3323,6 +3432,7 @@ static void ensure_band_exchange(SharedComm &sc, cudaStream_t st, long long coun
     }
   }
   sc.band_cap = sc.band_ok ? cap : 0;
+  sc.band_pslot = pslot;
   if (getenv("BA_B200_VERBOSE")) fprintf(stderr, "[ba_b200] rank %d/%d: band exchange over %s (%lld doubles per slot)\n", sc.rank, sc.n_ranks, sc.band_ok ? "peer memory (CUDA IPC)" : "ncclAllReduce", cap);
 }
 
