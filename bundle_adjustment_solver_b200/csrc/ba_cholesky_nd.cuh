@@ -58,8 +58,14 @@ struct NdArgs {
   const double *S;        // (n+1)^2, entry (r, c), r >= c, at S[c * ld + r]; rhs in row n
   int n, ld, bw;
   double *Lws, *Uws, *x;
-  int *flags;             // persistent driver: [n_nodes] forward done, [n_nodes] backward done, abort, sticky error
+  int *flags;             // persistent driver: [n_nodes] forward done, [n_nodes] backward done, [n_step_flags] panel
+                          // steps of the helped fronts, abort, sticky error
   int n_nodes;
+  int abort_idx;          // index of the abort word (the sticky error word follows it)
+  int step_base;          // index of the first per-step flag
+  int n_main;             // CTAs that walk front lists; CTA n_main + h is helper h
+  const int *helper_list; // front of every helper CTA
+  int use_helpers;        // 0 in the one-launch-per-level driver
   int max_R8, max_tiles, max_KT;  // shared-memory carve-up
 };
 
@@ -145,6 +151,14 @@ __device__ __forceinline__ void nd_stage_node(const NdArgs &g, const NdSmem &sm,
 // ------------------------------------------------------------------------------------------------------------
 // forward elimination of one front.  TPW: boundary x boundary tiles per consumer warp (register accumulators)
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nd_ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void nd_st_release(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // Everything of a front that does not depend on its children's results: node records and index tables in shared
 // memory.  The persistent driver runs it BEFORE it waits for the children's flags (off the critical path).
 __device__ void nd_forward_prepare(const NdArgs &g, const NdSmem &sm, int node_id) {
@@ -204,6 +218,7 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
   gq.U0 = nd.child[0] >= 0 ? g.Uws + sm.cn[0].U_off : nullptr;
   gq.U1 = nd.child[1] >= 0 ? g.Uws + sm.cn[1].U_off : nullptr;
   const bool has_children = gq.U0 || gq.U1;
+  const bool helped = g.use_helpers && nd.helper >= 0;     // a helper CTA holds the boundary x boundary accumulators
   // ---- assembly of the own columns: a warp takes UN tiles per round, lane (fr, fc) two adjacent entries of each:
   //      the band of S (gathered) plus the children's contribution tiles (already in this front's layout: coalesced)
   {
@@ -249,7 +264,7 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
     acc[q] = make_double2(0.0, 0.0);
     ub[q] = -1;
   }
-  if (!is_diag && !is_idle) {
+  if (!is_diag && !is_idle && !helped) {
 #pragma unroll
     for (int q = 0; q < TPW; ++q) {
       const int e = cwi + kNdCons * q;
@@ -393,6 +408,10 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
         else *reinterpret_cast<double2 *>(Lg + gs + (size_t)I * 64 + offC) = make_double2(0.0, 0.0);
       }
       asm volatile("bar.sync %0, %1;" ::"n"(kNdBarB), "n"(kNdCntB) : "memory");
+      if (helped && cwi == 0 && lane == 0) {      // panel s is solved and in global memory: the helper may take it
+        __threadfence();
+        nd_st_release(g.flags + g.step_base + nd.step_flag0 + s, 1);
+      }
       // trailing update, two rows at a time (they share the column operands), two columns per round
       const int Jlim = min(KT - 1, rmax);                            // live column tiles of the trailing block
       for (int I1 = I0; I1 < NT; I1 += 2 * kNdCons) {
@@ -452,7 +471,7 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
     }
     // ---- contribution block: my Schur complement, scattered into the layout of my parent's front (own-column tiles
     //      swizzled like its shared-memory window, then its boundary x boundary tiles)
-    if (nd.parent >= 0) {
+    if (nd.parent >= 0 && !helped) {
       double *Ug = g.Uws + nd.U_off;
       const int KTp = sm.par->k8 >> 3, NTp = (sm.par->k8 + sm.par->b8) >> 3, k8p = sm.par->k8;
       const int ntp = KTp * NTp - (KTp * (KTp - 1)) / 2;
@@ -595,22 +614,14 @@ k_nd_backward_level(NdArgs g, int list_begin, const LmState *st) {
   nd_backward_solve(g, sm);
 }
 
-__device__ __forceinline__ int nd_ld_acquire(const int *p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void nd_st_release(int *p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // thread 0 spins (bounded: a lost hand-over must not hang the device), everybody follows through the barrier
 __device__ __forceinline__ void nd_wait_flag(const NdArgs &g, int idx) {
   if (threadIdx.x == 0) {
     int it = 0;
     while (nd_ld_acquire(g.flags + idx) == 0) {
-      if (++it > kNdSpinLimit || nd_ld_acquire(g.flags + 2 * g.n_nodes) != 0) {
-        atomicExch(g.flags + 2 * g.n_nodes, 1);       // abort this launch
-        atomicExch(g.flags + 2 * g.n_nodes + 1, 1);   // sticky: reported by the host (never cleared by the launch)
+      if (++it > kNdSpinLimit || nd_ld_acquire(g.flags + g.abort_idx) != 0) {
+        atomicExch(g.flags + g.abort_idx, 1);         // abort this launch
+        atomicExch(g.flags + g.abort_idx + 1, 1);     // sticky: reported by the host (never cleared by the launch)
         break;
       }
       __nanosleep(20);
@@ -626,6 +637,96 @@ __device__ __forceinline__ void nd_set_flag(const NdArgs &g, int idx) {
   }
 }
 
+// Helper CTA of a large front: holds the boundary x boundary accumulators (12 warps x TPW tiles), follows the main
+// CTA panel by panel (per-step flags), reads the solved boundary tiles of every panel from the factor in global memory
+// and scatters the finished Schur complement into the parent's layout.  It -- not the main CTA -- sets the front's
+// forward flag.
+template <int TPW>
+__device__ void nd_helper_node(const NdArgs &g, const NdSmem &sm, int node_id) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  nd_forward_prepare(g, sm, node_id);
+  const NdNode &nd = *sm.node;
+  for (int c = 0; c < 2; ++c)
+    if (nd.child[c] >= 0) nd_wait_flag(g, nd.child[c]);
+  const int KT = nd.k8 >> 3, BT = nd.b8 >> 3, NT = KT + BT;
+  auto colbase = [&](int J) { return J * NT - (J * (J - 1)) / 2; };
+  const int n_tiles = colbase(KT);
+  const int LbT0 = (nd.k8 + nd.wr) >> 3;
+  const int fr = lane >> 2, fc = 2 * (lane & 3), kq = lane & 3;
+  const int swz = (fr & 2) << 1;
+  const int offA0 = fr * 8 + (kq ^ swz), offA1 = offA0 ^ 4, offU = fr * 8 + fc;
+  const double *U0 = nd.child[0] >= 0 ? g.Uws + sm.cn[0].U_off : nullptr;
+  const double *U1 = nd.child[1] >= 0 ? g.Uws + sm.cn[1].U_off : nullptr;
+  const int n_utiles = BT * (BT + 1) / 2;
+  double2 acc[TPW];
+  int ub[TPW];
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    acc[q] = make_double2(0.0, 0.0);
+    ub[q] = -1;
+    const int e = warp + kNdWarps * q;
+    if (e < n_utiles) {
+      int I = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while (I * (I + 1) / 2 > e) --I;
+      while ((I + 1) * (I + 2) / 2 <= e) ++I;
+      ub[q] = (I << 8) | (e - I * (I + 1) / 2);
+      const size_t off = ((size_t)n_tiles + e) * 64 + offU;
+      const double2 a = U0 ? __ldcg(reinterpret_cast<const double2 *>(U0 + off)) : make_double2(0.0, 0.0);
+      const double2 b = U1 ? __ldcg(reinterpret_cast<const double2 *>(U1 + off)) : make_double2(0.0, 0.0);
+      acc[q] = make_double2(a.x + b.x, a.y + b.y);
+    }
+  }
+  const double *Lg = g.Lws + nd.L_off;
+  double *panel = sm.win;                       // [2][BT][64]
+#pragma unroll 1
+  for (int s = 0; s < KT; ++s) {
+    nd_wait_flag(g, g.step_base + nd.step_flag0 + s);
+    double *pb = panel + (size_t)(s & 1) * BT * 64;
+    const double2 *src = reinterpret_cast<const double2 *>(Lg + (size_t)(colbase(s) - s + KT) * 64);   // tiles (KT .. NT-1, s)
+    for (int e = t; e < BT * 32; e += kNdThreads) reinterpret_cast<double2 *>(pb)[e] = __ldcg(src + e);
+    __syncthreads();
+    const int rmax = min(NT - 1, s + nd.bandT);
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      if (ub[q] < 0) continue;
+      const int ra = KT + (ub[q] >> 8), rb = KT + (ub[q] & 0xff);
+      if (!((ra <= rmax || ra >= LbT0) && (rb <= rmax || rb >= LbT0))) continue;
+      const double *pa = pb + (size_t)(ub[q] >> 8) * 64, *pc = pb + (size_t)(ub[q] & 0xff) * 64;
+      const double a0 = -pa[offA0], a1 = -pa[offA1], b0 = pc[offA0], b1 = pc[offA1];
+      dmma_884b(acc[q].x, acc[q].y, a0, b0);
+      dmma_884b(acc[q].x, acc[q].y, a1, b1);
+    }
+  }
+  // Schur complement into the parent's layout (same scatter as nd_forward_node)
+  {
+    double *Ug = g.Uws + nd.U_off;
+    const int KTp = sm.par->k8 >> 3, NTp = (sm.par->k8 + sm.par->b8) >> 3, k8p = sm.par->k8;
+    const int ntp = KTp * NTp - (KTp * (KTp - 1)) / 2;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      if (ub[q] < 0) continue;
+      const int bi = 8 * (ub[q] >> 8) + fr, bj0 = 8 * (ub[q] & 0xff) + fc;
+      const int pi = sm.pm[bi];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int bj = bj0 + e;
+        if (bj > bi || pi < 0) continue;
+        const int pj = sm.pm[bj];
+        if (pj < 0) continue;
+        const int a = max(pi, pj), b = min(pi, pj);
+        const double v = e ? acc[q].y : acc[q].x;
+        if (b < k8p) {
+          const int I = a >> 3, J = b >> 3;
+          Ug[(size_t)(J * NTp - (J * (J - 1)) / 2 + I - J) * 64 + nd_sw(a & 7, b & 7)] = v;
+        } else {
+          Ug[((size_t)ntp + nd_tidx((a - k8p) >> 3, (b - k8p) >> 3)) * 64 + ((a - k8p) & 7) * 8 + ((b - k8p) & 7)] = v;
+        }
+      }
+    }
+  }
+  nd_set_flag(g, node_id);
+}
+
 // One launch: every CTA walks its list of fronts forward (children first) and then backward; a front whose child
 // (forward) or parent (backward) belongs to another CTA waits for that CTA's flag.  The flags are cleared by a
 // memset node that precedes the launch.  Requires all CTAs to be co-resident (grid <= SM count, one CTA per SM).
@@ -635,6 +736,10 @@ k_nd_persistent(NdArgs g, int timing, const LmState *st) {
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char nd_raw[];
   const NdSmem sm = nd_carve(nd_raw, g);
+  if ((int)blockIdx.x >= g.n_main) {      // helper CTA: one front's boundary x boundary block, forward pass only
+    nd_helper_node<TPW>(g, sm, g.helper_list[blockIdx.x - g.n_main]);
+    return;
+  }
   const int lb = g.list_ptr[blockIdx.x], le = g.list_ptr[blockIdx.x + 1];
   const int me = blockIdx.x;
   unsigned long long t0 = 0;
@@ -646,12 +751,12 @@ k_nd_persistent(NdArgs g, int timing, const LmState *st) {
     if (timing && threadIdx.x == 0) tw = gtime();
     for (int c = 0; c < 2; ++c) {
       const int ch = sm.node->child[c];
-      if (ch >= 0 && sm.cn[c].cta != me) nd_wait_flag(g, ch);
+      if (ch >= 0 && (sm.cn[c].cta != me || sm.cn[c].helper >= 0)) nd_wait_flag(g, ch);   // another CTA or a helper finishes it
     }
     if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[9] += gtime() - tw;
     nd_forward_node<TPW, NC>(g, sm, id, timing);
     if (timing && threadIdx.x == 0) tw = gtime();
-    nd_set_flag(g, id);
+    if (sm.node->helper < 0) nd_set_flag(g, id);        // a helped front is complete when its helper says so
     if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[12] += gtime() - tw;
   }
   if (timing && threadIdx.x == 0 && blockIdx.x == 0) g_nd_dbg[0] = gtime() - t0;
@@ -701,12 +806,12 @@ inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Sau
     cudaFuncSetAttribute(k_nd_backward_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmemLimit);
   }
   if (mode == 6) {
-    cudaMemsetAsync(dv.cta_args.flags, 0, (size_t)(2 * dv.cta_args.n_nodes + 1) * sizeof(int), stream);
+    cudaMemsetAsync(dv.cta_args.flags, 0, (size_t)(dv.cta_args.abort_idx + 1) * sizeof(int), stream);
     NdArgs a = dv.cta_args;
     a.S = Saug; a.x = x;
     void *args[] = {(void *)&a, (void *)&timing, (void *)&st};
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(pl.n_ctas);
+    cfg.gridDim = dim3(pl.n_ctas + pl.n_helpers);
     cfg.blockDim = dim3(kNdThreads);
     cfg.dynamicSmemBytes = dv.smem;
     cfg.stream = stream;
@@ -718,7 +823,7 @@ inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Sau
     cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)k_nd_persistent<TPW, NC>, args);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      k_nd_persistent<TPW, NC><<<pl.n_ctas, kNdThreads, dv.smem, stream>>>(a, timing, st);
+      k_nd_persistent<TPW, NC><<<pl.n_ctas + pl.n_helpers, kNdThreads, dv.smem, stream>>>(a, timing, st);
       e = cudaGetLastError();
     }
     if (launches) *launches += 1;

@@ -1627,7 +1627,7 @@ struct ba_solver {
   CholeskyPlan chol;
   DevBuf<int> d_chol_rows, d_chol_first, d_chol_rows_ptr;
   DevBuf<NdNode> d_nd_nodes;                       // partitioned banded solve (ba_cholesky_nd.cuh)
-  DevBuf<int> d_nd_level_nodes, d_nd_cta_nodes, d_nd_cta_ptr, d_nd_flags;
+  DevBuf<int> d_nd_level_nodes, d_nd_cta_nodes, d_nd_cta_ptr, d_nd_flags, d_nd_helpers;
   DevBuf<double> d_nd_L, d_nd_U;
   DevBuf<double> d_band;   // multi-GPU, banded S: band rows + rhs packed for the all-reduce
   int chol_mode = -1;  // -1 auto, 0 multi-kernel, 1 cluster
@@ -1711,7 +1711,7 @@ static void free_device(ba_solver *s) {
   s->d_inc_a.release(); s->d_inc_b.release(); s->d_tile_batches.release(); s->d_cta_batch_ptr.release(); s->d_cta_seg_ptr.release(); s->d_seg_off.release(); s->d_seg_win.release(); s->d_pose_seg.release(); s->d_stage.release(); s->d_chunks_fb.release(); s->d_chunk_pts_fb.release(); s->d_cpts_fb.release(); s->d_point_fb.release();
   s->d_chol_rows.release(); s->d_chol_first.release(); s->d_chol_rows_ptr.release(); s->d_band.release();
   s->d_nd_nodes.release(); s->d_nd_level_nodes.release(); s->d_nd_cta_nodes.release(); s->d_nd_cta_ptr.release();
-  s->d_nd_flags.release(); s->d_nd_L.release(); s->d_nd_U.release();
+  s->d_nd_flags.release(); s->d_nd_helpers.release(); s->d_nd_L.release(); s->d_nd_U.release();
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
@@ -1892,7 +1892,8 @@ static int upload_cholesky_plan(ba_solver *s) {
       CUDA_TRY(s->d_nd_level_nodes.upload(nd.level_nodes, st));
       CUDA_TRY(s->d_nd_cta_nodes.upload(nd.cta_nodes, st));
       CUDA_TRY(s->d_nd_cta_ptr.upload(nd.cta_ptr, st));
-      CUDA_TRY(s->d_nd_flags.alloc(2 * nd.nodes.size() + 2));
+      CUDA_TRY(s->d_nd_flags.alloc(2 * nd.nodes.size() + nd.n_step_flags + 2));
+      CUDA_TRY(s->d_nd_helpers.upload(nd.helper_nodes, st));
       CUDA_TRY(s->d_nd_L.alloc((size_t)nd.L_doubles));
       CUDA_TRY(s->d_nd_U.alloc((size_t)std::max<long long>(1, nd.U_doubles)));
       // entries of a parent's front that a child does not cover are never written: they must read as zero
@@ -1904,8 +1905,14 @@ static int upload_cholesky_plan(ba_solver *s) {
       a.Lws = s->d_nd_L.p; a.Uws = s->d_nd_U.p;
       a.flags = s->d_nd_flags.p; a.n_nodes = (int)nd.nodes.size();
       a.max_R8 = nd.max_R8; a.max_tiles = nd.max_tiles; a.max_KT = nd.max_KT;
+      a.step_base = 2 * (int)nd.nodes.size();
+      a.abort_idx = a.step_base + nd.n_step_flags;
+      a.n_main = nd.n_ctas;
+      a.helper_list = s->d_nd_helpers.p;
+      a.use_helpers = 0;
       dv.level_args = a; dv.level_args.list = s->d_nd_level_nodes.p; dv.level_args.list_ptr = nullptr;
       dv.cta_args = a; dv.cta_args.list = s->d_nd_cta_nodes.p; dv.cta_args.list_ptr = s->d_nd_cta_ptr.p;
+      dv.cta_args.use_helpers = nd.n_helpers > 0;
     }
   }
   return BA_OK;
@@ -2858,7 +2865,7 @@ static int check_nd_error(ba_solver *s) {
   }
   if (!s->chol.nd.valid || !s->d_nd_flags.p) return BA_OK;
   int err = 0;
-  CUDA_TRY(cudaMemcpy(&err, s->d_nd_flags.p + 2 * s->chol.nd.nodes.size() + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&err, s->d_nd_flags.p + 2 * s->chol.nd.nodes.size() + s->chol.nd.n_step_flags + 1, sizeof(int), cudaMemcpyDeviceToHost));
   if (err) { s->err = "partitioned reduced solve: hand-over between CTAs timed out"; return BA_ERR_CUDA; }
   return BA_OK;
 }
@@ -3250,7 +3257,7 @@ int ba_debug_solve_info(ba_solver *s, char *name, int cap, double *vals) {
       for (int c = 0; c < nd.k8; ++c) exec += (R - c) * (R - c);
     }
     chain = nd_plan_cost(pl.nd);
-    ctas = band_mode == 6 ? pl.nd.n_ctas : pl.nd.n_leaves;
+    ctas = band_mode == 6 ? pl.nd.n_ctas + pl.nd.n_helpers : pl.nd.n_leaves;
     char buf[256];
     snprintf(buf, sizeof(buf), "%s<%d,%d> (partitioned banded Cholesky: nested dissection depth %d, %d fronts, DMMA panel solves and updates)",
              band_mode == 6 ? "k_nd_persistent" : "k_nd_forward_level+k_nd_backward_level", pl.nd_dev.tpw, nd_cons_for(pl.nd.max_BT),
@@ -3281,7 +3288,7 @@ int ba_debug_solve_info(ba_solver *s, char *name, int cap, double *vals) {
 }
 
 // Host-only: the partition plan of the banded reduced solve for N free poses and track span b (no device needed).
-// nodes_out: [cap][20] = own0 k k8 rb0 wr lb0 wl b8 child0 child1 parent rb_off lb_off rhs_off level cta seq L_off U_off bandT
+// nodes_out: [cap][20] = own0 k k8 rb0 wr lb0 wl b8 child0 child1 parent rb_off lb_off rhs_off level cta seq L_off U_off helper
 // meta: [8] = valid depth n_leaves n_levels n_ctas max_tiles max_R8 smem_bytes.  Returns the number of nodes.
 int ba_debug_nd_plan(int N, int b, int max_ctas, int force_depth, int force_chunk, long long *meta,
                      long long *nodes_out, int cap) {
@@ -3295,7 +3302,7 @@ int ba_debug_nd_plan(int N, int b, int max_ctas, int force_depth, int force_chun
   for (int i = 0; i < std::min(nn, cap) && nodes_out; ++i) {
     const NdNode &d = pl.nodes[i];
     const long long v[20] = {d.own0, d.k, d.k8, d.rb0, d.wr, d.lb0, d.wl, d.b8, d.child[0], d.child[1], d.parent,
-                             d.rb_off, d.lb_off, d.rhs_off, d.level, d.cta, d.seq, d.L_off, d.U_off, d.bandT};
+                             d.rb_off, d.lb_off, d.rhs_off, d.level, d.cta, d.seq, d.L_off, d.U_off, d.helper};
     std::copy(v, v + 20, nodes_out + (size_t)i * 20);
   }
   return nn;

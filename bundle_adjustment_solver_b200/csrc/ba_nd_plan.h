@@ -34,6 +34,9 @@ struct NdNode {
   int rb_off, lb_off, rhs_off;   // this node's U rows in the PARENT's front-local index space
   int level;            // forward level (children have smaller levels); backward runs the levels in reverse
   int cta, seq;         // persistent kernel: CTA that owns the node and position in that CTA's list
+  int helper;           // persistent driver: CTA that holds this front's boundary x boundary accumulators (-1: the
+                        // front's own CTA does); the main CTA publishes one flag per panel step (step_flag0 + s)
+  int step_flag0;
   int bandT;            // row tiles below the diagonal tile of a column that can be nonzero in [own | Rb] (chain fronts:
                         // band of S; separators: all).  Rows outside (except Lb / rhs) are skipped by the factorisation
   long long L_off;      // doubles: factor tiles of the own columns [n_tiles][64] (swizzled 8 x 8 tiles, column by
@@ -54,11 +57,15 @@ struct NdPlan {
   std::vector<NdNode> nodes;
   std::vector<int> level_ptr, level_nodes;   // nodes by level
   std::vector<int> cta_ptr, cta_nodes;       // persistent kernel: per CTA, its nodes in forward order
+  int n_helpers = 0, n_step_flags = 0;       // helper CTAs (blockIdx >= n_ctas) and their per-step flags
+  std::vector<int> helper_nodes;             // front of every helper CTA
 };
 
 inline int nd_pad8(int v) { return (v + 7) / 8 * 8; }
 constexpr int kNdMaxBT = 22;            // boundary tile rows a consumer warp can hold in registers (9 warps x 30 tiles)
 constexpr size_t kNdSmemLimit = 227 * 1024;
+constexpr int kNdHelperMinBT = 12;      // boundary tile rows from which a front gets a helper CTA
+constexpr int kNdMaxSteps = 32;         // per-step flags reserved per helped front
 
 // shared memory of one front: own trapezoid tiles + inverses of the diagonal blocks + x / rhs vectors of the backward
 // pass + child index maps + tile table (+ node records)
@@ -231,6 +238,24 @@ inline void nd_make_plan_depth(NdPlan &pl, int N, int b, int max_ctas, int force
       ++n_cta;
     }
     pl.n_ctas = n_cta;
+    // Helper CTAs: on a large front half of the step is the rank-8 update of the boundary x boundary block, which is
+    // off the critical path (only the parent needs it).  A second CTA on another SM holds those accumulators, follows
+    // the main CTA panel by panel through per-step flags and reads the solved boundary tiles from the factor in global
+    // memory; the main CTA is left with the panel solve and the own-column update.
+    for (int i = 0; i < nn; ++i) { nodes[i].helper = -1; nodes[i].step_flag0 = -1; }
+    std::vector<int> cand;
+    for (int i = 0; i < nn; ++i)
+      if (nodes[i].b8 / 8 >= kNdHelperMinBT && nodes[i].k8 / 8 >= 4 && nodes[i].k8 / 8 <= kNdMaxSteps && nodes[i].parent >= 0) cand.push_back(i);
+    std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+      return (long long)nodes[a].b8 * nodes[a].b8 * nodes[a].k8 > (long long)nodes[b].b8 * nodes[b].b8 * nodes[b].k8; });
+    for (int i : cand) {
+      if (n_cta + pl.n_helpers >= std::max(kNdTotalCtas, max_ctas)) break;
+      nodes[i].helper = n_cta + pl.n_helpers;
+      nodes[i].step_flag0 = pl.n_step_flags;
+      pl.n_step_flags += kNdMaxSteps;
+      pl.helper_nodes.push_back(i);
+      ++pl.n_helpers;
+    }
   }
   if (pl.smem_bytes > kNdSmemLimit || chunk_overflow) return;
   pl.valid = true;

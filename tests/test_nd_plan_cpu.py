@@ -10,7 +10,7 @@ import pytest
 from bundle_adjustment_solver_b200 import capi
 
 F = ["own0", "k", "k8", "rb0", "wr", "lb0", "wl", "b8", "child0", "child1", "parent", "rb_off", "lb_off",
-     "rhs_off", "level", "cta", "seq", "L_off", "U_off", "bandT"]
+     "rhs_off", "level", "cta", "seq", "L_off", "U_off", "helper"]
 
 
 def nd_plan(N, b, max_ctas=128, depth=-1, chunk=-1):
@@ -136,6 +136,9 @@ def test_partition_plan_solves_banded_system(N, b, depth, chunk):
     # persistent driver: every node belongs to exactly one CTA list; inside a list a front follows its child0 (the
     # CTA climbs the tree), a front whose children belong to other CTAs starts a list; all CTAs are co-resident
     assert meta["n_ctas"] <= 148
+    helpers = sorted(nd["helper"] for nd in nodes if nd["helper"] >= 0)
+    assert helpers == list(range(meta["n_ctas"], meta["n_ctas"] + len(helpers))) and meta["n_ctas"] + len(helpers) <= 148
+    assert all(nd["b8"] >= 96 for nd in nodes if nd["helper"] >= 0)          # only large boundary blocks get a helper
     lists = {}
     for t, nd in enumerate(nodes):
         lists.setdefault(nd["cta"], []).append((nd["seq"], t))
