@@ -67,7 +67,34 @@ def main():
         np.testing.assert_allclose(poses, full.get_poses(), atol=1e-8)
         lo, hi = sh.meta["landmark_range"]
         np.testing.assert_allclose(e.get_points(), full.get_points()[lo:hi], atol=1e-8)
-        print("MGPU_OK", world, costs[-1])
+    # a second, larger problem in the same process ATTACHES to the communicator (no second NCCL set-up); its band
+    # needs a larger exchange buffer than the first one's (the old set is retired, not freed) and its reduced system
+    # goes through the partitioned solve
+    sc2 = scenes.scene_trajectory(150, 9000, 8, stereo=True, seed=22, n_fixed=2)
+    sh2 = sharding.shard_scene(sc2, rank, world)
+    e2 = S.load_scene(S.FullBundleAdjustmentSolver(device=local), sh2)
+    e2._upload()
+    sz2 = e2.sizes()
+    tot2 = torch.tensor([sz2["M"], sz2["n_obs"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot2)
+    rc = L.ba_comm_attach(e2.h, int(tot2[0]), int(tot2[1]))
+    assert rc == 0, L.ba_last_error(e2.h)
+    s2 = S.Summary()
+    e2.solve(capi.default_options(max_num_iterations=6, threshold_cost_change=0.0, threshold_step_size=0.0), s2)
+    costs2 = np.array([i.cost for i in s2.optimization_info_list])
+    buf2 = torch.from_numpy(np.concatenate([costs2, e2.get_poses().reshape(-1)])).to(dev)
+    ref2 = buf2.clone()
+    dist.broadcast(ref2, 0)
+    assert torch.equal(buf2, ref2), "ranks diverged on the attached solver"
+    # the first solver still works after the exchange buffers were replaced
+    e.solve(capi.default_options(max_num_iterations=2, threshold_cost_change=0.0, threshold_step_size=0.0), S.Summary())
+    if rank == 0:
+        full2 = S.load_scene(S.FullBundleAdjustmentSolver(device=local), sc2)
+        s3 = S.Summary()
+        full2.solve(capi.default_options(max_num_iterations=6, threshold_cost_change=0.0, threshold_step_size=0.0), s3)
+        np.testing.assert_allclose(costs2, [i.cost for i in s3.optimization_info_list], rtol=1e-8)
+        np.testing.assert_allclose(e2.get_poses(), full2.get_poses(), atol=1e-8)
+        print("MGPU_OK", world, costs[-1], costs2[-1])
     dist.barrier()
     dist.destroy_process_group()
 

@@ -16,15 +16,17 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("hetero", [0, 1])
+@pytest.mark.parametrize("hetero,xchg", [(0, 1), (1, 1), (0, 2), (0, 0)])
 @pytest.mark.parametrize("world", [2])
-def test_sharded_solve_matches_single_gpu(world, hetero):
+def test_sharded_solve_matches_single_gpu(world, hetero, xchg):
+    """xchg: 1 one-shot / 2 two-shot band exchange through peer memory, 0 = no peer memory at all (NCCL all-reduces)."""
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     port = 29700 + (os.getpid() % 200)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1", BA_MGPU_HETERO=str(hetero)))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1", BA_MGPU_HETERO=str(hetero),
+                                  **({"BA_B200_BAND_XCHG": str(xchg)} if xchg else {"BA_B200_NO_PEER_EXCHANGE": "1"})))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MGPU_OK" in out.stdout
 
