@@ -595,3 +595,30 @@ def test_c4_c5_full_size_properties(workload, engine_lib):
             prev = i.cost
     assert infos[-1].cost < 0.9 * c_full
     assert np.isfinite(e.get_poses()).all() and np.isfinite(e.get_points()).all()
+
+
+def test_bal_file_round_trip_solves_on_the_device(tmp_path, oracle_mod, engine_lib):
+    """bal.py end to end: a mono trajectory scene written in the 'Bundle Adjustment in the Large' layout, read back and
+    solved on the device follows the oracle's LM trajectory on the same file."""
+    from bundle_adjustment_solver_b200 import bal
+    from bundle_adjustment_solver_b200.solver import Summary
+    sc = scenes.scene_trajectory(40, 1500, 6, stereo=False, seed=13, n_fixed=2)
+    sc.cam_intr[0, 2:] = 0.0                               # the format has no principal point
+    T_cw = scenes.inv_T(sc.poses_true)
+    Xc = np.einsum("nij,nj->ni", T_cw[sc.obs_pose, :3, :3], sc.points_true[sc.obs_point]) + T_cw[sc.obs_pose, :3, 3]
+    f0 = sc.cam_intr[0, 0]
+    sc.obs_uv = np.stack([f0 * Xc[:, 0] / Xc[:, 2], f0 * Xc[:, 1] / Xc[:, 2]], axis=1)
+    path = tmp_path / "problem.txt"
+    bal.save_bal(sc, path)
+    back = bal.load_bal(path, n_fixed=2)
+    oo, eo = options_pair(max_num_iterations=8, threshold_cost_change=0.0, threshold_step_size=0.0)
+    o = load_oracle(back)
+    infos_o, _ = o.solve(oo)
+    e = load_engine(back)
+    summ = Summary()
+    e.solve(eo, summ)
+    infos_e = summ.optimization_info_list
+    assert len(infos_e) == len(infos_o) == 8
+    for a, b in zip(infos_e, infos_o):
+        assert abs(a.cost - b.cost) <= 1e-8 * abs(b.cost) and a.iteration_status == b.iteration_status
+    assert infos_e[-1].cost < 0.2 * infos_e[0].cost
