@@ -161,7 +161,7 @@ __device__ __forceinline__ void nd_st_release(int *p, int v) {
 }
 // Everything of a front that does not depend on its children's results: node records and index tables in shared
 // memory.  The persistent driver runs it BEFORE it waits for the children's flags (off the critical path).
-__device__ void nd_forward_prepare(const NdArgs &g, const NdSmem &sm, int node_id) {
+__device__ void nd_forward_prepare(const NdArgs &g, const NdSmem &sm, int node_id, bool with_S = true) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   nd_stage_node(g, sm, node_id, true);
   const NdNode &nd = *sm.node;
@@ -192,6 +192,43 @@ __device__ void nd_forward_prepare(const NdArgs &g, const NdSmem &sm, int node_i
     for (int I = J + lane; I < NT; I += 32) sm.tt[base + I] = (I << 16) | J;
   }
   __syncthreads();
+  if (!with_S) return;
+  // the band of S for the own columns (does not depend on the children either): a warp takes UN tiles per round, lane
+  // (fr, fc) two adjacent entries of each; gathered through the row table with every load of the round in flight
+  {
+    const int fr = lane >> 2, fc = 2 * (lane & 3);
+    const int offC = fr * 8 + (fc ^ ((fr & 2) << 1));
+    const int n_tiles = colbase(KT);
+    NdGather gq;
+    gq.S = g.S; gq.ld = g.ld; gq.n = g.n; gq.bw = g.bw; gq.U0 = gq.U1 = nullptr;
+    constexpr int UN = 8;
+    for (int tb0 = warp; tb0 < n_tiles; tb0 += kNdWarps * UN) {
+      unsigned src[UN][2];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int tile = tb0 + kNdWarps * u;
+        const bool live = tile < n_tiles;
+        const int ij = sm.tt[live ? tile : tb0];
+        const int I = ij >> 16, J = ij & 0xffff;
+        const int i = 8 * I + fr, j = 8 * J + fc;
+        bool in_band = true;            // tiles entirely outside the band of S hold no entry of S
+        if (I > J) {
+          const int gr = sm.grow[8 * I], gr7 = sm.grow[8 * I + 7], gc = sm.grow[8 * J], gc7 = sm.grow[8 * J + 7];
+          const bool rows_ok = gr >= 0 && gr7 - gr == 7 && gr7 != g.n;     // eight consecutive rows of S
+          in_band = !(rows_ok && ((gc7 >= 0 && gr - gc7 > g.bw) || gc - gr7 > g.bw));
+        }
+        src[u][0] = nd_front_src(gq, sm, i, j, live && in_band && i >= j);
+        src[u][1] = nd_front_src(gq, sm, i, j + 1, live && in_band && i >= j + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int tile = tb0 + kNdWarps * u;
+        if (tile < n_tiles)
+          *reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC) = make_double2(nd_src_value(gq, src[u][0]), nd_src_value(gq, src[u][1]));
+      }
+    }
+  }
+  __syncthreads();
 }
 
 template <int TPW, int NC>
@@ -219,38 +256,27 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
   gq.U1 = nd.child[1] >= 0 ? g.Uws + sm.cn[1].U_off : nullptr;
   const bool has_children = gq.U0 || gq.U1;
   const bool helped = g.use_helpers && nd.helper >= 0;     // a helper CTA holds the boundary x boundary accumulators
-  // ---- assembly of the own columns: a warp takes UN tiles per round, lane (fr, fc) two adjacent entries of each:
-  //      the band of S (gathered) plus the children's contribution tiles (already in this front's layout: coalesced)
-  {
+  // ---- assembly of the own columns: the band of S is already in the window (nd_forward_prepare); the children's
+  //      contribution tiles arrive in this front's layout and are added as whole tiles (coalesced double2 loads)
+  if (has_children) {
     constexpr int UN = 8;
     for (int tb0 = warp; tb0 < n_tiles; tb0 += kNdWarps * UN) {
-      unsigned src[UN][2];
       double2 c0[UN], c1[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int tile = tb0 + kNdWarps * u;
         const bool live = tile < n_tiles;
-        const int ij = sm.tt[live ? tile : tb0];
-        const int I = ij >> 16, J = ij & 0xffff;
-        const int i = 8 * I + fr, j = 8 * J + fc;
-        // a front without children holds nothing but the band of S: tiles entirely outside it are zero
-        bool in_band = true;
-        if (I > J) {
-          const int gr = sm.grow[8 * I], gr7 = sm.grow[8 * I + 7], gc = sm.grow[8 * J], gc7 = sm.grow[8 * J + 7];
-          const bool rows_ok = gr >= 0 && gr7 - gr == 7 && gr7 != g.n;     // eight consecutive rows of S
-          in_band = !(rows_ok && ((gc7 >= 0 && gr - gc7 > g.bw) || gc - gr7 > g.bw));
-        }
-        src[u][0] = nd_front_src(gq, sm, i, j, live && in_band && i >= j);
-        src[u][1] = nd_front_src(gq, sm, i, j + 1, live && in_band && i >= j + 1);
         c0[u] = (live && gq.U0) ? __ldcg(reinterpret_cast<const double2 *>(gq.U0 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
         c1[u] = (live && gq.U1) ? __ldcg(reinterpret_cast<const double2 *>(gq.U1 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
       }
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int tile = tb0 + kNdWarps * u;
-        if (tile < n_tiles)
-          *reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC) =
-              make_double2(nd_src_value(gq, src[u][0]) + (c0[u].x + c1[u].x), nd_src_value(gq, src[u][1]) + (c0[u].y + c1[u].y));
+        if (tile < n_tiles) {
+          double2 *w = reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC);
+          const double2 v = *w;
+          *w = make_double2(v.x + (c0[u].x + c1[u].x), v.y + (c0[u].y + c1[u].y));
+        }
       }
     }
   }
@@ -644,7 +670,7 @@ __device__ __forceinline__ void nd_set_flag(const NdArgs &g, int idx) {
 template <int TPW>
 __device__ void nd_helper_node(const NdArgs &g, const NdSmem &sm, int node_id) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  nd_forward_prepare(g, sm, node_id);
+  nd_forward_prepare(g, sm, node_id, false);
   const NdNode &nd = *sm.node;
   for (int c = 0; c < 2; ++c)
     if (nd.child[c] >= 0) nd_wait_flag(g, nd.child[c]);
