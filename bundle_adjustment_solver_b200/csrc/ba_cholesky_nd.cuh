@@ -256,32 +256,8 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
   gq.U1 = nd.child[1] >= 0 ? g.Uws + sm.cn[1].U_off : nullptr;
   const bool has_children = gq.U0 || gq.U1;
   const bool helped = g.use_helpers && nd.helper >= 0;     // a helper CTA holds the boundary x boundary accumulators
-  // ---- assembly of the own columns: the band of S is already in the window (nd_forward_prepare); the children's
-  //      contribution tiles arrive in this front's layout and are added as whole tiles (coalesced double2 loads)
-  if (has_children) {
-    constexpr int UN = 8;
-    for (int tb0 = warp; tb0 < n_tiles; tb0 += kNdWarps * UN) {
-      double2 c0[UN], c1[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int tile = tb0 + kNdWarps * u;
-        const bool live = tile < n_tiles;
-        c0[u] = (live && gq.U0) ? __ldcg(reinterpret_cast<const double2 *>(gq.U0 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
-        c1[u] = (live && gq.U1) ? __ldcg(reinterpret_cast<const double2 *>(gq.U1 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int tile = tb0 + kNdWarps * u;
-        if (tile < n_tiles) {
-          double2 *w = reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC);
-          const double2 v = *w;
-          *w = make_double2(v.x + (c0[u].x + c1[u].x), v.y + (c0[u].y + c1[u].y));
-        }
-      }
-    }
-  }
-  if (timing && t == 0 && blockIdx.x == 0) g_nd_dbg[14] += gtime() - t_in;   // + own columns (warp 0's share)
-  // ---- boundary x boundary accumulators (consumers): children's contributions passed through
+  // ---- boundary x boundary accumulators (consumers): children's contributions passed through (loads issued first:
+  //      they are in flight while the own columns are assembled)
   const int n_utiles = BT * (BT + 1) / 2;
   double2 acc[TPW];
   int ub[TPW];                                   // (row tile << 8) | column tile of the boundary block, -1: none
@@ -314,6 +290,31 @@ __device__ void nd_forward_node(const NdArgs &g, const NdSmem &sm, int node_id, 
       }
     }
   }
+  // ---- assembly of the own columns: the band of S is already in the window (nd_forward_prepare); the children's
+  //      contribution tiles arrive in this front's layout and are added as whole tiles (coalesced double2 loads)
+  if (has_children) {
+    constexpr int UN = 8;
+    for (int tb0 = warp; tb0 < n_tiles; tb0 += kNdWarps * UN) {
+      double2 c0[UN], c1[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int tile = tb0 + kNdWarps * u;
+        const bool live = tile < n_tiles;
+        c0[u] = (live && gq.U0) ? __ldcg(reinterpret_cast<const double2 *>(gq.U0 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
+        c1[u] = (live && gq.U1) ? __ldcg(reinterpret_cast<const double2 *>(gq.U1 + (size_t)tile * 64 + offC)) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int tile = tb0 + kNdWarps * u;
+        if (tile < n_tiles) {
+          double2 *w = reinterpret_cast<double2 *>(sm.win + (size_t)tile * 64 + offC);
+          const double2 v = *w;
+          *w = make_double2(v.x + (c0[u].x + c1[u].x), v.y + (c0[u].y + c1[u].y));
+        }
+      }
+    }
+  }
+  if (timing && t == 0 && blockIdx.x == 0) g_nd_dbg[14] += gtime() - t_in;   // + own columns (warp 0's share)
   __syncthreads();
   unsigned long long t0 = 0;
   if (timing && t == 0) {
