@@ -847,14 +847,15 @@ inline bool nd_enqueue_t(const NdPlan &pl, const NdDevice &dv, const double *Sau
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)k_nd_persistent<TPW, NC>, args);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      k_nd_persistent<TPW, NC><<<pl.n_ctas + pl.n_helpers, kNdThreads, dv.smem, stream>>>(a, timing, st);
-      e = cudaGetLastError();
+    const cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)k_nd_persistent<TPW, NC>, args);
+    if (e == cudaSuccess) {
+      if (launches) *launches += 1;
+      return true;
     }
-    if (launches) *launches += 1;
-    return e == cudaSuccess;
+    // The cooperative launch guarantees that all CTAs are co-resident (the hand-over flags need it).  When it is
+    // refused (device shared with another process, fewer SMs than the plan's CTAs) the per-level launches below do
+    // the same work without any cross-CTA waiting.
+    cudaGetLastError();
   }
   NdArgs la = dv.level_args;
   la.S = Saug; la.x = x;
