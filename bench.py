@@ -686,7 +686,7 @@ def main():
                        "ctas": sinfo["ctas"], "dependent_panel_steps": sinfo["chain_steps"], "traffic": phase_traffic(tab, "solve")}
     t_build = ph["linearize"] + ph["schur"]
     kernels = {"linearize": "k_linearize_by_pose+k_finish_poses", "schur": "k_build_tiles (linearise + C^-1 + Schur DMMA GEMM) + k_tile_reduce",
-               "backsub": "k_backsub_pairs+k_backsub_points", "update_cost": "k_update_poses+k_cost_decide",
+               "backsub": "k_backsub_pairs+k_backsub_points_update_poses", "update_cost": "k_cost_decide",
                "solve": sinfo["kernel"]}
     # the dominant kernel of the step by device time
     dom = max(ph, key=lambda k: ph[k])

@@ -485,14 +485,13 @@ k_backsub_pairs(const Chunk *__restrict__ chunks, const int *__restrict__ chunk_
 
 // per point: y = Cinv_b - Cinv Btx (:916) ; model terms b.y + y^T C y + 2 y.Btx (:443-452) ;
 // |y| ; trial point X + y (:498).  Partials per block: {model, step}.
-__global__ void __launch_bounds__(kThreads)
-k_backsub_points(int M_total, const int *__restrict__ point_has_pairs, const uint8_t *__restrict__ point_free,
-                 const double *__restrict__ ptblk, size_t Mp, const double *__restrict__ Btx,
-                 double *__restrict__ y /*[M_total][3]*/, Params prm, ParamsW prw,
-                 double *__restrict__ partials /*[grid][2]*/, int method, const LmState *__restrict__ st) {
-  if (st->done) return;
+__device__ __forceinline__ void backsub_points_body(int blk, int M_total, const int *__restrict__ point_has_pairs,
+                                                    const uint8_t *__restrict__ point_free, const double *__restrict__ ptblk,
+                                                    size_t Mp, const double *__restrict__ Btx, double *__restrict__ y,
+                                                    const Params &prm, const ParamsW &prw, double *__restrict__ partials,
+                                                    int method, const LmState *__restrict__ st) {
   __shared__ double sm[kWarps][2];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blk * blockDim.x + threadIdx.x;
   double acc[2] = {0.0, 0.0};
   if (i < M_total) {
     const double *Xc = prm.points[st->cur] + (size_t)i * 3;
@@ -545,9 +544,17 @@ k_backsub_points(int M_total, const int *__restrict__ point_has_pairs, const uin
   }
   block_sum<2, kWarps>(acc, sm);
   if (threadIdx.x == 0) {
-    partials[(size_t)blockIdx.x * 2] = acc[0];
-    partials[(size_t)blockIdx.x * 2 + 1] = acc[1];
+    partials[(size_t)blk * 2] = acc[0];
+    partials[(size_t)blk * 2 + 1] = acc[1];
   }
+}
+__global__ void __launch_bounds__(kThreads)
+k_backsub_points(int M_total, const int *__restrict__ point_has_pairs, const uint8_t *__restrict__ point_free,
+                 const double *__restrict__ ptblk, size_t Mp, const double *__restrict__ Btx,
+                 double *__restrict__ y /*[M_total][3]*/, Params prm, ParamsW prw,
+                 double *__restrict__ partials /*[grid][2]*/, int method, const LmState *__restrict__ st) {
+  if (st->done) return;
+  backsub_points_body(blockIdx.x, M_total, point_has_pairs, point_free, ptblk, Mp, Btx, y, prm, prw, partials, method, st);
 }
 
 // SolveByGradientDescent, pose side (full_bundle_adjustment_solver_refactor.cpp:1274-1276): x_j = a_j clipped to
@@ -568,13 +575,12 @@ __global__ void k_gd_poses(int N, const double *__restrict__ a, double *__restri
 // ---------------------------------------------------------------------------
 // K7: pose update + pose part of the model change; trial cost; decision.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_update_poses(int N_total, const int *__restrict__ pose_opt, const double *__restrict__ x,
-               const double *__restrict__ A, const double *__restrict__ a, Params prm, ParamsW prw,
-               double *__restrict__ partials /*[grid][2]*/, const LmState *__restrict__ st) {
-  if (st->done) return;
+__device__ __forceinline__ void update_poses_body(int blk, int N_total, const int *__restrict__ pose_opt,
+                                                  const double *__restrict__ x, const double *__restrict__ A,
+                                                  const double *__restrict__ a, const Params &prm, const ParamsW &prw,
+                                                  double *__restrict__ partials, const LmState *__restrict__ st) {
   __shared__ double sm[kWarps][2];
-  const int jt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jt = blk * blockDim.x + threadIdx.x;
   double acc[2] = {0.0, 0.0};
   if (jt < N_total) {
     const double *Tc = prm.poses[st->cur] + (size_t)jt * 12;
@@ -610,9 +616,31 @@ k_update_poses(int N_total, const int *__restrict__ pose_opt, const double *__re
   }
   block_sum<2, kWarps>(acc, sm);
   if (threadIdx.x == 0) {
-    partials[(size_t)blockIdx.x * 2] = acc[0];
-    partials[(size_t)blockIdx.x * 2 + 1] = acc[1];
+    partials[(size_t)blk * 2] = acc[0];
+    partials[(size_t)blk * 2 + 1] = acc[1];
   }
+}
+__global__ void __launch_bounds__(kThreads)
+k_update_poses(int N_total, const int *__restrict__ pose_opt, const double *__restrict__ x,
+               const double *__restrict__ A, const double *__restrict__ a, Params prm, ParamsW prw,
+               double *__restrict__ partials /*[grid][2]*/, const LmState *__restrict__ st) {
+  if (st->done) return;
+  update_poses_body(blockIdx.x, N_total, pose_opt, x, A, a, prm, prw, partials, st);
+}
+// Back-substitution of the landmarks and the pose update in ONE launch: the two are independent (both only need x), the
+// pose update is a single latency-bound CTA (9 us on C3) that now runs beside the landmark CTAs
+__global__ void __launch_bounds__(kThreads)
+k_backsub_points_update_poses(int point_blocks, int M_total, const int *__restrict__ point_has_pairs,
+                              const uint8_t *__restrict__ point_free, const double *__restrict__ ptblk, size_t Mp,
+                              const double *__restrict__ Btx, double *__restrict__ y, Params prm, ParamsW prw,
+                              double *__restrict__ point_partials, int method, int N_total, const int *__restrict__ pose_opt,
+                              const double *__restrict__ x, const double *__restrict__ A, const double *__restrict__ a,
+                              double *__restrict__ pose_partials, const LmState *__restrict__ st) {
+  if (st->done) return;
+  if ((int)blockIdx.x < point_blocks)
+    backsub_points_body(blockIdx.x, M_total, point_has_pairs, point_free, ptblk, Mp, Btx, y, prm, prw, point_partials, method, st);
+  else
+    update_poses_body(blockIdx.x - point_blocks, N_total, pose_opt, x, A, a, prm, prw, pose_partials, st);
 }
 
 // EvaluateCurrentCost (:381-433): sum over observations of ||r||_2 ; which = 0 current, 1 trial.
@@ -2810,9 +2838,10 @@ static int enqueue_solve_backsub(ba_solver *s, const ba_options *opt, cudaEvent_
                                                       s->d_Btx.p, s->Mp, dst);
     s->launches++;
   }
-  k_backsub_points<<<s->point_grid, kThreads, 0, st>>>(s->M_total, s->d_point_has_pairs.p, s->d_point_free.p,
-                                                       s->d_ptblk.p, s->Mp, s->d_Btx.p, s->d_y.p, prm, prw,
-                                                       s->d_point_partials.p, opt->method, dst);
+  k_backsub_points_update_poses<<<s->point_grid + s->pose_grid, kThreads, 0, st>>>(
+      s->point_grid, s->M_total, s->d_point_has_pairs.p, s->d_point_free.p, s->d_ptblk.p, s->Mp, s->d_Btx.p, s->d_y.p, prm,
+      prw, s->d_point_partials.p, opt->method, s->N_total, s->d_pose_opt.p, s->d_x.p, s->d_A.p, s->d_a.p,
+      s->d_pose_partials.p, dst);
   s->launches++;
   return BA_OK;
 }
@@ -2820,25 +2849,22 @@ static int enqueue_solve_backsub(ba_solver *s, const ba_options *opt, cudaEvent_
 static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   cudaStream_t st = s->stream;
   const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
-  const ParamsW prw{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
   LmState *dst = s->d_state.p;
   if (ev) cudaEventRecord(ev[Phase::Update], st);
-  // (tried: the pose update on a forked graph branch beside the back-substitution -- the cross-stream edges cost more
-  //  than the 9 us they hide: C3 0.419 -> 0.431 ms per iteration)
-  k_update_poses<<<s->pose_grid, kThreads, 0, st>>>(s->N_total, s->d_pose_opt.p, s->d_x.p, s->d_A.p, s->d_a.p,
-                                                    prm, prw, s->d_pose_partials.p, dst);
+  // the pose update (se3Exp, pose part of the model change) ran with the back-substitution of the landmarks
+  // (k_backsub_points_update_poses; a forked graph branch for it cost more than the 9 us it hid)
   DecideArgs g = make_decide_args(s, opt);
   if (!s->comm) {
     k_cost_decide<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
                                                      s->d_obs_camflags.p, prm, s->d_cams.p, s->d_cost_partials.p,
                                                      s->d_ticket.p, g, dst, s->d_infos.p, (int)s->d_infos.n);
-    s->launches += 2;
+    s->launches += 1;
     if (ev) cudaEventRecord(ev[Phase::End], st);
     return BA_OK;
   }
   k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
                                             s->d_obs_camflags.p, prm, 1, s->d_cams.p, s->d_cost_partials.p, 0, dst);
-  s->launches += 2;
+  s->launches += 1;
   if (!s->comm) {
     k_reduce_decide<<<1, kThreads, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
     s->launches++;
