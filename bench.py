@@ -80,7 +80,7 @@ WORKLOAD_NAMES = {
 
 def algorithmic_bytes(sz, n_obs_free_pose, solve_info):
     """Algorithmic bytes per LM iteration of the implemented design (DESIGN.md 'Kernels').
-    pose side  (k_linearize_by_pose + k_finish_poses): 28 B/obs in pose order, A / a and the S diagonal; clearing S costs
+    pose side  (k_linearize_by_pose): 28 B/obs in pose order, A / a and the S diagonal; clearing S costs
                8 (6N+1)^2 bytes when the whole buffer is cleared and 8 (6N)(bw+2) when only the band is
     point side (k_build_tiles, fused K1+K3+K4): 20 B/obs (pixel, camera) + 24 B per (pose, landmark) incidence,
                pose / point gathers, B written once (144 B/pair), per-landmark blocks (144 B), S tile flush
@@ -685,7 +685,7 @@ def main():
                        "dense_equivalent_tflops": tf(sinfo["dense_flops"]), "half_bandwidth": sinfo["bw"],
                        "ctas": sinfo["ctas"], "dependent_panel_steps": sinfo["chain_steps"], "traffic": phase_traffic(tab, "solve")}
     t_build = ph["linearize"] + ph["schur"]
-    kernels = {"linearize": "k_linearize_by_pose+k_finish_poses", "schur": "k_build_tiles (linearise + C^-1 + Schur DMMA GEMM) + k_tile_reduce",
+    kernels = {"linearize": "k_linearize_by_pose (ordered per-pose finish in the last chunk)", "schur": "k_build_tiles (linearise + C^-1 + Schur DMMA GEMM) + k_tile_reduce",
                "backsub": "k_backsub_pairs+k_backsub_points_update_poses", "update_cost": "k_cost_decide",
                "solve": sinfo["kernel"]}
     # the dominant kernel of the step by device time

@@ -1,22 +1,29 @@
 // ba_engine.cu -- B200 (sm_100a) full bundle-adjustment engine behind the C-ABI of include/ba_b200.h.
 //
-// Device pipeline of one LM iteration (reference: core/full_bundle_adjustment_solver.cpp:709-1008):
+// Device pipeline of one LM iteration (reference: core/full_bundle_adjustment_solver.cpp:709-1008); seven launches on
+// one GPU for a sequential trajectory (C3 / C4), replayed as a CUDA graph:
 //   K2 k_linearize_by_pose  : per-observation projection / residual / Huber weight / Jacobians in pose order ->
-//      k_finish_poses         per-chunk partial A (21) / a (6); ordered sum, fill-lower, damping, S diagonal + rhs
-//                             (:795-810, :833-844, diagonal of :878-888)
+//                             per-chunk partial A (21) / a (6); the last chunk of a pose to finish sums the pose's
+//                             partials in chunk order, fills the lower triangle, damps and stores A, a, the S diagonal
+//                             block + rhs (:795-810, :833-844, diagonal of :878-888)
 //   K1b+K3+K4 k_build_tiles : landmarks whose poses fit a 16-pose window (ba_build_tiles.cuh): linearisation, C, b,
-//                             B (last-writer rule), damping + pivoted 3x3 LDLT inverse, E = B C^-1 and the Schur
-//                             products S -= E B^T as an FP64 tensor-core GEMM, fused (:716-831, :846-856, :858-888)
+//      + k_tile_reduce        B (last-writer rule), damping + pivoted 3x3 LDLT inverse, E = B C^-1 and the Schur
+//                             products S -= E B^T as an FP64 tensor-core GEMM, fused (:716-831, :846-856, :858-888);
+//                             windows flushed into private staging segments and added into S in segment order
 //   K1a/K3/K4 by-point path : everything else -- k_linearize_by_point (C, b), k_pair_blocks (B), k_finish_points
 //                             (C^-1), then k_schur_dense_gemm (small reduced systems: dense DMMA GEMM) or
 //                             k_schur_pairs_list (FP64 reds)
-//   K5 cholesky_solve       : FP64 Cholesky of S with the rhs carried as an extra row: banded (one CTA, DMMA window
-//                             update), cluster (small dense) or multi-kernel blocked DMMA (large dense) (:890-908)
-//   K6 k_backsub_pairs/points: y = C^-1 b - C^-1 sum_j B^T x_j, model change, trial points (:910-917,:435-455);
+//   K5 cholesky_solve       : FP64 Cholesky of S with the rhs carried along (:890-908): partitioned banded
+//                             (k_nd_persistent, nested-dissection fronts over many CTAs, ba_cholesky_nd.cuh), cluster
+//                             (small dense, ba_cholesky_cluster.cuh), multi-kernel blocked DMMA (large dense,
+//                             ba_cholesky.cuh); the serial window kernel of ba_cholesky_banded.cuh is the fallback
+//   K6 k_backsub_pairs, k_backsub_points_update_poses : y = C^-1 b - C^-1 sum_j B^T x_j, model change, trial points
+//                             (:910-917,:435-455) and, in the same launch, the se3Exp pose update (:922-927);
 //                             gradient-descent variant for FullBundleAdjustmentSolverRefactor::SolveByGradientDescent
-//   K7 k_update_poses, k_cost, k_reduce_decide : se3Exp update, trial cost, rho / accept / lambda / convergence
-//                             on the device (:922-1007)
-// Multi-GPU: landmarks sharded, k_band_pack / ncclAllReduce / k_band_unpack on [S | rhs] per iteration.
+//   K7 k_cost_decide        : trial cost; the last CTA sums the partials in order and takes the rho / accept / lambda /
+//                             convergence decision on the device (:930-1007)
+// Multi-GPU: landmarks sharded; the band of [S | rhs] is exchanged through peer memory (one-shot pushes + epoch flags,
+// summed in rank order; NCCL all-reduce as the fallback), the five LM scalars by k_exchange_decide.
 // There is no CPU fallback: every entry point that computes requires a CUDA device.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -267,15 +274,53 @@ k_finish_points(int M_total, const uint8_t *__restrict__ point_fb /*free landmar
 }
 
 // ---------------------------------------------------------------------------
-// K2: linearise in pose order -> per-chunk partial A (upper 21) and a (6).
+// K2: linearise in pose order -> per-chunk partial A (upper 21) and a (6); the LAST chunk of a pose to finish (ticket
+// per pose) sums the pose's partials in chunk order and stores A, a, the S diagonal block and the rhs (a pose without
+// observations keeps its zeros: A / a are cleared at finalisation, S every iteration).
 // ---------------------------------------------------------------------------
+// one warp per free pose: ordered sum of its chunk partials, fill-lower, damping, A/a store,
+// S diagonal block and rhs initialisation.
+__device__ __forceinline__ void finish_pose_warp(int j, int lane, const int *__restrict__ pose_chunk_ptr,
+                                                 const double *partials, double *__restrict__ A /*[N][36]*/,
+                                                 double *__restrict__ a /*[N][6]*/, double *__restrict__ Saug, int ld,
+                                                 const LmState *__restrict__ st) {
+  double s = 0.0;
+  if (lane < 27)
+    for (int c = pose_chunk_ptr[j]; c < pose_chunk_ptr[j + 1]; ++c) s += __ldcg(partials + (size_t)c * 27 + lane);
+  const double lp1 = 1.0 + st->lambda;
+  // lane e<21 holds packed upper element e ; lanes 21..26 hold a.  Scatter to the full 6x6 in two
+  // warp-wide rounds (36 entries > 32 lanes); every lane takes part in both shuffles.
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    const int e = lane + 32 * round;
+    const int ee = e < 36 ? e : 35;
+    const int r = ee / 6, c = ee % 6;
+    const int rr = r < c ? r : c, cc = r < c ? c : r;
+    const int idx = rr * 6 - rr * (rr - 1) / 2 + (cc - rr);  // packed upper index
+    double val = __shfl_sync(0xffffffffu, s, idx);
+    if (r == c) val *= lp1;
+    if (e < 36) {
+      A[(size_t)j * 36 + e] = val;
+      Saug[(size_t)(6 * j + r) * ld + 6 * j + c] = val;  // row-major (6j+r, 6j+c)
+    }
+  }
+  if (lane >= 21 && lane < 27) {
+    a[(size_t)j * 6 + (lane - 21)] = s;
+    Saug[(size_t)(6 * j + (lane - 21)) * ld + (ld - 1)] = s;  // rhs column
+  }
+}
+
+
 __global__ void __launch_bounds__(kThreads, 2)
 k_linearize_by_pose(const ChunkA *__restrict__ chunks, const double2 *__restrict__ uvA,
                     const int *__restrict__ pointA, const int *__restrict__ camA, const int *__restrict__ poseidA,
                     Params prm, const double *__restrict__ cams, double thres_huber,
-                    double *__restrict__ partials /*[n_chunks][27]*/, const LmState *__restrict__ st) {
+                    double *__restrict__ partials /*[n_chunks][27]*/, const int *__restrict__ pose_chunk_ptr,
+                    unsigned *__restrict__ pose_ticket, double *__restrict__ A, double *__restrict__ a,
+                    double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
   if (st->done) return;
   __shared__ double sm[kWarps][27];
+  __shared__ int is_last;
   const ChunkA ch = chunks[blockIdx.x];
   const double *poses = prm.poses[st->cur];
   const double *points = prm.points[st->cur];
@@ -317,42 +362,16 @@ k_linearize_by_pose(const ChunkA *__restrict__ chunks, const double2 *__restrict
   if (threadIdx.x == 0) {
     double *o = partials + (size_t)blockIdx.x * 27;
 #pragma unroll
-    for (int i = 0; i < 27; ++i) o[i] = acc[i];
+    for (int i = 0; i < 27; ++i) __stcg(o + i, acc[i]);
+    __threadfence();
+    const unsigned n_ck = (unsigned)(pose_chunk_ptr[ch.j_opt + 1] - pose_chunk_ptr[ch.j_opt]);
+    is_last = atomicAdd(pose_ticket + ch.j_opt, 1u) == n_ck - 1;
+    if (is_last) pose_ticket[ch.j_opt] = 0;
   }
-}
-
-// one warp per free pose: ordered sum of its chunk partials, fill-lower, damping, A/a store,
-// S diagonal block and rhs initialisation.
-__global__ void k_finish_poses(const int *__restrict__ pose_chunk_ptr, const double *__restrict__ partials,
-                               int N, double *__restrict__ A /*[N][36]*/, double *__restrict__ a /*[N][6]*/,
-                               double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
-  if (st->done) return;
-  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (j >= N) return;
-  double s = 0.0;
-  if (lane < 27)
-    for (int c = pose_chunk_ptr[j]; c < pose_chunk_ptr[j + 1]; ++c) s += partials[(size_t)c * 27 + lane];
-  const double lp1 = 1.0 + st->lambda;
-  // lane e<21 holds packed upper element e ; lanes 21..26 hold a.  Scatter to the full 6x6 in two
-  // warp-wide rounds (36 entries > 32 lanes); every lane takes part in both shuffles.
-#pragma unroll
-  for (int round = 0; round < 2; ++round) {
-    const int e = lane + 32 * round;
-    const int ee = e < 36 ? e : 35;
-    const int r = ee / 6, c = ee % 6;
-    const int rr = r < c ? r : c, cc = r < c ? c : r;
-    const int idx = rr * 6 - rr * (rr - 1) / 2 + (cc - rr);  // packed upper index
-    double val = __shfl_sync(0xffffffffu, s, idx);
-    if (r == c) val *= lp1;
-    if (e < 36) {
-      A[(size_t)j * 36 + e] = val;
-      Saug[(size_t)(6 * j + r) * ld + 6 * j + c] = val;  // row-major (6j+r, 6j+c)
-    }
-  }
-  if (lane >= 21 && lane < 27) {
-    a[(size_t)j * 6 + (lane - 21)] = s;
-    Saug[(size_t)(6 * j + (lane - 21)) * ld + (ld - 1)] = s;  // rhs column
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    finish_pose_warp(ch.j_opt, threadIdx.x, pose_chunk_ptr, partials, A, a, Saug, ld, st);
   }
 }
 
@@ -1666,6 +1685,7 @@ struct ba_solver {
   DevBuf<double> d_cost_partials, d_point_partials, d_pose_partials, d_scal;
   DevBuf<LmState> d_state;
   DevBuf<unsigned> d_ticket;     // k_cost_decide: CTAs that have finished
+  DevBuf<unsigned> d_pose_ticket;   // k_linearize_by_pose: chunks of every pose that have finished
   DevBuf<ba_iter_info> d_infos;
   int cost_grid = 0, point_grid = 0, pose_grid = 0;
   LmState *h_state = nullptr;  // pinned
@@ -1743,7 +1763,7 @@ static void free_device(ba_solver *s) {
   s->d_ptblk.release(); s->d_Bsoa.release();
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
-  s->d_point_partials.release(); s->d_pose_partials.release(); s->d_scal.release(); s->d_state.release(); s->d_ticket.release();
+  s->d_point_partials.release(); s->d_pose_partials.release(); s->d_scal.release(); s->d_state.release(); s->d_ticket.release(); s->d_pose_ticket.release();
   s->d_infos.release();
 }
 
@@ -2581,6 +2601,8 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(s->d_state.alloc(1));
   CUDA_TRY(s->d_ticket.alloc(1));
   CUDA_TRY(cudaMemsetAsync(s->d_ticket.p, 0, sizeof(unsigned), st));
+  CUDA_TRY(s->d_pose_ticket.alloc(std::max(1, s->N)));
+  CUDA_TRY(cudaMemsetAsync(s->d_pose_ticket.p, 0, s->d_pose_ticket.n * sizeof(unsigned), st));
   CUDA_TRY(cudaMemsetAsync(s->d_state.p, 0, sizeof(LmState), st));
   CUDA_TRY(cudaMemsetAsync(s->d_scal.p, 0, 8 * sizeof(double), st));
   static_assert(sizeof(LmState) <= kPinnedBlock, "pinned block");
@@ -2686,16 +2708,13 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
     k_zero_split<<<(s->n_split + 127) / 128, 128, 0, st>>>(s->d_split_points.p, s->n_split, s->d_ptblk.p, s->Mp, dst);
     s->launches++;
   }
-  // pose side first: k_finish_poses STORES the damped diagonal blocks and the rhs, everything after it adds
+  // pose side first: the per-pose finish of k_linearize_by_pose STORES the damped diagonal blocks and the rhs,
+  // everything after it adds
   if (s->n_chunksA > 0) {
     k_linearize_by_pose<<<s->n_chunksA, kThreads, 0, st>>>(s->d_chunksA.p, s->d_uvA.p, s->d_pointA.p,
                                                            s->d_camA.p, s->d_poseidA.p, prm, s->d_cams.p, thres,
-                                                           s->d_partialsA.p, dst);
-    s->launches++;
-  }
-  if (s->N > 0) {
-    k_finish_poses<<<(s->N + 3) / 4, 128, 0, st>>>(s->d_pose_chunk_ptr.p, s->d_partialsA.p, s->N, s->d_A.p,
-                                                    s->d_a.p, s->d_Saug.p, ld, dst);
+                                                           s->d_partialsA.p, s->d_pose_chunk_ptr.p, s->d_pose_ticket.p,
+                                                           s->d_A.p, s->d_a.p, s->d_Saug.p, ld, dst);
     s->launches++;
   }
   // landmarks on the by-point path (poses do not fit a window, or not enough neighbours for a chunk)
