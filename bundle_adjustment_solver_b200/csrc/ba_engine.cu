@@ -278,15 +278,18 @@ k_finish_points(int M_total, const uint8_t *__restrict__ point_fb /*free landmar
 // per pose) sums the pose's partials in chunk order and stores A, a, the S diagonal block and the rhs (a pose without
 // observations keeps its zeros: A / a are cleared at finalisation, S every iteration).
 // ---------------------------------------------------------------------------
-// one warp per free pose: ordered sum of its chunk partials, fill-lower, damping, A/a store,
-// S diagonal block and rhs initialisation.
-__device__ __forceinline__ void finish_pose_warp(int j, int lane, const int *__restrict__ pose_chunk_ptr,
-                                                 const double *partials, double *__restrict__ A /*[N][36]*/,
-                                                 double *__restrict__ a /*[N][6]*/, double *__restrict__ Saug, int ld,
-                                                 const LmState *__restrict__ st) {
+// one warp per free pose.  pose_partial_sum: ordered sum of the pose's chunk partials (lane e < 21: packed upper element
+// e of A, lanes 21..26: a).  pose_diag_store: fill-lower, damping, A / a store, S diagonal block and rhs initialisation.
+__device__ __forceinline__ double pose_partial_sum(int j, int lane, const int *__restrict__ pose_chunk_ptr,
+                                                   const double *partials) {
   double s = 0.0;
   if (lane < 27)
     for (int c = pose_chunk_ptr[j]; c < pose_chunk_ptr[j + 1]; ++c) s += __ldcg(partials + (size_t)c * 27 + lane);
+  return s;
+}
+__device__ __forceinline__ void pose_diag_store(int j, int lane, double s, double *__restrict__ A /*[N][36]*/,
+                                                double *__restrict__ a /*[N][6]*/, double *__restrict__ Saug, int ld,
+                                                const LmState *st) {
   const double lp1 = 1.0 + st->lambda;
   // lane e<21 holds packed upper element e ; lanes 21..26 hold a.  Scatter to the full 6x6 in two
   // warp-wide rounds (36 entries > 32 lanes); every lane takes part in both shuffles.
@@ -308,6 +311,26 @@ __device__ __forceinline__ void finish_pose_warp(int j, int lane, const int *__r
     a[(size_t)j * 6 + (lane - 21)] = s;
     Saug[(size_t)(6 * j + (lane - 21)) * ld + (ld - 1)] = s;  // rhs column
   }
+}
+__device__ __forceinline__ void finish_pose_warp(int j, int lane, const int *__restrict__ pose_chunk_ptr,
+                                                 const double *partials, double *__restrict__ A, double *__restrict__ a,
+                                                 double *__restrict__ Saug, int ld, const LmState *__restrict__ st) {
+  pose_diag_store(j, lane, pose_partial_sum(j, lane, pose_chunk_ptr, partials), A, a, Saug, ld, st);
+}
+
+// Speculative pose side (single launch with the trial cost, k_cost_linearize_by_pose below): the undamped sums of a
+// pose (27 values) live in Au[parameter buffer]; at the start of an iteration one warp per free pose damps the sums of
+// the ACCEPTED buffer with the current lambda and stores A, a, the S diagonal block and the rhs.
+__global__ void k_pose_diag(int N, const double *__restrict__ Au0, const double *__restrict__ Au1,
+                            double *__restrict__ A, double *__restrict__ a, double *__restrict__ Saug, int ld,
+                            const LmState *__restrict__ st) {
+  if (st->done) return;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= N) return;
+  const double *Au = st->cur ? Au1 : Au0;
+  const double s = lane < 27 ? Au[(size_t)j * 27 + lane] : 0.0;
+  pose_diag_store(j, lane, s, A, a, Saug, ld, st);
 }
 
 
@@ -993,6 +1016,113 @@ k_cost_decide(long long n_obs, const double2 *__restrict__ obs_uv, const int *__
     *ticket = 0;
 #pragma unroll
     for (int i = 0; i < 5; ++i) g.scal[i] = acc[i];
+    decide(g, st, infos, cap);
+  }
+}
+
+// Speculative pose side: the trial cost AND the pose-side linearisation at the trial parameters in ONE pass over the
+// observations in pose order.  When the step is accepted the trial parameters are the next iteration's linearisation
+// point, so its A / a sums are already there (Au[trial buffer]); when it is rejected the sums of the kept buffer are
+// still valid (RevertToReservedParameters re-linearises at the same point, :939-953) -- either way the next iteration
+// starts with k_pose_diag instead of a second pass over the observations (k_linearize_by_pose + the point-order cost
+// pass cost 57 us on C3, this pass costs as much as the linearisation alone).  Chunks of FIXED poses (j_opt < 0, at the
+// end of the list) contribute to the cost only.  Per pose the last chunk to finish sums the pose's partials in chunk
+// order (bit-reproducible, same sums as k_linearize_by_pose); with decide_here the last CTA of the grid sums all the
+// partials in their fixed order and takes the trust-region decision (as k_cost_decide).
+__global__ void __launch_bounds__(kThreads, 2)
+k_cost_linearize_by_pose(const ChunkA *__restrict__ chunks, const double2 *__restrict__ uvA,
+                         const int *__restrict__ pointA, const int *__restrict__ camA, const int *__restrict__ poseidA,
+                         Params prm, int which, const double *__restrict__ cams, double thres_huber,
+                         double *__restrict__ partials /*[free chunks][27]*/, double *__restrict__ cost_partials /*[grid]*/,
+                         const int *__restrict__ pose_chunk_ptr, unsigned *__restrict__ pose_ticket,
+                         double *__restrict__ Au0, double *__restrict__ Au1, unsigned *__restrict__ ticket,
+                         int decide_here, int ignore_done, DecideArgs g, LmState *st, ba_iter_info *infos, int cap) {
+  if (!ignore_done && st->done) return;
+  __shared__ double sm[kWarps][28];
+  __shared__ int is_last_pose, is_last;
+  const ChunkA ch = chunks[blockIdx.x];
+  const int buf = st->cur ^ which;
+  const double *poses = prm.poses[buf];
+  const double *points = prm.points[buf];
+  const bool free_pose = ch.j_opt >= 0;
+  double T[12];
+  {
+    const double *Tp = poses + (size_t)poseidA[ch.obs_start] * 12;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T[i] = __ldg(Tp + i);
+  }
+  double acc[28];
+#pragma unroll
+  for (int i = 0; i < 28; ++i) acc[i] = 0.0;
+  for (int t = threadIdx.x; t < ch.obs_count; t += kThreads) {
+    const int k = ch.obs_start + t;
+    const double2 uv = uvA[k];
+    const int pt = pointA[k];
+    const double *cam = cams + (camA[k] & kCamMask) * kCamStride;
+    double X[3] = {__ldg(points + (size_t)pt * 3), __ldg(points + (size_t)pt * 3 + 1),
+                   __ldg(points + (size_t)pt * 3 + 2)};
+    Proj p;
+    project(T, X, cam, uv.x, uv.y, p);
+    acc[27] += sqrt(p.r0 * p.r0 + p.r1 * p.r1);   // EvaluateCurrentCost (:381-433)
+    if (free_pose) {
+      const double w = huber_weight(p.r0, p.r1, thres_huber);
+      const double wr0 = w * p.r0, wr1 = w * p.r1;
+      double G[6], Q[12];
+      jac_G(p, cam, G);
+      jac_Q(G, p.Xb, Q);
+      // A_j(upper) += (w Q)^T Q (:519-556,807) ; a_j -= Q^T (w r) (:809)
+      int e = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double wa0 = w * Q[r], wa1 = w * Q[6 + r];
+#pragma unroll
+        for (int c = r; c < 6; ++c) acc[e++] += wa0 * Q[c] + wa1 * Q[6 + c];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[21 + r] -= Q[r] * wr0 + Q[6 + r] * wr1;
+    }
+  }
+  block_sum<28, kWarps>(acc, sm);
+  if (threadIdx.x == 0) {
+    __stcg(cost_partials + blockIdx.x, acc[27]);
+    is_last_pose = 0;
+    if (free_pose) {
+      double *o = partials + (size_t)blockIdx.x * 27;
+#pragma unroll
+      for (int i = 0; i < 27; ++i) __stcg(o + i, acc[i]);
+    }
+    __threadfence();
+    if (free_pose) {
+      const unsigned n_ck = (unsigned)(pose_chunk_ptr[ch.j_opt + 1] - pose_chunk_ptr[ch.j_opt]);
+      is_last_pose = atomicAdd(pose_ticket + ch.j_opt, 1u) == n_ck - 1;
+      if (is_last_pose) pose_ticket[ch.j_opt] = 0;
+    }
+    is_last = decide_here ? (atomicAdd(ticket, 1u) == gridDim.x - 1) : 0;
+  }
+  __syncthreads();
+  if (is_last_pose && threadIdx.x < 32) {
+    __threadfence();
+    const double v = pose_partial_sum(ch.j_opt, threadIdx.x, pose_chunk_ptr, partials);
+    if (threadIdx.x < 27) (buf ? Au1 : Au0)[(size_t)ch.j_opt * 27 + threadIdx.x] = v;
+  }
+  if (!is_last) return;
+  __threadfence();
+  __shared__ double sm2[kWarps][5];
+  double red[5] = {0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < g.n_cost; i += kThreads) red[0] += __ldcg(g.cost_partials + i);
+  for (int i = threadIdx.x; i < g.n_point; i += kThreads) {
+    red[1] += __ldcg(g.point_partials + 2 * i);
+    red[2] += __ldcg(g.point_partials + 2 * i + 1);
+  }
+  for (int i = threadIdx.x; i < g.n_pose; i += kThreads) {
+    red[3] += __ldcg(g.pose_partials + 2 * i);
+    red[4] += __ldcg(g.pose_partials + 2 * i + 1);
+  }
+  block_sum<5, kWarps>(red, sm2);
+  if (threadIdx.x == 0) {
+    *ticket = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) g.scal[i] = red[i];
     decide(g, st, infos, cap);
   }
 }
@@ -1686,6 +1816,10 @@ struct ba_solver {
   DevBuf<LmState> d_state;
   DevBuf<unsigned> d_ticket;     // k_cost_decide: CTAs that have finished
   DevBuf<unsigned> d_pose_ticket;   // k_linearize_by_pose: chunks of every pose that have finished
+  DevBuf<double> d_Au[2];           // speculative pose side: undamped A (21) / a (6) sums per free pose and parameter buffer
+  DevBuf<double> d_cost_partialsA;  // cost partials of k_cost_linearize_by_pose, one per pose-order chunk
+  int n_chunksA_all = 0;            // free-pose chunks (the first n_chunksA) + fixed-pose chunks
+  bool spec_now = false, graph_spec = false;   // speculative pose side: this ba_solve / the captured graph
   DevBuf<ba_iter_info> d_infos;
   int cost_grid = 0, point_grid = 0, pose_grid = 0;
   LmState *h_state = nullptr;  // pinned
@@ -1764,6 +1898,7 @@ static void free_device(ba_solver *s) {
   s->d_A.release(); s->d_a.release(); s->d_partialsA.release(); s->d_Saug.release(); s->d_Scopy.release();
   s->d_x.release(); s->d_z.release(); s->d_linv.release(); s->d_Btx.release(); s->d_y.release(); s->d_cost_partials.release();
   s->d_point_partials.release(); s->d_pose_partials.release(); s->d_scal.release(); s->d_state.release(); s->d_ticket.release(); s->d_pose_ticket.release();
+  s->d_Au[0].release(); s->d_Au[1].release(); s->d_cost_partialsA.release();
   s->d_infos.release();
 }
 
@@ -2452,7 +2587,7 @@ int ba_finalize(ba_solver *s) {
     for (int ps = 0; ps < Nt; ++ps)
       a_begin[ps + 1] = a_begin[ps] + (s->h_pose_opt[ps] >= 0 ? pose_begin[ps + 1] - pose_begin[ps] : 0);
     const long long nA = a_begin[Nt];
-    permA.resize(nA);
+    permA.resize(pose_begin[Nt]);   // free poses first (nA slots), the observations of fixed poses behind them
     // Chunk size: enough observations per thread to amortise the 27-value block reduction at the end of a chunk
     // (it costs as much as two observations), while the grid still fills the GPU (two 256-thread CTAs per SM);
     // a pose's observations are split evenly over its chunks.
@@ -2486,8 +2621,30 @@ int ba_finalize(ba_solver *s) {
     for (auto &c : chunksA) cnt[c.j_opt]++;
     pose_chunk_ptr[0] = 0;
     for (int j = 0; j < s->N; ++j) pose_chunk_ptr[j + 1] = pose_chunk_ptr[j] + cnt[j];
+    // observations of FIXED poses, behind the free ones (chunks with j_opt = -1): only the speculative pass
+    // (k_cost_linearize_by_pose) walks them, for the cost; k_linearize_by_pose launches the first n_chunksA chunks
+    s->n_chunksA = (int)chunksA.size();
+    long long f_at = nA;
+    std::vector<long long> f_begin(Nt, -1);
+    for (int ps = 0; ps < Nt; ++ps) {
+      const long long len = pose_begin[ps + 1] - pose_begin[ps];
+      if (s->h_pose_opt[ps] >= 0 || len == 0) continue;
+      f_begin[ps] = f_at;
+      const long long nck = (len + chunk_cap - 1) / chunk_cap;
+      const long long sz = ((len + nck - 1) / nck + 31) / 32 * 32;
+      for (long long a = f_at; a < f_at + len; a += sz)
+        chunksA.push_back(ChunkA{(int)a, (int)(std::min(f_at + len, a + sz) - a), -1, 0});
+      f_at += len;
+    }
+    if (f_at > nA) {
+      for (int ps = 0; ps < Nt; ++ps) {
+        if (f_begin[ps] < 0) continue;
+        const long long len = pose_begin[ps + 1] - pose_begin[ps];
+        for (long long r = 0; r < len; ++r) permA[f_begin[ps] + r] = pose_to_point_order[pose_begin[ps] + r];
+      }
+    }
   }
-  s->n_chunksA = (int)chunksA.size();
+  s->n_chunksA_all = (int)chunksA.size();
   lap("pose order");
   // --- upload
   early_upload.join();
@@ -2603,6 +2760,11 @@ int ba_finalize(ba_solver *s) {
   CUDA_TRY(cudaMemsetAsync(s->d_ticket.p, 0, sizeof(unsigned), st));
   CUDA_TRY(s->d_pose_ticket.alloc(std::max(1, s->N)));
   CUDA_TRY(cudaMemsetAsync(s->d_pose_ticket.p, 0, s->d_pose_ticket.n * sizeof(unsigned), st));
+  for (int b = 0; b < 2; ++b) {   // a pose without observations keeps its zeros
+    CUDA_TRY(s->d_Au[b].alloc(std::max<size_t>(1, (size_t)s->N * 27)));
+    CUDA_TRY(cudaMemsetAsync(s->d_Au[b].p, 0, s->d_Au[b].n * sizeof(double), st));
+  }
+  CUDA_TRY(s->d_cost_partialsA.alloc(std::max(1, s->n_chunksA_all)));
   CUDA_TRY(cudaMemsetAsync(s->d_state.p, 0, sizeof(LmState), st));
   CUDA_TRY(cudaMemsetAsync(s->d_scal.p, 0, 8 * sizeof(double), st));
   static_assert(sizeof(LmState) <= kPinnedBlock, "pinned block");
@@ -2653,9 +2815,18 @@ namespace {
 
 struct Phase { enum { Lin = 0, Schur, Solve, Backsub, Update, End, Count }; };
 
-static DecideArgs make_decide_args(ba_solver *s, const ba_options *opt) {
+// BA_B200_SPEC_LIN=0: the trial cost in point order and a separate pose-side pass per iteration (k_cost_decide +
+// k_linearize_by_pose) instead of the speculative pose side (k_cost_linearize_by_pose + k_pose_diag)
+// (read at every ba_solve, so that one process can run both forms; the captured graph is keyed on it)
+static bool spec_lin(const ba_solver *s) {
+  const char *e = getenv("BA_B200_SPEC_LIN");
+  return !(e && atoi(e) == 0) && s->n_chunksA_all > 0;
+}
+
+static DecideArgs make_decide_args(ba_solver *s, const ba_options *opt, bool spec = false) {
   DecideArgs g;
   g.cost_partials = s->d_cost_partials.p; g.n_cost = s->cost_grid;
+  if (spec) { g.cost_partials = s->d_cost_partialsA.p; g.n_cost = s->n_chunksA_all; }
   g.point_partials = s->d_point_partials.p; g.n_point = s->point_grid;
   g.pose_partials = s->d_pose_partials.p; g.n_pose = s->pose_grid;
   g.scal = s->d_scal.p;
@@ -2685,7 +2856,7 @@ static int ensure_S_clean(ba_solver *s) {
 }
 
 // Enqueue the build (K1..K4) on the stream.  ev: optional events at phase boundaries.
-static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
+static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev, bool spec = false) {
   cudaStream_t st = s->stream;
   const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
   const double thres = (double)opt->threshold_huber_loss;
@@ -2710,7 +2881,13 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
   }
   // pose side first: the per-pose finish of k_linearize_by_pose STORES the damped diagonal blocks and the rhs,
   // everything after it adds
-  if (s->n_chunksA > 0) {
+  if (spec) {
+    // the sums of the accepted buffer are there (the trial-cost pass of the previous iteration, or the initial pass)
+    if (s->N > 0) {
+      k_pose_diag<<<(s->N + 3) / 4, 128, 0, st>>>(s->N, s->d_Au[0].p, s->d_Au[1].p, s->d_A.p, s->d_a.p, s->d_Saug.p, ld, dst);
+      s->launches++;
+    }
+  } else if (s->n_chunksA > 0) {
     k_linearize_by_pose<<<s->n_chunksA, kThreads, 0, st>>>(s->d_chunksA.p, s->d_uvA.p, s->d_pointA.p,
                                                            s->d_camA.p, s->d_poseidA.p, prm, s->d_cams.p, thres,
                                                            s->d_partialsA.p, s->d_pose_chunk_ptr.p, s->d_pose_ticket.p,
@@ -2865,15 +3042,33 @@ static int enqueue_solve_backsub(ba_solver *s, const ba_options *opt, cudaEvent_
   return BA_OK;
 }
 
-static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
+// trial cost (which = 1) or initial cost (which = 0, ignore_done) together with the pose-side sums at those parameters
+static void launch_cost_linearize(ba_solver *s, const ba_options *opt, int which, int decide_here, int ignore_done,
+                                  const DecideArgs &g) {
+  const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
+  k_cost_linearize_by_pose<<<s->n_chunksA_all, kThreads, 0, s->stream>>>(
+      s->d_chunksA.p, s->d_uvA.p, s->d_pointA.p, s->d_camA.p, s->d_poseidA.p, prm, which, s->d_cams.p,
+      (double)opt->threshold_huber_loss, s->d_partialsA.p, s->d_cost_partialsA.p, s->d_pose_chunk_ptr.p,
+      s->d_pose_ticket.p, s->d_Au[0].p, s->d_Au[1].p, s->d_ticket.p, decide_here, ignore_done, g, s->d_state.p,
+      s->d_infos.p, (int)s->d_infos.n);
+  s->launches++;
+}
+
+static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_t *ev, bool spec = false) {
   cudaStream_t st = s->stream;
   const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
   LmState *dst = s->d_state.p;
   if (ev) cudaEventRecord(ev[Phase::Update], st);
   // the pose update (se3Exp, pose part of the model change) ran with the back-substitution of the landmarks
   // (k_backsub_points_update_poses; a forked graph branch for it cost more than the 9 us it hid)
-  DecideArgs g = make_decide_args(s, opt);
-  if (!s->comm) {
+  DecideArgs g = make_decide_args(s, opt, spec);
+  if (spec) {
+    launch_cost_linearize(s, opt, 1, s->comm ? 0 : 1, 0, g);
+    if (!s->comm) {
+      if (ev) cudaEventRecord(ev[Phase::End], st);
+      return BA_OK;
+    }
+  } else if (!s->comm) {
     k_cost_decide<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
                                                      s->d_obs_camflags.p, prm, s->d_cams.p, s->d_cost_partials.p,
                                                      s->d_ticket.p, g, dst, s->d_infos.p, (int)s->d_infos.n);
@@ -2881,9 +3076,11 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
     if (ev) cudaEventRecord(ev[Phase::End], st);
     return BA_OK;
   }
-  k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
-                                            s->d_obs_camflags.p, prm, 1, s->d_cams.p, s->d_cost_partials.p, 0, dst);
-  s->launches += 1;
+  if (!spec) {
+    k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                              s->d_obs_camflags.p, prm, 1, s->d_cams.p, s->d_cost_partials.p, 0, dst);
+    s->launches += 1;
+  }
   if (!s->comm) {
     k_reduce_decide<<<1, kThreads, 0, st>>>(g, dst, s->d_infos.p, (int)s->d_infos.n);
     s->launches++;
@@ -2916,10 +3113,11 @@ static int check_nd_error(ba_solver *s) {
 }
 
 static int enqueue_iteration(ba_solver *s, const ba_options *opt, cudaEvent_t *ev) {
-  if (int rc = enqueue_build(s, opt, ev)) return rc;
+  const bool spec = s->spec_now;
+  if (int rc = enqueue_build(s, opt, ev, spec)) return rc;
   if (int rc = enqueue_allreduce_S(s)) return rc;
   if (int rc = enqueue_solve_backsub(s, opt, ev)) return rc;
-  return enqueue_update_decide(s, opt, ev);
+  return enqueue_update_decide(s, opt, ev, spec);
 }
 
 }  // namespace
@@ -2964,10 +3162,14 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   // --- initial cost (:707) and state
   {
     const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
-    k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
-                                              s->d_obs_camflags.p, prm, 0, s->d_cams.p, s->d_cost_partials.p, 1,
-                                              s->d_state.p);
-    DecideArgs g = make_decide_args(s, &opt);
+    const bool spec = s->spec_now = spec_lin(s);
+    DecideArgs g = make_decide_args(s, &opt, spec);
+    if (spec)   // initial cost + the pose-side sums of the initial parameters (buffer cur)
+      launch_cost_linearize(s, &opt, 0, 0, 1, g), s->launches--;
+    else
+      k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
+                                                s->d_obs_camflags.p, prm, 0, s->d_cams.p, s->d_cost_partials.p, 1,
+                                                s->d_state.p);
     k_reduce_scalars<<<1, kThreads, 0, st>>>(g, 1, s->d_state.p);
     if (int rc = enqueue_allreduce_scal(s)) return rc;
     k_init_state<<<1, 1, 0, st>>>(s->d_state.p, s->d_scal.p, (double)opt.initial_lambda);
@@ -2999,7 +3201,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   if (use_graph && max_it > 0) {
     ba_options key = opt;
     key.check_every = 0;
-    if (!s->graph_exec || std::memcmp(&s->graph_opt, &key, sizeof(key)) != 0) {
+    if (!s->graph_exec || std::memcmp(&s->graph_opt, &key, sizeof(key)) != 0 || s->graph_spec != s->spec_now) {
       destroy_graph(s);
       cudaGraph_t graph;
       const long long l0 = s->launches;
@@ -3013,6 +3215,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
       CUDA_TRY(cudaGraphInstantiate(&s->graph_exec, graph, 0));
       cudaGraphDestroy(graph);
       s->graph_opt = key;
+      s->graph_spec = s->spec_now;
     }
   }
   std::vector<cudaEvent_t> &evp = s->ev;

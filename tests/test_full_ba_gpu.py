@@ -239,6 +239,48 @@ def test_graph_and_plain_launch_agree(oracle_mod, engine_lib):
     np.testing.assert_allclose(outs[0], outs[1], rtol=1e-10)
 
 
+@pytest.mark.parametrize("scene,kw,rtol", [
+    ("trajectory", dict(max_num_iterations=12), 1e-12),
+    ("c1", dict(max_num_iterations=15), 1e-8),
+    ("c1", dict(max_num_iterations=13, initial_lambda=1e-10, threshold_cost_change=1e-9, threshold_step_size=1e-9), 1e-4),
+])
+def test_speculative_pose_side_matches_separate_passes(scene, kw, rtol, monkeypatch, engine_lib):
+    """The trial-cost pass also linearises the pose side at the trial parameters (k_cost_linearize_by_pose; the next
+    iteration starts from those sums, k_pose_diag) instead of a cost pass in point order plus k_linearize_by_pose per
+    iteration (BA_B200_SPEC_LIN=0).  Same sums in the same order, so the accepted / rejected sequence, every lambda and
+    the parameters agree; the costs differ only by their summation order (pose order against point order).  The
+    undamped test_ba.cpp scene (third case) rejects seven steps in a row: the sums of the KEPT buffer must survive
+    them.  Tolerances: tile path (trajectory) is bit-reproducible -> 1e-12; the dense-GEMM Schur path of the
+    test_ba.cpp scene flushes with FP64 reds -> run-to-run drift, amplified when undamped (see the reject test)."""
+    from bundle_adjustment_solver_b200.solver import Summary
+    if scene == "trajectory":
+        sc = scenes.scene_trajectory(60, 3000, 10, stereo=True, seed=3, name="spec_traj")
+    else:
+        sc = scenes.scene_test_ba(seed=0)
+    runs = []
+    for spec in ("0", "1"):
+        monkeypatch.setenv("BA_B200_SPEC_LIN", spec)
+        _, eo = options_pair(**kw)
+        e = load_engine(sc)
+        summ = Summary()
+        e.solve(eo, summ)
+        T, X = e.get_internal()
+        runs.append((summ.optimization_info_list, T.copy(), X.copy(), e.last_result.kernel_launches))
+    (i0, T0, X0, l0), (i1, T1, X1, l1) = runs
+    assert len(i0) == len(i1) == kw["max_num_iterations"]
+    strict = len(i0) if rtol < 1e-6 else 13
+    assert [i.iteration_status for i in i0[:strict]] == [i.iteration_status for i in i1[:strict]]
+    if "initial_lambda" in kw:
+        assert [i.iteration_status for i in i1].count(2) >= 7
+    for a, b in zip(i0[:strict], i1[:strict]):
+        assert abs(a.cost - b.cost) <= rtol * abs(a.cost)
+        assert abs(a.damping_term - b.damping_term) <= 1e-12 * a.damping_term
+        assert abs(a.abs_step - b.abs_step) <= max(rtol, 1e-9) * abs(a.abs_step) + 1e-300
+    if rtol < 1e-6:
+        assert np.abs(T0 - T1).max() <= 1e-9 and np.abs(X0 - X1).max() <= 1e-9
+    assert l1 == l0                      # k_pose_diag takes the place of k_linearize_by_pose in the launch list
+
+
 def test_c3_scaled_blocks_and_iterations(oracle_mod, engine_lib):
     """Config C3 shape at 1/5 scale (40 poses x 10k landmarks would change the structure; keep 200
     poses, 10k landmarks): block parity + 3 LM iterations."""
