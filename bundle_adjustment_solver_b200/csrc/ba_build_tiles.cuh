@@ -430,23 +430,33 @@ k_build_tiles(const SchurChunk *__restrict__ chunks, const int4 *__restrict__ ba
     }
     if (cur_chunk >= 0) flush();
   }
-}// Second stage of the deterministic flush: S(r, c) += sum over the staging segments whose window holds (r, c), in
+}
+
+// Second stage of the deterministic flush: S(r, c) += sum over the staging segments whose window holds (r, c), in
 // segment order.  One CTA per scalar row; segments are sorted by their first pose, so the candidates of a row are a
 // contiguous range (pose_seg).
+// STORE form (store_bw >= 0; speculative pose side on a banded plan, ba_engine.cu enqueue_build): the row is WRITTEN
+// instead of added to -- band entries r .. r + store_bw and the rhs entry get (damped pose-side sums of the accepted
+// parameter buffer, Au) + (sum of the windows), everything else of the band gets the plain sum (zero where no window
+// reaches) -- so neither the clearing of S nor k_pose_diag is launched; the row's CTA also stores the row of A and the
+// entry of a that the back-substitution reads.  Same values as clear + k_pose_diag + add, bit for bit.
 __global__ void __launch_bounds__(96) k_tile_reduce(int n, int ld, int span /*largest column distance written*/,
                                                      const int4 *__restrict__ seg_win /*6 jmin, rows, offset lo, offset hi*/,
                                                      const int2 *__restrict__ pose_seg,
                                                      const double *__restrict__ stage, double *__restrict__ Saug,
-                                                     const LmState *__restrict__ st) {
+                                                     int store_bw, const double *__restrict__ Au0,
+                                                     const double *__restrict__ Au1, double *__restrict__ A,
+                                                     double *__restrict__ a, const LmState *__restrict__ st) {
   if (st->done) return;
   const int r = blockIdx.x;
   const int2 range = __ldg(pose_seg + r / 6);
+  const int cover = store_bw > span ? store_bw : span;   // column distances handled by this CTA (+ the rhs entry)
   // the segment records that hold this row, once per CTA and in segment order (read per entry they would be the bulk
   // of the traffic), kKeep at a time
   constexpr int kKeep = 128;
   __shared__ int4 rec[kKeep];
   __shared__ int n_rec;
-  double sum[2] = {0.0, 0.0};                 // up to two columns per thread (span + 2 <= 2 x 96)
+  double sum[2] = {0.0, 0.0};                 // up to two columns per thread (cover + 2 <= 2 x 96)
   for (int s0 = range.x; s0 < range.y; s0 += kKeep) {
     __syncthreads();
     if (threadIdx.x < 32) {       // ordered compaction of the segments that hold row r (warp 0, ballots)
@@ -467,8 +477,8 @@ __global__ void __launch_bounds__(96) k_tile_reduce(int n, int ld, int span /*la
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int t = threadIdx.x + u * blockDim.x;
-      if (t > span + 1) continue;
-      const bool rhs = t == span + 1;
+      if (t > cover + 1) continue;
+      const bool rhs = t == cover + 1;
       const int c = rhs ? n : r + t;
       if (!rhs && c >= n) continue;
       for (int k0 = 0; k0 < n_rec; k0 += 8) {        // eight loads in flight, summed in segment order
@@ -485,14 +495,39 @@ __global__ void __launch_bounds__(96) k_tile_reduce(int n, int ld, int span /*la
       }
     }
   }
+  const int j = r / 6, rr = r - 6 * j;
+  const double *Au = nullptr;
+  double lp1 = 1.0;
+  if (store_bw >= 0) {
+    Au = (st->cur ? Au1 : Au0) + (size_t)j * 27;
+    lp1 = 1.0 + st->lambda;
+    if (threadIdx.x < 6) {       // row rr of the damped 6 x 6 block A_j (both triangles)
+      const int cc = threadIdx.x, lo = rr < cc ? rr : cc, hi = rr < cc ? cc : rr;
+      double v = Au[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+      if (cc == rr) v *= lp1;
+      A[(size_t)j * 36 + rr * 6 + cc] = v;
+    }
+  }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int t = threadIdx.x + u * blockDim.x;
-    if (t > span + 1) continue;
-    const bool rhs = t == span + 1;
+    if (t > cover + 1) continue;
+    const bool rhs = t == cover + 1;
     const int c = rhs ? n : r + t;
-    if ((rhs || c < n) && sum[u] != 0.0) Saug[(size_t)r * ld + (rhs ? ld - 1 : c)] += sum[u];
+    if (!rhs && c >= n) continue;
+    double *dst = Saug + (size_t)r * ld + (rhs ? ld - 1 : c);
+    if (store_bw >= 0 && (rhs || t <= store_bw)) {
+      double base = 0.0;
+      if (rhs) {
+        base = Au[21 + rr];
+        a[(size_t)j * 6 + rr] = base;
+      } else if (t < 6 - rr) {   // (rr, rr + t) of the diagonal block, packed upper index
+        base = Au[rr * 6 - rr * (rr - 1) / 2 + t];
+        if (t == 0) base *= lp1;
+      }
+      *dst = base + sum[u];
+    } else if (sum[u] != 0.0) {
+      *dst += sum[u];
+    }
   }
 }
-
-

@@ -1820,6 +1820,7 @@ struct ba_solver {
   DevBuf<double> d_cost_partialsA;  // cost partials of k_cost_linearize_by_pose, one per pose-order chunk
   int n_chunksA_all = 0;            // free-pose chunks (the first n_chunksA) + fixed-pose chunks
   bool spec_now = false, graph_spec = false;   // speculative pose side: this ba_solve / the captured graph
+  bool rs_now = false, graph_rs = false;       // storing form of k_tile_reduce allowed (BA_B200_REDUCE_STORES)
   DevBuf<ba_iter_info> d_infos;
   int cost_grid = 0, point_grid = 0, pose_grid = 0;
   LmState *h_state = nullptr;  // pinned
@@ -2865,7 +2866,15 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev, b
   if (ev) cudaEventRecord(ev[Phase::Lin], st);
   // BA_B200_BAND_CLEAR_MIN_MB: size of the dense buffer above which only the band is cleared (tests force 0)
   static const size_t band_clear_min = (size_t)(getenv("BA_B200_BAND_CLEAR_MIN_MB") ? atoi(getenv("BA_B200_BAND_CLEAR_MIN_MB")) : 64) << 20;
-  if (s->chol.banded && s->S_clean_outside_band && (size_t)ld * ld * sizeof(double) > band_clear_min) {
+  // Speculative pose side on a banded plan with the deterministic tile flush: k_tile_reduce WRITES every band entry
+  // and rhs entry of S (damped pose-side sums + windows) and the rows of A / a, so nothing is cleared here and
+  // k_pose_diag is not launched (BA_B200_REDUCE_STORES=0: clear + k_pose_diag + adding reduce)
+  const bool reduce_stores = spec && s->rs_now && s->N > 0 && s->n_schur_chunks > 0 &&
+                             s->d_cta_seg_ptr.n > 0 && s->chol.banded && s->S_clean_outside_band &&
+                             std::max(s->stage_span, s->chol.bw) + 2 <= 2 * 96;
+  if (reduce_stores) {
+    // nothing to clear
+  } else if (s->chol.banded && s->S_clean_outside_band && (size_t)ld * ld * sizeof(double) > band_clear_min) {
     // large banded reduced system (C4: 1.15 GB dense; a small one is cleared faster by one linear memset): everything outside the band (and the rhs column) stays zero once cleared -- the
     // build, the factorisation and the exchange only touch row r's columns r .. r + bw and the last column
     const int n = 6 * s->N;
@@ -2883,7 +2892,7 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev, b
   // everything after it adds
   if (spec) {
     // the sums of the accepted buffer are there (the trial-cost pass of the previous iteration, or the initial pass)
-    if (s->N > 0) {
+    if (s->N > 0 && !reduce_stores) {
       k_pose_diag<<<(s->N + 3) / 4, 128, 0, st>>>(s->N, s->d_Au[0].p, s->d_Au[1].p, s->d_A.p, s->d_a.p, s->d_Saug.p, ld, dst);
       s->launches++;
     }
@@ -2941,7 +2950,9 @@ static int enqueue_build(ba_solver *s, const ba_options *opt, cudaEvent_t *ev, b
           s->Pp, s->d_ptblk.p, s->Mp, s->d_Saug.p, ld, stage_tab, s->d_seg_off.p, s->d_stage.p, dst);
     s->launches++;
     if (stage_tab && s->N > 0) {
-      k_tile_reduce<<<6 * s->N, 96, 0, st>>>(6 * s->N, ld, s->stage_span, s->d_seg_win.p, s->d_pose_seg.p, s->d_stage.p, s->d_Saug.p, dst);
+      k_tile_reduce<<<6 * s->N, 96, 0, st>>>(6 * s->N, ld, s->stage_span, s->d_seg_win.p, s->d_pose_seg.p, s->d_stage.p,
+                                             s->d_Saug.p, reduce_stores ? s->chol.bw : -1, s->d_Au[0].p, s->d_Au[1].p,
+                                             s->d_A.p, s->d_a.p, dst);
       s->launches++;
     }
   }
@@ -3163,6 +3174,10 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   {
     const Params prm{{s->d_poses[0].p, s->d_poses[1].p}, {s->d_points[0].p, s->d_points[1].p}};
     const bool spec = s->spec_now = spec_lin(s);
+    {
+      const char *e = getenv("BA_B200_REDUCE_STORES");
+      s->rs_now = !(e && atoi(e) == 0);
+    }
     DecideArgs g = make_decide_args(s, &opt, spec);
     if (spec)   // initial cost + the pose-side sums of the initial parameters (buffer cur)
       launch_cost_linearize(s, &opt, 0, 0, 1, g), s->launches--;
@@ -3201,7 +3216,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
   if (use_graph && max_it > 0) {
     ba_options key = opt;
     key.check_every = 0;
-    if (!s->graph_exec || std::memcmp(&s->graph_opt, &key, sizeof(key)) != 0 || s->graph_spec != s->spec_now) {
+    if (!s->graph_exec || std::memcmp(&s->graph_opt, &key, sizeof(key)) != 0 || s->graph_spec != s->spec_now || s->graph_rs != s->rs_now) {
       destroy_graph(s);
       cudaGraph_t graph;
       const long long l0 = s->launches;
@@ -3216,6 +3231,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
       cudaGraphDestroy(graph);
       s->graph_opt = key;
       s->graph_spec = s->spec_now;
+      s->graph_rs = s->rs_now;
     }
   }
   std::vector<cudaEvent_t> &evp = s->ev;

@@ -258,27 +258,37 @@ def test_speculative_pose_side_matches_separate_passes(scene, kw, rtol, monkeypa
     else:
         sc = scenes.scene_test_ba(seed=0)
     runs = []
-    for spec in ("0", "1"):
+    # (speculative pose side, storing form of k_tile_reduce): separate passes; speculative with clear + k_pose_diag +
+    # adding reduce; speculative with the reduce that writes the band (banded plans only: the trajectory scene)
+    for spec, stores in (("0", "1"), ("1", "0"), ("1", "1")):
         monkeypatch.setenv("BA_B200_SPEC_LIN", spec)
+        monkeypatch.setenv("BA_B200_REDUCE_STORES", stores)
         _, eo = options_pair(**kw)
         e = load_engine(sc)
         summ = Summary()
         e.solve(eo, summ)
         T, X = e.get_internal()
         runs.append((summ.optimization_info_list, T.copy(), X.copy(), e.last_result.kernel_launches))
-    (i0, T0, X0, l0), (i1, T1, X1, l1) = runs
-    assert len(i0) == len(i1) == kw["max_num_iterations"]
-    strict = len(i0) if rtol < 1e-6 else 13
-    assert [i.iteration_status for i in i0[:strict]] == [i.iteration_status for i in i1[:strict]]
-    if "initial_lambda" in kw:
-        assert [i.iteration_status for i in i1].count(2) >= 7
-    for a, b in zip(i0[:strict], i1[:strict]):
-        assert abs(a.cost - b.cost) <= rtol * abs(a.cost)
-        assert abs(a.damping_term - b.damping_term) <= 1e-12 * a.damping_term
-        assert abs(a.abs_step - b.abs_step) <= max(rtol, 1e-9) * abs(a.abs_step) + 1e-300
-    if rtol < 1e-6:
-        assert np.abs(T0 - T1).max() <= 1e-9 and np.abs(X0 - X1).max() <= 1e-9
-    assert l1 == l0                      # k_pose_diag takes the place of k_linearize_by_pose in the launch list
+    i0, T0, X0, l0 = runs[0]
+    for i1, T1, X1, l1 in runs[1:]:
+        assert len(i0) == len(i1) == kw["max_num_iterations"]
+        strict = len(i0) if rtol < 1e-6 else 13
+        assert [i.iteration_status for i in i0[:strict]] == [i.iteration_status for i in i1[:strict]]
+        if "initial_lambda" in kw:
+            assert [i.iteration_status for i in i1].count(2) >= 7
+        for a, b in zip(i0[:strict], i1[:strict]):
+            assert abs(a.cost - b.cost) <= rtol * abs(a.cost)
+            assert abs(a.damping_term - b.damping_term) <= 1e-12 * a.damping_term
+            assert abs(a.abs_step - b.abs_step) <= max(rtol, 1e-9) * abs(a.abs_step) + 1e-300
+        if rtol < 1e-6:
+            assert np.abs(T0 - T1).max() <= 1e-9 and np.abs(X0 - X1).max() <= 1e-9
+    # k_pose_diag takes the place of k_linearize_by_pose in the launch list; the storing reduce drops it (and the clear
+    # kernel of a large band) again
+    assert runs[1][3] == l0 and (runs[2][3] < l0 if scene == "trajectory" else runs[2][3] == l0)
+    if scene == "trajectory":
+        # the two speculative forms run the same arithmetic in the same order: bit-identical trajectories
+        assert [i.cost for i in runs[1][0]] == [i.cost for i in runs[2][0]]
+        assert np.array_equal(runs[1][1], runs[2][1]) and np.array_equal(runs[1][2], runs[2][2])
 
 
 def test_c3_scaled_blocks_and_iterations(oracle_mod, engine_lib):
