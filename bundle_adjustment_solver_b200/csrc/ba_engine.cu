@@ -1,11 +1,12 @@
 // ba_engine.cu -- B200 (sm_100a) full bundle-adjustment engine behind the C-ABI of include/ba_b200.h.
 //
-// Device pipeline of one LM iteration (reference: core/full_bundle_adjustment_solver.cpp:709-1008); seven launches on
+// Device pipeline of one LM iteration (reference: core/full_bundle_adjustment_solver.cpp:709-1008); six launches on
 // one GPU for a sequential trajectory (C3 / C4), replayed as a CUDA graph:
-//   K2 k_linearize_by_pose  : per-observation projection / residual / Huber weight / Jacobians in pose order ->
-//                             per-chunk partial A (21) / a (6); the last chunk of a pose to finish sums the pose's
-//                             partials in chunk order, fills the lower triangle, damps and stores A, a, the S diagonal
-//                             block + rhs (:795-810, :833-844, diagonal of :878-888)
+//   K2 pose side            : the sums A (21) / a (6) per pose come from the trial-cost pass of the previous iteration
+//                             (K7; speculative, Au[parameter buffer]); damped and stored at the start of the iteration
+//                             by the storing form of k_tile_reduce (banded plans) or k_pose_diag.  BA_B200_SPEC_LIN=0 and
+//                             ba_build_only: k_linearize_by_pose, per-observation Jacobians in pose order, per-chunk
+//                             partials, ordered per-pose sum in the pose's last chunk (:795-810, :833-844, :878-888)
 //   K1b+K3+K4 k_build_tiles : landmarks whose poses fit a 16-pose window (ba_build_tiles.cuh): linearisation, C, b,
 //      + k_tile_reduce        B (last-writer rule), damping + pivoted 3x3 LDLT inverse, E = B C^-1 and the Schur
 //                             products S -= E B^T as an FP64 tensor-core GEMM, fused (:716-831, :846-856, :858-888);
@@ -20,8 +21,9 @@
 //   K6 k_backsub_pairs, k_backsub_points_update_poses : y = C^-1 b - C^-1 sum_j B^T x_j, model change, trial points
 //                             (:910-917,:435-455) and, in the same launch, the se3Exp pose update (:922-927);
 //                             gradient-descent variant for FullBundleAdjustmentSolverRefactor::SolveByGradientDescent
-//   K7 k_cost_decide        : trial cost; the last CTA sums the partials in order and takes the rho / accept / lambda /
-//                             convergence decision on the device (:930-1007)
+//   K7 k_cost_linearize_by_pose : trial cost in pose order + the pose-side sums at the trial parameters; the last CTA
+//                             sums the partials in order and takes the rho / accept / lambda / convergence decision
+//                             on the device (:930-1007).  k_cost_decide (point order) with BA_B200_SPEC_LIN=0
 // Multi-GPU: landmarks sharded; the band of [S | rhs] is exchanged through peer memory (one-shot pushes + epoch flags,
 // summed in rank order; NCCL all-reduce as the fallback), the five LM scalars by k_exchange_decide.
 // There is no CPU fallback: every entry point that computes requires a CUDA device.
@@ -2596,7 +2598,8 @@ int ba_finalize(ba_solver *s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
     // measured on B200 (C3: 4 / 8 / 13 observations per thread -> 55 / 47 / 56 us; C4: 4 / 8 / 16 -> 0.46 / 0.41 /
     // 0.39 ms): about three CTAs per slot, between 4 and 16 observations per thread
-    const int per_thread = (int)std::min<long long>(16, std::max<long long>(4, nA / ((long long)3 * sms * kThreads)));
+    int per_thread = (int)std::min<long long>(16, std::max<long long>(4, nA / ((long long)3 * sms * kThreads)));
+    if (const char *e = getenv("BA_B200_POSE_CHUNK_OBS")) per_thread = std::max(1, atoi(e));   // A/B runs
     const long long chunk_cap = (long long)kThreads * per_thread;
     for (int ps = 0; ps < Nt; ++ps) {
       const int j = s->h_pose_opt[ps];
