@@ -95,11 +95,16 @@ def algorithmic_bytes(sz, n_obs_free_pose, solve_info):
     clear = 8 * n * (int(solve_info["bw"]) + 2) if solve_info["band_clear"] else 8 * (n + 1) * (n + 1)
     b = {}
     b["linearize"] = 28 * n_obs_free_pose + 96 * Nt + 24 * Mt + 2 * 336 * N + clear
+    banded = "k_nd" in solve_info["kernel"] or "banded" in solve_info["kernel"]
+    stores = SPEC_LIN and banded and os.environ.get("BA_B200_REDUCE_STORES", "1") != "0"
     if SPEC_LIN:
         # speculative pose side: the pass over the observations in pose order is the trial-cost pass (update_cost);
-        # the linearize phase only clears S and damps / stores the per-pose sums (216 B read, 336 B + 336 B written)
-        b["linearize"] = (216 + 2 * 336) * N + clear
+        # the linearize phase only clears S and damps / stores the per-pose sums (216 B read, 336 B + 336 B written) --
+        # and is empty on banded plans, where the storing form of k_tile_reduce does both (charged to schur)
+        b["linearize"] = 0 if stores else (216 + 2 * 336) * N + clear
     b["schur"] = 20 * O + 24 * P + 96 * Nt + 24 * Mt + 144 * P + 144 * M + int(solve_info["alg_bytes"])
+    if stores:
+        b["schur"] += (216 + 2 * 336) * N
     b["backsub"] = 144 * P + 8 * P + 48 * N + 24 * M + (144 + 24 + 24 + 24 + 24) * Mt
     b["update_cost"] = 28 * O + 96 * Nt * 2 + 24 * Mt + (216 * N if SPEC_LIN else 0)
     b["schur_flops"] = 330.0 * O
@@ -696,7 +701,10 @@ def main():
     # Jacobian / Schur build time: with the speculative pose side the pose-side Jacobians are formed in the trial-cost
     # pass, so that pass is charged to the build as well (conservative: it also evaluates the cost)
     t_build = ph["linearize"] + ph["schur"] + (ph["update_cost"] if SPEC_LIN else 0.0)
-    kernels = {"linearize": "k_pose_diag (damps and stores the per-pose sums of the accepted parameters)" if SPEC_LIN
+    banded = "k_nd" in sinfo["kernel"] or "banded" in sinfo["kernel"]
+    stores = SPEC_LIN and banded and os.environ.get("BA_B200_REDUCE_STORES", "1") != "0"
+    kernels = {"linearize": ("(none: the storing form of k_tile_reduce writes the damped pose-side blocks, S is not cleared)" if stores
+                             else "k_pose_diag (damps and stores the per-pose sums of the accepted parameters)") if SPEC_LIN
                else "k_linearize_by_pose (ordered per-pose finish in the last chunk)",
                "schur": "k_build_tiles (linearise + C^-1 + Schur DMMA GEMM) + k_tile_reduce",
                "backsub": "k_backsub_pairs+k_backsub_points_update_poses",

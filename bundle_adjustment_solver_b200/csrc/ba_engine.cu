@@ -1031,7 +1031,10 @@ k_cost_decide(long long n_obs, const double2 *__restrict__ obs_uv, const int *__
 // end of the list) contribute to the cost only.  Per pose the last chunk to finish sums the pose's partials in chunk
 // order (bit-reproducible, same sums as k_linearize_by_pose); with decide_here the last CTA of the grid sums all the
 // partials in their fixed order and takes the trust-region decision (as k_cost_decide).
-__global__ void __launch_bounds__(kThreads, 2)
+#ifndef BA_K7_MINB
+#define BA_K7_MINB 2   // resident CTAs per SM the register allocation aims at (A/B builds: 3 -> 85 registers, spills)
+#endif
+__global__ void __launch_bounds__(kThreads, BA_K7_MINB)
 k_cost_linearize_by_pose(const ChunkA *__restrict__ chunks, const double2 *__restrict__ uvA,
                          const int *__restrict__ pointA, const int *__restrict__ camA, const int *__restrict__ poseidA,
                          Params prm, int which, const double *__restrict__ cams, double thres_huber,
