@@ -3068,7 +3068,6 @@ static void launch_cost_linearize(ba_solver *s, const ba_options *opt, int which
       (double)opt->threshold_huber_loss, s->d_partialsA.p, s->d_cost_partialsA.p, s->d_pose_chunk_ptr.p,
       s->d_pose_ticket.p, s->d_Au[0].p, s->d_Au[1].p, s->d_ticket.p, decide_here, ignore_done, g, s->d_state.p,
       s->d_infos.p, (int)s->d_infos.n);
-  s->launches++;
 }
 
 static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_t *ev, bool spec = false) {
@@ -3081,6 +3080,7 @@ static int enqueue_update_decide(ba_solver *s, const ba_options *opt, cudaEvent_
   DecideArgs g = make_decide_args(s, opt, spec);
   if (spec) {
     launch_cost_linearize(s, opt, 1, s->comm ? 0 : 1, 0, g);
+    s->launches++;
     if (!s->comm) {
       if (ev) cudaEventRecord(ev[Phase::End], st);
       return BA_OK;
@@ -3186,7 +3186,7 @@ int ba_solve(ba_solver *s, const ba_options *opt_in, ba_iter_info *infos, int ca
     }
     DecideArgs g = make_decide_args(s, &opt, spec);
     if (spec)   // initial cost + the pose-side sums of the initial parameters (buffer cur)
-      launch_cost_linearize(s, &opt, 0, 0, 1, g), s->launches--;
+      launch_cost_linearize(s, &opt, 0, 0, 1, g);
     else
       k_cost<<<s->cost_grid, kThreads, 0, st>>>(s->n_obs, s->d_obs_uv.p, s->d_obs_pose.p, s->d_obs_point.p,
                                                 s->d_obs_camflags.p, prm, 0, s->d_cams.p, s->d_cost_partials.p, 1,
