@@ -292,3 +292,34 @@ def test_cpp_bal_loader_matches_python_loader(tmp_path):
     assert np.array_equal(obs[:, 0], sc.obs_pose) and np.array_equal(obs[:, 1], sc.obs_point)
     assert np.abs(obs[:, 2:] - sc.obs_uv).max() < 1e-9
     assert subprocess.run([str(exe), str(tmp_path / "missing.txt")], capture_output=True, text=True).returncode == 2
+
+
+def test_bench_byte_accounting_moves_with_the_pose_side_forms(monkeypatch):
+    """bench.py's algorithmic bytes per phase follow the engine's switches: with the speculative pose side the pass
+    over the observations is charged to the trial-cost phase, with the storing reduce (banded plans) the linearize
+    phase holds no kernel at all -- and no form counts the pass over the observations twice."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import importlib
+    import bench
+    sz = dict(n_obs=1_000_484, N_total=200, M_total=50_000, N=198, M=50_000, P=499_479)
+    banded = dict(kernel="k_nd_persistent<14,11> (partitioned banded Cholesky)", bw=71, band_clear=False, alg_bytes=7.0e5)
+    dense = dict(banded, kernel="k_chol_cluster (blocked Cholesky in one thread-block-cluster launch)")
+    free_obs = 990_000
+    out = {}
+    for name, spec, stores, info in (("separate", "0", "1", banded), ("spec", "1", "0", banded),
+                                     ("spec_stores", "1", "1", banded), ("spec_dense", "1", "1", dense)):
+        monkeypatch.setenv("BA_B200_SPEC_LIN", spec)
+        monkeypatch.setenv("BA_B200_REDUCE_STORES", stores)
+        importlib.reload(bench)
+        out[name] = bench.algorithmic_bytes(sz, free_obs, info)
+    monkeypatch.delenv("BA_B200_SPEC_LIN"); monkeypatch.delenv("BA_B200_REDUCE_STORES")
+    importlib.reload(bench)
+    assert out["separate"]["linearize"] > 28 * free_obs and out["separate"]["update_cost"] >= 28 * sz["n_obs"]
+    for k in ("spec", "spec_stores", "spec_dense"):
+        assert out[k]["linearize"] < 28 * free_obs          # no pass over the observations in the linearize phase
+        assert out[k]["update_cost"] > out["separate"]["update_cost"]
+    assert out["spec_stores"]["linearize"] == 0 and out["spec_dense"]["linearize"] > 0
+    assert out["spec_stores"]["schur"] > out["spec"]["schur"]          # the storing reduce writes the pose-side blocks
+    total = lambda b: b["linearize"] + b["schur"] + b["backsub"] + b["update_cost"]
+    assert total(out["spec_stores"]) < total(out["spec"]) < total(out["separate"])
